@@ -1,0 +1,296 @@
+/*
+ * rs_b200.h — C-ABI of the B200-native CTR training hot path.
+ *
+ * Boundary that replaces, for the hot path of yueshifeng/recommendSystem
+ * (SURVEY.md §8), the arithmetic that the reference reaches through Keras
+ * layers + the `tensornet` sparse runtime.  The reference has no FFI of its
+ * own (it is pure Python over TensorFlow); every entry point below cites the
+ * reference call site whose arithmetic it replaces (paths relative to the
+ * reference repo root).
+ *
+ * Conventions
+ *   - extern "C"; plain pointers and sizes only.  No torch / STL types.
+ *   - every pointer is CALLER-OWNED DEVICE memory unless the name ends in
+ *     `_host`; the library never allocates behind the caller's back
+ *     (workspaces are sized with rs_*_workspace_bytes and passed in).
+ *   - every call is asynchronous on the `stream` passed (a cudaStream_t cast
+ *     to void*; NULL = legacy default stream) and is CUDA-graph capturable.
+ *   - return value: 0 = ok, otherwise an rs_status / cudaError_t code; the
+ *     text is available from rs_last_error().  Never aborts the process.
+ *   - matrices are row-major.  Keras `Dense.kernel` layout is kept: [in, out],
+ *     y = x @ kernel + bias.
+ *   - dtype codes: RS_F32 = 0, RS_BF16 = 1.
+ */
+#ifndef RS_B200_H_
+#define RS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_ABI_VERSION 1
+
+enum rs_dtype { RS_F32 = 0, RS_BF16 = 1 };
+
+enum rs_status {
+  RS_OK = 0,
+  RS_ERR_INVALID = 10001,     /* bad argument (shape / dtype / alignment) */
+  RS_ERR_UNSUPPORTED = 10002, /* combination not built */
+  RS_ERR_WORKSPACE = 10003    /* workspace too small */
+};
+
+/* GEMM epilogues (rs_gemm).  `aux` is an [M,N] tensor with leading dim ldaux. */
+enum rs_epilogue {
+  RS_EPI_NONE = 0,         /* C = A·B                               */
+  RS_EPI_BIAS = 1,         /* C = A·B + bias[n]                      */
+  RS_EPI_BIAS_RELU = 2,    /* C = relu(A·B + bias)      Dense(relu)  */
+  RS_EPI_BIAS_SIGMOID = 3, /* C = sigmoid(A·B + bias)   Dense(sigmoid) */
+  RS_EPI_MUL_RELU_MASK = 4,/* C = (A·B) * (aux > 0)     dgrad through relu */
+  RS_EPI_MUL_DSIGMOID = 5, /* C = (A·B) * aux*(1-aux)   dgrad through sigmoid */
+  RS_EPI_ACCUM = 6         /* C += A·B                               */
+};
+
+/* DIN attention-unit variants. */
+enum rs_din_mode {
+  RS_DIN_A = 0, /* din.py:18-47           [q,k,q*k] relu/relu, zero mask, sum pool   */
+  RS_DIN_B = 1  /* staytime/layer.py:16-41 [q,f,q-f,q*f] sigmoid/linear, softmax pool */
+};
+
+/* ------------------------------------------------------------------ misc -- */
+int rs_abi_version(void);
+const char* rs_last_error(void);
+/* Number of kernels this library has launched since load (bench.py's
+ * `gpu_launches` claim is read from here). */
+uint64_t rs_launch_count(void);
+/* 1 if the library was compiled for sm_100a (it never is anything else). */
+int rs_built_for_sm100a(void);
+
+/* ------------------------------------------------- K1/K2 embedding gather --
+ * Replaces tn.layers.EmbeddingFeatures(...)(inputs) for single-valued slots
+ * (bag = 1, `combiner='mean'` degenerates to a gather):
+ *   staytime/VideoDnn.py:224-226,237   rough_rank/model.py:96-107
+ *   rank/ctr/base_model.py:210-216     rank/finish/videodnn.py:60-66
+ *
+ * Tables of all fields live in one fp32 arena `table[total_rows, d]`.
+ * Lookup i (i in [0,n)) belongs to field f = i % F and reads arena row
+ *   row = row_base[f] + (ids[i] mod rows[f])       (ids[i] >= 0)
+ * ids[i] < 0 is a padding id: the output row is zeros and row = -1.
+ * `sort_keys` (nullable) receives (uint64(row) << 32) | i  — the key the
+ * sparse-gradient path sorts (padding rows get row = 0xFFFFFFFF).
+ * `rows_out` (nullable) receives the int32 arena row.
+ * Integer addressing and the fp32 payload copy are bit-exact.
+ */
+int rs_embed_gather_fwd(const float* table, const int64_t* ids,
+                        const int64_t* row_base, const int64_t* rows,
+                        int64_t n, int F, int d,
+                        void* out, int out_dtype,
+                        uint64_t* sort_keys, int32_t* rows_out, void* stream);
+
+/* Gather by precomputed arena rows (used by the row-sharded multi-GPU path
+ * after id routing, and for sequence slots: staytime/VideoDnn.py:228-231
+ * `combiner=None, seq_max_len=N` -> ([B,T,d], mask[B,T])).
+ * rowidx[i] < 0 -> zeros and mask 0.  `mask_out` nullable (uint8). */
+int rs_embed_gather_rows(const float* table, const int32_t* rowidx, int64_t n,
+                         int d, void* out, int out_dtype, uint8_t* mask_out,
+                         uint64_t* sort_keys, void* stream);
+
+/* Multi-valued slots: `combiner='mean'` over a CSR bag
+ * (staytime/VideoDnn.py:224-226 with VarLenFeature ids, staytime/parse.py:22-23).
+ * bag b of field f covers ids[offsets[b*F+f] .. offsets[b*F+f+1]). Empty bag -> zeros. */
+int rs_embed_gather_bag_mean(const float* table, const int64_t* ids,
+                             const int64_t* offsets, const int64_t* row_base,
+                             const int64_t* rows, int64_t n_bags, int F, int d,
+                             void* out, int out_dtype, void* stream);
+
+/* --------------------------------- K3 sparse gradient + fused optimizer --
+ * Replaces the backward of EmbeddingFeatures + the server-side sparse
+ * optimizers tn.core.Adam(learning_rate, beta1, beta2, epsilon)
+ *   (rank/multi_head/multidnn.py:235, rank/ctr/base_model.py:163,
+ *    rough_rank/model.py:106)
+ * and tn.core.AdaGrad(learning_rate, initial_g2sum, initial_scale)
+ *   (staytime/VideoDnn.py:233,259).
+ * Deterministic: keys are radix-sorted (stable) by row; each run of equal
+ * rows is summed left-to-right in lookup order by one thread group, then the
+ * optimizer is applied once per touched row.  No atomics.
+ */
+size_t rs_embed_sort_workspace_bytes(int64_t n);
+/* Sorts `keys` by their high 32 bits restricted to `row_bits` significant
+ * bits (row_bits = ceil(log2(total_rows+1)), or 32 to be safe). */
+int rs_embed_sort_keys(const uint64_t* keys, uint64_t* keys_sorted, int64_t n,
+                       int row_bits, void* ws, size_t ws_bytes, void* stream);
+
+/* opt_scalars: device float[4] = {step, beta1^t, beta2^t, corr} maintained by
+ * rs_adam_advance; the effective rate is lr * corr with
+ * corr = sqrt(1-beta2^t)/(1-beta1^t) (Keras/TF Adam form):
+ *   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; w -= lr*corr * m/(sqrt(v)+eps)
+ * grad is [n, d] in lookup order (row i = gradient of lookup i), scaled by
+ * grad_scale before use. */
+int rs_embed_segsum_adam(float* w, float* m, float* v,
+                         const void* grad, int grad_dtype,
+                         const uint64_t* keys_sorted, int64_t n, int d,
+                         float lr, float beta1, float beta2, float eps,
+                         const float* opt_scalars, float grad_scale, void* stream);
+
+/* TensorNet AdaGrad: g2sum is ONE scalar per row:
+ *   g2sum += mean_d(g*g) ; w -= lr * g / (sqrt(g2sum) + eps)
+ * per_element != 0 switches to the classic per-element accumulator
+ * (g2sum then has shape [rows, d]). */
+int rs_embed_segsum_adagrad(float* w, float* g2sum,
+                            const void* grad, int grad_dtype,
+                            const uint64_t* keys_sorted, int64_t n, int d,
+                            float lr, float eps, int per_element,
+                            float grad_scale, void* stream);
+
+/* Deterministic sorted-segment sum only (no optimizer).  Output is indexed by
+ * SORTED position p in [0,n): seg_rows[p] = arena row if p is the first
+ * position of its run (a segment head) else -1; seg_sum[p, :] = the run's
+ * summed gradient at heads (unspecified elsewhere).  Used by the parity tests
+ * and by the multi-GPU path's checks. */
+int rs_embed_segsum(const void* grad, int grad_dtype, const uint64_t* keys_sorted,
+                    int64_t n, int d, int32_t* seg_rows, float* seg_sum,
+                    void* stream);
+
+/* step += 1; beta powers and corr refreshed (device-side so that a captured
+ * CUDA graph advances the optimizer on every replay). */
+int rs_adam_advance(float* opt_scalars, float beta1, float beta2, void* stream);
+
+/* Dense Adam over a flat fp32 parameter buffer (tn.optimizer.Optimizer(
+ * tn.core.Adam(...)), rank/multi_head/model.py:53, staytime/model.py:72).
+ * Optionally refreshes a bf16 shadow copy used by the tensor-core GEMMs. */
+int rs_dense_adam(float* w, float* m, float* v, const float* g, int64_t n,
+                  float lr, float beta1, float beta2, float eps,
+                  const float* opt_scalars, void* w_bf16_shadow, void* stream);
+
+/* ------------------------------------------------ K7 id routing (sharded) --
+ * Row-sharded tables: owner(i) = (ids[i] mod rows[f]) mod world,
+ * local arena row = local_base[f] + (ids[i] mod rows[f]) / world.
+ * Stable bucket-by-owner: send_rows[ send_offsets[o] + k ] is the k-th lookup
+ * (in lookup order) owned by rank o; inverse[i] = its slot. Bit-exact vs the
+ * CPU oracle.  Replaces TensorNet's sign->shard routing (only trace in the
+ * reference: tn.core.shard_num()/self_shard_id(), staytime/parse.py:78-79).
+ * counts/offsets are int32[world] / int32[world+1] device arrays. */
+size_t rs_route_workspace_bytes(int64_t n, int world);
+int rs_route_ids(const int64_t* ids, int64_t n, int F, const int64_t* rows,
+                 const int64_t* local_base, int world,
+                 int32_t* send_rows, int32_t* inverse,
+                 int32_t* send_counts, int32_t* send_offsets,
+                 void* ws, size_t ws_bytes, void* stream);
+/* out[i, :] = src[inverse[i], :] (un-permute received rows) and its adjoint
+ * out[inverse[i], :] = src[i, :]. */
+int rs_permute_rows(const void* src, void* out, const int32_t* index, int64_t n,
+                    int d, int dtype, int scatter, void* stream);
+
+/* ------------------------------------------------- K4 InteractingLayer ----
+ * InteractingLayer.call (InteractingLayer.py:37-61; duplicate at
+ * rank/multi_head/interacting_layer.py): L iterations with SHARED weights of
+ *   Q,K,V,R = relu(X·W{q,k,v,r} + b)         (:42-46)
+ *   per head: P = softmax(Q_h K_hᵀ / sqrt(U/H))  (:47-52)
+ *   X <- LayerNorm(relu(P V_h [+ R]))         (:55-60)
+ * Wqkvr is [D, 4U] = [Wq | Wk | Wv | Wr] (Keras [in,out] kernels side by
+ * side), bqkvr [4U].  D must equal U when L > 1.  x, y are [B, F, D|U] with
+ * row strides x_ld / y_ld (elements) between samples' field rows, i.e.
+ * element (b,f,c) at ptr[(b*F+f)*ld + c].
+ * `saved` (training): [L, B*F, U] inputs of every iteration after the first
+ * plus nothing else — the backward recomputes the rest.  May be NULL for
+ * inference.  dtype applies to x, y, saved.  Parameters are fp32.
+ * compute_bf16 != 0 runs the projections on tcgen05 tensor cores (bf16
+ * operands, fp32 TMEM accumulators); 0 = fp32 FFMA everywhere (parity mode).
+ */
+size_t rs_interacting_workspace_bytes(int B, int F, int D, int U);
+int rs_interacting_fwd(const void* x, int64_t x_ld, int dtype,
+                       const float* Wqkvr, const float* bqkvr,
+                       const float* ln_gamma, const float* ln_beta, float ln_eps,
+                       void* y, int64_t y_ld, void* saved,
+                       int B, int F, int D, int U, int H, int L, int use_res,
+                       int compute_bf16, void* stream);
+/* dx [B,F,D] (ld dx_ld), dparams: fp32 [D*4U + 4U + U + U] = dW | db | dgamma |
+ * dbeta, OVERWRITTEN.  ws >= rs_interacting_workspace_bytes. */
+int rs_interacting_bwd(const void* x, int64_t x_ld, const void* saved, int dtype,
+                       const float* Wqkvr, const float* bqkvr,
+                       const float* ln_gamma, const float* ln_beta, float ln_eps,
+                       const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld,
+                       float* dparams, int B, int F, int D, int U, int H, int L,
+                       int use_res, int compute_bf16, void* ws, size_t ws_bytes,
+                       void* stream);
+
+/* --------------------------------------------------------- K6 DIN unit ----
+ * mode RS_DIN_A  din.py:18-47:
+ *   s_t = relu(relu([q,k_t,q*k_t]·W1+b1)·W2+b2); s_t = t < seq_len[b] ? s_t : 0
+ *   out = Σ_t s_t · values_t
+ * mode RS_DIN_B  staytime/layer.py:16-41:
+ *   s_t = sigmoid([q,f_t,q-f_t,q*f_t]·W1+b1)·W2+b2; s_t = mask ? s_t : -2^32+1
+ *   out = Σ_t softmax(s)_t · f_t        (values == keys == facts)
+ * q [B,H]; keys/values [B,T,H] (element (b,t,c) at ptr[(b*T+t)*kv_ld + c], so
+ * the first 16 columns of a wider [B,T,32] tensor can be used in place,
+ * staytime/VideoDnn.py:68); seq_len int32 [B] (mode A) or mask uint8 [B,T]
+ * (mode B; NULL = all valid).  W1 [3H|4H, Hd], b1 [Hd], W2 [Hd,1], b2 [1]
+ * with Hd = 16 in both reference variants.  out [B,H] fp32|bf16.
+ */
+int rs_din_fwd(int mode, const void* q, const void* keys, const void* values,
+               int64_t kv_ld, int dtype, const int32_t* seq_len,
+               const uint8_t* mask, const float* W1, const float* b1,
+               const float* W2, const float* b2, void* out,
+               int B, int T, int H, int Hd, void* stream);
+size_t rs_din_workspace_bytes(int mode, int B, int T, int H, int Hd);
+/* dq [B,H], dkeys/dvalues [B,T,H] (ld dkv_ld; in mode B dvalues is ignored and
+ * dkeys holds the full facts gradient), dparams fp32 = dW1|db1|dW2|db2
+ * OVERWRITTEN. */
+int rs_din_bwd(int mode, const void* q, const void* keys, const void* values,
+               int64_t kv_ld, int dtype, const int32_t* seq_len,
+               const uint8_t* mask, const float* W1, const float* b1,
+               const float* W2, const float* b2, const void* dout,
+               void* dq, void* dkeys, void* dvalues, int64_t dkv_ld,
+               float* dparams, int B, int T, int H, int Hd,
+               void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------- K5 MLP tower ----
+ * One Dense layer and its gradients as a GEMM with a fused epilogue:
+ *   C[M,N] = epi( op(A)[M,K] · op(B)[K,N] )
+ * (`DNN.call` rough_rank/layer.py:100-109; MultiLayerDense autoint:40-41,49-50;
+ *  expert/gate Dense staytime/VideoDnn.py:135-147, multidnn.py:62-63,83-85.)
+ * transA: A is stored [K,M] (ld lda); transB: B is stored [N,K] (ld ldb).
+ * dtype_ab RS_BF16 -> tcgen05 tensor-core kernel (fp32 TMEM accumulation);
+ * RS_F32 -> fp32 FFMA kernel (parity mode).  dtype_c is the dtype of C/aux.
+ */
+int rs_gemm(const void* A, int64_t lda, int transA,
+            const void* B, int64_t ldb, int transB,
+            void* C, int64_t ldc, const float* bias,
+            const void* aux, int64_t ldaux, int epilogue,
+            int M, int N, int K, int dtype_ab, int dtype_c, void* stream);
+/* out[n] = Σ_m x[m, n]  (bias gradient); deterministic two-level reduce
+ * (fixed row-block order, no atomics). ws >= rs_colsum_workspace_bytes. */
+size_t rs_colsum_workspace_bytes(int M, int N);
+int rs_colsum(const void* x, int64_t ldx, int dtype, float* out, int M, int N,
+              void* ws, size_t ws_bytes, void* stream);
+/* y = x * (ref > 0) or x * ref*(1-ref) elementwise (activation backward on a
+ * [M,N] tile with leading dims). kind: 0 relu-mask, 1 dsigmoid. */
+int rs_act_bwd(const void* x, int64_t ldx, const void* ref, int64_t ldref,
+               void* y, int64_t ldy, int M, int N, int dtype, int kind,
+               void* stream);
+/* dst[m, 0:N] = src[m, 0:N] with dtype conversion and leading dims
+ * (concat / slice / cast glue). */
+int rs_copy2d(const void* src, int64_t lds, int src_dtype, void* dst,
+              int64_t ldd, int dst_dtype, int M, int N, void* stream);
+/* y[m, n] = a[m, n] + b[m, n] with leading dims. */
+int rs_add2d(const void* a, int64_t lda, const void* b, int64_t ldb, void* y,
+             int64_t ldy, int M, int N, int dtype, void* stream);
+
+/* ----------------------------------------------------------- K8 losses ----
+ * p = clip(p_raw, 1e-6, 1)                                  (autoint:52)
+ * loss = mean_b Σ_k ( -y log(p+1e-6) - (a-y) log(1-p+1e-6) )
+ *                                  (rank/ctr/base_model.py:7-12; a = 1)
+ * p_raw is the output of the final Dense(·, sigmoid); dz is the gradient wrt
+ * that layer's PRE-activation (sigmoid' and the clip's pass-through folded in).
+ * loss_out: device float[1], overwritten (deterministic block-ordered sum).
+ */
+int rs_bce_sigmoid_fwd_bwd(const void* p_raw, int dtype, const float* y,
+                           float a, float* loss_out, void* dz, int B, int k,
+                           void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RS_B200_H_ */

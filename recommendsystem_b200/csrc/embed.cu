@@ -1,0 +1,652 @@
+// embed.cu — K1/K2 embedding gather, K3 sorted-segment gradient + fused sparse
+// optimizers, K7 id routing.  All HBM-bound integer / copy work: the design
+// goals are full-sector coalescing (a thread group covers one whole row with
+// 16-B loads), many independent loads in flight per lane, and index math done
+// once per lookup per warp (one lane per lookup, then shuffled to the group).
+#include "common.cuh"
+#include <cub/device/device_radix_sort.cuh>
+
+namespace rs {
+
+// ---------------------------------------------------------------- gather ---
+// One warp handles 32*LPL lookups per iteration.
+//   phase 1: lane l owns lookups base + l (+32, ...): loads the id (coalesced),
+//            reduces it to an arena row with 32-bit math when it fits, emits
+//            the sort key / row index.
+//   phase 2: the warp is split in 32/G groups of G lanes; in step s group j
+//            serves lookup s*(32/G)+j: the owning lane's row is shuffled in,
+//            every lane of the group loads 16 B of the row.  All G*LPL loads
+//            are issued before the first store.
+template <int G, int LPL, typename OutT, bool FROM_IDS>
+__global__ void __launch_bounds__(128)
+embed_gather_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids,
+                    const int32_t* __restrict__ rowidx,
+                    const int64_t* __restrict__ row_base, const int64_t* __restrict__ rows,
+                    int64_t n, int F, int d, OutT* __restrict__ out,
+                    uint64_t* __restrict__ sort_keys, int32_t* __restrict__ rows_out,
+                    uint8_t* __restrict__ mask_out) {
+  constexpr int GROUPS = 32 / G;  // lookups served per step
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;        // lane within group
+  const int gj = lane / G;        // group within warp
+  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const bool col_ok = gl * 4 < d;
+
+  for (int64_t base = warp_global * (32 * LPL); base < n; base += nwarps * (32 * LPL)) {
+    int32_t myrow[LPL];
+#pragma unroll
+    for (int k = 0; k < LPL; ++k) {
+      const int64_t i = base + k * 32 + lane;
+      int32_t r = -1;
+      if (i < n) {
+        if (FROM_IDS) {
+          const int64_t id = ids[i];
+          if (id >= 0) {
+            int f;
+            if (n < (int64_t)0x7fffffff) f = (int)((uint32_t)i % (uint32_t)F);
+            else f = (int)(i % F);
+            const uint64_t R = (uint64_t)__ldg(rows + f);
+            uint64_t rr;
+            if (((uint64_t)id | R) >> 32) rr = (uint64_t)id % R;
+            else rr = (uint32_t)id % (uint32_t)R;
+            r = (int32_t)(__ldg(row_base + f) + (int64_t)rr);
+          }
+        } else {
+          r = rowidx[i];
+        }
+        if (sort_keys) sort_keys[i] = ((uint64_t)(uint32_t)r << 32) | (uint64_t)(uint32_t)i;
+        if (rows_out) rows_out[i] = r;
+        if (mask_out) mask_out[i] = r >= 0 ? 1 : 0;
+      }
+      myrow[k] = r;
+    }
+
+    float4 v[LPL][G];
+#pragma unroll
+    for (int k = 0; k < LPL; ++k) {
+#pragma unroll
+      for (int s = 0; s < G; ++s) {
+        const int src = s * GROUPS + gj;
+        const int32_t r = __shfl_sync(0xffffffffu, myrow[k], src);
+        v[k][s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r >= 0 && col_ok)
+          v[k][s] = ldg_nc_f4(reinterpret_cast<const float4*>(table + (int64_t)r * d) + gl);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < LPL; ++k) {
+#pragma unroll
+      for (int s = 0; s < G; ++s) {
+        const int64_t i = base + k * 32 + s * GROUPS + gj;
+        if (i < n && col_ok) store4<OutT>(out + i * d + gl * 4, v[k][s]);
+      }
+    }
+  }
+}
+
+template <int G, int LPL, bool FROM_IDS>
+static int launch_gather(const float* table, const int64_t* ids, const int32_t* rowidx,
+                         const int64_t* row_base, const int64_t* rows, int64_t n, int F,
+                         int d, void* out, int out_dtype, uint64_t* sort_keys,
+                         int32_t* rows_out, uint8_t* mask_out, cudaStream_t st) {
+  const int threads = 128;
+  const int64_t per_block = (int64_t)(threads / 32) * 32 * LPL;
+  int64_t blocks = cdiv(n, per_block);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (out_dtype == RS_F32)
+    embed_gather_kernel<G, LPL, float, FROM_IDS><<<(unsigned)blocks, threads, 0, st>>>(
+        table, ids, rowidx, row_base, rows, n, F, d, (float*)out, sort_keys, rows_out, mask_out);
+  else
+    embed_gather_kernel<G, LPL, __nv_bfloat16, FROM_IDS><<<(unsigned)blocks, threads, 0, st>>>(
+        table, ids, rowidx, row_base, rows, n, F, d, (__nv_bfloat16*)out, sort_keys, rows_out,
+        mask_out);
+  return check_launch("embed_gather");
+}
+
+template <bool FROM_IDS>
+static int dispatch_gather(const float* table, const int64_t* ids, const int32_t* rowidx,
+                           const int64_t* row_base, const int64_t* rows, int64_t n, int F,
+                           int d, void* out, int out_dtype, uint64_t* sort_keys,
+                           int32_t* rows_out, uint8_t* mask_out, cudaStream_t st) {
+  RS_REQUIRE(d > 0 && d % 4 == 0 && d <= 128, "embed_gather: d=%d must be a multiple of 4, <= 128", d);
+  RS_REQUIRE(out_dtype == RS_F32 || out_dtype == RS_BF16, "embed_gather: bad out dtype %d", out_dtype);
+  RS_REQUIRE(n >= 0 && n < ((int64_t)1 << 32), "embed_gather: n=%lld out of range", (long long)n);
+  if (n == 0) return 0;
+  const int g = d / 4;
+#define RS_GATHER_CASE(G, LPL)                                                                  \
+  return launch_gather<G, LPL, FROM_IDS>(table, ids, rowidx, row_base, rows, n, F, d, out,      \
+                                         out_dtype, sort_keys, rows_out, mask_out, st)
+  if (g <= 1) RS_GATHER_CASE(1, 4);
+  if (g <= 2) RS_GATHER_CASE(2, 4);
+  if (g <= 4) RS_GATHER_CASE(4, 2);
+  if (g <= 8) RS_GATHER_CASE(8, 1);
+  if (g <= 16) RS_GATHER_CASE(16, 1);
+  RS_GATHER_CASE(32, 1);
+#undef RS_GATHER_CASE
+}
+
+// ------------------------------------------------------------- bag mean ----
+// One group of G lanes per bag; ids of a bag are walked in order (mean is the
+// fp32 sum in id order divided by the count — the order tf's
+// embedding_lookup_sparse(combiner='mean') segment-sum uses).
+template <typename OutT>
+__global__ void embed_bag_mean_kernel(const float* __restrict__ table,
+                                      const int64_t* __restrict__ ids,
+                                      const int64_t* __restrict__ offsets,
+                                      const int64_t* __restrict__ row_base,
+                                      const int64_t* __restrict__ rows, int64_t n_bags, int F,
+                                      int d, int G, OutT* __restrict__ out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t bag = t / G;
+  const int gl = (int)(t % G);
+  if (bag >= n_bags || gl * 4 >= d) return;
+  const int f = (int)(bag % F);
+  const int64_t lo = offsets[bag], hi = offsets[bag + 1];
+  const uint64_t R = (uint64_t)rows[f];
+  const int64_t rb = row_base[f];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cnt = 0;
+  for (int64_t p = lo; p < hi; ++p) {
+    const int64_t id = ids[p];
+    if (id < 0) continue;
+    const int64_t r = rb + (int64_t)((uint64_t)id % R);
+    const float4 v = ldg_nc_f4(reinterpret_cast<const float4*>(table + r * d) + gl);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    ++cnt;
+  }
+  if (cnt > 0) {
+    const float inv = (float)cnt;
+    acc.x /= inv; acc.y /= inv; acc.z /= inv; acc.w /= inv;
+  }
+  store4<OutT>(out + bag * d + gl * 4, acc);
+}
+
+// ----------------------------------------------- segment sum + optimizers ---
+enum { OPT_NONE = 0, OPT_ADAM = 1, OPT_ADAGRAD_ROW = 2, OPT_ADAGRAD_ELEM = 3 };
+
+struct OptArgs {
+  float* w; float* s0; float* s1;   // adam: m, v ; adagrad: g2sum, -
+  float lr, beta1, beta2, eps;
+  const float* scalars;             // device {step, b1^t, b2^t, corr}
+  float grad_scale;
+  int32_t* seg_rows; float* seg_sum; // OPT_NONE outputs
+};
+
+template <typename GT>
+__device__ __forceinline__ float4 load_grad(const GT* grad, uint32_t pos, int d, int gl, float sc) {
+  float4 g = load4<GT>(grad + (int64_t)pos * d + gl * 4);
+  g.x *= sc; g.y *= sc; g.z *= sc; g.w *= sc;
+  return g;
+}
+
+// Same warp structure as the gather: lane l owns sorted position base+l
+// (key, predecessor and successor rows are exchanged by shuffle), then group
+// j serves position s*(32/G)+j in step s.  Only segment HEADS do work: the
+// head's group walks its run left-to-right (fixed order => deterministic) and
+// applies the optimizer once.  With uniform ids almost every position is a
+// head of a length-1 run, so the G steps issue G independent grad loads and
+// then 2-3 independent state-row loads each.
+template <int G, int OPT, typename GT>
+__global__ void __launch_bounds__(128)
+embed_segsum_kernel(const uint64_t* __restrict__ keys, const GT* __restrict__ grad, int64_t n,
+                    int d, OptArgs a) {
+  constexpr int GROUPS = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;
+  const int gj = lane / G;
+  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const bool col_ok = gl * 4 < d;
+  float lr_eff = a.lr;
+  if (OPT == OPT_ADAM) lr_eff = a.lr * __ldg(a.scalars + 3);
+
+  for (int64_t base = warp_global * 32; base < n; base += nwarps * 32) {
+    const int64_t i = base + lane;
+    uint64_t key = ~0ull;
+    if (i < n) key = keys[i];
+    uint32_t row = (uint32_t)(key >> 32);
+    uint32_t prev = __shfl_up_sync(0xffffffffu, row, 1);
+    uint32_t next = __shfl_down_sync(0xffffffffu, row, 1);
+    if (lane == 0) prev = (base > 0) ? (uint32_t)(keys[base - 1] >> 32) : 0xffffffffu;
+    if (lane == 31) next = (base + 32 < n) ? (uint32_t)(keys[base + 32] >> 32) : 0xffffffffu;
+    // a head: first of its run, and a real (non-padding) row
+    const bool head = (i < n) && (row != 0xffffffffu) && (i == 0 || row != prev);
+    const bool more = head && (i + 1 < n) && (next == row);
+
+    float4 acc[G];
+    uint32_t srow[G];
+    bool shead[G];
+#pragma unroll
+    for (int s = 0; s < G; ++s) {
+      const int src = s * GROUPS + gj;
+      srow[s] = __shfl_sync(0xffffffffu, row, src);
+      shead[s] = __shfl_sync(0xffffffffu, (int)head, src) != 0;
+      const uint32_t pos = __shfl_sync(0xffffffffu, (uint32_t)key, src);
+      acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (shead[s] && col_ok) acc[s] = load_grad<GT>(grad, pos, d, gl, a.grad_scale);
+    }
+    // runs longer than one: walk the rest of the run in order.
+#pragma unroll
+    for (int s = 0; s < G; ++s) {
+      const int src = s * GROUPS + gj;
+      const bool smore = __shfl_sync(0xffffffffu, (int)more, src) != 0;
+      if (smore && col_ok) {
+        int64_t q = base + src + 1;
+        while (q < n) {
+          const uint64_t kq = keys[q];
+          if ((uint32_t)(kq >> 32) != srow[s]) break;
+          const float4 g = load_grad<GT>(grad, (uint32_t)kq, d, gl, a.grad_scale);
+          acc[s].x += g.x; acc[s].y += g.y; acc[s].z += g.z; acc[s].w += g.w;
+          ++q;
+        }
+      }
+    }
+
+    if (OPT == OPT_NONE) {
+#pragma unroll
+      for (int s = 0; s < G; ++s) {
+        const int64_t p = base + s * GROUPS + gj;
+        if (p < n && col_ok) {
+          store4<float>(a.seg_sum + p * d + gl * 4, acc[s]);
+          if (gl == 0) a.seg_rows[p] = shead[s] ? (int32_t)srow[s] : -1;
+        }
+      }
+    } else if (OPT == OPT_ADAM) {
+      float4 w[G], m[G], v[G];
+#pragma unroll
+      for (int s = 0; s < G; ++s) {
+        if (shead[s] && col_ok) {
+          const int64_t off = (int64_t)srow[s] * d + gl * 4;
+          w[s] = *reinterpret_cast<const float4*>(a.w + off);
+          m[s] = *reinterpret_cast<const float4*>(a.s0 + off);
+          v[s] = *reinterpret_cast<const float4*>(a.s1 + off);
+        }
+      }
+      const float b1 = a.beta1, b2 = a.beta2, eps = a.eps;
+#pragma unroll
+      for (int s = 0; s < G; ++s) {
+        if (shead[s] && col_ok) {
+          const int64_t off = (int64_t)srow[s] * d + gl * 4;
+          const float4 g = acc[s];
+#define RS_ADAM1(c)                                              \
+  m[s].c = b1 * m[s].c + (1.f - b1) * g.c;                       \
+  v[s].c = b2 * v[s].c + (1.f - b2) * g.c * g.c;                 \
+  w[s].c = w[s].c - lr_eff * m[s].c / (sqrtf(v[s].c) + eps);
+          RS_ADAM1(x) RS_ADAM1(y) RS_ADAM1(z) RS_ADAM1(w)
+#undef RS_ADAM1
+          *reinterpret_cast<float4*>(a.w + off) = w[s];
+          *reinterpret_cast<float4*>(a.s0 + off) = m[s];
+          *reinterpret_cast<float4*>(a.s1 + off) = v[s];
+        }
+      }
+    } else {  // AdaGrad
+      float4 w[G], e[G];
+      float g2[G];
+#pragma unroll
+      for (int s = 0; s < G; ++s) {
+        g2[s] = 0.f;
+        if (shead[s] && col_ok) {
+          const int64_t off = (int64_t)srow[s] * d + gl * 4;
+          w[s] = *reinterpret_cast<const float4*>(a.w + off);
+          if (OPT == OPT_ADAGRAD_ELEM) e[s] = *reinterpret_cast<const float4*>(a.s0 + off);
+          else g2[s] = a.s0[srow[s]];
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < G; ++s) {
+        const float4 g = acc[s];
+        if (OPT == OPT_ADAGRAD_ROW) {
+          // mean over the row of g*g: reduce over the G lanes of the group in a
+          // fixed butterfly order (all lanes of the group take part).
+          float sq = (shead[s] && col_ok) ? (g.x * g.x + g.y * g.y + g.z * g.z + g.w * g.w) : 0.f;
+#pragma unroll
+          for (int o = G / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+          if (shead[s] && col_ok) {
+            const int64_t off = (int64_t)srow[s] * d + gl * 4;
+            const float acc2 = g2[s] + sq / (float)d;
+            const float den = sqrtf(acc2) + a.eps;
+            w[s].x -= a.lr * g.x / den; w[s].y -= a.lr * g.y / den;
+            w[s].z -= a.lr * g.z / den; w[s].w -= a.lr * g.w / den;
+            *reinterpret_cast<float4*>(a.w + off) = w[s];
+            if (gl == 0) a.s0[srow[s]] = acc2;
+          }
+        } else if (shead[s] && col_ok) {
+          const int64_t off = (int64_t)srow[s] * d + gl * 4;
+#define RS_ADAG1(c)                                   \
+  e[s].c += g.c * g.c;                                \
+  w[s].c -= a.lr * g.c / (sqrtf(e[s].c) + a.eps);
+          RS_ADAG1(x) RS_ADAG1(y) RS_ADAG1(z) RS_ADAG1(w)
+#undef RS_ADAG1
+          *reinterpret_cast<float4*>(a.w + off) = w[s];
+          *reinterpret_cast<float4*>(a.s0 + off) = e[s];
+        }
+      }
+    }
+  }
+}
+
+template <int OPT>
+static int dispatch_segsum(const uint64_t* keys, const void* grad, int grad_dtype, int64_t n,
+                           int d, const OptArgs& a, cudaStream_t st) {
+  RS_REQUIRE(d > 0 && d % 4 == 0 && d <= 128, "embed_segsum: d=%d must be a multiple of 4, <= 128", d);
+  RS_REQUIRE(grad_dtype == RS_F32 || grad_dtype == RS_BF16, "embed_segsum: bad grad dtype");
+  if (n == 0) return 0;
+  const int threads = 128;
+  int64_t blocks = cdiv(n, (threads / 32) * 32);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  const int g = d / 4;
+#define RS_SEG_LAUNCH(G)                                                                          \
+  do {                                                                                            \
+    if (grad_dtype == RS_F32)                                                                     \
+      embed_segsum_kernel<G, OPT, float><<<(unsigned)blocks, threads, 0, st>>>(                   \
+          keys, (const float*)grad, n, d, a);                                                     \
+    else                                                                                          \
+      embed_segsum_kernel<G, OPT, __nv_bfloat16><<<(unsigned)blocks, threads, 0, st>>>(           \
+          keys, (const __nv_bfloat16*)grad, n, d, a);                                             \
+    return check_launch("embed_segsum");                                                          \
+  } while (0)
+  if (g <= 1) RS_SEG_LAUNCH(1);
+  if (g <= 2) RS_SEG_LAUNCH(2);
+  if (g <= 4) RS_SEG_LAUNCH(4);
+  if (g <= 8) RS_SEG_LAUNCH(8);
+  if (g <= 16) RS_SEG_LAUNCH(16);
+  RS_SEG_LAUNCH(32);
+#undef RS_SEG_LAUNCH
+}
+
+// -------------------------------------------------------- optimizer glue ---
+__global__ void adam_advance_kernel(float* s, float b1, float b2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const float step = s[0] + 1.f;
+    // powers are carried multiplicatively in fp32 like TF's beta_power vars
+    const float p1 = (s[0] == 0.f ? 1.f : s[1]) * b1;
+    const float p2 = (s[0] == 0.f ? 1.f : s[2]) * b2;
+    s[0] = step; s[1] = p1; s[2] = p2;
+    s[3] = sqrtf(1.f - p2) / (1.f - p1);
+  }
+}
+
+__global__ void dense_adam_kernel(float* __restrict__ w, float* __restrict__ m,
+                                  float* __restrict__ v, const float* __restrict__ g, int64_t n,
+                                  float lr, float b1, float b2, float eps,
+                                  const float* __restrict__ scalars,
+                                  __nv_bfloat16* __restrict__ shadow) {
+  const float lr_eff = lr * __ldg(scalars + 3);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    const float wi = w[i] - lr_eff * mi / (sqrtf(vi) + eps);
+    m[i] = mi; v[i] = vi; w[i] = wi;
+    if (shadow) shadow[i] = __float2bfloat16_rn(wi);
+  }
+}
+
+// --------------------------------------------------------------- routing ---
+// Stable bucket-by-owner in three launches: per-block owner histograms, a
+// single-block exclusive scan in (owner-major, block-minor) order, and a
+// scatter where each block ranks its lookups with warp ballots (stable).
+constexpr int ROUTE_BLOCK = 256;
+constexpr int ROUTE_MAX_WORLD = 64;
+
+__device__ __forceinline__ void route_of(const int64_t* ids, const int64_t* rows,
+                                         const int64_t* local_base, int64_t i, int F, int world,
+                                         int& owner, int32_t& lrow) {
+  const int64_t id = ids[i];
+  if (id < 0) {  // padding: keep it on its own rank as row -1 (owner 0 by convention)
+    owner = 0; lrow = -1; return;
+  }
+  const int f = (int)(i % F);
+  const uint64_t r = (uint64_t)id % (uint64_t)rows[f];
+  owner = (int)(r % (uint64_t)world);
+  lrow = (int32_t)(local_base[f] + (int64_t)(r / (uint64_t)world));
+}
+
+__global__ void route_hist_kernel(const int64_t* ids, int64_t n, int F, const int64_t* rows,
+                                  const int64_t* local_base, int world, int32_t* hist /*[world][nblk]*/) {
+  __shared__ int cnt[ROUTE_MAX_WORLD];
+  if (threadIdx.x < ROUTE_MAX_WORLD) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * ROUTE_BLOCK + threadIdx.x;
+  if (i < n) {
+    int owner; int32_t lrow;
+    route_of(ids, rows, local_base, i, F, world, owner, lrow);
+    atomicAdd(&cnt[owner], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < world) hist[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = cnt[threadIdx.x];
+}
+
+__global__ void route_scan_kernel(int32_t* hist, int64_t total, int nblk, int world,
+                                  int32_t* send_counts, int32_t* send_offsets) {
+  // single block; sequential chunks of blockDim with a running carry.
+  __shared__ int32_t buf[1024];
+  __shared__ int32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < total; base += blockDim.x) {
+    const int64_t i = base + threadIdx.x;
+    const int32_t v = i < total ? hist[i] : 0;
+    buf[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < (int)blockDim.x; o <<= 1) {
+      int32_t t = threadIdx.x >= (unsigned)o ? buf[threadIdx.x - o] : 0;
+      __syncthreads();
+      buf[threadIdx.x] += t;
+      __syncthreads();
+    }
+    const int32_t incl = buf[threadIdx.x];
+    const int32_t c = carry;
+    if (i < total) {
+      hist[i] = c + incl - v;  // exclusive
+      if (i % nblk == 0) send_offsets[i / nblk] = c + incl - v;
+    }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry = c + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) send_offsets[world] = carry;
+  __syncthreads();
+  if (threadIdx.x < world) {
+    // counts from consecutive offsets (offsets[world] just written by thread 0)
+    send_counts[threadIdx.x] = send_offsets[threadIdx.x + 1] - send_offsets[threadIdx.x];
+  }
+}
+
+__global__ void route_scatter_kernel(const int64_t* ids, int64_t n, int F, const int64_t* rows,
+                                     const int64_t* local_base, int world,
+                                     const int32_t* hist /*exclusive, [world][nblk]*/,
+                                     int32_t* send_rows, int32_t* inverse) {
+  __shared__ int warp_cnt[ROUTE_BLOCK / 32][ROUTE_MAX_WORLD];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * ROUTE_BLOCK + threadIdx.x;
+  int owner = -1; int32_t lrow = -1;
+  if (i < n) route_of(ids, rows, local_base, i, F, world, owner, lrow);
+  // rank within warp among same-owner lanes with lower lane id
+  int my_rank = 0;
+  for (int o = 0; o < world; ++o) {
+    const unsigned m = __ballot_sync(0xffffffffu, owner == o);
+    if (owner == o) my_rank = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) warp_cnt[wid][o] = __popc(m);
+  }
+  __syncthreads();
+  if (i < n) {
+    int before = 0;
+    for (int w = 0; w < wid; ++w) before += warp_cnt[w][owner];
+    const int32_t slot = hist[(int64_t)owner * gridDim.x + blockIdx.x] + before + my_rank;
+    send_rows[slot] = lrow;
+    inverse[i] = slot;
+  }
+}
+
+template <typename T>
+__global__ void permute_rows_kernel(const T* __restrict__ src, T* __restrict__ out,
+                                    const int32_t* __restrict__ index, int64_t n, int vec_per_row,
+                                    int scatter) {
+  // rows are moved in 8-byte units (vec_per_row of them)
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = t / vec_per_row;
+  const int c = (int)(t % vec_per_row);
+  if (i >= n) return;
+  const int64_t j = index[i];
+  const uint2* s = reinterpret_cast<const uint2*>(src);
+  uint2* o = reinterpret_cast<uint2*>(out);
+  if (scatter) o[j * vec_per_row + c] = s[i * vec_per_row + c];
+  else o[i * vec_per_row + c] = s[j * vec_per_row + c];
+}
+
+}  // namespace rs
+
+using namespace rs;
+
+extern "C" {
+
+int rs_embed_gather_fwd(const float* table, const int64_t* ids, const int64_t* row_base,
+                        const int64_t* rows, int64_t n, int F, int d, void* out, int out_dtype,
+                        uint64_t* sort_keys, int32_t* rows_out, void* stream) {
+  RS_REQUIRE(F > 0, "embed_gather_fwd: F=%d", F);
+  return dispatch_gather<true>(table, ids, nullptr, row_base, rows, n, F, d, out, out_dtype,
+                               sort_keys, rows_out, nullptr, as_stream(stream));
+}
+
+int rs_embed_gather_rows(const float* table, const int32_t* rowidx, int64_t n, int d, void* out,
+                         int out_dtype, uint8_t* mask_out, uint64_t* sort_keys, void* stream) {
+  return dispatch_gather<false>(table, nullptr, rowidx, nullptr, nullptr, n, 1, d, out, out_dtype,
+                                sort_keys, nullptr, mask_out, as_stream(stream));
+}
+
+int rs_embed_gather_bag_mean(const float* table, const int64_t* ids, const int64_t* offsets,
+                             const int64_t* row_base, const int64_t* rows, int64_t n_bags, int F,
+                             int d, void* out, int out_dtype, void* stream) {
+  RS_REQUIRE(d > 0 && d % 4 == 0 && d <= 128, "embed_gather_bag_mean: d=%d", d);
+  if (n_bags == 0) return 0;
+  int G = 1;
+  while (G * 4 < d) G <<= 1;
+  const int threads = 128;
+  const int64_t blocks = cdiv(n_bags * G, threads);
+  if (out_dtype == RS_F32)
+    embed_bag_mean_kernel<float><<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(
+        table, ids, offsets, row_base, rows, n_bags, F, d, G, (float*)out);
+  else
+    embed_bag_mean_kernel<__nv_bfloat16><<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(
+        table, ids, offsets, row_base, rows, n_bags, F, d, G, (__nv_bfloat16*)out);
+  return check_launch("embed_bag_mean");
+}
+
+size_t rs_embed_sort_workspace_bytes(int64_t n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortKeys((void*)nullptr, bytes, (const uint64_t*)nullptr,
+                                 (uint64_t*)nullptr, (int)n, 32, 64, (cudaStream_t)0);
+  return bytes + 256;
+}
+
+int rs_embed_sort_keys(const uint64_t* keys, uint64_t* keys_sorted, int64_t n, int row_bits,
+                       void* ws, size_t ws_bytes, void* stream) {
+  RS_REQUIRE(row_bits >= 1 && row_bits <= 32, "embed_sort_keys: row_bits=%d", row_bits);
+  RS_REQUIRE(n < ((int64_t)1 << 31), "embed_sort_keys: n too large");
+  if (n == 0) return 0;
+  size_t need = 0;
+  cub::DeviceRadixSort::SortKeys((void*)nullptr, need, keys, keys_sorted, (int)n, 32,
+                                 32 + row_bits, as_stream(stream));
+  if (need > ws_bytes) {
+    set_error("embed_sort_keys: workspace %zu < %zu", ws_bytes, need);
+    return RS_ERR_WORKSPACE;
+  }
+  RS_CUDA(cub::DeviceRadixSort::SortKeys(ws, need, keys, keys_sorted, (int)n, 32, 32 + row_bits,
+                                         as_stream(stream)));
+  g_launches.fetch_add(row_bits > 24 ? 6 : (row_bits > 16 ? 5 : 4), std::memory_order_relaxed);
+  return 0;
+}
+
+int rs_embed_segsum_adam(float* w, float* m, float* v, const void* grad, int grad_dtype,
+                         const uint64_t* keys_sorted, int64_t n, int d, float lr, float beta1,
+                         float beta2, float eps, const float* opt_scalars, float grad_scale,
+                         void* stream) {
+  RS_REQUIRE(opt_scalars != nullptr, "embed_segsum_adam: opt_scalars is NULL");
+  OptArgs a{};
+  a.w = w; a.s0 = m; a.s1 = v; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+  a.scalars = opt_scalars; a.grad_scale = grad_scale;
+  return dispatch_segsum<OPT_ADAM>(keys_sorted, grad, grad_dtype, n, d, a, as_stream(stream));
+}
+
+int rs_embed_segsum_adagrad(float* w, float* g2sum, const void* grad, int grad_dtype,
+                            const uint64_t* keys_sorted, int64_t n, int d, float lr, float eps,
+                            int per_element, float grad_scale, void* stream) {
+  OptArgs a{};
+  a.w = w; a.s0 = g2sum; a.lr = lr; a.eps = eps; a.grad_scale = grad_scale;
+  if (per_element)
+    return dispatch_segsum<OPT_ADAGRAD_ELEM>(keys_sorted, grad, grad_dtype, n, d, a, as_stream(stream));
+  return dispatch_segsum<OPT_ADAGRAD_ROW>(keys_sorted, grad, grad_dtype, n, d, a, as_stream(stream));
+}
+
+int rs_embed_segsum(const void* grad, int grad_dtype, const uint64_t* keys_sorted, int64_t n,
+                    int d, int32_t* seg_rows, float* seg_sum, void* stream) {
+  OptArgs a{};
+  a.grad_scale = 1.f; a.seg_rows = seg_rows; a.seg_sum = seg_sum;
+  return dispatch_segsum<OPT_NONE>(keys_sorted, grad, grad_dtype, n, d, a, as_stream(stream));
+}
+
+int rs_adam_advance(float* opt_scalars, float beta1, float beta2, void* stream) {
+  adam_advance_kernel<<<1, 32, 0, as_stream(stream)>>>(opt_scalars, beta1, beta2);
+  return check_launch("adam_advance");
+}
+
+int rs_dense_adam(float* w, float* m, float* v, const float* g, int64_t n, float lr, float beta1,
+                  float beta2, float eps, const float* opt_scalars, void* w_bf16_shadow,
+                  void* stream) {
+  RS_REQUIRE(opt_scalars != nullptr, "dense_adam: opt_scalars is NULL");
+  if (n == 0) return 0;
+  const int threads = 256;
+  int64_t blocks = cdiv(n, threads);
+  if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+  dense_adam_kernel<<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(
+      w, m, v, g, n, lr, beta1, beta2, eps, opt_scalars, (__nv_bfloat16*)w_bf16_shadow);
+  return check_launch("dense_adam");
+}
+
+size_t rs_route_workspace_bytes(int64_t n, int world) {
+  return (size_t)(cdiv(n, ROUTE_BLOCK) * world + 8) * sizeof(int32_t);
+}
+
+int rs_route_ids(const int64_t* ids, int64_t n, int F, const int64_t* rows,
+                 const int64_t* local_base, int world, int32_t* send_rows, int32_t* inverse,
+                 int32_t* send_counts, int32_t* send_offsets, void* ws, size_t ws_bytes,
+                 void* stream) {
+  RS_REQUIRE(world >= 1 && world <= ROUTE_MAX_WORLD, "route_ids: world=%d", world);
+  RS_REQUIRE(F > 0 && n >= 0 && n < ((int64_t)1 << 31), "route_ids: n/F out of range");
+  if (ws_bytes < rs_route_workspace_bytes(n, world)) {
+    set_error("route_ids: workspace too small");
+    return RS_ERR_WORKSPACE;
+  }
+  cudaStream_t st = as_stream(stream);
+  int32_t* hist = (int32_t*)ws;
+  const int nblk = (int)cdiv(n > 0 ? n : 1, ROUTE_BLOCK);
+  route_hist_kernel<<<nblk, ROUTE_BLOCK, 0, st>>>(ids, n, F, rows, local_base, world, hist);
+  if (int e = check_launch("route_hist")) return e;
+  route_scan_kernel<<<1, 1024, 0, st>>>(hist, (int64_t)nblk * world, nblk, world, send_counts,
+                                        send_offsets);
+  if (int e = check_launch("route_scan")) return e;
+  route_scatter_kernel<<<nblk, ROUTE_BLOCK, 0, st>>>(ids, n, F, rows, local_base, world, hist,
+                                                     send_rows, inverse);
+  return check_launch("route_scatter");
+}
+
+int rs_permute_rows(const void* src, void* out, const int32_t* index, int64_t n, int d, int dtype,
+                    int scatter, void* stream) {
+  const int64_t row_bytes = (int64_t)d * (dtype == RS_F32 ? 4 : 2);
+  RS_REQUIRE(row_bytes % 8 == 0, "permute_rows: row bytes %lld not a multiple of 8", (long long)row_bytes);
+  if (n == 0) return 0;
+  const int vec = (int)(row_bytes / 8);
+  const int threads = 256;
+  const int64_t blocks = cdiv(n * vec, threads);
+  permute_rows_kernel<float><<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(
+      (const float*)src, (float*)out, index, n, vec, scatter);
+  return check_launch("permute_rows");
+}
+
+}  // extern "C"

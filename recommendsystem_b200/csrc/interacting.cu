@@ -1,0 +1,70 @@
+// interacting.cu — C-ABI entry points of K4 (InteractingLayer.py:37-61); the
+// kernels live in interacting_kernels.cuh and are instantiated per (D, U, H)
+// shape in interacting_inst.cu.
+#include "interacting_args.cuh"
+
+namespace rs {
+// Shapes built (keep in sync with build.py INTERACT_SHAPES).
+#define RS_INTERACT_SHAPES(X) X(16, 16, 1) X(16, 16, 2) X(16, 16, 4) X(8, 8, 1) X(8, 8, 2) X(16, 8, 2)
+#define RS_DECL(DD, UU, HH)                                   \
+  int interacting_fwd_##DD##_##UU##_##HH(const IFwdArgs& a); \
+  int interacting_bwd_##DD##_##UU##_##HH(const IBwdArgs& a);
+RS_INTERACT_SHAPES(RS_DECL)
+#undef RS_DECL
+}  // namespace rs
+
+using namespace rs;
+
+extern "C" {
+
+size_t rs_interacting_workspace_bytes(int B, int F, int D, int U) {
+  (void)B; (void)F;
+  return (size_t)(sm_count() * 2) * (size_t)(D * 4 * U + 6 * U) * sizeof(float);
+}
+
+int rs_interacting_fwd(const void* x, int64_t x_ld, int dtype, const float* Wqkvr,
+                       const float* bqkvr, const float* ln_gamma, const float* ln_beta,
+                       float ln_eps, void* y, int64_t y_ld, void* saved, int B, int F, int D, int U,
+                       int H, int L, int use_res, int compute_bf16, void* stream) {
+  RS_REQUIRE(B > 0 && F > 0 && L >= 1, "interacting_fwd: B=%d F=%d L=%d", B, F, L);
+  RS_REQUIRE(H > 0 && U % H == 0, "interacting_fwd: head_num %d must divide unit_num %d", H, U);
+  RS_REQUIRE(L == 1 || D == U, "interacting_fwd: layer_num>1 needs input dim %d == unit_num %d", D, U);
+  RS_REQUIRE(F <= 256, "interacting_fwd: F=%d > 256 fields not supported", F);
+  RS_REQUIRE(dtype == RS_F32 || dtype == RS_BF16, "interacting_fwd: bad dtype");
+  RS_REQUIRE(x_ld % 4 == 0 && y_ld % 4 == 0, "interacting_fwd: leading dims must be multiples of 4");
+  (void)compute_bf16;
+  IFwdArgs a{x, x_ld, Wqkvr, bqkvr, ln_gamma, ln_beta, ln_eps, y, y_ld, saved, B, F, L, use_res,
+             dtype, as_stream(stream)};
+#define RS_CASE(DD, UU, HH) \
+  if (D == DD && U == UU && H == HH) return interacting_fwd_##DD##_##UU##_##HH(a);
+  RS_INTERACT_SHAPES(RS_CASE)
+#undef RS_CASE
+  set_error("interacting_fwd: (D=%d, U=%d, H=%d) not built", D, U, H);
+  return RS_ERR_UNSUPPORTED;
+}
+
+int rs_interacting_bwd(const void* x, int64_t x_ld, const void* saved, int dtype,
+                       const float* Wqkvr, const float* bqkvr, const float* ln_gamma,
+                       const float* ln_beta, float ln_eps, const void* dy, int64_t dy_ld, void* dx,
+                       int64_t dx_ld, float* dparams, int B, int F, int D, int U, int H, int L,
+                       int use_res, int compute_bf16, void* ws, size_t ws_bytes, void* stream) {
+  RS_REQUIRE(B > 0 && F > 0 && L >= 1, "interacting_bwd: B=%d F=%d L=%d", B, F, L);
+  RS_REQUIRE(H > 0 && U % H == 0, "interacting_bwd: head_num %d must divide unit_num %d", H, U);
+  RS_REQUIRE(L == 1 || D == U, "interacting_bwd: layer_num>1 needs input dim == unit_num");
+  RS_REQUIRE(L == 1 || saved != nullptr, "interacting_bwd: saved activations required for L>1");
+  RS_REQUIRE(F <= 256, "interacting_bwd: F=%d > 256 fields not supported", F);
+  RS_REQUIRE(dtype == RS_F32 || dtype == RS_BF16, "interacting_bwd: bad dtype");
+  RS_REQUIRE(x_ld % 4 == 0 && dy_ld % 4 == 0 && dx_ld % 4 == 0,
+             "interacting_bwd: leading dims must be multiples of 4");
+  (void)compute_bf16;
+  IBwdArgs a{x, x_ld, saved, Wqkvr, bqkvr, ln_gamma, ln_beta, ln_eps, dy, dy_ld, dx, dx_ld, dparams,
+             B, F, L, use_res, dtype, ws, ws_bytes, as_stream(stream)};
+#define RS_CASE(DD, UU, HH) \
+  if (D == DD && U == UU && H == HH) return interacting_bwd_##DD##_##UU##_##HH(a);
+  RS_INTERACT_SHAPES(RS_CASE)
+#undef RS_CASE
+  set_error("interacting_bwd: (D=%d, U=%d, H=%d) not built", D, U, H);
+  return RS_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

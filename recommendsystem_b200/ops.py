@@ -1,0 +1,279 @@
+"""Thin host-side wrappers: torch CUDA tensors in, C-ABI calls (include/rs_b200.h) on
+torch's current stream out.  torch is used for device memory and streams only; every
+kernel that runs here is a hand-written sm_100a kernel from librs_b200.so.  No CPU
+or eager-PyTorch fallback exists: a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import cabi
+from .cabi import RS_BF16, RS_F32, call
+
+_DT = {torch.float32: RS_F32, torch.bfloat16: RS_BF16}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {t.dtype} (float32 / bfloat16 only)") from None
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("recommendsystem_b200 kernels need CUDA tensors (no CPU fallback)")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need(cond, msg):
+    if not cond:
+        raise ValueError(msg)
+
+
+class _Workspace:
+    """Per-device grow-only scratch buffers keyed by purpose (stable addresses once
+    warmed up, so CUDA-graph capture sees fixed pointers)."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, key, nbytes, device):
+        k = (key, device)
+        b = self.bufs.get(k)
+        if b is None or b.numel() < nbytes:
+            b = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self.bufs[k] = b
+        return b
+
+
+WS = _Workspace()
+
+# ----------------------------------------------------------------- embedding
+
+
+def embed_gather(table, ids, row_base, rows, out_dtype=torch.float32, want_keys=False, want_rows=False):
+    """ids int64 [..., F] -> out [..., F, d]; optional sort keys / arena rows."""
+    _need(ids.dtype == torch.int64 and ids.is_contiguous(), "ids must be contiguous int64")
+    _need(table.dtype == torch.float32 and table.is_contiguous() and table.dim() == 2, "table must be fp32 [R,d]")
+    F = ids.shape[-1]
+    n, d = ids.numel(), table.shape[1]
+    out = torch.empty(*ids.shape, d, dtype=out_dtype, device=table.device)
+    keys = torch.empty(n, dtype=torch.int64, device=table.device) if want_keys else None
+    rws = torch.empty(ids.shape, dtype=torch.int32, device=table.device) if want_rows else None
+    call("rs_embed_gather_fwd", _ptr(table), _ptr(ids), _ptr(row_base), _ptr(rows), n, F, d, _ptr(out),
+         _DT[out_dtype], _ptr(keys), _ptr(rws), _stream())
+    return out, keys, rws
+
+
+def embed_gather_rows(table, rowidx, out_dtype=torch.float32, want_mask=False, want_keys=False):
+    _need(rowidx.dtype == torch.int32 and rowidx.is_contiguous(), "rowidx must be contiguous int32")
+    n, d = rowidx.numel(), table.shape[1]
+    out = torch.empty(*rowidx.shape, d, dtype=out_dtype, device=table.device)
+    mask = torch.empty(rowidx.shape, dtype=torch.uint8, device=table.device) if want_mask else None
+    keys = torch.empty(n, dtype=torch.int64, device=table.device) if want_keys else None
+    call("rs_embed_gather_rows", _ptr(table), _ptr(rowidx), n, d, _ptr(out), _DT[out_dtype], _ptr(mask),
+         _ptr(keys), _stream())
+    return out, mask, keys
+
+
+def embed_gather_bag_mean(table, ids, offsets, row_base, rows, F, out_dtype=torch.float32):
+    n_bags, d = offsets.numel() - 1, table.shape[1]
+    out = torch.empty(n_bags, d, dtype=out_dtype, device=table.device)
+    call("rs_embed_gather_bag_mean", _ptr(table), _ptr(ids), _ptr(offsets), _ptr(row_base), _ptr(rows),
+         n_bags, F, d, _ptr(out), _DT[out_dtype], _stream())
+    return out
+
+
+def row_bits(total_rows: int) -> int:
+    return max(1, min(32, int(math.ceil(math.log2(total_rows + 1)))))
+
+
+def sort_keys(keys, rbits=32, out=None):
+    n = keys.numel()
+    out = torch.empty_like(keys) if out is None else out
+    nbytes = cabi.load().rs_embed_sort_workspace_bytes(n)
+    ws = WS.get("sort", nbytes, keys.device)
+    call("rs_embed_sort_keys", _ptr(keys), _ptr(out), n, rbits, _ptr(ws), ws.numel(), _stream())
+    return out
+
+
+def segsum(grad, keys_sorted):
+    n, d = keys_sorted.numel(), grad.shape[-1]
+    seg_rows = torch.empty(n, dtype=torch.int32, device=grad.device)
+    seg_sum = torch.empty(n, d, dtype=torch.float32, device=grad.device)
+    call("rs_embed_segsum", _ptr(grad), _dt(grad), _ptr(keys_sorted), n, d, _ptr(seg_rows), _ptr(seg_sum),
+         _stream())
+    return seg_rows, seg_sum
+
+
+def segsum_adam(w, m, v, grad, keys_sorted, lr, beta1, beta2, eps, scalars, grad_scale=1.0):
+    call("rs_embed_segsum_adam", _ptr(w), _ptr(m), _ptr(v), _ptr(grad), _dt(grad), _ptr(keys_sorted),
+         keys_sorted.numel(), w.shape[1], lr, beta1, beta2, eps, _ptr(scalars), grad_scale, _stream())
+
+
+def segsum_adagrad(w, g2sum, grad, keys_sorted, lr, eps, per_element=False, grad_scale=1.0):
+    call("rs_embed_segsum_adagrad", _ptr(w), _ptr(g2sum), _ptr(grad), _dt(grad), _ptr(keys_sorted),
+         keys_sorted.numel(), w.shape[1], lr, eps, int(per_element), grad_scale, _stream())
+
+
+def adam_advance(scalars, beta1, beta2):
+    call("rs_adam_advance", _ptr(scalars), beta1, beta2, _stream())
+
+
+def dense_adam(w, m, v, g, lr, beta1, beta2, eps, scalars, shadow=None):
+    call("rs_dense_adam", _ptr(w), _ptr(m), _ptr(v), _ptr(g), w.numel(), lr, beta1, beta2, eps,
+         _ptr(scalars), _ptr(shadow), _stream())
+
+
+def route_ids(ids, F, rows, local_base, world):
+    n = ids.numel()
+    dev = ids.device
+    send_rows = torch.empty(n, dtype=torch.int32, device=dev)
+    inverse = torch.empty(n, dtype=torch.int32, device=dev)
+    counts = torch.empty(world, dtype=torch.int32, device=dev)
+    offsets = torch.empty(world + 1, dtype=torch.int32, device=dev)
+    nbytes = cabi.load().rs_route_workspace_bytes(n, world)
+    ws = WS.get("route", nbytes, dev)
+    call("rs_route_ids", _ptr(ids), n, F, _ptr(rows), _ptr(local_base), world, _ptr(send_rows),
+         _ptr(inverse), _ptr(counts), _ptr(offsets), _ptr(ws), ws.numel(), _stream())
+    return send_rows, inverse, counts, offsets
+
+
+def permute_rows(src, index, scatter=False, out=None):
+    n, d = index.numel(), src.shape[-1]
+    out = torch.empty(n, d, dtype=src.dtype, device=src.device) if out is None else out
+    call("rs_permute_rows", _ptr(src), _ptr(out), _ptr(index), n, d, _dt(src), int(scatter), _stream())
+    return out
+
+
+# ------------------------------------------------------------- interacting
+
+
+def interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res=True, save=True, compute_bf16=False):
+    B, F, D = x.shape
+    U = Wqkvr.shape[1] // 4
+    _need(x.is_contiguous(), "x must be contiguous")
+    y = torch.empty(B, F, U, dtype=x.dtype, device=x.device)
+    saved = torch.empty(max(L - 1, 0), B * F, U, dtype=x.dtype, device=x.device) if (save and L > 1) else None
+    call("rs_interacting_fwd", _ptr(x), D, _dt(x), _ptr(Wqkvr), _ptr(bqkvr), _ptr(gamma), _ptr(beta),
+         ln_eps, _ptr(y), U, _ptr(saved), B, F, D, U, H, L, int(use_res), int(compute_bf16), _stream())
+    return y, saved
+
+
+def interacting_bwd(x, saved, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, dy, use_res=True, compute_bf16=False):
+    B, F, D = x.shape
+    U = Wqkvr.shape[1] // 4
+    dx = torch.empty_like(x)
+    dparams = torch.empty(D * 4 * U + 4 * U + 2 * U, dtype=torch.float32, device=x.device)
+    nbytes = cabi.load().rs_interacting_workspace_bytes(B, F, D, U)
+    ws = WS.get("interacting", nbytes, x.device)
+    dy = dy.contiguous()
+    call("rs_interacting_bwd", _ptr(x), D, _ptr(saved), _dt(x), _ptr(Wqkvr), _ptr(bqkvr), _ptr(gamma),
+         _ptr(beta), ln_eps, _ptr(dy), U, _ptr(dx), D, _ptr(dparams), B, F, D, U, H, L, int(use_res),
+         int(compute_bf16), _ptr(ws), ws.numel(), _stream())
+    nW = D * 4 * U
+    return dx, dparams[:nW].view(D, 4 * U), dparams[nW:nW + 4 * U], dparams[nW + 4 * U:nW + 5 * U], dparams[nW + 5 * U:]
+
+
+# --------------------------------------------------------------------- DIN
+
+
+def din_fwd(mode, q, keys, values, seq_len, mask, W1, b1, W2, b2, kv_ld=None):
+    B, T = keys.shape[0], keys.shape[1]
+    H = q.shape[1]
+    Hd = W1.shape[1]
+    kv_ld = kv_ld or keys.stride(1)
+    out = torch.empty(B, H, dtype=q.dtype, device=q.device)
+    call("rs_din_fwd", mode, _ptr(q), _ptr(keys), _ptr(values), kv_ld, _dt(q), _ptr(seq_len), _ptr(mask),
+         _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), _ptr(out), B, T, H, Hd, _stream())
+    return out
+
+
+def din_bwd(mode, q, keys, values, seq_len, mask, W1, b1, W2, b2, dout, kv_ld=None):
+    B, T = keys.shape[0], keys.shape[1]
+    H = q.shape[1]
+    Hd = W1.shape[1]
+    kv_ld = kv_ld or keys.stride(1)
+    dq = torch.empty_like(q)
+    dkeys = torch.empty(B, T, H, dtype=q.dtype, device=q.device)
+    dvalues = torch.empty(B, T, H, dtype=q.dtype, device=q.device) if mode == cabi.DIN_A else None
+    nparams = W1.numel() + b1.numel() + W2.numel() + b2.numel()
+    dparams = torch.empty(nparams, dtype=torch.float32, device=q.device)
+    nbytes = cabi.load().rs_din_workspace_bytes(mode, B, T, H, Hd)
+    ws = WS.get("din", nbytes, q.device)
+    call("rs_din_bwd", mode, _ptr(q), _ptr(keys), _ptr(values), kv_ld, _dt(q), _ptr(seq_len), _ptr(mask),
+         _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), _ptr(dout.contiguous()), _ptr(dq), _ptr(dkeys),
+         _ptr(dvalues), H, _ptr(dparams), B, T, H, Hd, _ptr(ws), ws.numel(), _stream())
+    o = 0
+    parts = []
+    for t in (W1, b1, W2, b2):
+        parts.append(dparams[o:o + t.numel()].view(t.shape))
+        o += t.numel()
+    return (dq, dkeys, dvalues, *parts)
+
+
+# -------------------------------------------------------------------- GEMM
+
+
+def gemm(A, B, C=None, bias=None, aux=None, epilogue=cabi.EPI_NONE, transA=False, transB=False,
+         out_dtype=None):
+    """C[M,N] = epi(op(A) @ op(B)).  A, B are 2-D views whose last dim is contiguous."""
+    _need(A.dim() == 2 and B.dim() == 2 and A.stride(1) == 1 and B.stride(1) == 1, "gemm: 2-D row-major views")
+    M, K = (A.shape[1], A.shape[0]) if transA else A.shape
+    K2, N = (B.shape[1], B.shape[0]) if transB else B.shape
+    _need(K == K2, f"gemm: inner dims {K} vs {K2}")
+    _need(A.dtype == B.dtype, "gemm: A/B dtype mismatch")
+    if C is None:
+        C = torch.empty(M, N, dtype=out_dtype or A.dtype, device=A.device)
+    _need(C.stride(1) == 1, "gemm: C last dim must be contiguous")
+    call("rs_gemm", _ptr(A), A.stride(0), int(transA), _ptr(B), B.stride(0), int(transB), _ptr(C), C.stride(0),
+         _ptr(bias), _ptr(aux), aux.stride(0) if aux is not None else 0, epilogue, M, N, K, _dt(A), _dt(C),
+         _stream())
+    return C
+
+
+def colsum(x, out=None):
+    _need(x.dim() == 2 and x.stride(1) == 1, "colsum: 2-D row-major view")
+    M, N = x.shape
+    out = torch.empty(N, dtype=torch.float32, device=x.device) if out is None else out
+    nbytes = cabi.load().rs_colsum_workspace_bytes(M, N)
+    ws = WS.get("colsum", nbytes, x.device)
+    call("rs_colsum", _ptr(x), x.stride(0), _dt(x), _ptr(out), M, N, _ptr(ws), ws.numel(), _stream())
+    return out
+
+
+def act_bwd(g, ref, kind, out=None):
+    M, N = g.shape
+    out = torch.empty(M, N, dtype=g.dtype, device=g.device) if out is None else out
+    call("rs_act_bwd", _ptr(g), g.stride(0), _ptr(ref), ref.stride(0), _ptr(out), out.stride(0), M, N, _dt(g),
+         kind, _stream())
+    return out
+
+
+def copy2d(src, dst):
+    M, N = src.shape
+    call("rs_copy2d", _ptr(src), src.stride(0), _dt(src), _ptr(dst), dst.stride(0), _dt(dst), M, N, _stream())
+    return dst
+
+
+def add2d(a, b, out):
+    M, N = a.shape
+    call("rs_add2d", _ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(out), out.stride(0), M, N, _dt(a), _stream())
+    return out
+
+
+def bce_sigmoid_fwd_bwd(p_raw, y, a=1.0, want_grad=True):
+    B, k = p_raw.shape
+    loss = torch.empty(1, dtype=torch.float32, device=p_raw.device)
+    dz = torch.empty_like(p_raw) if want_grad else None
+    call("rs_bce_sigmoid_fwd_bwd", _ptr(p_raw), _dt(p_raw), _ptr(y), a, _ptr(loss), _ptr(dz), B, k, _stream())
+    return loss, dz

@@ -1,0 +1,84 @@
+"""GPU parity: K4 fused InteractingLayer forward/backward through the C-ABI vs
+oracle/oracle_np.py (fp64 restatement of InteractingLayer.py:37-61)."""
+import numpy as np
+import pytest
+
+from util import REL_BF16, REL_F32, assert_close, interacting_params
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+# (B, F, D, U, H, L)
+SHAPES = [
+    (5, 39, 16, 16, 2, 3),      # BASELINE cfg1/cfg2 layer
+    (64, 39, 16, 16, 2, 1),
+    (33, 7, 8, 8, 2, 1),        # rank/multi_head: unit 8, 2 heads (multidnn.py:54)
+    (3, 175, 8, 8, 2, 1),       # rank/ctr: F=175 (model_init.py:54-59)
+    (17, 39, 16, 8, 2, 1),      # D != U, single iteration
+    (9, 1, 16, 16, 4, 2),       # F=1: softmax over a single field
+    (130, 128, 16, 16, 1, 2),
+    (257, 40, 8, 8, 1, 2),
+]
+
+
+def _t(a, dev, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    return t.to(dtype) if dtype is not None else t
+
+
+@pytest.mark.parametrize("B,F,D,U,H,L", SHAPES)
+@pytest.mark.parametrize("ln_eps", [1e-3, 1e-9])
+@pytest.mark.parametrize("use_res", [True, False])
+def test_interacting_fp32(cuda_dev, B, F, D, U, H, L, ln_eps, use_res):
+    from oracle import oracle_np as onp
+    from recommendsystem_b200 import ops
+    rng = np.random.default_rng(B + F + D + H + L)
+    W, b, gamma, beta = interacting_params(rng, D, U)
+    x = rng.standard_normal((B, F, D)).astype(np.float32)
+    dy = rng.standard_normal((B, F, U)).astype(np.float32)
+    f64 = lambda a: a.astype(np.float64)
+    ref = onp.interacting_fwd(f64(x), f64(W), f64(b), f64(gamma), f64(beta), ln_eps, H, L, use_res)
+    rdx, rdW, rdb, rdg, rdbt = onp.interacting_bwd(f64(x), f64(W), f64(b), f64(gamma), f64(beta), ln_eps, H, L,
+                                                   f64(dy), use_res)
+    xt = _t(x, cuda_dev)
+    Wt, bt, gt, bet = (_t(a, cuda_dev) for a in (W, b, gamma, beta))
+    y, saved = ops.interacting_fwd(xt, Wt, bt, gt, bet, ln_eps, H, L, use_res)
+    assert_close(y.cpu().numpy(), ref, REL_F32, "interacting fwd")
+    dx, dW, db, dg, dbt = ops.interacting_bwd(xt, saved, Wt, bt, gt, bet, ln_eps, H, L, _t(dy, cuda_dev), use_res)
+    assert_close(dx.cpu().numpy(), rdx, REL_F32, "dx")
+    assert_close(dW.cpu().numpy(), rdW, REL_F32, "dW")
+    assert_close(db.cpu().numpy(), rdb, REL_F32, "db")
+    assert_close(dg.cpu().numpy(), rdg, REL_F32, "dgamma")
+    assert_close(dbt.cpu().numpy(), rdbt, REL_F32, "dbeta")
+    # deterministic: a second run gives identical bits
+    dx2, dW2, *_ = ops.interacting_bwd(xt, saved, Wt, bt, gt, bet, ln_eps, H, L, _t(dy, cuda_dev), use_res)
+    assert torch.equal(dx, dx2) and torch.equal(dW, dW2)
+
+
+@pytest.mark.parametrize("B,F,D,U,H,L", SHAPES[:3])
+def test_interacting_bf16(cuda_dev, B, F, D, U, H, L):
+    from oracle import oracle_np as onp
+    from recommendsystem_b200 import ops
+    rng = np.random.default_rng(B + F)
+    W, b, gamma, beta = interacting_params(rng, D, U)
+    xt = _t(rng.standard_normal((B, F, D)).astype(np.float32), cuda_dev, torch.bfloat16)
+    dyt = _t(rng.standard_normal((B, F, U)).astype(np.float32), cuda_dev, torch.bfloat16)
+    f64 = lambda a: a.astype(np.float64)
+    x, dy = xt.float().cpu().numpy(), dyt.float().cpu().numpy()
+    ref = onp.interacting_fwd(f64(x), f64(W), f64(b), f64(gamma), f64(beta), 1e-3, H, L)
+    rdx, rdW, rdb, rdg, rdbt = onp.interacting_bwd(f64(x), f64(W), f64(b), f64(gamma), f64(beta), 1e-3, H, L, f64(dy))
+    Wt, bt, gt, bet = (_t(a, cuda_dev) for a in (W, b, gamma, beta))
+    y, saved = ops.interacting_fwd(xt, Wt, bt, gt, bet, 1e-3, H, L)
+    assert_close(y.float().cpu().numpy(), ref, REL_BF16, "bf16 fwd")
+    dx, dW, db, dg, dbt = ops.interacting_bwd(xt, saved, Wt, bt, gt, bet, 1e-3, H, L, dyt)
+    assert_close(dx.float().cpu().numpy(), rdx, 2 * REL_BF16, "bf16 dx")
+    assert_close(dW.cpu().numpy(), rdW, 2 * REL_BF16, "bf16 dW")
+    assert_close(dg.cpu().numpy(), rdg, 2 * REL_BF16, "bf16 dgamma")
+
+
+def test_interacting_unsupported_shape_raises(cuda_dev):
+    from recommendsystem_b200 import cabi, ops
+    x = torch.zeros(2, 3, 24, device=cuda_dev)
+    with pytest.raises(cabi.RsError):
+        ops.interacting_fwd(x, torch.zeros(24, 96, device=cuda_dev), torch.zeros(96, device=cuda_dev),
+                            torch.ones(24, device=cuda_dev), torch.zeros(24, device=cuda_dev), 1e-3, 2, 1)
