@@ -193,9 +193,11 @@ int rs_permute_rows(const void* src, void* out, const int32_t* index, int64_t n,
  * side), bqkvr [4U].  D must equal U when L > 1.  x, y are [B, F, D|U] with
  * row strides x_ld / y_ld (elements) between samples' field rows, i.e.
  * element (b,f,c) at ptr[(b*F+f)*ld + c].
- * `saved` (training): [L, B*F, U] inputs of every iteration after the first
- * plus nothing else — the backward recomputes the rest.  May be NULL for
- * inference.  dtype applies to x, y, saved.  Parameters are fp32.
+ * `saved` (training): fp32 [L-1, B*F, U], the input of every iteration after
+ * the first (kept in fp32 whatever `dtype` is, so a bf16 run rounds only at the
+ * layer's input and output); the backward recomputes everything else.  May be
+ * NULL for inference or L == 1.  dtype applies to x, y (and dy, dx).
+ * Parameters are fp32.
  * compute_bf16 != 0 runs the projections on tcgen05 tensor cores (bf16
  * operands, fp32 TMEM accumulators); 0 = fp32 FFMA everywhere (parity mode).
  */

@@ -178,11 +178,13 @@ def sparse_adam(w, m, v, rowidx, grad, lr, beta1, beta2, eps, corr, grad_scale=1
     w, m, v = w.copy(), m.copy(), v.copy()
     dt = w.dtype.type
     uniq, g = _scaled_segment_sum(rowidx, grad, grad_scale, sum_dtype, w.dtype)
-    b1, b2 = dt(beta1), dt(beta2)
+    # hyper-parameters are fp32 values (TF holds them as float32 tensors): 1 - float32(0.999)
+    # differs from 1 - 0.999 by 1.3e-5 relative
+    b1, b2, lr_, eps_ = (dt(np.float32(t)) for t in (beta1, beta2, lr, eps))
     for r, gr in zip(uniq, g):
         m[r] = b1 * m[r] + (dt(1) - b1) * gr
         v[r] = b2 * v[r] + (dt(1) - b2) * gr * gr
-        w[r] = w[r] - dt(lr) * dt(corr) * m[r] / (np.sqrt(v[r]) + dt(eps))
+        w[r] = w[r] - lr_ * dt(corr) * m[r] / (np.sqrt(v[r]) + eps_)
     return w, m, v
 
 
@@ -210,9 +212,10 @@ def dense_adam(w, m, v, g, lr, beta1, beta2, eps, corr):
     """tn.optimizer.Optimizer(tn.core.Adam(...)) on a flat dense buffer
     (rank/multi_head/model.py:53, staytime/model.py:72)."""
     dt = w.dtype.type
-    m2 = dt(beta1) * m + (dt(1) - dt(beta1)) * g
-    v2 = dt(beta2) * v + (dt(1) - dt(beta2)) * g * g
-    w2 = w - dt(lr) * dt(corr) * m2 / (np.sqrt(v2) + dt(eps))
+    b1, b2, lr_, eps_ = (dt(np.float32(t)) for t in (beta1, beta2, lr, eps))
+    m2 = b1 * m + (dt(1) - b1) * g
+    v2 = b2 * v + (dt(1) - b2) * g * g
+    w2 = w - lr_ * dt(corr) * m2 / (np.sqrt(v2) + eps_)
     return w2, m2, v2
 
 

@@ -1,0 +1,300 @@
+"""AutoInt train step on one B200: the reference's CTR hot path as one captured stream of
+hand-written sm_100a kernels (include/rs_b200.h).
+
+    ids [B,F] -> embedding gather -> X [B,F,d] --+-> InteractingLayer (L x, shared weights) -> A
+                                                 +-> Flatten -> MultiLayerDense(relu)       -> deep
+    Z = concat[deep, Flatten(A)] -> Dense(1, sigmoid) -> clip(1e-6, 1) -> cross_entropy
+    backward -> dense Adam (flat buffer) + sorted-segment sparse Adam on the touched rows
+
+Reference: AutoInt.model_layer (autoint:18-56), BaseModel.output_layer / cross_entropy
+(rank/ctr/base_model.py:7-12,160-201), InteractingLayer.call (InteractingLayer.py:37-61).
+`model_config['model_param']` is not shipped by the reference; the defaults below are the
+BASELINE.json configuration (SURVEY.md §8c lists them as explicit choices).
+
+torch supplies device memory, streams and CUDA-graph capture; every kernel in the step
+comes from librs_b200.so.  There is no CPU path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import List, Sequence
+
+import numpy as np
+import torch
+
+from . import cabi, ops
+
+
+@dataclass
+class AutoIntConfig:
+    num_fields: int = 39
+    rows_per_field: int | Sequence[int] = 1_000_000
+    embed_dim: int = 16
+    # model_param.interact
+    layer_num: int = 3
+    unit_num: int = 16
+    head_num: int = 2
+    use_res: bool = True
+    ln_eps: float = 1e-3
+    # model_param.mlp / logits
+    mlp_hidden: Sequence[int] = (256, 128)
+    batch: int = 8192
+    dtype: str = "f32"              # activation dtype: "f32" | "bf16" (tables and master weights stay fp32)
+    lr_dense: float = 5e-5          # rank/ctr/base_model.py:192
+    lr_sparse: float = 5e-5         # rank/ctr/base_model.py:163
+    beta1: float = 0.9
+    beta2: float = 0.999
+    eps: float = 1e-8
+    table_init_scale: float = 0.1
+    seed: int = 20261018
+
+    def rows(self) -> List[int]:
+        if isinstance(self.rows_per_field, int):
+            return [self.rows_per_field] * self.num_fields
+        assert len(self.rows_per_field) == self.num_fields
+        return list(self.rows_per_field)
+
+
+class AutoIntTrainer:
+    """Owns tables, optimizer state and dense parameters; `step()` launches one train step."""
+
+    def __init__(self, cfg: AutoIntConfig, device="cuda:0", tables: torch.Tensor | None = None,
+                 dense_init: dict | None = None):
+        cabi.load()
+        self.cfg = cfg
+        self.dev = torch.device(device)
+        if self.dev.type != "cuda":
+            raise RuntimeError("AutoIntTrainer runs on a CUDA device only (no CPU fallback)")
+        self.act_dtype = {"f32": torch.float32, "bf16": torch.bfloat16}[cfg.dtype]
+        F, d, U, B = cfg.num_fields, cfg.embed_dim, cfg.unit_num, cfg.batch
+        if cfg.layer_num > 1 and d != U:
+            raise ValueError("layer_num > 1 needs embed_dim == unit_num (InteractingLayer.py:41-46)")
+        rows = cfg.rows()
+        self.rows_host = np.asarray(rows, np.int64)
+        self.base_host = np.concatenate([[0], np.cumsum(self.rows_host)[:-1]]).astype(np.int64)
+        self.total_rows = int(self.rows_host.sum())
+        if self.total_rows >= 2 ** 31 - 1:
+            raise ValueError("arena rows must fit int32")
+        self.rows_t = torch.from_numpy(self.rows_host).to(self.dev)
+        self.base_t = torch.from_numpy(self.base_host).to(self.dev)
+        gen = torch.Generator(device=self.dev).manual_seed(cfg.seed)
+        if tables is None:
+            self.table = torch.empty(self.total_rows, d, device=self.dev)
+            self.table.normal_(0.0, cfg.table_init_scale, generator=gen)
+        else:
+            self.table = tables.to(self.dev, torch.float32).contiguous()
+            assert self.table.shape == (self.total_rows, d)
+        self.table_m = torch.zeros_like(self.table)
+        self.table_v = torch.zeros_like(self.table)
+        self.row_bits = ops.row_bits(self.total_rows)
+
+        # ---- dense parameters: one flat fp32 buffer (+ grads, m, v, bf16 shadow) with views
+        self.spec = []
+        widths = [F * d] + list(cfg.mlp_hidden)
+        self.n_deep = widths[-1]
+        self.zw = self.n_deep + F * U
+        self._add("Wqkvr", (d, 4 * U)); self._add("bqkvr", (4 * U,))
+        self._add("gamma", (U,)); self._add("beta", (U,))
+        for i in range(len(cfg.mlp_hidden)):
+            self._add(f"mlp_W{i}", (widths[i], widths[i + 1])); self._add(f"mlp_b{i}", (widths[i + 1],))
+        self._add("out_W", (self.zw, 1)); self._add("out_b", (1,))
+        n = (self.spec[-1][2] + int(np.prod(self.spec[-1][1])) + 3) // 4 * 4
+        self.n_dense = n
+        self.flat = torch.zeros(n, device=self.dev)
+        self.flat_g = torch.zeros(n, device=self.dev)
+        self.flat_m = torch.zeros(n, device=self.dev)
+        self.flat_v = torch.zeros(n, device=self.dev)
+        self.flat_bf16 = torch.zeros(n, device=self.dev, dtype=torch.bfloat16)
+        self.P = {k: self.flat[o:o + int(np.prod(s))].view(s) for k, s, o in self.spec}
+        self.G = {k: self.flat_g[o:o + int(np.prod(s))].view(s) for k, s, o in self.spec}
+        self.P16 = {k: self.flat_bf16[o:o + int(np.prod(s))].view(s) for k, s, o in self.spec}
+        self._init_dense(dense_init)
+        self.adam_scalars = torch.zeros(4, device=self.dev)
+
+        # ---- static activation buffers (fixed addresses => CUDA-graph capturable)
+        T = self.act_dtype
+        e = lambda *shape, dtype=T: torch.empty(*shape, device=self.dev, dtype=dtype)
+        self.ids = torch.zeros(B, F, dtype=torch.int64, device=self.dev)
+        self.labels = torch.zeros(B, 1, device=self.dev)
+        self.X = e(B, F, d)
+        self.keys = torch.empty(B * F, dtype=torch.int64, device=self.dev)
+        self.keys_sorted = torch.empty_like(self.keys)
+        self.A = e(B, F, U)
+        self.saved = e(max(cfg.layer_num - 1, 1), B * F, U, dtype=torch.float32)
+        self.H = [e(B, w) for w in cfg.mlp_hidden[:-1]]
+        self.Z = e(B, self.zw)
+        self.p_raw = e(B, 1)
+        self.loss = torch.zeros(1, device=self.dev)
+        self.dzl = e(B, 1)
+        self.dZ = e(B, self.zw)
+        self.dH = [e(B, w) for w in cfg.mlp_hidden]
+        self.dX = e(B, F, d)
+        self.graph = None
+        self._h_ids = None
+        n_ws = max(cabi.load().rs_interacting_workspace_bytes(B, F, d, U),
+                   cabi.load().rs_embed_sort_workspace_bytes(B * F),
+                   cabi.load().rs_colsum_workspace_bytes(B, max(widths + [self.zw])))
+        self.ws = torch.empty(int(n_ws) + 256, dtype=torch.uint8, device=self.dev)
+
+    # ------------------------------------------------------------------ setup
+    def _add(self, name, shape):
+        off = 0
+        if self.spec:
+            _, s, o = self.spec[-1]
+            off = (o + int(np.prod(s)) + 3) // 4 * 4      # 16-byte aligned views
+        self.spec.append((name, tuple(shape), off))
+
+    def _init_dense(self, init):
+        """Keras defaults: Dense kernels glorot_uniform, biases zero; LayerNorm gamma 1 / beta 0."""
+        rng = np.random.default_rng(self.cfg.seed)
+        U = self.cfg.unit_num
+        for name, shape, _ in self.spec:
+            if init is not None and name in init:
+                v = np.asarray(init[name], np.float32).reshape(shape)
+            elif name == "Wqkvr":
+                lim = np.sqrt(6.0 / (shape[0] + U))      # four separate Dense(U) kernels side by side
+                v = rng.uniform(-lim, lim, size=shape).astype(np.float32)
+            elif name == "gamma":
+                v = np.ones(shape, np.float32)
+            elif len(shape) == 2:
+                lim = np.sqrt(6.0 / (shape[0] + shape[1]))
+                v = rng.uniform(-lim, lim, size=shape).astype(np.float32)
+            else:
+                v = np.zeros(shape, np.float32)
+            self.P[name].copy_(torch.from_numpy(v))
+        self.flat_bf16.copy_(self.flat)
+
+    def dense_state(self):
+        return {k: v.detach().cpu().numpy().copy() for k, v in self.P.items()}
+
+    # ------------------------------------------------------------------- step
+    def _w(self, name):
+        """Weights as the GEMM consumes them (fp32 master or bf16 shadow)."""
+        return self.P[name] if self.act_dtype == torch.float32 else self.P16[name]
+
+    def _launch_step(self):
+        """One train step on torch's current stream using the static buffers."""
+        c = self.cfg
+        F, d, U, B = c.num_fields, c.embed_dim, c.unit_num, c.batch
+        E = cabi
+        st = ops._stream()
+        T = ops._DT[self.act_dtype]
+        P, G = self.P, self.G
+        nmlp = len(c.mlp_hidden)
+        # K1: gather + sort keys
+        cabi.call("rs_embed_gather_fwd", self.table.data_ptr(), self.ids.data_ptr(), self.base_t.data_ptr(),
+                  self.rows_t.data_ptr(), B * F, F, d, self.X.data_ptr(), T, self.keys.data_ptr(), None, st)
+        # K4: InteractingLayer forward
+        cabi.call("rs_interacting_fwd", self.X.data_ptr(), d, T, P["Wqkvr"].data_ptr(), P["bqkvr"].data_ptr(),
+                  P["gamma"].data_ptr(), P["beta"].data_ptr(), c.ln_eps, self.A.data_ptr(), U,
+                  self.saved.data_ptr() if c.layer_num > 1 else None, B, F, d, U, c.head_num, c.layer_num,
+                  int(c.use_res), int(self.act_dtype == torch.bfloat16), st)
+        # K5: MLP tower; last hidden layer lands in Z[:, :n_deep], Flatten(A) in Z[:, n_deep:]
+        Xf = self.X.view(B, F * d)
+        acts = [Xf] + self.H + [self.Z[:, :self.n_deep]]
+        for i in range(nmlp):
+            ops.gemm(acts[i], self._w(f"mlp_W{i}"), acts[i + 1], bias=P[f"mlp_b{i}"], epilogue=E.EPI_BIAS_RELU)
+        ops.copy2d(self.A.view(B, F * U), self.Z[:, self.n_deep:])
+        ops.gemm(self.Z, self._w("out_W"), self.p_raw, bias=P["out_b"], epilogue=E.EPI_BIAS_SIGMOID)
+        # K8: clip + BCE, gradient wrt the logit pre-activation
+        cabi.call("rs_bce_sigmoid_fwd_bwd", self.p_raw.data_ptr(), T, self.labels.data_ptr(), 1.0,
+                  self.loss.data_ptr(), self.dzl.data_ptr(), B, 1, st)
+        # ---- backward: logits layer
+        self._wgrad(self.Z, self.dzl, "out_W", "out_b")
+        ops.gemm(self.dzl, self._w("out_W"), self.dZ, transB=True)
+        # MLP backward (relu masks from the saved activations)
+        ops.act_bwd(self.dZ[:, :self.n_deep], acts[nmlp], 0, out=self.dH[nmlp - 1])
+        for i in reversed(range(nmlp)):
+            self._wgrad(acts[i], self.dH[i], f"mlp_W{i}", f"mlp_b{i}")
+            if i > 0:
+                ops.gemm(self.dH[i], self._w(f"mlp_W{i}"), self.dH[i - 1], aux=acts[i],
+                         epilogue=E.EPI_MUL_RELU_MASK, transB=True)
+        # InteractingLayer backward -> dX, then dX += dH0 @ W0^T
+        nW = d * 4 * U
+        dparams = self.flat_g[self.spec[0][2]:]       # Wqkvr | bqkvr | gamma | beta are contiguous
+        assert self.spec[1][2] == nW and self.spec[2][2] == nW + 4 * U and self.spec[3][2] == nW + 5 * U
+        self._interacting_bwd(dparams, st, T)
+        ops.gemm(self.dH[0], self._w("mlp_W0"), self.dX.view(B, F * d), epilogue=E.EPI_ACCUM, transB=True)
+        # K3: sparse Adam on touched rows; dense Adam on the flat buffer
+        ops.adam_advance(self.adam_scalars, c.beta1, c.beta2)
+        ops.sort_keys(self.keys, self.row_bits, out=self.keys_sorted)
+        ops.segsum_adam(self.table, self.table_m, self.table_v, self.dX.view(B * F, d), self.keys_sorted,
+                        c.lr_sparse, c.beta1, c.beta2, c.eps, self.adam_scalars)
+        ops.dense_adam(self.flat, self.flat_m, self.flat_v, self.flat_g, c.lr_dense, c.beta1, c.beta2, c.eps,
+                       self.adam_scalars, self.flat_bf16)
+
+    def _interacting_bwd(self, dparams, st, T):
+        c = self.cfg
+        F, d, U, B = c.num_fields, c.embed_dim, c.unit_num, c.batch
+        P = self.P
+        # dA arrives as Z-gradient columns [n_deep:], i.e. rows of F*U values with row stride zw:
+        # repack to [B,F,U] (contiguous) for the kernel's (b*F+f)*ld addressing.
+        dA = self.A                      # reuse A's storage: its values are no longer needed
+        ops.copy2d(self.dZ[:, self.n_deep:], dA.view(B, F * U))
+        cabi.call("rs_interacting_bwd", self.X.data_ptr(), d, self.saved.data_ptr() if c.layer_num > 1 else None,
+                  T, P["Wqkvr"].data_ptr(), P["bqkvr"].data_ptr(), P["gamma"].data_ptr(), P["beta"].data_ptr(),
+                  c.ln_eps, dA.data_ptr(), U, self.dX.data_ptr(), d, dparams.data_ptr(), B, F, d, U, c.head_num,
+                  c.layer_num, int(c.use_res), int(self.act_dtype == torch.bfloat16), self.ws.data_ptr(),
+                  self.ws.numel(), st)
+
+    def _wgrad(self, x, dy, wname, bname):
+        """G[w] = x^T dy ; G[b] = colsum(dy)."""
+        ops.gemm(x, dy, self.G[wname], transA=True, out_dtype=torch.float32)
+        ops.colsum(dy, out=self.G[bname])
+
+    # --------------------------------------------------------------- frontends
+    def step(self, ids: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """Device-resident inputs -> one train step; returns the loss tensor (device, 1 element)."""
+        self.ids.copy_(ids, non_blocking=True)
+        self.labels.copy_(labels, non_blocking=True)
+        self.run()
+        return self.loss
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._launch_step()
+
+    def capture(self):
+        """Capture the step into a CUDA graph (after a warm-up launch on a side stream)."""
+        s = torch.cuda.Stream(device=self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            self._launch_step()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._launch_step()
+        self.graph = g
+        return g
+
+    def step_from_host(self, ids_pinned: torch.Tensor, labels_pinned: torch.Tensor) -> float:
+        """End-to-end call: pinned host ids/labels -> H2D -> step -> loss read back (D2H)."""
+        self.ids.copy_(ids_pinned, non_blocking=True)
+        self.labels.copy_(labels_pinned, non_blocking=True)
+        self.run()
+        return float(self.loss.item())
+
+    @torch.no_grad()
+    def predict(self, ids: torch.Tensor) -> torch.Tensor:
+        """Forward only (clip(sigmoid) probabilities), eager launches."""
+        c = self.cfg
+        F, d, U, B = c.num_fields, c.embed_dim, c.unit_num, c.batch
+        assert ids.shape == (B, F)
+        self.ids.copy_(ids)
+        T = ops._DT[self.act_dtype]
+        st = ops._stream()
+        P = self.P
+        cabi.call("rs_embed_gather_fwd", self.table.data_ptr(), self.ids.data_ptr(), self.base_t.data_ptr(),
+                  self.rows_t.data_ptr(), B * F, F, d, self.X.data_ptr(), T, None, None, st)
+        cabi.call("rs_interacting_fwd", self.X.data_ptr(), d, T, P["Wqkvr"].data_ptr(), P["bqkvr"].data_ptr(),
+                  P["gamma"].data_ptr(), P["beta"].data_ptr(), c.ln_eps, self.A.data_ptr(), U, None, B, F, d, U,
+                  c.head_num, c.layer_num, int(c.use_res), 0, st)
+        acts = [self.X.view(B, F * d)] + self.H + [self.Z[:, :self.n_deep]]
+        for i in range(len(c.mlp_hidden)):
+            ops.gemm(acts[i], self._w(f"mlp_W{i}"), acts[i + 1], bias=P[f"mlp_b{i}"], epilogue=cabi.EPI_BIAS_RELU)
+        ops.copy2d(self.A.view(B, F * U), self.Z[:, self.n_deep:])
+        ops.gemm(self.Z, self._w("out_W"), self.p_raw, bias=P["out_b"], epilogue=cabi.EPI_BIAS_SIGMOID)
+        return self.p_raw.float().clamp(1e-6, 1.0)

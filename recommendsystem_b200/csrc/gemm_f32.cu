@@ -18,7 +18,7 @@ __device__ __forceinline__ float epi_apply(float acc, int epi, const float* bias
   switch (epi) {
     case RS_EPI_BIAS: return acc + bias[n];
     case RS_EPI_BIAS_RELU: return fmaxf(acc + bias[n], 0.f);
-    case RS_EPI_BIAS_SIGMOID: return 1.f / (1.f + __expf(-(acc + bias[n])));
+    case RS_EPI_BIAS_SIGMOID: return 1.f / (1.f + expf(-(acc + bias[n])));
     case RS_EPI_MUL_RELU_MASK: return to_f<CT>(aux[m * ldaux + n]) > 0.f ? acc : 0.f;
     case RS_EPI_MUL_DSIGMOID: {
       const float r = to_f<CT>(aux[m * ldaux + n]);

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(NT)
 interacting_fwd_kernel(const T* __restrict__ x, int64_t x_ld, const float* __restrict__ W,
                        const float* __restrict__ bias, const float* __restrict__ gamma,
                        const float* __restrict__ beta, float eps, T* __restrict__ y, int64_t y_ld,
-                       T* __restrict__ saved, int B, int F, int L, int use_res) {
+                       float* __restrict__ saved, int B, int F, int L, int use_res) {
   static_assert(U <= 32, "tmask is 32 bits");
   constexpr int DH = U / H;
   constexpr int N4 = 4 * U;
@@ -242,11 +242,10 @@ interacting_fwd_kernel(const T* __restrict__ x, int64_t x_ld, const float* __res
         float xhat[U], rstd;
         uint32_t tmask;
         res_relu_ln<U>(o, r, use_res, gs, be, eps, yv, xhat, rstd, tmask);
-        round_row<U, T>(yv);
       }
       __syncthreads();
       if (it + 1 < L) {
-        if (active && saved) store_row<U, T>(saved + ((int64_t)it * total_rows + row) * U, yv);
+        if (active && saved) store_row<U, float>(saved + ((int64_t)it * total_rows + row) * U, yv);
         if constexpr (D == U) {
 #pragma unroll
           for (int u = 0; u < U; ++u) xr[u] = yv[u];
@@ -260,7 +259,7 @@ interacting_fwd_kernel(const T* __restrict__ x, int64_t x_ld, const float* __res
 // ----------------------------------------------------------------- backward
 template <int D, int U, int H, int NT, typename T>
 __global__ void __launch_bounds__(NT)
-interacting_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const T* __restrict__ saved,
+interacting_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const float* __restrict__ saved,
                        const float* __restrict__ W, const float* __restrict__ bias,
                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                        const T* __restrict__ dy, int64_t dy_ld, T* __restrict__ dx, int64_t dx_ld,
@@ -323,7 +322,7 @@ interacting_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const T* __restric
       if (active) {
         if (it == 0) load_row<D, T>(x + row * x_ld, xr);
         else {
-          if constexpr (D == U) load_row<U, T>(saved + ((int64_t)(it - 1) * total_rows + row) * U, xr);
+          if constexpr (D == U) load_row<U, float>(saved + ((int64_t)(it - 1) * total_rows + row) * U, xr);
         }
       } else {
 #pragma unroll
@@ -540,8 +539,7 @@ interacting_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const T* __restric
       if (it > 0) {
         if constexpr (D == U) {
 #pragma unroll
-          for (int u = 0; u < U; ++u) g[u] = dxr[u];
-          round_row<U, T>(g);
+          for (int u = 0; u < U; ++u) g[u] = dxr[u];   // stays fp32 between iterations
         }
       } else if (active) {
         store_row<D, T>(dx + row * dx_ld, dxr);
@@ -597,7 +595,7 @@ static int launch_fwd(const IFwdArgs& a) {
   int grid = sm_count() * 4;
   if (grid > ntiles) grid = ntiles;
   kern<<<grid, NT, smem, a.st>>>((const T*)a.x, a.x_ld, a.W, a.b, a.gm, a.bt, a.eps, (T*)a.y, a.y_ld,
-                                 (T*)a.saved, a.B, a.F, a.L, a.use_res);
+                                 (float*)a.saved, a.B, a.F, a.L, a.use_res);
   return check_launch("interacting_fwd");
 }
 
@@ -612,7 +610,7 @@ static int launch_bwd(const IBwdArgs& a) {
     set_error("interacting_bwd: workspace %zu < %zu", a.ws_bytes, (size_t)grid * np * sizeof(float));
     return RS_ERR_WORKSPACE;
   }
-  kern<<<grid, NT, smem, a.st>>>((const T*)a.x, a.x_ld, (const T*)a.saved, a.W, a.b, a.gm, a.bt, a.eps,
+  kern<<<grid, NT, smem, a.st>>>((const T*)a.x, a.x_ld, (const float*)a.saved, a.W, a.b, a.gm, a.bt, a.eps,
                                  (const T*)a.dy, a.dy_ld, (T*)a.dx, a.dx_ld, (float*)a.ws, a.B, a.F,
                                  a.L, a.use_res);
   if (int e = check_launch("interacting_bwd")) return e;

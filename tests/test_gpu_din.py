@@ -79,7 +79,9 @@ def test_din_b(cuda_dev, B, T, H, with_mask):
         assert_close(out[0].cpu().numpy(), facts[0].astype(np.float64).mean(0), REL_F32, "all-masked row")
     dq, dfacts, _none, dW1, db1, dW2, db2 = ops.din_bwd(cabi.DIN_B, qt, ft, None, None, mt, *Ws, _t(dout, cuda_dev))
     for g, r, name in zip((dq, dfacts, dW1, db1, dW2, db2), refs, ["dq", "dfacts", "dW1", "db1", "dW2", "db2"]):
-        assert_close(g.cpu().numpy().reshape(r.shape), r, 2 * REL_F32, "din B " + name)
+        # db2 is analytically 0 (softmax is shift invariant): absolute bound instead
+        assert_close(g.cpu().numpy().reshape(r.shape), r, 2 * REL_F32, "din B " + name,
+                     atol=1e-4 if name == "db2" else 0.0)
 
 
 def test_din_b_strided_bf16(cuda_dev):

@@ -39,7 +39,7 @@ def test_gemm_f32(cuda_dev, M, N, K, tA, tB, epi):
     from recommendsystem_b200 import ops
     rng = np.random.default_rng(M + N + K + epi)
     A = rng.standard_normal((K, M) if tA else (M, K)).astype(np.float32)
-    B = rng.standard_normal((N, K) if tB else (K, N)).astype(np.float32)
+    B = (rng.standard_normal((N, K) if tB else (K, N)) / np.sqrt(K)).astype(np.float32)   # Glorot-like scale
     bias = rng.standard_normal(N).astype(np.float32)
     aux = rng.random((M, N)).astype(np.float32) - 0.3
     cold = rng.standard_normal((M, N)).astype(np.float32)

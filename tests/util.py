@@ -22,9 +22,17 @@ def rel_err(a, ref):
     return float(np.max(np.abs(a - ref)) / (np.max(np.abs(ref)) + 1e-30))
 
 
-def assert_close(a, ref, rel, what=""):
-    e = rel_err(a, ref)
-    assert e <= rel, f"{what}: relative error {e:.3e} > {rel:.1e}"
+def assert_close(a, ref, rel, what="", atol=0.0):
+    """max|a-ref| <= rel * max|ref| + atol (norm-wise relative error; atol only for
+    quantities that are analytically zero, e.g. the softmax-shift gradient db2 of DIN-B)."""
+    a64 = np.asarray(a, dtype=np.float64)
+    r64 = np.asarray(ref, dtype=np.float64)
+    assert a64.shape == r64.shape, (what, a64.shape, r64.shape)
+    if a64.size == 0:
+        return
+    err = float(np.max(np.abs(a64 - r64)))
+    bound = rel * float(np.max(np.abs(r64))) + atol
+    assert err <= bound, f"{what}: max abs error {err:.3e} > {bound:.3e} (rel {rel:.1e}, max|ref| {np.max(np.abs(r64)):.3e})"
 
 
 def glorot_uniform(rng, fan_in, fan_out, shape=None):
