@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — AutoInt train samples/s on synthetic Criteo-shape batches (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype f32|bf16] [--impl reference]
+
+Workload (BASELINE.json configs[1]): AutoInt (InteractingLayer layer_num=3, unit 16, 2 heads)
++ DNN tower 624->256->128, 39 fields, 1M-row fp32 tables (d=16), batch 8192 per GPU,
+forward + backward + sparse Adam on touched rows + dense Adam.  A "step" is one train step on
+one fresh batch of uniform ids.
+
+Own arm: `value` = samples/s with ids/labels already resident in HBM (CUDA-graph replay per
+step, CUDA events, max over ranks); `e2e` = the same through AutoIntTrainer.step_from_host with
+pinned HOST ids/labels (H2D every step, loss read back every step).  `roofline` is the phase
+with the largest share of the step; `kernels` lists every phase with its algorithmic
+bytes/FLOPs.  `cpu_baseline` / `--impl reference`: the op-for-op torch-CPU restatement of the
+reference TF graph (oracle/oracle_torch.py — TensorFlow is not installable offline) on the
+box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+F, D, U, H, L = 39, 16, 16, 2, 3
+ROWS = 1_000_000
+BATCH = 8192
+MLP = (256, 128)
+SEED = 20261018
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(hbm_gbs=j["hbm_gbs"], bf16_tflops=j["bf16_tflops"],
+                    bf16_tflops_sustained=j.get("bf16_tflops_sustained", j["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------ reference / CPU arm
+def cpu_autoint_samples_per_s(batch, steps, warmup, rows_per_field, threads=None):
+    """The reference graph restated op-for-op in torch on the CPU (oracle/oracle_torch.py)."""
+    import numpy as np
+    import torch
+    from oracle import oracle_torch as ot
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(SEED)
+    total = rows_per_field * F
+    table = torch.empty(total, D).normal_(0, 0.1, generator=g)
+    rng = np.random.default_rng(SEED)
+
+    def glorot(fi, fo, shape=None):
+        lim = (6.0 / (fi + fo)) ** 0.5
+        return torch.from_numpy(rng.uniform(-lim, lim, size=shape or (fi, fo)).astype(np.float32))
+
+    params = {"Wqkvr": glorot(D, U, (D, 4 * U)), "bqkvr": torch.zeros(4 * U), "gamma": torch.ones(U),
+              "beta": torch.zeros(U)}
+    w = [F * D] + list(MLP)
+    for i in range(len(MLP)):
+        params[f"mlp_W{i}"] = glorot(w[i], w[i + 1]); params[f"mlp_b{i}"] = torch.zeros(w[i + 1])
+    params["out_W"] = glorot(MLP[-1] + F * U, 1); params["out_b"] = torch.zeros(1)
+    model = ot.AutoIntCPU(table, params, H, L, 1e-3)
+    base = (torch.arange(F) * rows_per_field)[None, :]
+    times = []
+    for i in range(warmup + steps):
+        ids = torch.randint(0, rows_per_field, (batch, F), generator=g) + base
+        y = (torch.rand(batch, 1, generator=g) < 0.25).float()
+        t0 = time.perf_counter()
+        model.train_step(ids, y)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return batch * len(times) / sum(times), 1e3 * sum(times) / len(times), threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import psutil
+    rows = ROWS if psutil.virtual_memory().available > 14e9 else 100_000
+    sps, ms, threads = cpu_autoint_samples_per_s(BATCH, args.steps, args.warmup, rows)
+    sample = (f"{args.steps} train steps (after {args.warmup} warm-up) of batch {BATCH}, {rows} rows/field, "
+              "torch-CPU op-for-op restatement of the reference TF graph (TensorFlow unavailable offline)")
+    print(json.dumps({
+        "impl": "reference", "metric": "autoint_train_samples_per_s", "value": sps, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, "cpu"),
+        "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, dtype):
+    return {"workload": "AutoInt(layer_num=3,unit_num=16,head_num=2)+DNN(256,128), 39 fields, 1M-row tables d=16, "
+                        f"batch {BATCH}/GPU, fwd+bwd+sparse Adam+dense Adam (BASELINE configs[1])",
+            "batch_per_gpu": BATCH, "global_batch": BATCH * args.gpus, "fields": F, "embed_dim": D,
+            "rows_per_field": ROWS, "act_dtype": dtype, "ids": "uniform, fresh batch every step",
+            "l2": "tables+Adam state 7.5 GB per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)",
+            "parallelism": f"dp{args.gpus}" + ("+row-sharded tables (all-to-all)" if args.gpus > 1 else "")}
+
+
+# ------------------------------------------------------------------------------ own arm
+def algorithmic(phase, B, act_bytes, n_unique):
+    """(bytes, flops) per launch of each phase — DESIGN.md §kernels; SURVEY.md §8d."""
+    n = B * F
+    zw = MLP[-1] + F * U
+    gemm = 2 * B * (F * D * MLP[0] + MLP[0] * MLP[1])
+    inter_f = L * (2 * 4 * F * D * U + 2 * 2 * H * F * F * (U // H)) * B
+    t = {
+        "embed_gather": (n * (8 + D * 4 + D * act_bytes + 8), 0),          # + 8 B sort key written
+        "interacting_fwd": (n * (D + U) * act_bytes + (L - 1) * n * U * 4, inter_f),
+        "interacting_bwd": (n * (2 * U + 2 * D) * act_bytes + (L - 1) * n * U * 4, 3 * inter_f),
+        "mlp_fwd": (B * (F * D + 2 * MLP[0] + MLP[1]) * act_bytes, gemm),
+        "mlp_bwd": (B * (F * D + 3 * MLP[0] + 3 * MLP[1]) * act_bytes, gemm + 2 * B * MLP[0] * MLP[1]),
+        "mlp_dgrad_x": (B * (MLP[0] + 2 * F * D) * act_bytes, 2 * B * F * D * MLP[0]),
+        "logits_loss": (B * zw * act_bytes * 5, 6 * B * zw),
+        "sort_keys": (n * 8 * 2, 0),
+        "embed_segsum_adam": (n * (8 + D * act_bytes) + n_unique * 2 * 3 * D * 4, 0),
+        "dense_adam": (0, 0),
+    }
+    return t.get(phase, (0, 0))
+
+
+def run_own(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from recommendsystem_b200 import cabi
+    from recommendsystem_b200.autoint import AutoIntConfig, AutoIntTrainer, PhaseTimer
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        from recommendsystem_b200.sharded import ShardedAutoIntTrainer as Trainer
+    else:
+        Trainer = AutoIntTrainer
+    cfg = AutoIntConfig(num_fields=F, rows_per_field=ROWS, embed_dim=D, layer_num=L, unit_num=U, head_num=H,
+                        mlp_hidden=MLP, batch=BATCH, dtype=args.dtype, seed=SEED)
+    tr = Trainer(cfg, dev)
+    K, W = args.steps, args.warmup
+    g = torch.Generator(device=dev).manual_seed(SEED + rank)
+    nb = K + W
+    ids_dev = torch.randint(0, ROWS, (nb, BATCH, F), device=dev, generator=g)
+    y_dev = (torch.rand(nb, BATCH, 1, device=dev, generator=g) < 0.25).float()
+    act_bytes = 4 if args.dtype == "f32" else 2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- instrumented eager pass: per-phase CUDA-event times + launches per step (rank 0 reports)
+    tr.step(ids_dev[0], y_dev[0])
+    torch.cuda.synchronize()
+    n0 = cabi.launch_count()
+    tr.timer = PhaseTimer()
+    for i in range(min(K, 20)):
+        tr.step(ids_dev[i % nb], y_dev[i % nb])
+    phases = tr.timer.summary()
+    launches_per_step = (cabi.launch_count() - n0) // min(K, 20)
+    tr.timer = None
+    n_unique = int(torch.unique(ids_dev[0] + torch.arange(F, device=dev)[None, :] * ROWS).numel())
+
+    # ---- device-resident timing (CUDA graph replay)
+    tr.capture()
+    for i in range(W):
+        tr.step(ids_dev[i], y_dev[i])
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(W, W + K):
+        tr.step(ids_dev[i], y_dev[i])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    loss_dev = float(tr.loss.item())
+
+    # ---- end to end: pinned host inputs, H2D + step + loss D2H every step
+    ids_host = ids_dev.cpu().pin_memory()
+    y_host = y_dev.cpu().pin_memory()
+    for i in range(W):
+        tr.step_from_host(ids_host[i], y_host[i])
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for i in range(W, W + K):
+        last = tr.step_from_host(ids_host[i], y_host[i])
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    step_ms_sum = sum(v[0] for v in phases.values())
+    kernels = []
+    for name, (pms, nl) in sorted(phases.items(), key=lambda kv: -kv[1][0]):
+        by, fl = algorithmic(name, BATCH, act_bytes, n_unique)
+        kernels.append({"phase": name, "ms": round(pms, 4), "share": round(pms / step_ms_sum, 4), "launches": nl,
+                        "alg_bytes": by, "alg_flops": fl,
+                        "GBps": round(by / pms / 1e6, 1) if by else None,
+                        "TFLOPps": round(fl / pms / 1e9, 2) if fl else None})
+    top = kernels[0]
+    if top["phase"].startswith("mlp") and args.dtype == "bf16":
+        roof = {"bound": "tensor", "achieved": top["TFLOPps"], "peak": pk["bf16_tflops_sustained"],
+                "unit": "TFLOP/s", "frac": top["TFLOPps"] / pk["bf16_tflops_sustained"], "traffic": None}
+    else:
+        roof = {"bound": "hbm", "achieved": top["GBps"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": (top["GBps"] or 0) / pk["hbm_gbs"], "traffic": None}
+    roof.update({"kernel": top["phase"], "peak_source": pk["source"] + " (sustained: kernel timed inside the step)",
+                 "share_of_step": top["share"]})
+    gk = next(k for k in kernels if k["phase"] == "embed_gather")
+    sk = next(k for k in kernels if k["phase"] == "embed_segsum_adam")
+    embed = {"gather_GBps": gk["GBps"], "gather_frac_of_measured_hbm": gk["GBps"] / pk["hbm_gbs"],
+             "gather_frac_of_8TBps": gk["GBps"] / 8000.0, "scatter_adam_GBps": sk["GBps"],
+             "scatter_adam_frac_of_measured_hbm": sk["GBps"] / pk["hbm_gbs"], "unique_rows": n_unique}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        import psutil
+        rows = ROWS if psutil.virtual_memory().available > 14e9 else 100_000
+        sps, cms, threads = cpu_autoint_samples_per_s(BATCH, 6, 2, rows)
+        cpu = {"value": sps, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": f"6 train steps (after 2 warm-up) of batch {BATCH}, {rows} rows/field; torch-CPU op-for-op "
+                         "restatement of the reference TF graph (TensorFlow unavailable offline)",
+               "ms_per_step": cms}
+
+    out = {
+        "metric": "autoint_train_samples_per_s", "value": BATCH * world * K / (ms / 1e3), "unit": "samples/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": workload_config(args, args.dtype),
+        "e2e": {"value": BATCH * world * K / (ms_e2e / 1e3), "unit": "samples/s",
+                "h2d_bytes_per_step": BATCH * F * 8 + BATCH * 4, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / K},
+        "gpu_launches": int(launches_per_step * K), "launches_per_step": int(launches_per_step),
+        "clocks": clk, "roofline": roof, "embed_roofline": embed, "kernels": kernels,
+        "cpu_baseline": cpu, "loss": loss_dev, "loss_e2e_last": last,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--dtype", default=os.environ.get("RS_BENCH_DTYPE", "f32"), choices=["f32", "bf16"])
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -25,6 +25,44 @@ import torch
 from . import cabi, ops
 
 
+class PhaseTimer:
+    """CUDA-event timing of the phases of an eagerly launched step (bench.py's per-kernel
+    breakdown).  Events are recorded on the stream the kernels are launched on."""
+
+    def __init__(self):
+        self.records = {}      # phase -> list of (start, stop) events
+        self.launches = {}     # phase -> library launches per occurrence
+
+    def phase(self, name):
+        return _Phase(self, name)
+
+    def summary(self):
+        """phase -> (mean ms, launches per step)"""
+        torch.cuda.synchronize()
+        return {k: (float(np.mean([a.elapsed_time(b) for a, b in v])), self.launches.get(k, 0))
+                for k, v in self.records.items()}
+
+
+class _Phase:
+    def __init__(self, timer, name):
+        self.t, self.name = timer, name
+
+    def __enter__(self):
+        if self.t is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.n0 = cabi.launch_count()
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.t is not None:
+            self.b.record()
+            self.t.records.setdefault(self.name, []).append((self.a, self.b))
+            self.t.launches[self.name] = cabi.launch_count() - self.n0
+        return False
+
+
 @dataclass
 class AutoIntConfig:
     num_fields: int = 39
@@ -130,7 +168,7 @@ class AutoIntTrainer:
         self.dH = [e(B, w) for w in cfg.mlp_hidden]
         self.dX = e(B, F, d)
         self.graph = None
-        self._h_ids = None
+        self.timer = None               # set to a PhaseTimer for an instrumented (eager) step
         n_ws = max(cabi.load().rs_interacting_workspace_bytes(B, F, d, U),
                    cabi.load().rs_embed_sort_workspace_bytes(B * F),
                    cabi.load().rs_colsum_workspace_bytes(B, max(widths + [self.zw])))
@@ -181,47 +219,58 @@ class AutoIntTrainer:
         T = ops._DT[self.act_dtype]
         P, G = self.P, self.G
         nmlp = len(c.mlp_hidden)
-        # K1: gather + sort keys
-        cabi.call("rs_embed_gather_fwd", self.table.data_ptr(), self.ids.data_ptr(), self.base_t.data_ptr(),
-                  self.rows_t.data_ptr(), B * F, F, d, self.X.data_ptr(), T, self.keys.data_ptr(), None, st)
+        ph = lambda name: _Phase(self.timer, name)
+        # K1: gather (+ sort keys emitted for the backward)
+        with ph("embed_gather"):
+            cabi.call("rs_embed_gather_fwd", self.table.data_ptr(), self.ids.data_ptr(), self.base_t.data_ptr(),
+                      self.rows_t.data_ptr(), B * F, F, d, self.X.data_ptr(), T, self.keys.data_ptr(), None, st)
         # K4: InteractingLayer forward
-        cabi.call("rs_interacting_fwd", self.X.data_ptr(), d, T, P["Wqkvr"].data_ptr(), P["bqkvr"].data_ptr(),
-                  P["gamma"].data_ptr(), P["beta"].data_ptr(), c.ln_eps, self.A.data_ptr(), U,
-                  self.saved.data_ptr() if c.layer_num > 1 else None, B, F, d, U, c.head_num, c.layer_num,
-                  int(c.use_res), int(self.act_dtype == torch.bfloat16), st)
+        with ph("interacting_fwd"):
+            cabi.call("rs_interacting_fwd", self.X.data_ptr(), d, T, P["Wqkvr"].data_ptr(),
+                      P["bqkvr"].data_ptr(), P["gamma"].data_ptr(), P["beta"].data_ptr(), c.ln_eps,
+                      self.A.data_ptr(), U, self.saved.data_ptr() if c.layer_num > 1 else None, B, F, d, U,
+                      c.head_num, c.layer_num, int(c.use_res), int(self.act_dtype == torch.bfloat16), st)
         # K5: MLP tower; last hidden layer lands in Z[:, :n_deep], Flatten(A) in Z[:, n_deep:]
         Xf = self.X.view(B, F * d)
         acts = [Xf] + self.H + [self.Z[:, :self.n_deep]]
-        for i in range(nmlp):
-            ops.gemm(acts[i], self._w(f"mlp_W{i}"), acts[i + 1], bias=P[f"mlp_b{i}"], epilogue=E.EPI_BIAS_RELU)
-        ops.copy2d(self.A.view(B, F * U), self.Z[:, self.n_deep:])
-        ops.gemm(self.Z, self._w("out_W"), self.p_raw, bias=P["out_b"], epilogue=E.EPI_BIAS_SIGMOID)
-        # K8: clip + BCE, gradient wrt the logit pre-activation
-        cabi.call("rs_bce_sigmoid_fwd_bwd", self.p_raw.data_ptr(), T, self.labels.data_ptr(), 1.0,
-                  self.loss.data_ptr(), self.dzl.data_ptr(), B, 1, st)
-        # ---- backward: logits layer
-        self._wgrad(self.Z, self.dzl, "out_W", "out_b")
-        ops.gemm(self.dzl, self._w("out_W"), self.dZ, transB=True)
+        with ph("mlp_fwd"):
+            for i in range(nmlp):
+                ops.gemm(acts[i], self._w(f"mlp_W{i}"), acts[i + 1], bias=P[f"mlp_b{i}"], epilogue=E.EPI_BIAS_RELU)
+        with ph("logits_loss"):
+            ops.copy2d(self.A.view(B, F * U), self.Z[:, self.n_deep:])
+            ops.gemm(self.Z, self._w("out_W"), self.p_raw, bias=P["out_b"], epilogue=E.EPI_BIAS_SIGMOID)
+            # K8: clip + BCE, gradient wrt the logit pre-activation
+            cabi.call("rs_bce_sigmoid_fwd_bwd", self.p_raw.data_ptr(), T, self.labels.data_ptr(), 1.0,
+                      self.loss.data_ptr(), self.dzl.data_ptr(), B, 1, st)
+            # backward of the logits layer
+            self._wgrad(self.Z, self.dzl, "out_W", "out_b")
+            ops.gemm(self.dzl, self._w("out_W"), self.dZ, transB=True)
         # MLP backward (relu masks from the saved activations)
-        ops.act_bwd(self.dZ[:, :self.n_deep], acts[nmlp], 0, out=self.dH[nmlp - 1])
-        for i in reversed(range(nmlp)):
-            self._wgrad(acts[i], self.dH[i], f"mlp_W{i}", f"mlp_b{i}")
-            if i > 0:
-                ops.gemm(self.dH[i], self._w(f"mlp_W{i}"), self.dH[i - 1], aux=acts[i],
-                         epilogue=E.EPI_MUL_RELU_MASK, transB=True)
+        with ph("mlp_bwd"):
+            ops.act_bwd(self.dZ[:, :self.n_deep], acts[nmlp], 0, out=self.dH[nmlp - 1])
+            for i in reversed(range(nmlp)):
+                self._wgrad(acts[i], self.dH[i], f"mlp_W{i}", f"mlp_b{i}")
+                if i > 0:
+                    ops.gemm(self.dH[i], self._w(f"mlp_W{i}"), self.dH[i - 1], aux=acts[i],
+                             epilogue=E.EPI_MUL_RELU_MASK, transB=True)
         # InteractingLayer backward -> dX, then dX += dH0 @ W0^T
         nW = d * 4 * U
         dparams = self.flat_g[self.spec[0][2]:]       # Wqkvr | bqkvr | gamma | beta are contiguous
         assert self.spec[1][2] == nW and self.spec[2][2] == nW + 4 * U and self.spec[3][2] == nW + 5 * U
-        self._interacting_bwd(dparams, st, T)
-        ops.gemm(self.dH[0], self._w("mlp_W0"), self.dX.view(B, F * d), epilogue=E.EPI_ACCUM, transB=True)
+        with ph("interacting_bwd"):
+            self._interacting_bwd(dparams, st, T)
+        with ph("mlp_dgrad_x"):
+            ops.gemm(self.dH[0], self._w("mlp_W0"), self.dX.view(B, F * d), epilogue=E.EPI_ACCUM, transB=True)
         # K3: sparse Adam on touched rows; dense Adam on the flat buffer
-        ops.adam_advance(self.adam_scalars, c.beta1, c.beta2)
-        ops.sort_keys(self.keys, self.row_bits, out=self.keys_sorted)
-        ops.segsum_adam(self.table, self.table_m, self.table_v, self.dX.view(B * F, d), self.keys_sorted,
-                        c.lr_sparse, c.beta1, c.beta2, c.eps, self.adam_scalars)
-        ops.dense_adam(self.flat, self.flat_m, self.flat_v, self.flat_g, c.lr_dense, c.beta1, c.beta2, c.eps,
-                       self.adam_scalars, self.flat_bf16)
+        with ph("sort_keys"):
+            ops.adam_advance(self.adam_scalars, c.beta1, c.beta2)
+            ops.sort_keys(self.keys, self.row_bits, out=self.keys_sorted)
+        with ph("embed_segsum_adam"):
+            ops.segsum_adam(self.table, self.table_m, self.table_v, self.dX.view(B * F, d), self.keys_sorted,
+                            c.lr_sparse, c.beta1, c.beta2, c.eps, self.adam_scalars)
+        with ph("dense_adam"):
+            ops.dense_adam(self.flat, self.flat_m, self.flat_v, self.flat_g, c.lr_dense, c.beta1, c.beta2, c.eps,
+                           self.adam_scalars, self.flat_bf16)
 
     def _interacting_bwd(self, dparams, st, T):
         c = self.cfg
