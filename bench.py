@@ -318,7 +318,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--dtype", default=os.environ.get("RS_BENCH_DTYPE", "f32"), choices=["f32", "bf16"])
+    ap.add_argument("--dtype", default=os.environ.get("RS_BENCH_DTYPE", "bf16"), choices=["f32", "bf16"])
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -254,14 +254,22 @@ int rs_din_bwd(int mode, const void* q, const void* keys, const void* values,
  * (`DNN.call` rough_rank/layer.py:100-109; MultiLayerDense autoint:40-41,49-50;
  *  expert/gate Dense staytime/VideoDnn.py:135-147, multidnn.py:62-63,83-85.)
  * transA: A is stored [K,M] (ld lda); transB: B is stored [N,K] (ld ldb).
- * dtype_ab RS_BF16 -> tcgen05 tensor-core kernel (fp32 TMEM accumulation);
- * RS_F32 -> fp32 FFMA kernel (parity mode).  dtype_c is the dtype of C/aux.
- */
+ * dtype_ab RS_F32  -> fp32 FFMA kernel (parity mode), any transA/transB.
+ * dtype_ab RS_BF16 -> tcgen05 tensor-core kernel (TMA-fed, fp32 accumulation in
+ *   TMEM).  It consumes K-major operands only: transA = 0 and transB = 1 (weights
+ *   are kept as bf16 [out,in] shadows; activations feeding a weight gradient are
+ *   transposed with rs_transpose2d), lda/ldb multiples of 8, 16-byte aligned
+ *   bases.  Deep-K, small-output problems (weight gradients) are split along K
+ *   into fp32 partials in `ws` and summed in split order (deterministic).
+ * dtype_c is the dtype of C / aux.  ws >= rs_gemm_workspace_bytes() (may be
+ * NULL for RS_F32). */
+size_t rs_gemm_workspace_bytes(void);
 int rs_gemm(const void* A, int64_t lda, int transA,
             const void* B, int64_t ldb, int transB,
             void* C, int64_t ldc, const float* bias,
             const void* aux, int64_t ldaux, int epilogue,
-            int M, int N, int K, int dtype_ab, int dtype_c, void* stream);
+            int M, int N, int K, int dtype_ab, int dtype_c,
+            void* ws, size_t ws_bytes, void* stream);
 /* out[n] = Σ_m x[m, n]  (bias gradient); deterministic two-level reduce
  * (fixed row-block order, no atomics). ws >= rs_colsum_workspace_bytes. */
 size_t rs_colsum_workspace_bytes(int M, int N);
@@ -291,6 +299,24 @@ int rs_add2d(const void* a, int64_t lda, const void* b, int64_t ldb, void* y,
 int rs_bce_sigmoid_fwd_bwd(const void* p_raw, int dtype, const float* y,
                            float a, float* loss_out, void* dz, int B, int k,
                            void* stream);
+
+/* Fused logits head for k = 1 (AutoInt): final Dense(1, sigmoid) + clip + the
+ * loss above + the head's backward in ONE pass over Z:
+ *   p_out[b] = sigmoid(Z[b,:]·w + bias)            (autoint:49-50)
+ *   loss     = as rs_bce_sigmoid_fwd_bwd            (autoint:52, base_model.py:7-12)
+ *   dZ[b,:]  = dz_b * w ;  dw = Z^T dz ;  db = Σ dz
+ * Z, dZ are [B, zw] with leading dims ldz / lddz (zw % 4 == 0, zw <= 2048);
+ * w, bias, dw, db, loss_out, y are fp32.  Deterministic (ordered partial sums). */
+size_t rs_logit_head_workspace_bytes(int B, int zw);
+int rs_logit_head_fwd_bwd(const void* Z, int64_t ldz, int dtype, const float* w,
+                          const float* bias, const float* y, float a, void* p_out,
+                          float* loss_out, void* dZ, int64_t lddz, float* dw, float* db,
+                          int B, int zw, void* ws, size_t ws_bytes, void* stream);
+
+/* dst[n, m] = src[m, n] (2-D transpose with leading dims; bf16 or fp32).  Used to
+ * present activations K-major to the tensor-core weight-gradient GEMMs. */
+int rs_transpose2d(const void* src, int64_t lds, void* dst, int64_t ldd, int M, int N,
+                   int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -163,10 +163,19 @@ class AutoIntTrainer:
         self.Z = e(B, self.zw)
         self.p_raw = e(B, 1)
         self.loss = torch.zeros(1, device=self.dev)
-        self.dzl = e(B, 1)
         self.dZ = e(B, self.zw)
         self.dH = [e(B, w) for w in cfg.mlp_hidden]
         self.dX = e(B, F, d)
+        self.bf16 = self.act_dtype == torch.bfloat16
+        if self.bf16:
+            # tensor-core GEMMs take K-major operands: [out,in] weight shadows for the forward,
+            # transposed activations / gradients ([features, batch]) for the weight gradients
+            self.WT16 = {f"mlp_W{i}": torch.zeros(widths[i + 1], widths[i], dtype=torch.bfloat16, device=self.dev)
+                         for i in range(len(cfg.mlp_hidden))}
+            wmax = max(widths)
+            self.xT = torch.zeros(wmax, B, dtype=torch.bfloat16, device=self.dev)
+            self.dyT = torch.zeros(wmax, B, dtype=torch.bfloat16, device=self.dev)
+            self._refresh_wt()
         self.graph = None
         self.timer = None               # set to a PhaseTimer for an instrumented (eager) step
         n_ws = max(cabi.load().rs_interacting_workspace_bytes(B, F, d, U),
@@ -202,6 +211,10 @@ class AutoIntTrainer:
             self.P[name].copy_(torch.from_numpy(v))
         self.flat_bf16.copy_(self.flat)
 
+    def _refresh_wt(self):
+        for k, wt in self.WT16.items():
+            ops.transpose2d(self.P16[k], wt)
+
     def dense_state(self):
         return {k: v.detach().cpu().numpy().copy() for k, v in self.P.items()}
 
@@ -235,22 +248,18 @@ class AutoIntTrainer:
         acts = [Xf] + self.H + [self.Z[:, :self.n_deep]]
         with ph("mlp_fwd"):
             for i in range(nmlp):
-                ops.gemm(acts[i], self._w(f"mlp_W{i}"), acts[i + 1], bias=P[f"mlp_b{i}"], epilogue=E.EPI_BIAS_RELU)
+                self._dense_fwd(acts[i], f"mlp_W{i}", f"mlp_b{i}", acts[i + 1])
         with ph("logits_loss"):
             ops.copy2d(self.A.view(B, F * U), self.Z[:, self.n_deep:])
-            ops.gemm(self.Z, self._w("out_W"), self.p_raw, bias=P["out_b"], epilogue=E.EPI_BIAS_SIGMOID)
-            # K8: clip + BCE, gradient wrt the logit pre-activation
-            cabi.call("rs_bce_sigmoid_fwd_bwd", self.p_raw.data_ptr(), T, self.labels.data_ptr(), 1.0,
-                      self.loss.data_ptr(), self.dzl.data_ptr(), B, 1, st)
-            # backward of the logits layer
-            self._wgrad(self.Z, self.dzl, "out_W", "out_b")
-            ops.gemm(self.dzl, self._w("out_W"), self.dZ, transB=True)
+            # final Dense(1, sigmoid) + clip + BCE + the head's backward, one pass over Z
+            ops.logit_head(self.Z, P["out_W"], P["out_b"], self.labels, self.dZ, G["out_W"], G["out_b"],
+                           p_out=self.p_raw, loss=self.loss)
         # MLP backward (relu masks from the saved activations)
         with ph("mlp_bwd"):
             ops.act_bwd(self.dZ[:, :self.n_deep], acts[nmlp], 0, out=self.dH[nmlp - 1])
             for i in reversed(range(nmlp)):
                 self._wgrad(acts[i], self.dH[i], f"mlp_W{i}", f"mlp_b{i}")
-                if i > 0:
+                if i > 0:   # dH[i-1] = (dH[i] @ W_i^T) * relu'(h_{i-1}); W_i [in,out] is the K-major B operand
                     ops.gemm(self.dH[i], self._w(f"mlp_W{i}"), self.dH[i - 1], aux=acts[i],
                              epilogue=E.EPI_MUL_RELU_MASK, transB=True)
         # InteractingLayer backward -> dX, then dX += dH0 @ W0^T
@@ -271,6 +280,8 @@ class AutoIntTrainer:
         with ph("dense_adam"):
             ops.dense_adam(self.flat, self.flat_m, self.flat_v, self.flat_g, c.lr_dense, c.beta1, c.beta2, c.eps,
                            self.adam_scalars, self.flat_bf16)
+            if self.bf16:
+                self._refresh_wt()
 
     def _interacting_bwd(self, dparams, st, T):
         c = self.cfg
@@ -286,9 +297,24 @@ class AutoIntTrainer:
                   c.layer_num, int(c.use_res), int(self.act_dtype == torch.bfloat16), self.ws.data_ptr(),
                   self.ws.numel(), st)
 
+    def _dense_fwd(self, x, wname, bname, out):
+        """out = relu(x @ W + b)  (Dense(relu))."""
+        if self.bf16:
+            ops.gemm(x, self.WT16[wname], out, bias=self.P[bname], epilogue=cabi.EPI_BIAS_RELU, transB=True)
+        else:
+            ops.gemm(x, self.P[wname], out, bias=self.P[bname], epilogue=cabi.EPI_BIAS_RELU)
+
     def _wgrad(self, x, dy, wname, bname):
         """G[w] = x^T dy ; G[b] = colsum(dy)."""
-        ops.gemm(x, dy, self.G[wname], transA=True, out_dtype=torch.float32)
+        if self.bf16:
+            B = x.shape[0]
+            xT = self.xT[:x.shape[1]]
+            dyT = self.dyT[:dy.shape[1]]
+            ops.transpose2d(x, xT)
+            ops.transpose2d(dy, dyT)
+            ops.gemm(xT, dyT, self.G[wname], transB=True)
+        else:
+            ops.gemm(x, dy, self.G[wname], transA=True)
         ops.colsum(dy, out=self.G[bname])
 
     # --------------------------------------------------------------- frontends
@@ -343,7 +369,9 @@ class AutoIntTrainer:
                   c.head_num, c.layer_num, int(c.use_res), 0, st)
         acts = [self.X.view(B, F * d)] + self.H + [self.Z[:, :self.n_deep]]
         for i in range(len(c.mlp_hidden)):
-            ops.gemm(acts[i], self._w(f"mlp_W{i}"), acts[i + 1], bias=P[f"mlp_b{i}"], epilogue=cabi.EPI_BIAS_RELU)
+            self._dense_fwd(acts[i], f"mlp_W{i}", f"mlp_b{i}", acts[i + 1])
         ops.copy2d(self.A.view(B, F * U), self.Z[:, self.n_deep:])
-        ops.gemm(self.Z, self._w("out_W"), self.p_raw, bias=P["out_b"], epilogue=cabi.EPI_BIAS_SIGMOID)
+        # the head kernel also produces gradients; they land in scratch and are ignored here
+        ops.logit_head(self.Z, P["out_W"], P["out_b"], self.labels, self.dZ, self.G["out_W"], self.G["out_b"],
+                       p_out=self.p_raw, loss=self.loss)
         return self.p_raw.float().clamp(1e-6, 1.0)

@@ -45,13 +45,17 @@ PROTOTYPES = {
     "rs_din_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "rs_din_bwd": (_i, [_i, _p, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p,
                         _i, _i, _i, _i, _p, _sz, _p]),
-    "rs_gemm": (_i, [_p, _i64, _i, _p, _i64, _i, _p, _i64, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _p]),
+    "rs_gemm_workspace_bytes": (_sz, []),
+    "rs_gemm": (_i, [_p, _i64, _i, _p, _i64, _i, _p, _i64, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
     "rs_colsum_workspace_bytes": (_sz, [_i, _i]),
     "rs_colsum": (_i, [_p, _i64, _i, _p, _i, _i, _p, _sz, _p]),
     "rs_act_bwd": (_i, [_p, _i64, _p, _i64, _p, _i64, _i, _i, _i, _i, _p]),
     "rs_copy2d": (_i, [_p, _i64, _i, _p, _i64, _i, _i, _i, _p]),
     "rs_add2d": (_i, [_p, _i64, _p, _i64, _p, _i64, _i, _i, _i, _p]),
     "rs_bce_sigmoid_fwd_bwd": (_i, [_p, _i, _p, _f, _p, _p, _i, _i, _p]),
+    "rs_logit_head_workspace_bytes": (_sz, [_i, _i]),
+    "rs_logit_head_fwd_bwd": (_i, [_p, _i64, _i, _p, _p, _p, _f, _p, _p, _p, _i64, _p, _p, _i, _i, _p, _sz, _p]),
+    "rs_transpose2d": (_i, [_p, _i64, _p, _i64, _i, _i, _i, _p]),
 }
 
 _lib = None

@@ -130,6 +130,24 @@ __global__ void bce_kernel(const T* __restrict__ p_raw, const float* __restrict_
   if (threadIdx.x == 0) loss_out[0] = red[0] * invB;
 }
 
+// dst[n][m] = src[m][n]; 32x32 tiles through padded shared memory so that both the
+// global read (along n) and the global write (along m) are coalesced.
+template <typename E>
+__global__ void transpose2d_kernel(const E* __restrict__ src, int64_t lds, E* __restrict__ dst,
+                                   int64_t ldd, int M, int N) {
+  __shared__ E tile[32][33];
+  const int n0 = blockIdx.x * 32, m0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int m = m0 + r, n = n0 + threadIdx.x;
+    if (m < M && n < N) tile[r][threadIdx.x] = src[(int64_t)m * lds + n];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int n = n0 + r, m = m0 + threadIdx.x;
+    if (m < M && n < N) dst[(int64_t)n * ldd + m] = tile[threadIdx.x][r];
+  }
+}
+
 }  // namespace rs
 
 using namespace rs;
@@ -213,6 +231,18 @@ int rs_colsum(const void* x, int64_t ldx, int dtype, float* out, int M, int N, v
   if (int e = check_launch("colsum_partial")) return e;
   colsum_final_kernel<<<(unsigned)cdiv(N, 128), 128, 0, st>>>((const float*)ws, out, nparts, N);
   return check_launch("colsum_final");
+}
+
+int rs_transpose2d(const void* src, int64_t lds, void* dst, int64_t ldd, int M, int N, int dtype,
+                   void* stream) {
+  if (M <= 0 || N <= 0) return 0;
+  dim3 grid((unsigned)cdiv(N, 32), (unsigned)cdiv(M, 32)), block(32, 8);
+  if (dtype == RS_F32)
+    transpose2d_kernel<float><<<grid, block, 0, as_stream(stream)>>>((const float*)src, lds, (float*)dst, ldd, M, N);
+  else if (dtype == RS_BF16)
+    transpose2d_kernel<uint16_t><<<grid, block, 0, as_stream(stream)>>>((const uint16_t*)src, lds, (uint16_t*)dst, ldd, M, N);
+  else { set_error("transpose2d: bad dtype"); return RS_ERR_INVALID; }
+  return check_launch("transpose2d");
 }
 
 int rs_bce_sigmoid_fwd_bwd(const void* p_raw, int dtype, const float* y, float a, float* loss_out,

@@ -1,11 +1,380 @@
-// gemm_tc.cu — bf16 tensor-core GEMM (tcgen05 + TMEM + TMA) for the MLP tower.
-// Placeholder until the tcgen05 kernel lands: reports RS_ERR_UNSUPPORTED so that
-// callers fail loudly instead of silently falling back.
+// gemm_tc.cu — bf16 tensor-core GEMM for the MLP tower (K5) on sm_100a:
+//   C[M,N] = epi( A[M,K] · B[N,K]^T )      A, B bf16 K-major; fp32 accumulation in TMEM.
+//
+// One CTA computes one 128 x BN output tile (optionally one K-split of it):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles (64-element = 128-byte K slabs,
+//               SWIZZLE_128B) of A and B into a 4-stage shared-memory ring, mbarrier expect_tx
+//   warp 1      TMEM allocator + MMA issuer: one elected thread issues tcgen05.mma
+//               (cta_group::1, kind::f16, M=128, N=BN, K=16) four times per stage and
+//               tcgen05.commit's the stage back to the producer / the accumulator to the epilogue
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp and step) -> registers ->
+//               bias / activation / mask epilogue -> 16-byte global stores (a thread owns a row)
+// Split-K (weight gradients: K = batch) writes fp32 partial tiles that a second kernel sums in
+// split order (deterministic).  K tails and M/N tails rely on TMA zero fill + guarded stores.
 #include "common.cuh"
+#include <cuda.h>
+
 namespace rs {
-int gemm_bf16_tc(const void*, int64_t, int, const void*, int64_t, int, void*, int64_t, const float*,
-                 const void*, int64_t, int, int, int, int, int, cudaStream_t) {
-  set_error("gemm: bf16 tensor-core path not built yet");
-  return RS_ERR_UNSUPPORTED;
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;          // bf16 elements per stage along K = one 128-byte swizzle row
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 192;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread (thread = lane = row).
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (ignored for swizzled K-major) | [32,46) SBO >> 4
+//   (8 rows x 128 B = 1024 B between 8-row groups) | [46,48) version = 1 | [61,64) layout = 2 (SW128)
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 (1<<4), a=b=bf16 (1<<7, 1<<10),
+// both K-major, N>>3 at bit 17, M>>4 at bit 24.
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <typename CT>
+__device__ __forceinline__ float tc_epi(float acc, int epi, const float* bias, float auxv, float cold, int n) {
+  switch (epi) {
+    case RS_EPI_BIAS: return acc + bias[n];
+    case RS_EPI_BIAS_RELU: return fmaxf(acc + bias[n], 0.f);
+    case RS_EPI_BIAS_SIGMOID: return 1.f / (1.f + __expf(-(acc + bias[n])));
+    case RS_EPI_MUL_RELU_MASK: return auxv > 0.f ? acc : 0.f;
+    case RS_EPI_MUL_DSIGMOID: return acc * auxv * (1.f - auxv);
+    case RS_EPI_ACCUM: return acc + cold;
+    default: return acc;
+  }
+}
+
+template <int BN>
+struct TcSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int TOTAL = TC_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, typename CT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               CT* __restrict__ C, int64_t ldc, const float* __restrict__ bias,
+               const CT* __restrict__ aux, int64_t ldaux, int epi, int M, int N, int K,
+               int kb_per_split, float* __restrict__ partial, int vec_ok) {
+  using S = TcSmem<BN>;
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + TC_STAGES;
+  uint64_t* acc_bar = empty_bar + TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int kb_total = (K + TC_BK - 1) / TC_BK;
+  const int kb0 = blockIdx.z * kb_per_split;
+  const int kb1 = min(kb_total, kb0 + kb_per_split);
+  const int nkb = kb1 - kb0;       // >= 1 by construction of the grid
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM: BN fp32 accumulator columns (power of two >= 32)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % TC_STAGES;
+        const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);            // first pass through the ring falls through
+        mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+        uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+        tma_load_2d(a_dst, &tmA, &full_bar[s], (kb0 + i) * TC_BK, m0);
+        tma_load_2d(a_dst + S::A_BYTES, &tmB, &full_bar[s], (kb0 + i) * TC_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % TC_STAGES;
+        const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
+        const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + S::A_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k)      // +32 B (>>4 = 2) per K=16 step inside the swizzle row
+          tc_mma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+        tc_commit(&empty_bar[s]);                  // stage free once these MMAs have read it
+      }
+      tc_commit(acc_bar);                          // accumulator complete
+    }
+  } else {
+    // ---- epilogue warps 2..5: TMEM lane group = warp % 4
+    const int lg = warp & 3;
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const int row = m0 + lg * 32 + lane;
+    const bool row_ok = row < M;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= N) break;                     // warp-uniform
+      uint32_t r[32];
+      tc_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, r);
+      if (!row_ok) continue;
+      const int nbase = n0 + c0;
+      if (partial) {
+        float* dst = partial + ((int64_t)blockIdx.z * M + row) * N + nbase;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (nbase + j < N) dst[j] = __uint_as_float(r[j]);
+        continue;
+      }
+      CT* crow = C + (int64_t)row * ldc + nbase;
+      const CT* arow = aux ? aux + (int64_t)row * ldaux + nbase : nullptr;
+      const bool full = vec_ok && (nbase + 32 <= N);
+      if (full) {
+        float v[32];
+        if (epi == RS_EPI_MUL_RELU_MASK || epi == RS_EPI_MUL_DSIGMOID) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 a4 = load4<CT>(arow + j);
+            v[j] = a4.x; v[j + 1] = a4.y; v[j + 2] = a4.z; v[j + 3] = a4.w;
+          }
+        } else if (epi == RS_EPI_ACCUM) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 a4 = load4<CT>(crow + j);
+            v[j] = a4.x; v[j + 1] = a4.y; v[j + 2] = a4.z; v[j + 3] = a4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          v[j] = tc_epi<CT>(__uint_as_float(r[j]), epi, bias, v[j], v[j], nbase + j);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) store4<CT>(crow + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (nbase + j < N) {
+            const float av = arow ? to_f<CT>(arow[j]) : 0.f;
+            const float cv = epi == RS_EPI_ACCUM ? to_f<CT>(crow[j]) : 0.f;
+            crow[j] = from_f<CT>(tc_epi<CT>(__uint_as_float(r[j]), epi, bias, av, cv, nbase + j));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
+  }
+}
+
+// C = [C +] sum_z partial[z]  (split order fixed => deterministic)
+template <typename CT>
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, CT* __restrict__ C,
+                                     int64_t ldc, int M, int N, int accumulate) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = t / N;
+    const int n = (int)(t % N);
+    float s = accumulate ? to_f<CT>(C[m * ldc + n]) : 0.f;
+    for (int z = 0; z < splits; ++z) s += partial[(int64_t)z * total + t];
+    C[m * ldc + n] = from_f<CT>(s);
+  }
+}
+
+int splitk_reduce(const float* partial, int splits, void* C, int64_t ldc, int M, int N, int accumulate,
+                  int dtype_c, cudaStream_t st) {
+  const int64_t total = (int64_t)M * N;
+  int64_t blocks = cdiv(total, 256);
+  if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
+  if (dtype_c == RS_F32)
+    splitk_reduce_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(partial, splits, (float*)C, ldc, M, N, accumulate);
+  else
+    splitk_reduce_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(partial, splits, (__nv_bfloat16*)C, ldc, M,
+                                                                          N, accumulate);
+  return check_launch("splitk_reduce");
+}
+
+// ---- host side --------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with leading dim ld (elements); box = 64 cols x box_rows rows.
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("gemm_tc: cuTensorMapEncodeTiled unavailable"); return RS_ERR_UNSUPPORTED; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gemm_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return RS_ERR_INVALID; }
+  return 0;
+}
+
+template <int BN, typename CT>
+static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int64_t ldc, const float* bias,
+                     const void* aux, int64_t ldaux, int epi, int M, int N, int K, int splits, int kbps,
+                     float* partial, int vec_ok, cudaStream_t st) {
+  auto kern = gemm_tc_kernel<BN, CT>;
+  const int smem = TcSmem<BN>::TOTAL;
+  RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid((unsigned)cdiv(N, BN), (unsigned)cdiv(M, TC_BM), (unsigned)splits);
+  kern<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, (CT*)C, ldc, bias, (const CT*)aux, ldaux, epi, M, N, K, kbps,
+                                       partial, vec_ok);
+  return check_launch("gemm_tc");
+}
+
+// splits * M * N <= (sms / tiles) * tiles * 128 * 128 floats
+size_t gemm_tc_workspace_bytes() { return (size_t)sm_count() * TC_BM * 128 * sizeof(float); }
+
+int gemm_bf16_tc(const void* A, int64_t lda, int transA, const void* B, int64_t ldb, int transB, void* C,
+                 int64_t ldc, const float* bias, const void* aux, int64_t ldaux, int epilogue, int M, int N,
+                 int K, int dtype_c, void* ws, size_t ws_bytes, cudaStream_t st) {
+  RS_REQUIRE(!transA && transB,
+             "gemm(bf16): tensor-core path needs K-major operands: A stored [M,K] (transA=0) and B stored "
+             "[N,K] (transB=1); transpose with rs_transpose2d first");
+  RS_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm(bf16): lda/ldb must be multiples of 8 elements (16-byte TMA strides)");
+  RS_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0), "gemm(bf16): A/B must be 16-byte aligned");
+  RS_REQUIRE(dtype_c == RS_F32 || dtype_c == RS_BF16, "gemm(bf16): bad C dtype");
+  // tile width: the widest BN that still gives >= ~1 wave of CTAs
+  const int sms = sm_count();
+  int BN = 128;
+  if (N <= 32) BN = 32;
+  else if (N <= 64) BN = 64;
+  else if ((int64_t)cdiv(M, TC_BM) * cdiv(N, 128) < sms && N % 128 != 0) BN = 64;
+  else if ((int64_t)cdiv(M, TC_BM) * cdiv(N, 128) * 2 <= sms) BN = 64;
+  const int tiles = (int)(cdiv(M, TC_BM) * cdiv(N, BN));
+  const int kb_total = (int)cdiv(K, TC_BK);
+  // split-K when the tile grid cannot fill the machine and K is deep (weight gradients)
+  int splits = 1;
+  if ((epilogue == RS_EPI_NONE || epilogue == RS_EPI_ACCUM) && tiles * 2 <= sms && kb_total >= 8) {
+    splits = sms / tiles;
+    if (splits > kb_total / 2) splits = kb_total / 2;
+    if (splits < 1) splits = 1;
+  }
+  int kbps = (int)cdiv(kb_total, splits);
+  splits = (int)cdiv(kb_total, kbps);
+  float* partial = nullptr;
+  if (splits > 1) {
+    const size_t need = (size_t)splits * M * N * sizeof(float);
+    if (ws == nullptr || ws_bytes < need) {
+      set_error("gemm(bf16): split-K workspace %zu < %zu", ws_bytes, need);
+      return RS_ERR_WORKSPACE;
+    }
+    partial = (float*)ws;
+  }
+  CUtensorMap tmA, tmB;
+  if (int e = make_map(&tmA, A, M, K, lda, TC_BM)) return e;
+  if (int e = make_map(&tmB, B, N, K, ldb, BN)) return e;
+  const int esz = dtype_c == RS_F32 ? 4 : 2;
+  int vec_ok = ((uintptr_t)C % 16 == 0) && ((ldc * esz) % 16 == 0);
+  if (aux) vec_ok = vec_ok && ((uintptr_t)aux % 16 == 0) && ((ldaux * esz) % 16 == 0);
+  int rc;
+#define RS_TC_GO(BNV)                                                                                   \
+  rc = dtype_c == RS_F32                                                                                \
+           ? launch_tc<BNV, float>(tmA, tmB, C, ldc, bias, aux, ldaux, epilogue, M, N, K, splits, kbps, \
+                                   partial, vec_ok, st)                                                 \
+           : launch_tc<BNV, __nv_bfloat16>(tmA, tmB, C, ldc, bias, aux, ldaux, epilogue, M, N, K,      \
+                                           splits, kbps, partial, vec_ok, st)
+  if (BN == 32) RS_TC_GO(32);
+  else if (BN == 64) RS_TC_GO(64);
+  else RS_TC_GO(128);
+#undef RS_TC_GO
+  if (rc) return rc;
+  if (splits > 1)
+    return splitk_reduce(partial, splits, C, ldc, M, N, epilogue == RS_EPI_ACCUM, dtype_c, st);
+  return 0;
+}
+
 }  // namespace rs

@@ -235,10 +235,30 @@ def gemm(A, B, C=None, bias=None, aux=None, epilogue=cabi.EPI_NONE, transA=False
     if C is None:
         C = torch.empty(M, N, dtype=out_dtype or A.dtype, device=A.device)
     _need(C.stride(1) == 1, "gemm: C last dim must be contiguous")
+    ws = WS.get("gemm", cabi.load().rs_gemm_workspace_bytes(), A.device)
     call("rs_gemm", _ptr(A), A.stride(0), int(transA), _ptr(B), B.stride(0), int(transB), _ptr(C), C.stride(0),
          _ptr(bias), _ptr(aux), aux.stride(0) if aux is not None else 0, epilogue, M, N, K, _dt(A), _dt(C),
-         _stream())
+         _ptr(ws), ws.numel(), _stream())
     return C
+
+
+def transpose2d(src, out=None):
+    _need(src.dim() == 2 and src.stride(1) == 1, "transpose2d: 2-D row-major view")
+    M, N = src.shape
+    out = torch.empty(N, M, dtype=src.dtype, device=src.device) if out is None else out
+    call("rs_transpose2d", _ptr(src), src.stride(0), _ptr(out), out.stride(0), M, N, _dt(src), _stream())
+    return out
+
+
+def logit_head(Z, w, bias, y, dZ, dw, db, p_out=None, loss=None, a=1.0):
+    """Fused Dense(1, sigmoid) + clip + BCE + head backward (rs_logit_head_fwd_bwd)."""
+    B, zw = Z.shape
+    p_out = torch.empty(B, 1, dtype=Z.dtype, device=Z.device) if p_out is None else p_out
+    loss = torch.empty(1, dtype=torch.float32, device=Z.device) if loss is None else loss
+    ws = WS.get("head", cabi.load().rs_logit_head_workspace_bytes(B, zw), Z.device)
+    call("rs_logit_head_fwd_bwd", _ptr(Z), Z.stride(0), _dt(Z), _ptr(w), _ptr(bias), _ptr(y), a, _ptr(p_out),
+         _ptr(loss), _ptr(dZ), dZ.stride(0), _ptr(dw), _ptr(db), B, zw, _ptr(ws), ws.numel(), _stream())
+    return p_out, loss
 
 
 def colsum(x, out=None):

@@ -91,3 +91,35 @@ def test_autoint_loss_decreases(cuda_dev):
         tr.step(ids, y)
     last = float(tr.loss)
     assert np.isfinite(first) and np.isfinite(last) and last < 0.5 * first, (first, last)
+
+
+def test_autoint_step_bf16(cuda_dev):
+    """bf16 activations + tcgen05 GEMMs: loss / gradients within the 1e-2 bf16 tolerance of the
+    fp64 oracle evaluated on the same (fp32) tables and weights."""
+    from oracle import oracle_np as onp
+    from recommendsystem_b200.autoint import AutoIntConfig, AutoIntTrainer
+    rng = np.random.default_rng(7)
+    B, F, d, H, L, hidden = 256, 39, 16, 2, 3, (256, 128)
+    cfg = AutoIntConfig(num_fields=F, rows_per_field=200, embed_dim=d, unit_num=d, head_num=H, layer_num=L,
+                        mlp_hidden=hidden, batch=B, dtype="bf16", lr_dense=1e-3, lr_sparse=1e-2)
+    tr = AutoIntTrainer(cfg, cuda_dev)
+    P0 = tr.dense_state()
+    table0 = tr.table.cpu().numpy().copy()
+    ids = rng.integers(0, 2 ** 40, size=(B, F)).astype(np.int64)
+    y = (rng.random((B, 1)) < 0.25).astype(np.float32)
+    loss = tr.step(torch.from_numpy(ids).to(cuda_dev), torch.from_numpy(y).to(cuda_dev))
+    torch.cuda.synchronize()
+    X, rows = onp.embed_gather(table0, ids, tr.rows_host, tr.base_host)
+    res = onp.autoint_fwd_bwd(f64(X), _oracle_params(P0), f64(y), H, L, cfg.ln_eps)
+    assert abs(float(loss) - res["loss"]) <= REL_BF16 * abs(res["loss"])
+    assert_close(tr.p_raw.float().cpu().numpy(), res["p_raw"], REL_BF16, "bf16 logits")
+    # gradients accumulate bf16 roundings of several layers: 3e-2 norm-wise bound, stated here
+    assert_close(tr.dX.float().cpu().numpy(), res["dX"], 3e-2, "bf16 dX")
+    G = {k: v.cpu().numpy() for k, v in tr.G.items()}
+    assert_close(G["mlp_W0"], res["grads"]["mlp_W"][0], 3e-2, "bf16 dmlp_W0")
+    assert_close(G["mlp_W1"], res["grads"]["mlp_W"][1], 3e-2, "bf16 dmlp_W1")
+    assert_close(G["out_W"], res["grads"]["out_W"], 3e-2, "bf16 dout_W")
+    assert_close(G["Wqkvr"], res["grads"]["Wqkvr"], 3e-2, "bf16 dWqkvr")
+    # bf16 weight shadows track the fp32 masters after the step
+    assert torch.equal(tr.P16["mlp_W0"], tr.P["mlp_W0"].to(torch.bfloat16))
+    assert torch.equal(tr.WT16["mlp_W0"], tr.P["mlp_W0"].to(torch.bfloat16).t())
