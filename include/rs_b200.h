@@ -190,9 +190,10 @@ int rs_permute_rows(const void* src, void* out, const int32_t* index, int64_t n,
  *   per head: P = softmax(Q_h K_hᵀ / sqrt(U/H))  (:47-52)
  *   X <- LayerNorm(relu(P V_h [+ R]))         (:55-60)
  * Wqkvr is [D, 4U] = [Wq | Wk | Wv | Wr] (Keras [in,out] kernels side by
- * side), bqkvr [4U].  D must equal U when L > 1.  x, y are [B, F, D|U] with
- * row strides x_ld / y_ld (elements) between samples' field rows, i.e.
- * element (b,f,c) at ptr[(b*F+f)*ld + c].
+ * side), bqkvr [4U].  D must equal U when L > 1.  x, y are [B, F, D|U]:
+ * element (b,f,c) lives at ptr[b*bs + f*ld + c] (ld = field stride, bs = sample
+ * stride in elements; bs = 0 means F*ld), so the layer can read / write the
+ * Flatten()ed [B, F*U] columns of a wider concat buffer in place (autoint:36,45).
  * `saved` (training): fp32 [L-1, B*F, U], the input of every iteration after
  * the first (kept in fp32 whatever `dtype` is, so a bf16 run rounds only at the
  * layer's input and output); the backward recomputes everything else.  May be
@@ -202,18 +203,19 @@ int rs_permute_rows(const void* src, void* out, const int32_t* index, int64_t n,
  * operands, fp32 TMEM accumulators); 0 = fp32 FFMA everywhere (parity mode).
  */
 size_t rs_interacting_workspace_bytes(int B, int F, int D, int U);
-int rs_interacting_fwd(const void* x, int64_t x_ld, int dtype,
+int rs_interacting_fwd(const void* x, int64_t x_ld, int64_t x_bs, int dtype,
                        const float* Wqkvr, const float* bqkvr,
                        const float* ln_gamma, const float* ln_beta, float ln_eps,
-                       void* y, int64_t y_ld, void* saved,
+                       void* y, int64_t y_ld, int64_t y_bs, void* saved,
                        int B, int F, int D, int U, int H, int L, int use_res,
                        int compute_bf16, void* stream);
 /* dx [B,F,D] (ld dx_ld), dparams: fp32 [D*4U + 4U + U + U] = dW | db | dgamma |
  * dbeta, OVERWRITTEN.  ws >= rs_interacting_workspace_bytes. */
-int rs_interacting_bwd(const void* x, int64_t x_ld, const void* saved, int dtype,
+int rs_interacting_bwd(const void* x, int64_t x_ld, int64_t x_bs, const void* saved, int dtype,
                        const float* Wqkvr, const float* bqkvr,
                        const float* ln_gamma, const float* ln_beta, float ln_eps,
-                       const void* dy, int64_t dy_ld, void* dx, int64_t dx_ld,
+                       const void* dy, int64_t dy_ld, int64_t dy_bs,
+                       void* dx, int64_t dx_ld, int64_t dx_bs,
                        float* dparams, int B, int F, int D, int U, int H, int L,
                        int use_res, int compute_bf16, void* ws, size_t ws_bytes,
                        void* stream);

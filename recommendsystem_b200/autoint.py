@@ -157,7 +157,6 @@ class AutoIntTrainer:
         self.X = e(B, F, d)
         self.keys = torch.empty(B * F, dtype=torch.int64, device=self.dev)
         self.keys_sorted = torch.empty_like(self.keys)
-        self.A = e(B, F, U)
         self.saved = e(max(cfg.layer_num - 1, 1), B * F, U, dtype=torch.float32)
         self.H = [e(B, w) for w in cfg.mlp_hidden[:-1]]
         self.Z = e(B, self.zw)
@@ -239,9 +238,11 @@ class AutoIntTrainer:
                       self.rows_t.data_ptr(), B * F, F, d, self.X.data_ptr(), T, self.keys.data_ptr(), None, st)
         # K4: InteractingLayer forward
         with ph("interacting_fwd"):
-            cabi.call("rs_interacting_fwd", self.X.data_ptr(), d, T, P["Wqkvr"].data_ptr(),
+            # writes Flatten(A) straight into its columns of the concat buffer Z (autoint:36,45)
+            cabi.call("rs_interacting_fwd", self.X.data_ptr(), d, 0, T, P["Wqkvr"].data_ptr(),
                       P["bqkvr"].data_ptr(), P["gamma"].data_ptr(), P["beta"].data_ptr(), c.ln_eps,
-                      self.A.data_ptr(), U, self.saved.data_ptr() if c.layer_num > 1 else None, B, F, d, U,
+                      self.Z[:, self.n_deep:].data_ptr(), U, self.zw,
+                      self.saved.data_ptr() if c.layer_num > 1 else None, B, F, d, U,
                       c.head_num, c.layer_num, int(c.use_res), int(self.act_dtype == torch.bfloat16), st)
         # K5: MLP tower; last hidden layer lands in Z[:, :n_deep], Flatten(A) in Z[:, n_deep:]
         Xf = self.X.view(B, F * d)
@@ -250,7 +251,6 @@ class AutoIntTrainer:
             for i in range(nmlp):
                 self._dense_fwd(acts[i], f"mlp_W{i}", f"mlp_b{i}", acts[i + 1])
         with ph("logits_loss"):
-            ops.copy2d(self.A.view(B, F * U), self.Z[:, self.n_deep:])
             # final Dense(1, sigmoid) + clip + BCE + the head's backward, one pass over Z
             ops.logit_head(self.Z, P["out_W"], P["out_b"], self.labels, self.dZ, G["out_W"], G["out_b"],
                            p_out=self.p_raw, loss=self.loss)
@@ -287,15 +287,12 @@ class AutoIntTrainer:
         c = self.cfg
         F, d, U, B = c.num_fields, c.embed_dim, c.unit_num, c.batch
         P = self.P
-        # dA arrives as Z-gradient columns [n_deep:], i.e. rows of F*U values with row stride zw:
-        # repack to [B,F,U] (contiguous) for the kernel's (b*F+f)*ld addressing.
-        dA = self.A                      # reuse A's storage: its values are no longer needed
-        ops.copy2d(self.dZ[:, self.n_deep:], dA.view(B, F * U))
-        cabi.call("rs_interacting_bwd", self.X.data_ptr(), d, self.saved.data_ptr() if c.layer_num > 1 else None,
+        # dA is read in place from the Z-gradient columns [n_deep:] (sample stride zw)
+        cabi.call("rs_interacting_bwd", self.X.data_ptr(), d, 0, self.saved.data_ptr() if c.layer_num > 1 else None,
                   T, P["Wqkvr"].data_ptr(), P["bqkvr"].data_ptr(), P["gamma"].data_ptr(), P["beta"].data_ptr(),
-                  c.ln_eps, dA.data_ptr(), U, self.dX.data_ptr(), d, dparams.data_ptr(), B, F, d, U, c.head_num,
-                  c.layer_num, int(c.use_res), int(self.act_dtype == torch.bfloat16), self.ws.data_ptr(),
-                  self.ws.numel(), st)
+                  c.ln_eps, self.dZ[:, self.n_deep:].data_ptr(), U, self.zw, self.dX.data_ptr(), d, 0,
+                  dparams.data_ptr(), B, F, d, U, c.head_num, c.layer_num, int(c.use_res),
+                  int(self.act_dtype == torch.bfloat16), self.ws.data_ptr(), self.ws.numel(), st)
 
     def _dense_fwd(self, x, wname, bname, out):
         """out = relu(x @ W + b)  (Dense(relu))."""
@@ -364,13 +361,12 @@ class AutoIntTrainer:
         P = self.P
         cabi.call("rs_embed_gather_fwd", self.table.data_ptr(), self.ids.data_ptr(), self.base_t.data_ptr(),
                   self.rows_t.data_ptr(), B * F, F, d, self.X.data_ptr(), T, None, None, st)
-        cabi.call("rs_interacting_fwd", self.X.data_ptr(), d, T, P["Wqkvr"].data_ptr(), P["bqkvr"].data_ptr(),
-                  P["gamma"].data_ptr(), P["beta"].data_ptr(), c.ln_eps, self.A.data_ptr(), U, None, B, F, d, U,
-                  c.head_num, c.layer_num, int(c.use_res), 0, st)
+        cabi.call("rs_interacting_fwd", self.X.data_ptr(), d, 0, T, P["Wqkvr"].data_ptr(), P["bqkvr"].data_ptr(),
+                  P["gamma"].data_ptr(), P["beta"].data_ptr(), c.ln_eps, self.Z[:, self.n_deep:].data_ptr(), U,
+                  self.zw, None, B, F, d, U, c.head_num, c.layer_num, int(c.use_res), 0, st)
         acts = [self.X.view(B, F * d)] + self.H + [self.Z[:, :self.n_deep]]
         for i in range(len(c.mlp_hidden)):
             self._dense_fwd(acts[i], f"mlp_W{i}", f"mlp_b{i}", acts[i + 1])
-        ops.copy2d(self.A.view(B, F * U), self.Z[:, self.n_deep:])
         # the head kernel also produces gradients; they land in scratch and are ignored here
         ops.logit_head(self.Z, P["out_W"], P["out_b"], self.labels, self.dZ, self.G["out_W"], self.G["out_b"],
                        p_out=self.p_raw, loss=self.loss)

@@ -55,6 +55,22 @@ __device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
                : "l"(p));
   return r;
 }
+// Random-row accesses (embedding rows, optimizer state): ask L2 to fetch 64 B, not its
+// default larger granule — a d=16 fp32 row is exactly 64 B and its neighbours are never used.
+__device__ __forceinline__ float4 ldg_row_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ld_row_f4(const float4* p) {   // read-write data (no .nc)
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.L2::64B.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p) : "memory");
+  return r;
+}
 __device__ __forceinline__ uint2 ldg_nc_u2(const uint2* p) {
   uint2 r;
   asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
@@ -124,6 +140,15 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// Sum of part[p * stride] for p in [0, nparts) by one full warp, in a FIXED order (lane l adds
+// p = l, l+32, ... sequentially, then a fixed butterfly) => run-to-run deterministic.
+__device__ __forceinline__ float warp_ordered_sum(const float* __restrict__ base, int nparts, int64_t stride) {
+  const int lane = threadIdx.x & 31;
+  float s = 0.f;
+  for (int p = lane; p < nparts; p += 32) s += base[(int64_t)p * stride];
+  return warp_sum(s);
 }
 
 }  // namespace rs

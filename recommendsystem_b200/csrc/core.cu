@@ -68,37 +68,57 @@ __global__ void act_bwd_kernel(const T* __restrict__ x, int64_t ldx, const T* __
   }
 }
 
-// Deterministic column sum: block (bx, by) sums rows [by*ROWS, (by+1)*ROWS) of
-// 32 columns into partial[by][n]; the last-arriving... no atomics: a second
-// launch adds the partials in row-block order.
-constexpr int CS_ROWS = 256;
+// Deterministic column sum in two launches (no atomics): block (bx, by) sums rows
+// [by*CS_ROWS, (by+1)*CS_ROWS) of a 128-column strip; a thread owns 4 adjacent columns (one
+// 16-/8-byte load per row), the 8 row-lanes of the block are combined in a fixed order, and
+// a second launch adds the per-strip partials in row-block order.
+constexpr int CS_ROWS = 128;
 template <typename T>
 __global__ void colsum_partial_kernel(const T* __restrict__ x, int64_t ldx, float* __restrict__ part,
-                                      int M, int N) {
-  __shared__ float sm[8][33];
-  const int col = blockIdx.x * 32 + threadIdx.x;
+                                      int M, int N, int vec_ok) {
+  __shared__ float4 sm[8][32];
+  const int col = (blockIdx.x * 32 + threadIdx.x) * 4;
   const int r0 = blockIdx.y * CS_ROWS;
-  float acc = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (col < N) {
     const int r1 = min(M, r0 + CS_ROWS);
-    for (int r = r0 + threadIdx.y; r < r1; r += 8) acc += to_f<T>(x[(int64_t)r * ldx + col]);
+    if (vec_ok && col + 4 <= N) {
+      for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+        const float4 v = load4<T>(x + (int64_t)r * ldx + col);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    } else {
+      for (int r = r0 + threadIdx.y; r < r1; r += 8) {
+        const T* p = x + (int64_t)r * ldx + col;
+        acc.x += to_f<T>(p[0]);
+        if (col + 1 < N) acc.y += to_f<T>(p[1]);
+        if (col + 2 < N) acc.z += to_f<T>(p[2]);
+        if (col + 3 < N) acc.w += to_f<T>(p[3]);
+      }
+    }
   }
   sm[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.y == 0 && col < N) {
-    float s = 0.f;
+    float4 s = sm[0][threadIdx.x];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += sm[k][threadIdx.x];
-    part[(int64_t)blockIdx.y * N + col] = s;
+    for (int k = 1; k < 8; ++k) {
+      const float4 v = sm[k][threadIdx.x];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    float* dst = part + (int64_t)blockIdx.y * N + col;
+    dst[0] = s.x;
+    if (col + 1 < N) dst[1] = s.y;
+    if (col + 2 < N) dst[2] = s.z;
+    if (col + 3 < N) dst[3] = s.w;
   }
 }
 __global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int nparts,
                                     int N) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const int col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per column
   if (col >= N) return;
-  float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += part[(int64_t)p * N + col];
-  out[col] = s;
+  const float s = warp_ordered_sum(part + col, nparts, N);
+  if ((threadIdx.x & 31) == 0) out[col] = s;
 }
 
 // BCE on clip(p_raw,1e-6,1) with the sigmoid' of the producing Dense folded in.
@@ -222,14 +242,16 @@ int rs_colsum(const void* x, int64_t ldx, int dtype, float* out, int M, int N, v
   if (ws_bytes < rs_colsum_workspace_bytes(M, N)) { set_error("colsum: workspace too small"); return RS_ERR_WORKSPACE; }
   cudaStream_t st = as_stream(stream);
   const int nparts = (int)cdiv(M, CS_ROWS);
-  dim3 grid((unsigned)cdiv(N, 32), (unsigned)nparts), block(32, 8);
+  dim3 grid((unsigned)cdiv(N, 128), (unsigned)nparts), block(32, 8);
+  const int esz = dtype == RS_F32 ? 4 : 2;
+  const int vec_ok = ((uintptr_t)x % (4 * esz) == 0) && ((ldx * esz) % (4 * esz) == 0);
   if (dtype == RS_F32)
-    colsum_partial_kernel<float><<<grid, block, 0, st>>>((const float*)x, ldx, (float*)ws, M, N);
+    colsum_partial_kernel<float><<<grid, block, 0, st>>>((const float*)x, ldx, (float*)ws, M, N, vec_ok);
   else if (dtype == RS_BF16)
-    colsum_partial_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, ldx, (float*)ws, M, N);
+    colsum_partial_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)x, ldx, (float*)ws, M, N, vec_ok);
   else { set_error("colsum: bad dtype"); return RS_ERR_INVALID; }
   if (int e = check_launch("colsum_partial")) return e;
-  colsum_final_kernel<<<(unsigned)cdiv(N, 128), 128, 0, st>>>((const float*)ws, out, nparts, N);
+  colsum_final_kernel<<<(unsigned)cdiv((int64_t)N * 32, 256), 256, 0, st>>>((const float*)ws, out, nparts, N);
   return check_launch("colsum_final");
 }
 

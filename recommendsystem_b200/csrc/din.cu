@@ -463,26 +463,22 @@ template <int MODE, int H, int HD>
 __global__ void din_reduce_kernel(const float* __restrict__ part, int nparts, float* __restrict__ dparams) {
   using S = DinShape<H, HD>;
   constexpr int NIN = (MODE == RS_DIN_A ? 3 : 4) * H;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per output
   const int total = NIN * HD + 2 * HD + 1;
   if (i >= total) return;
-  auto sum_of = [&](int idx) {
-    float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += part[(int64_t)p * S::NP + idx];
-    return s;
-  };
+  auto sum_of = [&](int idx) { return warp_ordered_sum(part + idx, nparts, S::NP); };
+  float v;
   if (i < NIN * HD) {
     const int blk = i / S::NW, e = i % S::NW;
-    float v;
     if (MODE == RS_DIN_A) v = sum_of(blk * S::NW + e);
     else if (blk == 0) v = sum_of(e);
     else if (blk == 1) v = sum_of(S::NW + e);
     else if (blk == 2) v = sum_of(e) - sum_of(S::NW + e);
     else v = sum_of(2 * S::NW + e);
-    dparams[i] = v;
   } else {
-    dparams[i] = sum_of(3 * S::NW + (i - NIN * HD));
+    v = sum_of(3 * S::NW + (i - NIN * HD));
   }
+  if ((threadIdx.x & 31) == 0) dparams[i] = v;
 }
 
 template <int H, int HD>
@@ -544,7 +540,7 @@ static int din_launch_bwd(const DinArgs& a) {
   if (int e = check_launch("din_bwd")) return e;
   constexpr int NIN = (MODE == RS_DIN_A ? 3 : 4) * H;
   const int total = NIN * HD + 2 * HD + 1;
-  din_reduce_kernel<MODE, H, HD><<<(total + 127) / 128, 128, 0, a.st>>>((const float*)a.ws, grid, a.dparams);
+  din_reduce_kernel<MODE, H, HD><<<(total * 32 + 255) / 256, 256, 0, a.st>>>((const float*)a.ws, grid, a.dparams);
   return check_launch("din_bwd_reduce");
 }
 

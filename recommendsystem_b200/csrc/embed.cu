@@ -71,7 +71,7 @@ embed_gather_kernel(const float* __restrict__ table, const int64_t* __restrict__
         const int32_t r = __shfl_sync(0xffffffffu, myrow[k], src);
         v[k][s] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r >= 0 && col_ok)
-          v[k][s] = ldg_nc_f4(reinterpret_cast<const float4*>(table + (int64_t)r * d) + gl);
+          v[k][s] = ldg_row_f4(reinterpret_cast<const float4*>(table + (int64_t)r * d) + gl);
       }
     }
 #pragma unroll
@@ -260,9 +260,9 @@ embed_segsum_kernel(const uint64_t* __restrict__ keys, const GT* __restrict__ gr
       for (int s = 0; s < G; ++s) {
         if (shead[s] && col_ok) {
           const int64_t off = (int64_t)srow[s] * d + gl * 4;
-          w[s] = *reinterpret_cast<const float4*>(a.w + off);
-          m[s] = *reinterpret_cast<const float4*>(a.s0 + off);
-          v[s] = *reinterpret_cast<const float4*>(a.s1 + off);
+          w[s] = ld_row_f4(reinterpret_cast<const float4*>(a.w + off));
+          m[s] = ld_row_f4(reinterpret_cast<const float4*>(a.s0 + off));
+          v[s] = ld_row_f4(reinterpret_cast<const float4*>(a.s1 + off));
         }
       }
       const float b1 = a.beta1, b2 = a.beta2, eps = a.eps;

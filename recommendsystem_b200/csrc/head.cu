@@ -89,11 +89,11 @@ logit_head_kernel(const T* __restrict__ Z, int64_t ldz, const float* __restrict_
 __global__ void logit_head_reduce_kernel(const float* __restrict__ part, int nparts, int zw,
                                          float* __restrict__ dw, float* __restrict__ db,
                                          float* __restrict__ loss, float invB) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per output
   const int np = zw + 2;
   if (i >= np) return;
-  float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += part[(int64_t)p * np + i];
+  const float s = warp_ordered_sum(part + i, nparts, np);
+  if ((threadIdx.x & 31) != 0) return;
   if (i < zw) dw[i] = s;
   else if (i == zw) db[0] = s;
   else loss[0] = s * invB;
@@ -144,7 +144,7 @@ int rs_logit_head_fwd_bwd(const void* Z, int64_t ldz, int dtype, const float* w,
   }
 #undef RS_HEAD_GO
   if (int e = check_launch("logit_head")) return e;
-  logit_head_reduce_kernel<<<(unsigned)cdiv(zw + 2, 128), 128, 0, st>>>((const float*)ws, grid, zw, dw, db,
+  logit_head_reduce_kernel<<<(unsigned)cdiv((zw + 2) * 32, 256), 256, 0, st>>>((const float*)ws, grid, zw, dw, db,
                                                                          loss_out, 1.f / (float)B);
   return check_launch("logit_head_reduce");
 }

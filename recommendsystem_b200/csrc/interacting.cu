@@ -22,9 +22,9 @@ size_t rs_interacting_workspace_bytes(int B, int F, int D, int U) {
   return (size_t)(sm_count() * 2) * (size_t)(D * 4 * U + 6 * U) * sizeof(float);
 }
 
-int rs_interacting_fwd(const void* x, int64_t x_ld, int dtype, const float* Wqkvr,
+int rs_interacting_fwd(const void* x, int64_t x_ld, int64_t x_bs, int dtype, const float* Wqkvr,
                        const float* bqkvr, const float* ln_gamma, const float* ln_beta,
-                       float ln_eps, void* y, int64_t y_ld, void* saved, int B, int F, int D, int U,
+                       float ln_eps, void* y, int64_t y_ld, int64_t y_bs, void* saved, int B, int F, int D, int U,
                        int H, int L, int use_res, int compute_bf16, void* stream) {
   RS_REQUIRE(B > 0 && F > 0 && L >= 1, "interacting_fwd: B=%d F=%d L=%d", B, F, L);
   RS_REQUIRE(H > 0 && U % H == 0, "interacting_fwd: head_num %d must divide unit_num %d", H, U);
@@ -33,7 +33,10 @@ int rs_interacting_fwd(const void* x, int64_t x_ld, int dtype, const float* Wqkv
   RS_REQUIRE(dtype == RS_F32 || dtype == RS_BF16, "interacting_fwd: bad dtype");
   RS_REQUIRE(x_ld % 4 == 0 && y_ld % 4 == 0, "interacting_fwd: leading dims must be multiples of 4");
   (void)compute_bf16;
-  IFwdArgs a{x, x_ld, Wqkvr, bqkvr, ln_gamma, ln_beta, ln_eps, y, y_ld, saved, B, F, L, use_res,
+  if (x_bs == 0) x_bs = (int64_t)F * x_ld;
+  if (y_bs == 0) y_bs = (int64_t)F * y_ld;
+  RS_REQUIRE(x_bs % 4 == 0 && y_bs % 4 == 0, "interacting_fwd: batch strides must be multiples of 4");
+  IFwdArgs a{x, x_ld, x_bs, Wqkvr, bqkvr, ln_gamma, ln_beta, ln_eps, y, y_ld, y_bs, saved, B, F, L, use_res,
              dtype, as_stream(stream)};
 #define RS_CASE(DD, UU, HH) \
   if (D == DD && U == UU && H == HH) return interacting_fwd_##DD##_##UU##_##HH(a);
@@ -43,10 +46,10 @@ int rs_interacting_fwd(const void* x, int64_t x_ld, int dtype, const float* Wqkv
   return RS_ERR_UNSUPPORTED;
 }
 
-int rs_interacting_bwd(const void* x, int64_t x_ld, const void* saved, int dtype,
+int rs_interacting_bwd(const void* x, int64_t x_ld, int64_t x_bs, const void* saved, int dtype,
                        const float* Wqkvr, const float* bqkvr, const float* ln_gamma,
-                       const float* ln_beta, float ln_eps, const void* dy, int64_t dy_ld, void* dx,
-                       int64_t dx_ld, float* dparams, int B, int F, int D, int U, int H, int L,
+                       const float* ln_beta, float ln_eps, const void* dy, int64_t dy_ld,
+                       int64_t dy_bs, void* dx, int64_t dx_ld, int64_t dx_bs, float* dparams, int B, int F, int D, int U, int H, int L,
                        int use_res, int compute_bf16, void* ws, size_t ws_bytes, void* stream) {
   RS_REQUIRE(B > 0 && F > 0 && L >= 1, "interacting_bwd: B=%d F=%d L=%d", B, F, L);
   RS_REQUIRE(H > 0 && U % H == 0, "interacting_bwd: head_num %d must divide unit_num %d", H, U);
@@ -57,7 +60,11 @@ int rs_interacting_bwd(const void* x, int64_t x_ld, const void* saved, int dtype
   RS_REQUIRE(x_ld % 4 == 0 && dy_ld % 4 == 0 && dx_ld % 4 == 0,
              "interacting_bwd: leading dims must be multiples of 4");
   (void)compute_bf16;
-  IBwdArgs a{x, x_ld, saved, Wqkvr, bqkvr, ln_gamma, ln_beta, ln_eps, dy, dy_ld, dx, dx_ld, dparams,
+  if (x_bs == 0) x_bs = (int64_t)F * x_ld;
+  if (dy_bs == 0) dy_bs = (int64_t)F * dy_ld;
+  if (dx_bs == 0) dx_bs = (int64_t)F * dx_ld;
+  RS_REQUIRE(x_bs % 4 == 0 && dy_bs % 4 == 0 && dx_bs % 4 == 0, "interacting_bwd: batch strides must be multiples of 4");
+  IBwdArgs a{x, x_ld, x_bs, saved, Wqkvr, bqkvr, ln_gamma, ln_beta, ln_eps, dy, dy_ld, dy_bs, dx, dx_ld, dx_bs, dparams,
              B, F, L, use_res, dtype, ws, ws_bytes, as_stream(stream)};
 #define RS_CASE(DD, UU, HH) \
   if (D == DD && U == UU && H == HH) return interacting_bwd_##DD##_##UU##_##HH(a);

@@ -4,12 +4,12 @@
 #include "common.cuh"
 namespace rs {
 struct IFwdArgs {
-  const void* x; int64_t x_ld; const float* W; const float* b; const float* gm; const float* bt;
-  float eps; void* y; int64_t y_ld; void* saved; int B, F, L, use_res, dtype; cudaStream_t st;
+  const void* x; int64_t x_ld, x_bs; const float* W; const float* b; const float* gm; const float* bt;
+  float eps; void* y; int64_t y_ld, y_bs; void* saved; int B, F, L, use_res, dtype; cudaStream_t st;
 };
 struct IBwdArgs {
-  const void* x; int64_t x_ld; const void* saved; const float* W; const float* b; const float* gm;
-  const float* bt; float eps; const void* dy; int64_t dy_ld; void* dx; int64_t dx_ld;
+  const void* x; int64_t x_ld, x_bs; const void* saved; const float* W; const float* b; const float* gm;
+  const float* bt; float eps; const void* dy; int64_t dy_ld, dy_bs; void* dx; int64_t dx_ld, dx_bs;
   float* dparams; int B, F, L, use_res, dtype; void* ws; size_t ws_bytes; cudaStream_t st;
 };
 }  // namespace rs

@@ -171,9 +171,9 @@ __device__ __forceinline__ void res_relu_ln(const float (&o)[U], const float (&r
 // ------------------------------------------------------------------ forward
 template <int D, int U, int H, int NT, typename T>
 __global__ void __launch_bounds__(NT)
-interacting_fwd_kernel(const T* __restrict__ x, int64_t x_ld, const float* __restrict__ W,
+interacting_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, const float* __restrict__ W,
                        const float* __restrict__ bias, const float* __restrict__ gamma,
-                       const float* __restrict__ beta, float eps, T* __restrict__ y, int64_t y_ld,
+                       const float* __restrict__ beta, float eps, T* __restrict__ y, int64_t y_ld, int64_t y_bs,
                        float* __restrict__ saved, int B, int F, int L, int use_res) {
   static_assert(U <= 32, "tmask is 32 bits");
   constexpr int DH = U / H;
@@ -204,7 +204,10 @@ interacting_fwd_kernel(const T* __restrict__ x, int64_t x_ld, const float* __res
     const int64_t row = (int64_t)tile * rows_per_tile + tid;
     const bool active = tid < rows_per_tile && row < total_rows;
     float xr[D];
-    if (active) load_row<D, T>(x + row * x_ld, xr);
+    // element (b, f, c) lives at ptr[b * bs + f * ld + c]
+    const int64_t smp = (int64_t)tile * SPT + ls;
+    const int fld = tid - ls * F;
+    if (active) load_row<D, T>(x + smp * x_bs + fld * x_ld, xr);
     else {
 #pragma unroll
       for (int d = 0; d < D; ++d) xr[d] = 0.f;
@@ -252,17 +255,18 @@ interacting_fwd_kernel(const T* __restrict__ x, int64_t x_ld, const float* __res
         }
       }
     }
-    if (active) store_row<U, T>(y + row * y_ld, yv);
+    if (active) store_row<U, T>(y + smp * y_bs + fld * y_ld, yv);
   }
 }
 
 // ----------------------------------------------------------------- backward
 template <int D, int U, int H, int NT, typename T>
 __global__ void __launch_bounds__(NT)
-interacting_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const float* __restrict__ saved,
+interacting_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, const float* __restrict__ saved,
                        const float* __restrict__ W, const float* __restrict__ bias,
                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                       const T* __restrict__ dy, int64_t dy_ld, T* __restrict__ dx, int64_t dx_ld,
+                       const T* __restrict__ dy, int64_t dy_ld, int64_t dy_bs, T* __restrict__ dx, int64_t dx_ld,
+                       int64_t dx_bs,
                        float* __restrict__ part, int B, int F, int L, int use_res) {
   constexpr int DH = U / H;
   constexpr int N4 = 4 * U;
@@ -311,7 +315,9 @@ interacting_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const float* __res
     const bool active = tid < rows_per_tile && row < total_rows;
     const int rows_here = (int)min((int64_t)rows_per_tile, total_rows - (int64_t)tile * rows_per_tile);
     float g[U];  // gradient wrt the output of the current iteration
-    if (active) load_row<U, T>(dy + row * dy_ld, g);
+    const int64_t smp = (int64_t)tile * SPT + ls;
+    const int fld = tid - ls * F;
+    if (active) load_row<U, T>(dy + smp * dy_bs + fld * dy_ld, g);
     else {
 #pragma unroll
       for (int u = 0; u < U; ++u) g[u] = 0.f;
@@ -320,7 +326,7 @@ interacting_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const float* __res
     for (int it = L - 1; it >= 0; --it) {
       float xr[D];
       if (active) {
-        if (it == 0) load_row<D, T>(x + row * x_ld, xr);
+        if (it == 0) load_row<D, T>(x + smp * x_bs + fld * x_ld, xr);
         else {
           if constexpr (D == U) load_row<U, float>(saved + ((int64_t)(it - 1) * total_rows + row) * U, xr);
         }
@@ -542,7 +548,7 @@ interacting_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const float* __res
           for (int u = 0; u < U; ++u) g[u] = dxr[u];   // stays fp32 between iterations
         }
       } else if (active) {
-        store_row<D, T>(dx + row * dx_ld, dxr);
+        store_row<D, T>(dx + smp * dx_bs + fld * dx_ld, dxr);
       }
     }
   }
@@ -557,13 +563,13 @@ interacting_bwd_kernel(const T* __restrict__ x, int64_t x_ld, const float* __res
   }
 }
 
+// out[i] = sum over CTAs of part[cta][i]; one warp per output (ordered => deterministic)
 static __global__ void reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out,
-                                       int nparts, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                                              int nparts, int n) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= n) return;
-  float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += part[(int64_t)p * n + i];
-  out[i] = s;
+  const float s = warp_ordered_sum(part + i, nparts, n);
+  if ((threadIdx.x & 31) == 0) out[i] = s;
 }
 
 // ------------------------------------------------------------ host dispatch
@@ -594,7 +600,7 @@ static int launch_fwd(const IFwdArgs& a) {
   const int ntiles = (a.B + SPT - 1) / SPT;
   int grid = sm_count() * 4;
   if (grid > ntiles) grid = ntiles;
-  kern<<<grid, NT, smem, a.st>>>((const T*)a.x, a.x_ld, a.W, a.b, a.gm, a.bt, a.eps, (T*)a.y, a.y_ld,
+  kern<<<grid, NT, smem, a.st>>>((const T*)a.x, a.x_ld, a.x_bs, a.W, a.b, a.gm, a.bt, a.eps, (T*)a.y, a.y_ld, a.y_bs,
                                  (float*)a.saved, a.B, a.F, a.L, a.use_res);
   return check_launch("interacting_fwd");
 }
@@ -610,11 +616,11 @@ static int launch_bwd(const IBwdArgs& a) {
     set_error("interacting_bwd: workspace %zu < %zu", a.ws_bytes, (size_t)grid * np * sizeof(float));
     return RS_ERR_WORKSPACE;
   }
-  kern<<<grid, NT, smem, a.st>>>((const T*)a.x, a.x_ld, (const float*)a.saved, a.W, a.b, a.gm, a.bt, a.eps,
-                                 (const T*)a.dy, a.dy_ld, (T*)a.dx, a.dx_ld, (float*)a.ws, a.B, a.F,
+  kern<<<grid, NT, smem, a.st>>>((const T*)a.x, a.x_ld, a.x_bs, (const float*)a.saved, a.W, a.b, a.gm, a.bt, a.eps,
+                                 (const T*)a.dy, a.dy_ld, a.dy_bs, (T*)a.dx, a.dx_ld, a.dx_bs, (float*)a.ws, a.B, a.F,
                                  a.L, a.use_res);
   if (int e = check_launch("interacting_bwd")) return e;
-  reduce_partials_kernel<<<(np + 127) / 128, 128, 0, a.st>>>((const float*)a.ws, a.dparams, grid, np);
+  reduce_partials_kernel<<<(np * 32 + 255) / 256, 256, 0, a.st>>>((const float*)a.ws, a.dparams, grid, np);
   return check_launch("interacting_bwd_reduce");
 }
 

@@ -164,8 +164,8 @@ def interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res=True, sa
     _need(x.is_contiguous(), "x must be contiguous")
     y = torch.empty(B, F, U, dtype=x.dtype, device=x.device)
     saved = torch.empty(L - 1, B * F, U, dtype=torch.float32, device=x.device) if (save and L > 1) else None
-    call("rs_interacting_fwd", _ptr(x), D, _dt(x), _ptr(Wqkvr), _ptr(bqkvr), _ptr(gamma), _ptr(beta),
-         ln_eps, _ptr(y), U, _ptr(saved), B, F, D, U, H, L, int(use_res), int(compute_bf16), _stream())
+    call("rs_interacting_fwd", _ptr(x), D, 0, _dt(x), _ptr(Wqkvr), _ptr(bqkvr), _ptr(gamma), _ptr(beta),
+         ln_eps, _ptr(y), U, 0, _ptr(saved), B, F, D, U, H, L, int(use_res), int(compute_bf16), _stream())
     return y, saved
 
 
@@ -177,8 +177,8 @@ def interacting_bwd(x, saved, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, dy, use_r
     nbytes = cabi.load().rs_interacting_workspace_bytes(B, F, D, U)
     ws = WS.get("interacting", nbytes, x.device)
     dy = dy.contiguous()
-    call("rs_interacting_bwd", _ptr(x), D, _ptr(saved), _dt(x), _ptr(Wqkvr), _ptr(bqkvr), _ptr(gamma),
-         _ptr(beta), ln_eps, _ptr(dy), U, _ptr(dx), D, _ptr(dparams), B, F, D, U, H, L, int(use_res),
+    call("rs_interacting_bwd", _ptr(x), D, 0, _ptr(saved), _dt(x), _ptr(Wqkvr), _ptr(bqkvr), _ptr(gamma),
+         _ptr(beta), ln_eps, _ptr(dy), U, 0, _ptr(dx), D, 0, _ptr(dparams), B, F, D, U, H, L, int(use_res),
          int(compute_bf16), _ptr(ws), ws.numel(), _stream())
     nW = D * 4 * U
     return dx, dparams[:nW].view(D, 4 * U), dparams[nW:nW + 4 * U], dparams[nW + 4 * U:nW + 5 * U], dparams[nW + 5 * U:]

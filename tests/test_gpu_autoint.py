@@ -121,9 +121,9 @@ def test_autoint_step_bf16(cuda_dev):
     assert abs(float(loss) - res["loss"]) <= REL_BF16 * abs(res["loss"])
     assert_close(tr.p_raw.float().cpu().numpy(), res["p_raw"], REL_BF16, "bf16 logits")
     g = lambda t: f64(t.float().cpu().numpy())
-    # InteractingLayer backward on the bf16 dA it was given (tr.A holds dA after the step)
+    # InteractingLayer backward on the bf16 dA it was given (the Z-gradient columns [n_deep:])
     dXi, dW, db, dg, dbt = onp.interacting_bwd(f64(Xb), P["Wqkvr"], P["bqkvr"], P["gamma"], P["beta"], cfg.ln_eps,
-                                               H, L, g(tr.A))
+                                               H, L, g(tr.dZ[:, tr.n_deep:]).reshape(B, F, d))
     W0 = f64(tr.P16["mlp_W0"].float().cpu().numpy() if False else P0["mlp_W0"])
     dX_ref = dXi + (g(tr.dH[0]) @ W0.T).reshape(B, F, d)
     assert_close(g(tr.dX), dX_ref, 2 * REL_BF16, "bf16 dX")
