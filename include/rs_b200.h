@@ -178,8 +178,19 @@ int rs_route_ids(const int64_t* ids, int64_t n, int F, const int64_t* rows,
                  int32_t* send_rows, int32_t* inverse,
                  int32_t* send_counts, int32_t* send_offsets,
                  void* ws, size_t ws_bytes, void* stream);
-/* out[i, :] = src[inverse[i], :] (un-permute received rows) and its adjoint
- * out[inverse[i], :] = src[i, :]. */
+/* Fixed-capacity variant (no host round trip for the counts, so the whole sharded
+ * step, all-to-alls included, is CUDA-graph capturable): bucket o owns the slots
+ * [o*capacity, (o+1)*capacity) of send_rows[world*capacity]; unused slots hold row
+ * -1 (gathers as zeros, contributes no gradient).  inverse[i] = slot of lookup i.
+ * If a bucket would exceed `capacity`, *overflow is set to 1 (never cleared here)
+ * and the surplus lookups get inverse = -1: the caller must treat that as an error.
+ * ws >= rs_route_workspace_bytes(n, world) + (world+1)*4. */
+int rs_route_ids_padded(const int64_t* ids, int64_t n, int F, const int64_t* rows,
+                        const int64_t* local_base, int world, int capacity,
+                        int32_t* send_rows, int32_t* inverse, int32_t* send_counts,
+                        int32_t* overflow, void* ws, size_t ws_bytes, void* stream);
+/* out[i, :] = src[index[i], :] (un-permute received rows; index < 0 -> zeros) and
+ * its adjoint out[index[i], :] = src[i, :] (index < 0 skipped). */
 int rs_permute_rows(const void* src, void* out, const int32_t* index, int64_t n,
                     int d, int dtype, int scatter, void* stream);
 

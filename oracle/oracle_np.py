@@ -244,6 +244,22 @@ def route_ids(ids, F, rows, local_base, world):
     return send_rows, inverse, counts, offsets
 
 
+def route_ids_padded(ids, F, rows, local_base, world, capacity):
+    """Fixed-capacity layout of route_ids: bucket o owns slots [o*capacity, (o+1)*capacity),
+    unused slots hold row -1; returns send_rows[world*capacity], inverse[n], counts, overflow."""
+    sr, inv, cnt, off = route_ids(ids, F, rows, local_base, world)
+    send = np.full(world * capacity, -1, np.int32)
+    inverse = np.full(len(inv), -1, np.int32)
+    owner_of_slot = np.searchsorted(off, np.arange(len(sr)), side="right") - 1
+    k = np.arange(len(sr)) - off[owner_of_slot]
+    ok = k < capacity
+    new_slot = owner_of_slot * capacity + k
+    send[new_slot[ok]] = sr[ok]
+    remap = np.where(ok, new_slot, -1).astype(np.int32)
+    inverse[:] = remap[inv]
+    return send, inverse, cnt, int((cnt > capacity).any())
+
+
 # ------------------------------------------------------- K4 InteractingLayer
 
 

@@ -115,16 +115,7 @@ class AutoIntTrainer:
             raise ValueError("arena rows must fit int32")
         self.rows_t = torch.from_numpy(self.rows_host).to(self.dev)
         self.base_t = torch.from_numpy(self.base_host).to(self.dev)
-        gen = torch.Generator(device=self.dev).manual_seed(cfg.seed)
-        if tables is None:
-            self.table = torch.empty(self.total_rows, d, device=self.dev)
-            self.table.normal_(0.0, cfg.table_init_scale, generator=gen)
-        else:
-            self.table = tables.to(self.dev, torch.float32).contiguous()
-            assert self.table.shape == (self.total_rows, d)
-        self.table_m = torch.zeros_like(self.table)
-        self.table_v = torch.zeros_like(self.table)
-        self.row_bits = ops.row_bits(self.total_rows)
+        self._alloc_tables(tables)
 
         # ---- dense parameters: one flat fp32 buffer (+ grads, m, v, bf16 shadow) with views
         self.spec = []
@@ -183,6 +174,19 @@ class AutoIntTrainer:
         self.ws = torch.empty(int(n_ws) + 256, dtype=torch.uint8, device=self.dev)
 
     # ------------------------------------------------------------------ setup
+    def _alloc_tables(self, tables):
+        cfg, d = self.cfg, self.cfg.embed_dim
+        gen = torch.Generator(device=self.dev).manual_seed(cfg.seed)
+        if tables is None:
+            self.table = torch.empty(self.total_rows, d, device=self.dev)
+            self.table.normal_(0.0, cfg.table_init_scale, generator=gen)
+        else:
+            self.table = tables.to(self.dev, torch.float32).contiguous()
+            assert self.table.shape == (self.total_rows, d)
+        self.table_m = torch.zeros_like(self.table)
+        self.table_v = torch.zeros_like(self.table)
+        self.row_bits = ops.row_bits(self.total_rows)
+
     def _add(self, name, shape):
         off = 0
         if self.spec:
@@ -233,9 +237,7 @@ class AutoIntTrainer:
         nmlp = len(c.mlp_hidden)
         ph = lambda name: _Phase(self.timer, name)
         # K1: gather (+ sort keys emitted for the backward)
-        with ph("embed_gather"):
-            cabi.call("rs_embed_gather_fwd", self.table.data_ptr(), self.ids.data_ptr(), self.base_t.data_ptr(),
-                      self.rows_t.data_ptr(), B * F, F, d, self.X.data_ptr(), T, self.keys.data_ptr(), None, st)
+        self._embed_forward(ph, st, T)
         # K4: InteractingLayer forward
         with ph("interacting_fwd"):
             # writes Flatten(A) straight into its columns of the concat buffer Z (autoint:36,45)
@@ -271,17 +273,34 @@ class AutoIntTrainer:
         with ph("mlp_dgrad_x"):
             ops.gemm(self.dH[0], self._w("mlp_W0"), self.dX.view(B, F * d), epilogue=E.EPI_ACCUM, transB=True)
         # K3: sparse Adam on touched rows; dense Adam on the flat buffer
-        with ph("sort_keys"):
-            ops.adam_advance(self.adam_scalars, c.beta1, c.beta2)
-            ops.sort_keys(self.keys, self.row_bits, out=self.keys_sorted)
-        with ph("embed_segsum_adam"):
-            ops.segsum_adam(self.table, self.table_m, self.table_v, self.dX.view(B * F, d), self.keys_sorted,
-                            c.lr_sparse, c.beta1, c.beta2, c.eps, self.adam_scalars)
+        ops.adam_advance(self.adam_scalars, c.beta1, c.beta2)
+        self._embed_backward(ph, st, T)
+        self._dense_sync(ph)
         with ph("dense_adam"):
             ops.dense_adam(self.flat, self.flat_m, self.flat_v, self.flat_g, c.lr_dense, c.beta1, c.beta2, c.eps,
                            self.adam_scalars, self.flat_bf16)
             if self.bf16:
                 self._refresh_wt()
+
+    # ---- embedding halves of the step (overridden by the row-sharded multi-GPU trainer)
+    def _embed_forward(self, ph, st, T):
+        c = self.cfg
+        n = c.batch * c.num_fields
+        with ph("embed_gather"):
+            cabi.call("rs_embed_gather_fwd", self.table.data_ptr(), self.ids.data_ptr(), self.base_t.data_ptr(),
+                      self.rows_t.data_ptr(), n, c.num_fields, c.embed_dim, self.X.data_ptr(), T,
+                      self.keys.data_ptr(), None, st)
+
+    def _embed_backward(self, ph, st, T):
+        c = self.cfg
+        with ph("sort_keys"):
+            ops.sort_keys(self.keys, self.row_bits, out=self.keys_sorted)
+        with ph("embed_segsum_adam"):
+            ops.segsum_adam(self.table, self.table_m, self.table_v, self.dX.view(-1, c.embed_dim), self.keys_sorted,
+                            c.lr_sparse, c.beta1, c.beta2, c.eps, self.adam_scalars)
+
+    def _dense_sync(self, ph):
+        """Single GPU: nothing to exchange.  (Multi-GPU: all-reduce of the flat dense gradient.)"""
 
     def _interacting_bwd(self, dparams, st, T):
         c = self.cfg

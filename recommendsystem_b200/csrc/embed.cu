@@ -484,6 +484,41 @@ __global__ void route_scatter_kernel(const int64_t* ids, int64_t n, int F, const
   }
 }
 
+// Fixed-capacity variant for CUDA-graph-capturable all-to-alls: bucket o owns slots
+// [o*cap, (o+1)*cap); slot = o*cap + (stable rank of the lookup inside bucket o).  Lookups
+// beyond the capacity are dropped and raise the overflow flag (the caller must then fail).
+__global__ void route_scatter_padded_kernel(const int64_t* ids, int64_t n, int F, const int64_t* rows,
+                                            const int64_t* local_base, int world, int cap,
+                                            const int32_t* hist /*exclusive, [world][nblk]*/,
+                                            const int32_t* send_offsets, int32_t* send_rows,
+                                            int32_t* inverse, int32_t* overflow) {
+  __shared__ int warp_cnt[ROUTE_BLOCK / 32][ROUTE_MAX_WORLD];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * ROUTE_BLOCK + threadIdx.x;
+  int owner = -1; int32_t lrow = -1;
+  if (i < n) route_of(ids, rows, local_base, i, F, world, owner, lrow);
+  int my_rank = 0;
+  for (int o = 0; o < world; ++o) {
+    const unsigned m = __ballot_sync(0xffffffffu, owner == o);
+    if (owner == o) my_rank = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) warp_cnt[wid][o] = __popc(m);
+  }
+  __syncthreads();
+  if (i < n) {
+    int before = 0;
+    for (int w = 0; w < wid; ++w) before += warp_cnt[w][owner];
+    const int k = hist[(int64_t)owner * gridDim.x + blockIdx.x] - send_offsets[owner] + before + my_rank;
+    if (k < cap) {
+      const int32_t slot = owner * cap + k;
+      send_rows[slot] = lrow;
+      inverse[i] = slot;
+    } else {
+      inverse[i] = -1;
+      atomicExch(overflow, 1);
+    }
+  }
+}
+
 template <typename T>
 __global__ void permute_rows_kernel(const T* __restrict__ src, T* __restrict__ out,
                                     const int32_t* __restrict__ index, int64_t n, int vec_per_row,
@@ -496,8 +531,11 @@ __global__ void permute_rows_kernel(const T* __restrict__ src, T* __restrict__ o
   const int64_t j = index[i];
   const uint2* s = reinterpret_cast<const uint2*>(src);
   uint2* o = reinterpret_cast<uint2*>(out);
-  if (scatter) o[j * vec_per_row + c] = s[i * vec_per_row + c];
-  else o[i * vec_per_row + c] = s[j * vec_per_row + c];
+  if (scatter) {
+    if (j >= 0) o[j * vec_per_row + c] = s[i * vec_per_row + c];
+  } else {
+    o[i * vec_per_row + c] = j >= 0 ? s[j * vec_per_row + c] : make_uint2(0u, 0u);
+  }
 }
 
 }  // namespace rs
@@ -634,6 +672,29 @@ int rs_route_ids(const int64_t* ids, int64_t n, int F, const int64_t* rows,
   route_scatter_kernel<<<nblk, ROUTE_BLOCK, 0, st>>>(ids, n, F, rows, local_base, world, hist,
                                                      send_rows, inverse);
   return check_launch("route_scatter");
+}
+
+int rs_route_ids_padded(const int64_t* ids, int64_t n, int F, const int64_t* rows,
+                        const int64_t* local_base, int world, int capacity, int32_t* send_rows,
+                        int32_t* inverse, int32_t* send_counts, int32_t* overflow, void* ws,
+                        size_t ws_bytes, void* stream) {
+  RS_REQUIRE(world >= 1 && world <= ROUTE_MAX_WORLD, "route_ids_padded: world=%d", world);
+  RS_REQUIRE(F > 0 && n >= 0 && n < ((int64_t)1 << 31) && capacity > 0, "route_ids_padded: n/F/capacity out of range");
+  RS_REQUIRE((int64_t)world * capacity < ((int64_t)1 << 31), "route_ids_padded: world*capacity too large");
+  const size_t need = rs_route_workspace_bytes(n, world) + (size_t)(world + 1) * sizeof(int32_t);
+  if (ws_bytes < need) { set_error("route_ids_padded: workspace %zu < %zu", ws_bytes, need); return RS_ERR_WORKSPACE; }
+  cudaStream_t st = as_stream(stream);
+  int32_t* hist = (int32_t*)ws;
+  int32_t* offsets = (int32_t*)((char*)ws + rs_route_workspace_bytes(n, world));
+  const int nblk = (int)cdiv(n > 0 ? n : 1, ROUTE_BLOCK);
+  RS_CUDA(cudaMemsetAsync(send_rows, 0xFF, (size_t)world * capacity * sizeof(int32_t), st));   // row -1 = padding
+  route_hist_kernel<<<nblk, ROUTE_BLOCK, 0, st>>>(ids, n, F, rows, local_base, world, hist);
+  if (int e = check_launch("route_hist")) return e;
+  route_scan_kernel<<<1, 1024, 0, st>>>(hist, (int64_t)nblk * world, nblk, world, send_counts, offsets);
+  if (int e = check_launch("route_scan")) return e;
+  route_scatter_padded_kernel<<<nblk, ROUTE_BLOCK, 0, st>>>(ids, n, F, rows, local_base, world, capacity, hist,
+                                                            offsets, send_rows, inverse, overflow);
+  return check_launch("route_scatter_padded");
 }
 
 int rs_permute_rows(const void* src, void* out, const int32_t* index, int64_t n, int d, int dtype,

@@ -148,6 +148,21 @@ def route_ids(ids, F, rows, local_base, world):
     return send_rows, inverse, counts, offsets
 
 
+def route_ids_padded(ids, F, rows, local_base, world, capacity, send_rows=None, inverse=None, counts=None,
+                     overflow=None):
+    n = ids.numel()
+    dev = ids.device
+    send_rows = torch.empty(world * capacity, dtype=torch.int32, device=dev) if send_rows is None else send_rows
+    inverse = torch.empty(n, dtype=torch.int32, device=dev) if inverse is None else inverse
+    counts = torch.empty(world, dtype=torch.int32, device=dev) if counts is None else counts
+    overflow = torch.zeros(1, dtype=torch.int32, device=dev) if overflow is None else overflow
+    nbytes = cabi.load().rs_route_workspace_bytes(n, world) + (world + 1) * 4
+    ws = WS.get("route", nbytes, dev)
+    call("rs_route_ids_padded", _ptr(ids), n, F, _ptr(rows), _ptr(local_base), world, capacity, _ptr(send_rows),
+         _ptr(inverse), _ptr(counts), _ptr(overflow), _ptr(ws), ws.numel(), _stream())
+    return send_rows, inverse, counts, overflow
+
+
 def permute_rows(src, index, scatter=False, out=None):
     n, d = index.numel(), src.shape[-1]
     out = torch.empty(n, d, dtype=src.dtype, device=src.device) if out is None else out

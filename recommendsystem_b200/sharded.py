@@ -1,1 +1,161 @@
-"""Row-sharded tables + data-parallel dense part across GPUs (placeholder, next commit)."""
+"""Multi-GPU AutoInt: data-parallel dense part, embedding tables row-sharded across the ranks,
+ids / rows / gradients exchanged by NCCL all-to-all over NVLink (one process per GPU).
+
+    owner(row) = row mod W ; local row = local_base[f] + row div W         
+
+    ids [b,F] --route (K7, fixed-capacity buckets)--> all-to-all(ids) --> owner gathers (K1)
+        --> all-to-all(rows) --> un-permute --> X [b,F,d] --> dense step (as on one GPU) --> dX
+        --> permute --> all-to-all(grads) --> owner: sort + segment-sum + sparse Adam (K3)
+    dense gradients: one flat all-reduce (average) before the dense Adam.
+
+Buckets have a fixed capacity, so there is no host round trip for the counts and the whole
+step — collectives included — is one CUDA graph.  A bucket overflow (skewed ids) sets a device
+flag that `check_overflow()` turns into an exception; nothing is silently dropped.
+
+This replaces TensorNet's sparse pull/push (only trace in the reference: tn.core.shard_num() /
+self_shard_id(), staytime/parse.py:78-79).  The collective plumbing lives in `Exchange`, which
+is device-agnostic so that the protocol is tested on CPU with the gloo backend.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import cabi, ops
+from .autoint import AutoIntConfig, AutoIntTrainer
+
+
+def bucket_capacity(n_lookups: int, world: int, factor: float | None = None) -> int:
+    """Slots per (source, owner) pair.  Default: mean + 8 sigma of a uniform multinomial + 64,
+    rounded up to 128 (overflow probability for uniform ids < 1e-14 per bucket)."""
+    mean = n_lookups / world
+    if factor is not None:
+        cap = mean * factor
+    else:
+        cap = mean + 8.0 * math.sqrt(max(mean * (1 - 1.0 / world), 1.0)) + 64
+    return min(n_lookups, int(math.ceil(cap / 128.0) * 128))
+
+
+def shard_layout(rows_per_field, world):
+    """rows of field f on every rank = ceil(R_f / W); returns (local_rows[F], local_base[F])."""
+    rows = np.asarray(rows_per_field, np.int64)
+    local_rows = (rows + world - 1) // world
+    local_base = np.concatenate([[0], np.cumsum(local_rows)[:-1]]).astype(np.int64)
+    return local_rows, local_base
+
+
+class Exchange:
+    """The three all-to-alls of a sharded step (equal splits of `cap` slots per peer)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def all_to_all(self, out: torch.Tensor, inp: torch.Tensor):
+        dist.all_to_all_single(out, inp, group=self.group)
+        return out
+
+    def all_reduce_mean(self, t: torch.Tensor):
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+        else:   # gloo has no AVG
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            t.div_(self.world)
+        return t
+
+
+class ShardedAutoIntTrainer(AutoIntTrainer):
+    """AutoIntTrainer whose tables are row-sharded over the ranks of `group`.  `cfg.batch` is the
+    PER-RANK batch (weak scaling); the loss each rank reports is the mean over its own batch and
+    gradients are averaged over ranks, i.e. the update is that of the global batch W * batch."""
+
+    def __init__(self, cfg: AutoIntConfig, device, group=None, global_tables: torch.Tensor | None = None,
+                 dense_init: dict | None = None, capacity_factor: float | None = None):
+        self.ex = Exchange(group)
+        self.world, self.rank = self.ex.world, self.ex.rank
+        self._global_tables = global_tables
+        self._capacity_factor = capacity_factor
+        super().__init__(cfg, device, tables=None, dense_init=dense_init)
+        W, n, d = self.world, cfg.batch * cfg.num_fields, cfg.embed_dim
+        self.cap = bucket_capacity(n, W, capacity_factor)
+        T = self.act_dtype
+        dev = self.dev
+        self.send_rows = torch.empty(W * self.cap, dtype=torch.int32, device=dev)
+        self.recv_rows = torch.empty(W * self.cap, dtype=torch.int32, device=dev)
+        self.inverse = torch.empty(n, dtype=torch.int32, device=dev)
+        self.send_counts = torch.empty(W, dtype=torch.int32, device=dev)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.rows_out = torch.empty(W * self.cap, d, dtype=T, device=dev)      # gathered for the peers
+        self.rows_in = torch.empty(W * self.cap, d, dtype=T, device=dev)       # received for my lookups
+        self.g_send = torch.empty(W * self.cap, d, dtype=T, device=dev)
+        self.g_recv = torch.empty(W * self.cap, d, dtype=T, device=dev)
+        self.keys = torch.empty(W * self.cap, dtype=torch.int64, device=dev)
+        self.keys_sorted = torch.empty_like(self.keys)
+        self.lbase_t = torch.from_numpy(self.local_base).to(dev)
+
+    def _alloc_tables(self, tables):
+        cfg, d, W = self.cfg, self.cfg.embed_dim, self.world
+        self.local_rows, self.local_base = shard_layout(self.rows_host, W)
+        n_local = int(self.local_rows.sum())
+        if self._global_tables is not None:
+            # rows of field f owned by this rank: global rows rank, rank+W, ... (parity tests)
+            g = self._global_tables.to(torch.float32)
+            self.table = torch.zeros(n_local, d, device=self.dev)
+            for f in range(cfg.num_fields):
+                src = g[int(self.base_host[f]) + self.rank: int(self.base_host[f] + self.rows_host[f]): W]
+                self.table[int(self.local_base[f]): int(self.local_base[f]) + src.shape[0]] = src.to(self.dev)
+            self._global_tables = None
+        else:
+            gen = torch.Generator(device=self.dev).manual_seed(cfg.seed + 7919 * self.rank)
+            self.table = torch.empty(n_local, d, device=self.dev)
+            self.table.normal_(0.0, cfg.table_init_scale, generator=gen)
+        self.table_m = torch.zeros_like(self.table)
+        self.table_v = torch.zeros_like(self.table)
+        self.row_bits = ops.row_bits(n_local)
+
+    # ---- embedding halves of the step -----------------------------------------------------
+    def _embed_forward(self, ph, st, T):
+        c = self.cfg
+        F, d = c.num_fields, c.embed_dim
+        with ph("route_ids"):
+            ops.route_ids_padded(self.ids, F, self.rows_t, self.lbase_t, self.world, self.cap, self.send_rows,
+                                 self.inverse, self.send_counts, self.overflow)
+        with ph("a2a_ids"):
+            self.ex.all_to_all(self.recv_rows, self.send_rows)
+        with ph("embed_gather"):
+            cabi.call("rs_embed_gather_rows", self.table.data_ptr(), self.recv_rows.data_ptr(),
+                          self.recv_rows.numel(), d, self.rows_out.data_ptr(), T, None, self.keys.data_ptr(), st)
+        with ph("a2a_rows"):
+            self.ex.all_to_all(self.rows_in, self.rows_out)
+        with ph("unpermute"):
+            ops.permute_rows(self.rows_in, self.inverse, scatter=False, out=self.X.view(-1, d))
+
+    def _embed_backward(self, ph, st, T):
+        c = self.cfg
+        d = c.embed_dim
+        with ph("permute_grads"):
+            self.g_send.zero_()
+            ops.permute_rows(self.dX.view(-1, d), self.inverse, scatter=True, out=self.g_send)
+        with ph("a2a_grads"):
+            self.ex.all_to_all(self.g_recv, self.g_send)
+        with ph("sort_keys"):
+            ops.sort_keys(self.keys, self.row_bits, out=self.keys_sorted)
+        with ph("embed_segsum_adam"):
+            # local losses are means over the local batch: 1/W makes it the global-batch mean
+            ops.segsum_adam(self.table, self.table_m, self.table_v, self.g_recv, self.keys_sorted, c.lr_sparse,
+                            c.beta1, c.beta2, c.eps, self.adam_scalars, grad_scale=1.0 / self.world)
+
+    def _dense_sync(self, ph):
+        with ph("allreduce_dense"):
+            self.ex.all_reduce_mean(self.flat_g)
+
+    def check_overflow(self):
+        """Raise if any routing bucket ever exceeded its capacity (ids too skewed for `capacity_factor`)."""
+        if int(self.overflow.item()) != 0:
+            raise RuntimeError(f"routing bucket overflow: some owner received more than {self.cap} lookups from "
+                               "one rank; the step's result is invalid — re-create the trainer with a larger "
+                               "capacity_factor")

@@ -204,3 +204,29 @@ def test_dense_adam(cuda_dev):
                                 g.astype(np.float64), 1e-3, 0.9, 0.999, 1e-8, float(corr))
     assert_close(wt.cpu().numpy(), w2, REL_F32, "dense adam w")
     assert torch.equal(shadow, wt.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("n_b,F,world,cap", [(300, 39, 8, 1700), (1024, 39, 2, 20096), (77, 5, 4, 128),
+                                             (64, 1, 2, 16)])
+def test_route_ids_padded_bit_exact(cuda_dev, n_b, F, world, cap):
+    from oracle import oracle_np as onp
+    from recommendsystem_b200 import ops
+    rng = np.random.default_rng(n_b + F + world)
+    rows = rng.integers(10, 100000, size=F).astype(np.int64)
+    per = (rows + world - 1) // world
+    lbase = np.zeros(F, np.int64)
+    lbase[1:] = np.cumsum(per)[:-1]
+    ids = rng.integers(0, 2 ** 45, size=(n_b, F)).astype(np.int64)
+    ids[rng.random((n_b, F)) < 0.02] = -1
+    sr, inv, cnt, ovf = onp.route_ids_padded(ids, F, rows, lbase, world, cap)
+    g_sr, g_inv, g_cnt, g_ovf = ops.route_ids_padded(_t(ids, cuda_dev), F, _t(rows, cuda_dev), _t(lbase, cuda_dev),
+                                                     world, cap)
+    assert int(g_ovf.item()) == ovf
+    assert np.array_equal(g_cnt.cpu().numpy(), cnt)
+    assert np.array_equal(g_inv.cpu().numpy(), inv)
+    assert np.array_equal(g_sr.cpu().numpy(), sr)
+    # un-permute with dropped lookups (-1) yields zero rows; scatter skips them
+    src = torch.randn(world * cap, 16, device=cuda_dev)
+    got = ops.permute_rows(src, g_inv, scatter=False).cpu().numpy()
+    ref = np.where((inv >= 0)[:, None], src.cpu().numpy()[np.maximum(inv, 0)], 0)
+    assert np.array_equal(got, ref)
