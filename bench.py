@@ -175,6 +175,17 @@ def algorithmic(phase, B, act_bytes, n_unique):
     return t.get(phase, (0, 0))
 
 
+def _finish(world, dist):
+    """Multi-rank teardown: tearing the NCCL communicator down while captured graphs still
+    reference it can block, so synchronise, flush and leave without running destructors."""
+    import torch
+    torch.cuda.synchronize()
+    if world > 1:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def run_own(args):
     import numpy as np
     import torch
@@ -258,8 +269,7 @@ def run_own(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world, dist)
         return
 
     pk = peaks()
@@ -308,9 +318,8 @@ def run_own(args):
         "clocks": clk, "roofline": roof, "embed_roofline": embed, "kernels": kernels,
         "cpu_baseline": cpu, "loss": loss_dev, "loss_e2e_last": last,
     }
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(out), flush=True)
+    _finish(world, dist)
 
 
 def main():

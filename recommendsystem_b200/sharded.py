@@ -153,6 +153,14 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
         with ph("allreduce_dense"):
             self.ex.all_reduce_mean(self.flat_g)
 
+    def capture(self):
+        """Capture the sharded step (collectives included).  The warm-up launches run on whatever
+        the static id buffer holds (zeros unless the caller filled it), which may legitimately
+        overflow the buckets; the flag is cleared afterwards so it reports real steps only."""
+        g = super().capture()
+        self.overflow.zero_()
+        return g
+
     def check_overflow(self):
         """Raise if any routing bucket ever exceeded its capacity (ids too skewed for `capacity_factor`)."""
         if int(self.overflow.item()) != 0:

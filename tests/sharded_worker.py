@@ -33,11 +33,13 @@ def main():
     sh = ShardedAutoIntTrainer(AutoIntConfig(batch=b, **kw), dev, global_tables=torch.from_numpy(table))
     dense0 = sh.dense_state()
     steps = 3
-    if use_graph:
-        # capture launches two throw-away steps on the zero-filled static inputs; the reference
-        # trainer below replays exactly the same sequence
-        sh.capture()
     lo, hi = rank * b, (rank + 1) * b
+    if use_graph:
+        # capture launches two extra steps on whatever the static input buffers hold: fill them
+        # with the real batch; the reference trainer below replays the same two extra steps
+        sh.ids.copy_(torch.from_numpy(ids_all[lo:hi]))
+        sh.labels.copy_(torch.from_numpy(y_all[lo:hi]))
+        sh.capture()
     losses = []
     for _ in range(steps):
         l = sh.step(torch.from_numpy(ids_all[lo:hi]).to(dev), torch.from_numpy(y_all[lo:hi]).to(dev))
@@ -54,10 +56,8 @@ def main():
         ref = AutoIntTrainer(AutoIntConfig(batch=world * b, **kw), dev, tables=torch.from_numpy(table),
                              dense_init=dense0)
         if use_graph:
-            z_ids = torch.zeros(world * b, F, dtype=torch.int64, device=dev)
-            z_y = torch.zeros(world * b, 1, device=dev)
             for _ in range(2):
-                ref.step(z_ids, z_y)
+                ref.step(torch.from_numpy(ids_all).to(dev), torch.from_numpy(y_all).to(dev))
         ref_losses = []
         for _ in range(steps):
             ref_losses.append(float(ref.step(torch.from_numpy(ids_all).to(dev), torch.from_numpy(y_all).to(dev))))
@@ -87,8 +87,11 @@ def main():
         check("table shards after steps", worst <= 1e-5, f"rel {worst:.2e}")
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, src=0)
-    dist.destroy_process_group()
-    sys.exit(0 if int(flag.item()) == 1 else 1)
+    code = 0 if int(flag.item()) == 1 else 1
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(code)     # captured graphs still hold the NCCL communicator: skip destructor teardown
 
 
 if __name__ == "__main__":

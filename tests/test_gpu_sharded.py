@@ -18,7 +18,7 @@ def test_sharded_matches_single_gpu(mode):
     n = 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(HERE, "sharded_worker.py"), mode]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     print(r.stdout[-4000:])
     print(r.stderr[-4000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
