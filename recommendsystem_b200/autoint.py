@@ -166,6 +166,7 @@ class AutoIntTrainer:
             self.xT = torch.zeros(wmax, B, dtype=torch.bfloat16, device=self.dev)
             self.dyT = torch.zeros(wmax, B, dtype=torch.bfloat16, device=self.dev)
             self._refresh_wt()
+        self.side = torch.cuda.Stream(device=self.dev)
         self.graph = None
         self.timer = None               # set to a PhaseTimer for an instrumented (eager) step
         n_ws = max(cabi.load().rs_interacting_workspace_bytes(B, F, d, U),
@@ -238,6 +239,13 @@ class AutoIntTrainer:
         ph = lambda name: _Phase(self.timer, name)
         # K1: gather (+ sort keys emitted for the backward)
         self._embed_forward(ph, st, T)
+        # the key sort only needs the forward's keys: run it on the side stream, hidden behind the
+        # dense forward/backward (a parallel branch of the captured graph)
+        main = torch.cuda.current_stream(self.dev)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            with ph("sort_keys"):
+                ops.sort_keys(self.keys, self.row_bits, out=self.keys_sorted)
         # K4: InteractingLayer forward
         with ph("interacting_fwd"):
             # writes Flatten(A) straight into its columns of the concat buffer Z (autoint:36,45)
@@ -270,12 +278,16 @@ class AutoIntTrainer:
         assert self.spec[1][2] == nW and self.spec[2][2] == nW + 4 * U and self.spec[3][2] == nW + 5 * U
         with ph("interacting_bwd"):
             self._interacting_bwd(dparams, st, T)
+        # all dense gradients exist now: their all-reduce (multi-GPU) overlaps the embedding backward
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            self._dense_sync(ph)
         with ph("mlp_dgrad_x"):
             ops.gemm(self.dH[0], self._w("mlp_W0"), self.dX.view(B, F * d), epilogue=E.EPI_ACCUM, transB=True)
         # K3: sparse Adam on touched rows; dense Adam on the flat buffer
         ops.adam_advance(self.adam_scalars, c.beta1, c.beta2)
-        self._embed_backward(ph, st, T)
-        self._dense_sync(ph)
+        self._embed_backward(ph, st, T, main)
+        main.wait_stream(self.side)
         with ph("dense_adam"):
             ops.dense_adam(self.flat, self.flat_m, self.flat_v, self.flat_g, c.lr_dense, c.beta1, c.beta2, c.eps,
                            self.adam_scalars, self.flat_bf16)
@@ -291,10 +303,9 @@ class AutoIntTrainer:
                       self.rows_t.data_ptr(), n, c.num_fields, c.embed_dim, self.X.data_ptr(), T,
                       self.keys.data_ptr(), None, st)
 
-    def _embed_backward(self, ph, st, T):
+    def _embed_backward(self, ph, st, T, main):
         c = self.cfg
-        with ph("sort_keys"):
-            ops.sort_keys(self.keys, self.row_bits, out=self.keys_sorted)
+        main.wait_stream(self.side)            # sorted keys
         with ph("embed_segsum_adam"):
             ops.segsum_adam(self.table, self.table_m, self.table_v, self.dX.view(-1, c.embed_dim), self.keys_sorted,
                             c.lr_sparse, c.beta1, c.beta2, c.eps, self.adam_scalars)

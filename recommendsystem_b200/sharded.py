@@ -134,7 +134,7 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
         with ph("unpermute"):
             ops.permute_rows(self.rows_in, self.inverse, scatter=False, out=self.X.view(-1, d))
 
-    def _embed_backward(self, ph, st, T):
+    def _embed_backward(self, ph, st, T, main):
         c = self.cfg
         d = c.embed_dim
         with ph("permute_grads"):
@@ -142,8 +142,7 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
             ops.permute_rows(self.dX.view(-1, d), self.inverse, scatter=True, out=self.g_send)
         with ph("a2a_grads"):
             self.ex.all_to_all(self.g_recv, self.g_send)
-        with ph("sort_keys"):
-            ops.sort_keys(self.keys, self.row_bits, out=self.keys_sorted)
+        main.wait_stream(self.side)            # sorted keys + dense all-reduce (side stream)
         with ph("embed_segsum_adam"):
             # local losses are means over the local batch: 1/W makes it the global-batch mean
             ops.segsum_adam(self.table, self.table_m, self.table_v, self.g_recv, self.keys_sorted, c.lr_sparse,

@@ -35,8 +35,9 @@ def main():
     steps = 3
     lo, hi = rank * b, (rank + 1) * b
     if use_graph:
-        # capture launches two extra steps on whatever the static input buffers hold: fill them
-        # with the real batch; the reference trainer below replays the same two extra steps
+        # capture launches ONE real extra step (its warm-up; the captured launch itself does not
+        # execute) on whatever the static input buffers hold: fill them with the real batch; the
+        # reference trainer below replays the same extra step
         sh.ids.copy_(torch.from_numpy(ids_all[lo:hi]))
         sh.labels.copy_(torch.from_numpy(y_all[lo:hi]))
         sh.capture()
@@ -56,8 +57,7 @@ def main():
         ref = AutoIntTrainer(AutoIntConfig(batch=world * b, **kw), dev, tables=torch.from_numpy(table),
                              dense_init=dense0)
         if use_graph:
-            for _ in range(2):
-                ref.step(torch.from_numpy(ids_all).to(dev), torch.from_numpy(y_all).to(dev))
+            ref.step(torch.from_numpy(ids_all).to(dev), torch.from_numpy(y_all).to(dev))
         ref_losses = []
         for _ in range(steps):
             ref_losses.append(float(ref.step(torch.from_numpy(ids_all).to(dev), torch.from_numpy(y_all).to(dev))))

@@ -59,7 +59,9 @@ def test_autoint_step_fp32(cuda_dev, B, F, d, H, L, hidden, graph):
         assert_close(G[f"mlp_W{i}"], res["grads"]["mlp_W"][i], REL_F32, f"dmlp_W{i}")
         assert_close(G[f"mlp_b{i}"], res["grads"]["mlp_b"][i], REL_F32, f"dmlp_b{i}")
     assert_close(G["out_W"], res["grads"]["out_W"], REL_F32, "dout_W")
-    assert_close(G["out_b"], res["grads"]["out_b"], REL_F32, "dout_b")
+    # db = sum_b dz_b: B terms of magnitude <= 1/B that largely cancel -> bound the error by the
+    # summands' scale (1e-5 * 1/B * sqrt(B)) rather than by the cancelled sum
+    assert_close(G["out_b"], res["grads"]["out_b"], REL_F32, "dout_b", atol=1e-5 / np.sqrt(B))
     # optimizer: sparse Adam on touched rows (untouched rows bit-identical), dense Adam on the flat buffer
     _, _, corr = onp.adam_scalars(step0 + 1, cfg.beta1, cfg.beta2)
     w2, m2, v2 = onp.sparse_adam(f64(table0), f64(m0), f64(v0), rows.reshape(-1), tr.dX.cpu().numpy().reshape(B * F, d),
