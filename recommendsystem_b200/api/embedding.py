@@ -1,0 +1,152 @@
+"""Sparse embedding + sparse optimizer surface the reference reaches through `tensornet` (tn):
+    tn.feature_column.category_column / embedding_column, tn.layers.EmbeddingFeatures,
+    tn.core.Adam / tn.core.AdaGrad
+(call sites staytime/VideoDnn.py:217-244, rough_rank/model.py:89-115, rank/ctr/base_model.py:203-217).
+TensorNet itself is not vendored by the reference: table storage, the `bucket_size` semantics (ids
+are reduced mod bucket_size here) and the exact update rules are this repo's documented choices
+(DESIGN.md).  All tables of one EmbeddingFeatures layer live in ONE fp32 arena so a
+batch is served by a single gather launch and a single sorted-segment update launch."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .. import ops
+
+
+@dataclass
+class CategoryColumn:
+    key: str
+    bucket_size: int
+
+
+@dataclass
+class EmbeddingColumn:
+    categorical_column: CategoryColumn
+    dimension: int
+    combiner: Optional[str] = "mean"
+    seq_max_len: Optional[int] = None
+    name: Optional[str] = None
+
+    @property
+    def key(self):
+        return self.name or self.categorical_column.key
+
+
+def category_column(key, bucket_size):
+    return CategoryColumn(str(key), int(bucket_size))
+
+
+def embedding_column(categorical_column, dimension, combiner="mean", seq_max_len=None, name=None):
+    return EmbeddingColumn(categorical_column, int(dimension), combiner, seq_max_len, name)
+
+
+class Adam:
+    """tn.core.Adam(learning_rate, beta1, beta2, epsilon) — sparse rows touched by the batch."""
+
+    def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8):
+        self.learning_rate, self.beta1, self.beta2, self.epsilon = learning_rate, beta1, beta2, epsilon
+
+
+class AdaGrad:
+    """tn.core.AdaGrad(learning_rate, initial_g2sum, initial_scale[, feature_drop_show]).
+    One g2sum scalar per row (TensorNet style); rows are initialised N(0,1) * initial_scale."""
+
+    def __init__(self, learning_rate=0.01, initial_g2sum=0, initial_scale=1, epsilon=1e-8, feature_drop_show=-1,
+                 per_element=False):
+        self.learning_rate, self.initial_g2sum, self.initial_scale = learning_rate, initial_g2sum, initial_scale
+        self.epsilon, self.per_element = epsilon, per_element
+
+
+class EmbeddingFeatures:
+    """EmbeddingFeatures(embedding_columns, sparse_opt, name)(inputs: dict[key -> ids]) ->
+    dict[column key -> [B, d]]  (combiner='mean', dense [B] or [B, bag] ids; id < 0 = padding) or
+    ([B, T, d], mask [B, T]) for `combiner=None, seq_max_len=T` sequence columns.
+
+    `backward(grads)` applies the fused sorted-segment sparse optimizer to the rows the last
+    forward touched (the reference's server-side push); `grads` maps column key -> d(loss)/d(output)."""
+
+    def __init__(self, embedding_columns: List[EmbeddingColumn], sparse_opt, name="embedding", device="cuda:0",
+                 out_dtype=torch.float32, seed=0):
+        self.cols = list(embedding_columns)
+        self.opt = sparse_opt
+        self.dev = torch.device(device)
+        dims = {c.dimension for c in self.cols}
+        if len(dims) != 1:
+            raise ValueError("one EmbeddingFeatures layer holds columns of a single dimension (one arena)")
+        self.d = dims.pop()
+        self.out_dtype = out_dtype
+        rows = np.asarray([c.categorical_column.bucket_size for c in self.cols], np.int64)
+        self.base = np.concatenate([[0], np.cumsum(rows)[:-1]]).astype(np.int64)
+        self.rows = rows
+        total = int(rows.sum())
+        gen = torch.Generator(device=self.dev).manual_seed(seed)
+        scale = getattr(sparse_opt, "initial_scale", 0.1) if isinstance(sparse_opt, AdaGrad) else 0.1
+        self.table = torch.empty(total, self.d, device=self.dev).normal_(0.0, float(scale), generator=gen)
+        if isinstance(sparse_opt, Adam):
+            self.m, self.v = torch.zeros_like(self.table), torch.zeros_like(self.table)
+            self.scalars = torch.zeros(4, device=self.dev)
+        elif isinstance(sparse_opt, AdaGrad):
+            shape = (total, self.d) if sparse_opt.per_element else (total,)
+            self.g2sum = torch.full(shape, float(sparse_opt.initial_g2sum), device=self.dev)
+        else:
+            raise TypeError("sparse_opt must be api.embedding.Adam or AdaGrad")
+        self.row_bits = ops.row_bits(total)
+        self._last = None
+
+    def __call__(self, inputs: Dict[str, torch.Tensor]):
+        out, plan = {}, []
+        for ci, c in enumerate(self.cols):
+            ids = inputs[c.categorical_column.key].to(self.dev, torch.int64)
+            base = torch.tensor([int(self.base[ci])], device=self.dev)
+            rows = torch.tensor([int(self.rows[ci])], device=self.dev)
+            if c.combiner is None:                               # sequence column -> ([B,T,d], mask)
+                T = c.seq_max_len or ids.shape[1]
+                seq = ids[:, :T].contiguous()
+                emb, keys, arows = ops.embed_gather(self.table, seq.reshape(-1, 1), base, rows, self.out_dtype,
+                                                    want_keys=True, want_rows=True)
+                out[c.key] = (emb.view(seq.shape[0], T, self.d), (arows.view(seq.shape[0], T) >= 0))
+                plan.append((c.key, keys, 1.0, None))
+            else:
+                if ids.dim() == 1:
+                    ids = ids[:, None]
+                B, bag = ids.shape
+                emb, keys, arows = ops.embed_gather(self.table, ids.reshape(-1, 1).contiguous(), base, rows,
+                                                    torch.float32, want_keys=True, want_rows=True)
+                if bag == 1:
+                    out[c.key] = emb.view(B, self.d).to(self.out_dtype)
+                    plan.append((c.key, keys, 1.0, None))
+                else:                                            # combiner='mean' over the valid ids of the bag
+                    valid = (arows.view(B, bag) >= 0)
+                    cnt = valid.sum(1).clamp(min=1).to(torch.float32)
+                    out[c.key] = (emb.view(B, bag, self.d).sum(1) / cnt[:, None]).to(self.out_dtype)
+                    plan.append((c.key, keys, None, (bag, cnt)))
+        self._last = plan
+        return out
+
+    def backward(self, grads: Dict[str, torch.Tensor]):
+        """Push d(loss)/d(output) of every column: segment-sum per touched row + optimizer update."""
+        if self._last is None:
+            raise RuntimeError("EmbeddingFeatures.backward called before a forward")
+        if isinstance(self.opt, Adam):
+            ops.adam_advance(self.scalars, self.opt.beta1, self.opt.beta2)
+        for key, keys, scale, bag in self._last:
+            g = grads[key]
+            if isinstance(g, tuple):
+                g = g[0]
+            g = g.reshape(-1, self.d)
+            if bag is not None:                                   # mean combiner: 1/count per occurrence
+                b, cnt = bag
+                g = (g.float() / cnt[:, None]).repeat_interleave(b, dim=0)
+            g = g.contiguous()
+            ks = ops.sort_keys(keys, self.row_bits)
+            if isinstance(self.opt, Adam):
+                ops.segsum_adam(self.table, self.m, self.v, g, ks, self.opt.learning_rate, self.opt.beta1,
+                                self.opt.beta2, self.opt.epsilon, self.scalars)
+            else:
+                ops.segsum_adagrad(self.table, self.g2sum, g, ks, self.opt.learning_rate, self.opt.epsilon,
+                                   self.opt.per_element)
+        self._last = None

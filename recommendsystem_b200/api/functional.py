@@ -1,0 +1,122 @@
+"""torch.autograd.Function wrappers around the C-ABI kernels (forward AND backward are CUDA
+kernels from librs_b200.so; nothing here falls back to eager PyTorch math for the hot ops)."""
+from __future__ import annotations
+
+import torch
+
+from .. import cabi, ops
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("recommendsystem_b200 layers need CUDA tensors (no CPU fallback)")
+
+
+class InteractingFn(torch.autograd.Function):
+    """InteractingLayer.call (InteractingLayer.py:37-61) fused forward / backward."""
+
+    @staticmethod
+    def forward(ctx, x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res):
+        _require_cuda(x, Wqkvr)
+        x = x.contiguous()
+        y, saved = ops.interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res)
+        ctx.save_for_backward(x, saved if saved is not None else x.new_empty(0), Wqkvr, bqkvr, gamma, beta)
+        ctx.cfg = (ln_eps, H, L, use_res)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, saved, Wqkvr, bqkvr, gamma, beta = ctx.saved_tensors
+        ln_eps, H, L, use_res = ctx.cfg
+        dx, dW, db, dg, dbt = ops.interacting_bwd(x, saved if saved.numel() else None, Wqkvr, bqkvr, gamma, beta,
+                                                  ln_eps, H, L, dy.contiguous().to(x.dtype), use_res)
+        return dx, dW, db, dg, dbt, None, None, None, None
+
+
+class DinFn(torch.autograd.Function):
+    """DIN attention unit, mode A (din.py) or B (staytime/layer.py)."""
+
+    @staticmethod
+    def forward(ctx, mode, q, keys, values, seq_len, mask, W1, b1, W2, b2):
+        _require_cuda(q, keys)
+        q = q.contiguous()
+        if keys.stride(-1) != 1 or keys.stride(0) != keys.shape[1] * keys.stride(1):
+            keys = keys.contiguous()
+        if values is not None and (values.stride(-1) != 1 or values.stride(1) != keys.stride(1)):
+            values = values.contiguous()
+            keys = keys.contiguous()
+        out = ops.din_fwd(mode, q, keys, values, seq_len, mask, W1, b1.contiguous(), W2.contiguous(), b2.contiguous())
+        ctx.mode = mode
+        ctx.has_values = values is not None
+        ctx.save_for_backward(q, keys, values if values is not None else q.new_empty(0),
+                              seq_len if seq_len is not None else q.new_empty(0, dtype=torch.int32),
+                              mask if mask is not None else q.new_empty(0, dtype=torch.uint8), W1, b1, W2, b2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, keys, values, seq_len, mask, W1, b1, W2, b2 = ctx.saved_tensors
+        values = values if ctx.has_values else None
+        seq_len = seq_len if seq_len.numel() else None
+        mask = mask if mask.numel() else None
+        dq, dkeys, dvalues, dW1, db1, dW2, db2 = ops.din_bwd(ctx.mode, q, keys, values, seq_len, mask, W1,
+                                                             b1.contiguous(), W2.contiguous(), b2.contiguous(),
+                                                             dout.contiguous().to(q.dtype))
+        return None, dq, dkeys, (dvalues if ctx.has_values else None), None, None, dW1, db1, dW2, db2
+
+
+_ACT_EPI = {None: cabi.EPI_BIAS, "linear": cabi.EPI_BIAS, "relu": cabi.EPI_BIAS_RELU, "sigmoid": cabi.EPI_BIAS_SIGMOID}
+
+
+class DenseFn(torch.autograd.Function):
+    """y = act(x @ kernel[in,out] + bias) (tf.keras.layers.Dense / DNN.call, rough_rank/layer.py:100-109).
+    fp32 tensors -> FFMA parity kernel; bf16 activations -> tcgen05 kernel (weights cast to bf16 shadows,
+    fp32 master weights and fp32 weight gradients)."""
+
+    @staticmethod
+    def forward(ctx, x, kernel, bias, act):
+        _require_cuda(x, kernel)
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, x.shape[-1])
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        epi = _ACT_EPI[act]
+        if x2.dtype == torch.bfloat16:
+            wt = ops.transpose2d(kernel.to(torch.bfloat16).contiguous())          # [out,in] K-major
+            y = ops.gemm(x2, wt, bias=bias, epilogue=epi, transB=True)
+        else:
+            y = ops.gemm(x2, kernel.contiguous(), bias=bias, epilogue=epi)
+        ctx.act = act
+        ctx.save_for_backward(x2, kernel, y)
+        ctx.lead = lead
+        return y.reshape(*lead, kernel.shape[1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, kernel, y = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1]).to(y.dtype)
+        if dy2.stride(-1) != 1:
+            dy2 = dy2.contiguous()
+        if ctx.act == "relu":
+            dy2 = ops.act_bwd(dy2, y, 0)
+        elif ctx.act == "sigmoid":
+            dy2 = ops.act_bwd(dy2, y, 1)
+        db = ops.colsum(dy2)
+        if x2.dtype == torch.bfloat16:
+            w16 = kernel.to(torch.bfloat16).contiguous()                         # [in,out]: K-major B for dgrad
+            dx = ops.gemm(dy2, w16, transB=True) if ctx.needs_input_grad[0] else None
+            dW = ops.gemm(ops.transpose2d(x2), ops.transpose2d(dy2), transB=True, out_dtype=torch.float32)
+        else:
+            dx = ops.gemm(dy2, kernel.contiguous(), transB=True) if ctx.needs_input_grad[0] else None
+            dW = ops.gemm(x2, dy2, transA=True)
+        dx = dx.reshape(*ctx.lead, kernel.shape[0]) if dx is not None else None
+        return dx, dW.to(kernel.dtype), db.to(kernel.dtype), None
+
+
+def dense(x, kernel, bias, activation=None):
+    if activation == "softmax":
+        return torch.softmax(DenseFn.apply(x, kernel, bias, None), dim=-1)
+    if activation not in _ACT_EPI:
+        raise ValueError(f"unsupported activation {activation!r}")
+    return DenseFn.apply(x, kernel, bias, activation)
