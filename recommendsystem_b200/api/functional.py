@@ -82,7 +82,13 @@ class DenseFn(torch.autograd.Function):
         if x2.stride(-1) != 1:
             x2 = x2.contiguous()
         epi = _ACT_EPI[act]
-        if x2.dtype == torch.bfloat16:
+        K, N = kernel.shape
+        # the tensor-core kernel needs 16-byte TMA strides; narrow layers (heads, gates) use the fp32 kernel
+        ctx.tc = x2.dtype == torch.bfloat16 and K % 8 == 0 and N % 8 == 0
+        ctx.in_dtype = x2.dtype
+        if x2.dtype == torch.bfloat16 and not ctx.tc:
+            x2 = x2.float()
+        if ctx.tc:
             wt = ops.transpose2d(kernel.to(torch.bfloat16).contiguous())          # [out,in] K-major
             y = ops.gemm(x2, wt, bias=bias, epilogue=epi, transB=True)
         else:
@@ -90,7 +96,7 @@ class DenseFn(torch.autograd.Function):
         ctx.act = act
         ctx.save_for_backward(x2, kernel, y)
         ctx.lead = lead
-        return y.reshape(*lead, kernel.shape[1])
+        return y.reshape(*lead, kernel.shape[1]).to(ctx.in_dtype)
 
     @staticmethod
     def backward(ctx, dy):
@@ -103,14 +109,20 @@ class DenseFn(torch.autograd.Function):
         elif ctx.act == "sigmoid":
             dy2 = ops.act_bwd(dy2, y, 1)
         db = ops.colsum(dy2)
-        if x2.dtype == torch.bfloat16:
+        if ctx.tc:
             w16 = kernel.to(torch.bfloat16).contiguous()                         # [in,out]: K-major B for dgrad
             dx = ops.gemm(dy2, w16, transB=True) if ctx.needs_input_grad[0] else None
-            dW = ops.gemm(ops.transpose2d(x2), ops.transpose2d(dy2), transB=True, out_dtype=torch.float32)
+            M = x2.shape[0]
+            Mp = (M + 7) // 8 * 8                                                # 16-byte rows for TMA
+            xT = torch.zeros(x2.shape[1], Mp, dtype=x2.dtype, device=x2.device)
+            dyT = torch.zeros(dy2.shape[1], Mp, dtype=x2.dtype, device=x2.device)
+            ops.transpose2d(x2, xT[:, :M])
+            ops.transpose2d(dy2, dyT[:, :M])
+            dW = ops.gemm(xT[:, :M], dyT[:, :M], transB=True, out_dtype=torch.float32)
         else:
             dx = ops.gemm(dy2, kernel.contiguous(), transB=True) if ctx.needs_input_grad[0] else None
             dW = ops.gemm(x2, dy2, transA=True)
-        dx = dx.reshape(*ctx.lead, kernel.shape[0]) if dx is not None else None
+        dx = dx.reshape(*ctx.lead, kernel.shape[0]).to(ctx.in_dtype) if dx is not None else None
         return dx, dW.to(kernel.dtype), db.to(kernel.dtype), None
 
 

@@ -148,7 +148,7 @@ def test_crossnet_deepcross_fm_similarity(cuda_dev):
     assert_close(f64(y), c, REL_F32, "DeepCrossLayer")
     e = torch.randn(5, 7, 16, device=cuda_dev)
     fm = FMLayer()(e)
-    ref = 0.5 * ((f64(e).sum(1) ** 2) - (f64(e) ** 2).sum(1))
+    ref = 0.5 * ((f64(e).sum(1) ** 2) - (f64(e) ** 2).sum(1)).sum(-1, keepdims=True)   # [B,1]
     assert_close(f64(fm), ref, REL_F32, "FMLayer")
     with pytest.raises(ValueError):
         FMLayer()(x)
