@@ -11,6 +11,9 @@ namespace rs {
   int interacting_bwd_##DD##_##UU##_##HH(const IBwdArgs& a);
 RS_INTERACT_SHAPES(RS_DECL)
 #undef RS_DECL
+// tensor-core (tcgen05) path, interacting_tc.cu
+bool interacting_tc_supported(int F, int D, int U, int H, int dtype);
+int interacting_tc_fwd(const IFwdArgs& a);
 }  // namespace rs
 
 using namespace rs;
@@ -32,12 +35,12 @@ int rs_interacting_fwd(const void* x, int64_t x_ld, int64_t x_bs, int dtype, con
   RS_REQUIRE(F <= 256, "interacting_fwd: F=%d > 256 fields not supported", F);
   RS_REQUIRE(dtype == RS_F32 || dtype == RS_BF16, "interacting_fwd: bad dtype");
   RS_REQUIRE(x_ld % 4 == 0 && y_ld % 4 == 0, "interacting_fwd: leading dims must be multiples of 4");
-  (void)compute_bf16;
   if (x_bs == 0) x_bs = (int64_t)F * x_ld;
   if (y_bs == 0) y_bs = (int64_t)F * y_ld;
   RS_REQUIRE(x_bs % 4 == 0 && y_bs % 4 == 0, "interacting_fwd: batch strides must be multiples of 4");
   IFwdArgs a{x, x_ld, x_bs, Wqkvr, bqkvr, ln_gamma, ln_beta, ln_eps, y, y_ld, y_bs, saved, B, F, L, use_res,
              dtype, as_stream(stream)};
+  if (compute_bf16 && interacting_tc_supported(F, D, U, H, dtype)) return interacting_tc_fwd(a);
 #define RS_CASE(DD, UU, HH) \
   if (D == DD && U == UU && H == HH) return interacting_fwd_##DD##_##UU##_##HH(a);
   RS_INTERACT_SHAPES(RS_CASE)

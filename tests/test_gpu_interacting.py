@@ -82,3 +82,29 @@ def test_interacting_unsupported_shape_raises(cuda_dev):
     with pytest.raises(cabi.RsError):
         ops.interacting_fwd(x, torch.zeros(24, 96, device=cuda_dev), torch.zeros(96, device=cuda_dev),
                             torch.ones(24, device=cuda_dev), torch.zeros(24, device=cuda_dev), 1e-3, 2, 1)
+
+
+@pytest.mark.parametrize("B,F,L", [(1, 39, 1), (3, 39, 1), (5, 39, 3), (1000, 39, 3), (64, 33, 2), (7, 40, 1)])
+@pytest.mark.parametrize("use_res", [True, False])
+def test_interacting_tc_fwd(cuda_dev, B, F, L, use_res):
+    """tcgen05 forward (compute_bf16=1): bf16 projection operands, tf32 QK^T, bf16 P.V, fp32 accumulation
+    and fp32 softmax / LayerNorm — against the fp64 oracle on the same bf16 inputs (1e-2 bf16 bar; the
+    bf16 rounding of W and P inside the kernel is part of what the bar covers)."""
+    from oracle import oracle_np as onp
+    from recommendsystem_b200 import ops
+    D = U = 16
+    H = 2
+    rng = np.random.default_rng(B + F + L)
+    W, b, gamma, beta = interacting_params(rng, D, U)
+    xt = _t(rng.standard_normal((B, F, D)).astype(np.float32), cuda_dev, torch.bfloat16)
+    f64 = lambda a: a.astype(np.float64)
+    ref = onp.interacting_fwd(f64(xt.float().cpu().numpy()), f64(W), f64(b), f64(gamma), f64(beta), 1e-3, H, L, use_res)
+    Wt, bt, gt, bet = (_t(a, cuda_dev) for a in (W, b, gamma, beta))
+    y, saved = ops.interacting_fwd(xt, Wt, bt, gt, bet, 1e-3, H, L, use_res, compute_bf16=True)
+    y0, _ = ops.interacting_fwd(xt, Wt, bt, gt, bet, 1e-3, H, L, use_res, compute_bf16=False)
+    from util import rel_err
+    print("tc vs oracle", rel_err(y.float().cpu().numpy(), ref), "ffma vs oracle", rel_err(y0.float().cpu().numpy(), ref))
+    assert_close(y.float().cpu().numpy(), ref, REL_BF16, "tc fwd")
+    if L > 1:
+        ref1 = onp.interacting_fwd(f64(xt.float().cpu().numpy()), f64(W), f64(b), f64(gamma), f64(beta), 1e-3, H, 1, use_res)
+        assert_close(saved[0].cpu().numpy().reshape(B, F, U), ref1, REL_BF16, "saved[0]")
