@@ -263,7 +263,8 @@ def route_ids_padded(ids, F, rows, local_base, world, capacity):
 # ------------------------------------------------------- K4 InteractingLayer
 
 
-def interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res=True, keep_cache=False):
+def interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res=True, keep_cache=False,
+                    iter_inputs=None):
     """InteractingLayer.call (InteractingLayer.py:37-61; duplicate at
     rank/multi_head/interacting_layer.py).  Wqkvr = [Wq|Wk|Wv|Wr] ([D,4U], Keras
     [in,out] kernels side by side).  The four Dense(relu) layers and the
@@ -275,7 +276,12 @@ def interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res=True, ke
     B, F, _ = x.shape
     out = x
     cache = []
-    for _ in range(L):
+    for it in range(L):
+        if iter_inputs is not None and it > 0:
+            # evaluate iteration `it` at a GIVEN input (the activations an implementation stored for
+            # its backward) instead of this function's own chain — used to check a backward pass
+            # against the exact gradient at the same stored activations
+            out = np.asarray(iter_inputs[it - 1], dtype=x.dtype).reshape(x.shape[0], x.shape[1], -1)
         z = out @ Wqkvr + bqkvr                       # :42-46 (pre-activation)
         a = relu(z)
         q, k, v, r = a[..., :U], a[..., U:2 * U], a[..., 2 * U:3 * U], a[..., 3 * U:]
@@ -295,12 +301,14 @@ def interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res=True, ke
     return (out, cache) if keep_cache else out
 
 
-def interacting_bwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, dy, use_res=True):
-    """Manual backward of interacting_fwd.  Returns dx, dW[D,4U], db[4U], dgamma, dbeta."""
+def interacting_bwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, dy, use_res=True, iter_inputs=None):
+    """Manual backward of interacting_fwd.  Returns dx, dW[D,4U], db[4U], dgamma, dbeta.
+    iter_inputs: optional stored inputs of iterations 1..L-1 (see interacting_fwd)."""
     U = Wqkvr.shape[1] // 4
     dh = U // H
     B, F, _ = x.shape
-    _, cache = interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res, keep_cache=True)
+    _, cache = interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res, keep_cache=True,
+                               iter_inputs=iter_inputs)
     dW = np.zeros_like(Wqkvr)
     db = np.zeros_like(bqkvr)
     dgamma = np.zeros_like(gamma)
