@@ -205,15 +205,24 @@ int rs_permute_rows(const void* src, void* out, const int32_t* index, int64_t n,
  * element (b,f,c) lives at ptr[b*bs + f*ld + c] (ld = field stride, bs = sample
  * stride in elements; bs = 0 means F*ld), so the layer can read / write the
  * Flatten()ed [B, F*U] columns of a wider concat buffer in place (autoint:36,45).
- * `saved` (training): fp32 [L-1, B*F, U], the input of every iteration after
- * the first (kept in fp32 whatever `dtype` is, so a bf16 run rounds only at the
- * layer's input and output); the backward recomputes everything else.  May be
- * NULL for inference or L == 1.  dtype applies to x, y (and dy, dx).
+ * `saved` (training): rs_interacting_saved_bytes(B,F,U,L) bytes = fp32 [L, B*F, U],
+ * written by the forward and handed unchanged to the backward of the SAME
+ * compute_bf16 mode; its content is private to that pair (kept in fp32 whatever
+ * `dtype` is, so a bf16 run rounds only at the layer's input and output):
+ *   FFMA kernels       : slots 0..L-2 = the input of every iteration after the first;
+ *   tensor-core kernels: slots 0..L-1 = the pre-LayerNorm activations relu(o + r) of
+ *                        every iteration (the backward differentiates ReLU/LayerNorm at
+ *                        them and re-derives iteration inputs as LayerNorm(slot)).
+ * The backward recomputes everything else.  NULL = inference (forward only; the FFMA
+ * backward also accepts NULL when L == 1).  dtype applies to x, y (and dy, dx).
  * Parameters are fp32.
- * compute_bf16 != 0 runs the projections on tcgen05 tensor cores (bf16
- * operands, fp32 TMEM accumulators); 0 = fp32 FFMA everywhere (parity mode).
+ * compute_bf16 != 0 runs every contraction of the layer on tcgen05 tensor cores (tf32
+ * projections / QK^T, bf16 P.V and gradient products, fp32 TMEM accumulators) for the
+ * shapes built (D = U = 16, H = 2, 32 < F <= 40) and falls back to FFMA arithmetic for the
+ * others; 0 = fp32 FFMA everywhere (parity mode).
  */
 size_t rs_interacting_workspace_bytes(int B, int F, int D, int U);
+size_t rs_interacting_saved_bytes(int B, int F, int U, int L);
 int rs_interacting_fwd(const void* x, int64_t x_ld, int64_t x_bs, int dtype,
                        const float* Wqkvr, const float* bqkvr,
                        const float* ln_gamma, const float* ln_beta, float ln_eps,

@@ -264,7 +264,7 @@ def route_ids_padded(ids, F, rows, local_base, world, capacity):
 
 
 def interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res=True, keep_cache=False,
-                    iter_inputs=None):
+                    iter_inputs=None, stored_act=None):
     """InteractingLayer.call (InteractingLayer.py:37-61; duplicate at
     rank/multi_head/interacting_layer.py).  Wqkvr = [Wq|Wk|Wv|Wr] ([D,4U], Keras
     [in,out] kernels side by side).  The four Dense(relu) layers and the
@@ -282,6 +282,10 @@ def interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res=True, ke
             # its backward) instead of this function's own chain — used to check a backward pass
             # against the exact gradient at the same stored activations
             out = np.asarray(iter_inputs[it - 1], dtype=x.dtype).reshape(x.shape[0], x.shape[1], -1)
+        if stored_act is not None and it > 0:
+            # same idea when the implementation stored the pre-LayerNorm activations `act` of every
+            # iteration (the tcgen05 path): iteration `it` starts from LayerNorm(stored act of it-1)
+            out = layer_norm(np.asarray(stored_act[it - 1], dtype=x.dtype).reshape(B, F, U), gamma, beta, ln_eps)
         z = out @ Wqkvr + bqkvr                       # :42-46 (pre-activation)
         a = relu(z)
         q, k, v, r = a[..., :U], a[..., U:2 * U], a[..., 2 * U:3 * U], a[..., 3 * U:]
@@ -294,6 +298,10 @@ def interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res=True, ke
         o = (p @ vh).transpose(1, 2, 0, 3).reshape(B, F, U)  # :55-56
         t = o + r if use_res else o                         # :57-58
         act = relu(t)                                       # :59
+        if stored_act is not None:
+            # ... and its LayerNorm/ReLU are differentiated at the stored `act` itself
+            act = np.asarray(stored_act[it], dtype=x.dtype).reshape(B, F, U)
+            t = act
         y = layer_norm(act, gamma, beta, ln_eps)            # :60
         if keep_cache:
             cache.append(dict(x=out, z=z, p=p, qh=qh, kh=kh, vh=vh, t=t, act=act))
@@ -301,14 +309,16 @@ def interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res=True, ke
     return (out, cache) if keep_cache else out
 
 
-def interacting_bwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, dy, use_res=True, iter_inputs=None):
+def interacting_bwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, dy, use_res=True, iter_inputs=None,
+                    stored_act=None):
     """Manual backward of interacting_fwd.  Returns dx, dW[D,4U], db[4U], dgamma, dbeta.
-    iter_inputs: optional stored inputs of iterations 1..L-1 (see interacting_fwd)."""
+    iter_inputs: optional stored inputs of iterations 1..L-1; stored_act: optional stored
+    pre-LayerNorm activations of iterations 0..L-1 (see interacting_fwd)."""
     U = Wqkvr.shape[1] // 4
     dh = U // H
     B, F, _ = x.shape
     _, cache = interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res, keep_cache=True,
-                               iter_inputs=iter_inputs)
+                               iter_inputs=iter_inputs, stored_act=stored_act)
     dW = np.zeros_like(Wqkvr)
     db = np.zeros_like(bqkvr)
     dgamma = np.zeros_like(gamma)

@@ -148,7 +148,7 @@ class AutoIntTrainer:
         self.X = e(B, F, d)
         self.keys = torch.empty(B * F, dtype=torch.int64, device=self.dev)
         self.keys_sorted = torch.empty_like(self.keys)
-        self.saved = e(max(cfg.layer_num - 1, 1), B * F, U, dtype=torch.float32)
+        self.saved = e(cfg.layer_num, B * F, U, dtype=torch.float32)     # rs_interacting_saved_bytes
         self.H = [e(B, w) for w in cfg.mlp_hidden[:-1]]
         self.Z = e(B, self.zw)
         self.p_raw = e(B, 1)
@@ -252,7 +252,7 @@ class AutoIntTrainer:
             cabi.call("rs_interacting_fwd", self.X.data_ptr(), d, 0, T, P["Wqkvr"].data_ptr(),
                       P["bqkvr"].data_ptr(), P["gamma"].data_ptr(), P["beta"].data_ptr(), c.ln_eps,
                       self.Z[:, self.n_deep:].data_ptr(), U, self.zw,
-                      self.saved.data_ptr() if c.layer_num > 1 else None, B, F, d, U,
+                      self.saved.data_ptr(), B, F, d, U,
                       c.head_num, c.layer_num, int(c.use_res), int(self.act_dtype == torch.bfloat16), st)
         # K5: MLP tower; last hidden layer lands in Z[:, :n_deep], Flatten(A) in Z[:, n_deep:]
         Xf = self.X.view(B, F * d)
@@ -318,7 +318,7 @@ class AutoIntTrainer:
         F, d, U, B = c.num_fields, c.embed_dim, c.unit_num, c.batch
         P = self.P
         # dA is read in place from the Z-gradient columns [n_deep:] (sample stride zw)
-        cabi.call("rs_interacting_bwd", self.X.data_ptr(), d, 0, self.saved.data_ptr() if c.layer_num > 1 else None,
+        cabi.call("rs_interacting_bwd", self.X.data_ptr(), d, 0, self.saved.data_ptr(),
                   T, P["Wqkvr"].data_ptr(), P["bqkvr"].data_ptr(), P["gamma"].data_ptr(), P["beta"].data_ptr(),
                   c.ln_eps, self.dZ[:, self.n_deep:].data_ptr(), U, self.zw, self.dX.data_ptr(), d, 0,
                   dparams.data_ptr(), B, F, d, U, c.head_num, c.layer_num, int(c.use_res),

@@ -38,6 +38,7 @@ PROTOTYPES = {
     "rs_route_ids_padded": (_i, [_p, _i64, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "rs_permute_rows": (_i, [_p, _p, _p, _i64, _i, _i, _i, _p]),
     "rs_interacting_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "rs_interacting_saved_bytes": (_sz, [_i, _i, _i, _i]),
     "rs_interacting_fwd": (_i, [_p, _i64, _i64, _i, _p, _p, _p, _p, _f, _p, _i64, _i64, _p,
                                 _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "rs_interacting_bwd": (_i, [_p, _i64, _i64, _p, _i, _p, _p, _p, _p, _f, _p, _i64, _i64, _p, _i64, _i64, _p,

@@ -14,6 +14,7 @@ RS_INTERACT_SHAPES(RS_DECL)
 // tensor-core (tcgen05) path, interacting_tc.cu
 bool interacting_tc_supported(int F, int D, int U, int H, int dtype);
 int interacting_tc_fwd(const IFwdArgs& a);
+int interacting_tc_bwd(const IBwdArgs& a);
 }  // namespace rs
 
 using namespace rs;
@@ -23,6 +24,10 @@ extern "C" {
 size_t rs_interacting_workspace_bytes(int B, int F, int D, int U) {
   (void)B; (void)F;
   return (size_t)(sm_count() * 2) * (size_t)(D * 4 * U + 6 * U) * sizeof(float);
+}
+
+size_t rs_interacting_saved_bytes(int B, int F, int U, int L) {
+  return (size_t)L * (size_t)B * (size_t)F * (size_t)U * sizeof(float);
 }
 
 int rs_interacting_fwd(const void* x, int64_t x_ld, int64_t x_bs, int dtype, const float* Wqkvr,
@@ -62,13 +67,13 @@ int rs_interacting_bwd(const void* x, int64_t x_ld, int64_t x_bs, const void* sa
   RS_REQUIRE(dtype == RS_F32 || dtype == RS_BF16, "interacting_bwd: bad dtype");
   RS_REQUIRE(x_ld % 4 == 0 && dy_ld % 4 == 0 && dx_ld % 4 == 0,
              "interacting_bwd: leading dims must be multiples of 4");
-  (void)compute_bf16;
   if (x_bs == 0) x_bs = (int64_t)F * x_ld;
   if (dy_bs == 0) dy_bs = (int64_t)F * dy_ld;
   if (dx_bs == 0) dx_bs = (int64_t)F * dx_ld;
   RS_REQUIRE(x_bs % 4 == 0 && dy_bs % 4 == 0 && dx_bs % 4 == 0, "interacting_bwd: batch strides must be multiples of 4");
   IBwdArgs a{x, x_ld, x_bs, saved, Wqkvr, bqkvr, ln_gamma, ln_beta, ln_eps, dy, dy_ld, dy_bs, dx, dx_ld, dx_bs, dparams,
              B, F, L, use_res, dtype, ws, ws_bytes, as_stream(stream)};
+  if (compute_bf16 && interacting_tc_supported(F, D, U, H, dtype)) return interacting_tc_bwd(a);
 #define RS_CASE(DD, UU, HH) \
   if (D == DD && U == UU && H == HH) return interacting_bwd_##DD##_##UU##_##HH(a);
   RS_INTERACT_SHAPES(RS_CASE)

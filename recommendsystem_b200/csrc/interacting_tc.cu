@@ -7,7 +7,7 @@
 // the (sample, field) row and the row-wise softmax / residual / ReLU / LayerNorm need no
 // cross-thread traffic at all.  Per iteration of the layer_num loop (weights shared):
 //
-//   1. Z[128,4U]  = X[128,D] Wqkvr[D,4U]        kind::tf32 (fp32 operands as is), two MMAs of K = 8
+//   1. Z[128,4U]  = X[128,D] Wqkvr[D,4U]        kind::tf32, 3xTF32 split (fp32-grade), six MMAs of K = 8
 //      thread: tcgen05.ld its Z row, +bias, ReLU -> q, k, v, r
 //   2. S_h[128,128] = Q_h K_h^T  per head        kind::tf32, K = U/H = 8, one MMA per head
 //      (block diagonal in effect: a thread reads only the FP columns of its own sample)
@@ -25,14 +25,6 @@
 
 namespace rs {
 
-constexpr float ITC_LOG2E = 1.4426950408889634f;
-
-// byte offset of (row, 16-byte chunk c) in a no-swizzle tile whose rows hold NCH 16-byte chunks:
-// [row/8][chunk][row%8][16 B]
-template <int NCH>
-__device__ __forceinline__ uint32_t nosw_off(int row, int c) {
-  return (uint32_t)((row >> 3) * (NCH * 128) + c * 128 + (row & 7) * 16);
-}
 
 template <int D, int U, int H, int NCHF, typename T>
 __global__ void __launch_bounds__(128, 2)
@@ -48,12 +40,12 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
   // ---- shared memory carve-up (1024-byte aligned base for the swizzled P tiles)
   constexpr int P_BYTES = 128 * 256;             // [128 rows][128 keys] bf16
   constexpr int OFF_P = 0;                       // H buffers
-  constexpr int OFF_X = OFF_P + H * P_BYTES;     // [128][16] tf32, 4 chunks/row   8 KB
-  constexpr int OFF_V = OFF_X + 8192;            // [128 keys][16] bf16            4 KB
+  constexpr int OFF_X = OFF_P + H * P_BYTES;     // [128][x_hi(16) | x_lo(16)] tf32, 8 chunks/row  16 KB
+  constexpr int OFF_V = OFF_X + 16384;           // [128 keys][16] bf16            4 KB
   constexpr int OFF_Q = OFF_V + 4096;            // H x [128][8] tf32, 2 chunks/row
   constexpr int OFF_K = OFF_Q + H * 4096;
-  constexpr int OFF_W = OFF_K + H * 4096;        // [64 n][16 k] tf32              4 KB
-  constexpr int OFF_F = OFF_W + 4096;            // bias[64] gamma[16] beta[16] fp32
+  constexpr int OFF_W = OFF_K + H * 4096;        // W_hi | W_lo, each [64 n][16 k] tf32   8 KB
+  constexpr int OFF_F = OFF_W + 8192;            // bias[64] gamma[16] beta[16] fp32
   constexpr int OFF_BAR = OFF_F + (N4 + 2 * U) * 4;
   extern __shared__ uint8_t itc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(itc_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -75,11 +67,7 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
   }
   for (int i = tid; i < H * P_BYTES / 16; i += 128) reinterpret_cast<uint4*>(smem + OFF_P)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < N4 + 2 * U; i += 128) bs[i] = i < N4 ? bias[i] : (i < N4 + U ? gamma[i - N4] : beta[i - N4 - U]);
-  for (int i = tid; i < N4 * 4; i += 128) {      // B operand of the projection: row n, chunk c = k/4
-    const int n = i >> 2, c = i & 3;
-    *reinterpret_cast<float4*>(smem + OFF_W + nosw_off<4>(n, c)) =
-        make_float4(W[(c * 4 + 0) * N4 + n], W[(c * 4 + 1) * N4 + n], W[(c * 4 + 2) * N4 + n], W[(c * 4 + 3) * N4 + n]);
-  }
+  stage_w_3xtf32(smem + OFF_W, W, tid, 128);     // B operands of the projection
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -117,20 +105,16 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
     }
     float yv[U];
     for (int it = 0; it < L; ++it) {
-      // ---- 1. X tile (tf32: the fp32 row as is) -> Z = X W, two K = 8 steps
+      // ---- 1. X tile (3xTF32 split of the fp32 row) -> Z = X W, fp32-grade
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        *reinterpret_cast<float4*>(smem + OFF_X + nosw_off<4>(tid, c)) =
-            make_float4(xr[c * 4], xr[c * 4 + 1], xr[c * 4 + 2], xr[c * 4 + 3]);
+        stage_x4_3xtf32(smem + OFF_X, tid, c, xr[c * 4], xr[c * 4 + 1], xr[c * 4 + 2], xr[c * 4 + 3]);
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks)       // K step = 8 tf32 = 2 chunks = 256 B; rows of 4 chunks: SBO 512
-          tc_mma_tf32(tmem + TM_Z, make_nosw_desc(sbase + OFF_X + ks * 256, 128, 512),
-                      make_nosw_desc(sbase + OFF_W + ks * 256, 128, 512), ID_Z, ks ? 1u : 0u);
+        issue_proj_3xtf32(tmem + TM_Z, sbase + OFF_X, sbase + OFF_W, ID_Z);
         tc_commit(bar);
       }
       mbar_wait(bar, phase); phase ^= 1u;
@@ -260,26 +244,21 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
           for (int e = 0; e < DH; ++e) o[h * DH + e] = __uint_as_float(t16[h * DH + e]) * linv[h];
         }
         // residual, ReLU, LayerNorm (InteractingLayer.py:57-60)
-        float a[U], mean = 0.f;
+        float a[U], mean, rstd;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          a[u] = fmaxf(use_res ? o[u] + r[u] : o[u], 0.f);
-          mean += a[u];
-        }
-        mean *= (1.f / U);
-        float var = 0.f;
+        for (int u = 0; u < U; ++u) a[u] = fmaxf(use_res ? o[u] + r[u] : o[u], 0.f);
+        ln_row_stats<U>(a, eps, mean, rstd);
 #pragma unroll
-        for (int u = 0; u < U; ++u) var = fmaf(a[u] - mean, a[u] - mean, var);
-        const float rstd = rsqrtf(var * (1.f / U) + eps);
-#pragma unroll
-        for (int u = 0; u < U; ++u) yv[u] = fmaf((a[u] - mean) * rstd, gs[u], be[u]);
-      }
-      if (it + 1 < L) {
+        for (int u = 0; u < U; ++u) yv[u] = ln_apply(a[u], mean, rstd, gs[u], be[u]);
+        // saved for the backward: the pre-LayerNorm activations of EVERY iteration (the backward
+        // re-derives each iteration's input as LayerNorm(a) and differentiates ReLU/LayerNorm at a)
         if (active && saved) {
           float* sp = saved + ((int64_t)it * B * F + smp * F + f_loc) * U;
 #pragma unroll
-          for (int u = 0; u < U; u += 4) *reinterpret_cast<float4*>(sp + u) = make_float4(yv[u], yv[u + 1], yv[u + 2], yv[u + 3]);
+          for (int u = 0; u < U; u += 4) *reinterpret_cast<float4*>(sp + u) = make_float4(a[u], a[u + 1], a[u + 2], a[u + 3]);
         }
+      }
+      if (it + 1 < L) {
 #pragma unroll
         for (int u = 0; u < U; ++u) xr[u] = active ? yv[u] : 0.f;
       }
@@ -301,7 +280,7 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
 template <int NCHF, typename T>
 static int launch_itc_fwd(const IFwdArgs& a) {
   auto kern = interacting_tc_fwd_kernel<16, 16, 2, NCHF, T>;
-  constexpr int smem = 2 * 128 * 256 + 8192 + 4096 + 2 * 4096 + 2 * 4096 + 4096 + 96 * 4 + 64 + 1024;
+  constexpr int smem = 2 * 128 * 256 + 16384 + 4096 + 2 * 4096 + 2 * 4096 + 8192 + 96 * 4 + 64 + 1024;
   RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   constexpr int SPT = 128 / (NCHF * 8);
   const int ntiles = (a.B + SPT - 1) / SPT;

@@ -117,4 +117,75 @@ __device__ __forceinline__ void tc_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+constexpr float ITC_LOG2E = 1.4426950408889634f;
+
+// byte offset of (row, 16-byte chunk c) in a no-swizzle tile whose rows hold NCH 16-byte chunks:
+// [row/8][chunk][row%8][16 B].  The SAME bytes are a K-major operand (rows = M/N, chunks along K:
+// LBO = 128, SBO = NCH*128) and an MN-major operand (chunks along M/N, rows = K: SBO = 128,
+// LBO = NCH*128) — a tile written once can feed an MMA and its transpose.
+template <int NCH>
+__device__ __forceinline__ uint32_t nosw_off(int row, int c) {
+  return (uint32_t)((row >> 3) * (NCH * 128) + c * 128 + (row & 7) * 16);
+}
+
+// LayerNorm of one register row (InteractingLayer.py:60).  ONE definition, explicit fma/mul, shared by
+// the tcgen05 forward and backward so that the backward's recomputed iteration input is bit-identical
+// to what the forward fed to its next iteration.
+template <int U>
+__device__ __forceinline__ void ln_row_stats(const float (&a)[U], float eps, float& mean, float& rstd) {
+  float m = 0.f;
+#pragma unroll
+  for (int u = 0; u < U; ++u) m = __fadd_rn(m, a[u]);
+  m = __fmul_rn(m, 1.f / U);
+  float var = 0.f;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const float d = __fsub_rn(a[u], m);
+    var = __fmaf_rn(d, d, var);
+  }
+  mean = m;
+  rstd = rsqrtf(__fmaf_rn(var, 1.f / U, eps));
+}
+__device__ __forceinline__ float ln_apply(float a, float mean, float rstd, float gamma, float beta) {
+  return __fmaf_rn(__fmul_rn(__fsub_rn(a, mean), rstd), gamma, beta);
+}
+
+// 3xTF32 split: hi = the value with the 13 low mantissa bits cleared (exactly a tf32 number whatever
+// rounding the tensor core applies), lo = v - hi (exact in fp32; the MMA keeps its top 11 bits).
+// x.w ~ hi.Whi + lo.Whi + hi.Wlo to ~2^-21 relative: fp32-grade pre-activations, so the ReLU masks of
+// the projections agree with an fp32/fp64 evaluation of the layer.
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+// The projection Z[128, 64] = X[128, 16] W[16, 64] as six kind::tf32 MMAs (K = 8 each) over
+// A = [x_hi | x_lo] (no-swizzle, 8 chunks/row) and B = W_hi, W_lo ([64 n][16 k], 4 chunks/row each,
+// W_lo 4096 bytes after W_hi).
+__device__ __forceinline__ void issue_proj_3xtf32(uint32_t tmem_z, uint32_t x_addr, uint32_t w_addr, uint32_t idesc) {
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int ka = j < 4 ? j : j - 4;            // A K-step: 0,1 = hi ; 2,3 = lo
+    const int kb = j & 1;                        // B K-step
+    const uint32_t wb = w_addr + (j >= 4 ? 4096u : 0u);
+    tc_mma_tf32(tmem_z, make_nosw_desc(x_addr + ka * 256, 128, 1024), make_nosw_desc(wb + kb * 256, 128, 512), idesc,
+                j ? 1u : 0u);
+  }
+}
+// W[16][64] (row-major [in, out]) -> W_hi | W_lo operand tiles
+__device__ __forceinline__ void stage_w_3xtf32(uint8_t* w_smem, const float* __restrict__ W, int tid, int nthreads) {
+  for (int i = tid; i < 64 * 4; i += nthreads) {
+    const int n = i >> 2, c = i & 3;
+    float w[4], hi[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { w[e] = W[(c * 4 + e) * 64 + n]; hi[e] = tf32_hi(w[e]); }
+    *reinterpret_cast<float4*>(w_smem + nosw_off<4>(n, c)) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<float4*>(w_smem + 4096 + nosw_off<4>(n, c)) =
+        make_float4(w[0] - hi[0], w[1] - hi[1], w[2] - hi[2], w[3] - hi[3]);
+  }
+}
+// 4 consecutive x values of tile row `row` starting at column 4*c -> chunk c (hi) and chunk 4 + c (lo)
+__device__ __forceinline__ void stage_x4_3xtf32(uint8_t* x_smem, int row, int c, float a, float b, float cc, float d) {
+  const float ha = tf32_hi(a), hb = tf32_hi(b), hc = tf32_hi(cc), hd = tf32_hi(d);
+  *reinterpret_cast<float4*>(x_smem + nosw_off<8>(row, c)) = make_float4(ha, hb, hc, hd);
+  *reinterpret_cast<float4*>(x_smem + nosw_off<8>(row, 4 + c)) = make_float4(a - ha, b - hb, cc - hc, d - hd);
+}
+
 }  // namespace rs

@@ -178,7 +178,7 @@ def interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res=True, sa
     U = Wqkvr.shape[1] // 4
     _need(x.is_contiguous(), "x must be contiguous")
     y = torch.empty(B, F, U, dtype=x.dtype, device=x.device)
-    saved = torch.empty(L - 1, B * F, U, dtype=torch.float32, device=x.device) if (save and L > 1) else None
+    saved = torch.empty(L, B * F, U, dtype=torch.float32, device=x.device) if save else None   # rs_interacting_saved_bytes
     call("rs_interacting_fwd", _ptr(x), D, 0, _dt(x), _ptr(Wqkvr), _ptr(bqkvr), _ptr(gamma), _ptr(beta),
          ln_eps, _ptr(y), U, 0, _ptr(saved), B, F, D, U, H, L, int(use_res), int(compute_bf16), _stream())
     return y, saved

@@ -124,12 +124,12 @@ def test_autoint_step_bf16(cuda_dev):
     assert_close(tr.p_raw.float().cpu().numpy(), res["p_raw"], REL_BF16, "bf16 logits")
     g = lambda t: f64(t.float().cpu().numpy())
     # InteractingLayer backward on the bf16 dA it was given (the Z-gradient columns [n_deep:])
-    # ... evaluated at the activations the forward stored for it (`saved`): the layer's gradient is
+    # ... evaluated at the pre-LayerNorm activations the tcgen05 forward stored (`saved`): the layer's gradient is
     # ill-conditioned in its inputs, so the exact gradient AT THOSE activations is the
     # meaningful reference for the backward kernel
     dXi, dW, db, dg, dbt = onp.interacting_bwd(f64(Xb), P["Wqkvr"], P["bqkvr"], P["gamma"], P["beta"], cfg.ln_eps,
                                                H, L, g(tr.dZ[:, tr.n_deep:]).reshape(B, F, d),
-                                               iter_inputs=[f64(tr.saved[i].cpu().numpy()) for i in range(L - 1)])
+                                               stored_act=[f64(tr.saved[i].cpu().numpy()) for i in range(L)])
     W0 = f64(tr.P16["mlp_W0"].float().cpu().numpy() if False else P0["mlp_W0"])
     dX_ref = dXi + (g(tr.dH[0]) @ W0.T).reshape(B, F, d)
     assert_close(g(tr.dX), dX_ref, 2 * REL_BF16, "bf16 dX")

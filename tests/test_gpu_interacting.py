@@ -107,4 +107,44 @@ def test_interacting_tc_fwd(cuda_dev, B, F, L, use_res):
     assert_close(y.float().cpu().numpy(), ref, REL_BF16, "tc fwd")
     if L > 1:
         ref1 = onp.interacting_fwd(f64(xt.float().cpu().numpy()), f64(W), f64(b), f64(gamma), f64(beta), 1e-3, H, 1, use_res)
-        assert_close(saved[0].cpu().numpy().reshape(B, F, U), ref1, REL_BF16, "saved[0]")
+        # tensor-core mode saves the pre-LayerNorm activations; LayerNorm(saved[0]) is iteration 1's input
+        y1 = onp.layer_norm(f64(saved[0].cpu().numpy()).reshape(B, F, U), f64(gamma), f64(beta), 1e-3)
+        assert_close(y1, ref1, REL_BF16, "LayerNorm(saved[0])")
+
+
+@pytest.mark.parametrize("B,F,L", [(1, 39, 1), (3, 39, 1), (5, 39, 3), (1000, 39, 3), (64, 33, 2), (7, 40, 1)])
+@pytest.mark.parametrize("use_res", [True, False])
+def test_interacting_tc_bwd(cuda_dev, B, F, L, use_res):
+    """tcgen05 backward (compute_bf16=1) against the fp64 oracle gradient evaluated at the activations the
+    tcgen05 forward stored (`saved` = pre-LayerNorm activations), the point the kernel differentiates at.  db is checked per
+    q|k|v|r segment so that a wrong MMA is localised."""
+    from oracle import oracle_np as onp
+    from recommendsystem_b200 import ops
+    from util import rel_err
+    D = U = 16
+    H = 2
+    rng = np.random.default_rng(100 + B + F + L)
+    W, b, gamma, beta = interacting_params(rng, D, U)
+    gamma = (gamma + 0.1 * rng.standard_normal(U)).astype(np.float32)
+    beta = (beta + 0.1 * rng.standard_normal(U)).astype(np.float32)
+    b = (b + 0.1 * rng.standard_normal(4 * U)).astype(np.float32)
+    xt = _t(rng.standard_normal((B, F, D)).astype(np.float32), cuda_dev, torch.bfloat16)
+    dyt = _t(rng.standard_normal((B, F, U)).astype(np.float32), cuda_dev, torch.bfloat16)
+    f64 = lambda a: a.astype(np.float64)
+    Wt, bt, gt, bet = (_t(a, cuda_dev) for a in (W, b, gamma, beta))
+    y, saved = ops.interacting_fwd(xt, Wt, bt, gt, bet, 1e-3, H, L, use_res, compute_bf16=True)
+    acts = [f64(saved[i].cpu().numpy()) for i in range(L)]
+    rdx, rdW, rdb, rdg, rdbt = onp.interacting_bwd(f64(xt.float().cpu().numpy()), f64(W), f64(b), f64(gamma), f64(beta),
+                                                   1e-3, H, L, f64(dyt.float().cpu().numpy()), use_res, stored_act=acts)
+    dx, dW, db, dg, dbt = ops.interacting_bwd(xt, saved, Wt, bt, gt, bet, 1e-3, H, L, dyt, use_res, compute_bf16=True)
+    names = ["dx", "dW", "db", "dgamma", "dbeta"]
+    got = [t.float().cpu().numpy() for t in (dx, dW, db, dg, dbt)]
+    refs = [rdx, rdW, rdb, rdg, rdbt]
+    for n, a, r in zip(names, got, refs):
+        print(n, "tc", rel_err(a, r))
+    for i, seg in enumerate("qkvr"):
+        print("db", seg, rel_err(got[2][i * U:(i + 1) * U], rdb[i * U:(i + 1) * U]))
+    for n, a, r in zip(names, got, refs):
+        assert_close(a, r, 2 * REL_BF16, "tc " + n)
+    dx2, dW2, *_ = ops.interacting_bwd(xt, saved, Wt, bt, gt, bet, 1e-3, H, L, dyt, use_res, compute_bf16=True)
+    assert torch.equal(dx, dx2) and torch.equal(dW, dW2)
