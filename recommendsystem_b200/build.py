@@ -34,7 +34,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
-]
+] + os.environ.get("RS_NVCC_DEFS", "").split()      # developer switches, e.g. -DRS_ITB_PROFILE
 
 
 def _nvcc() -> str:

@@ -58,7 +58,7 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
   const int tid = threadIdx.x, warp = tid >> 5;
   // ---- one-time setup: barrier, TMEM, weights (bf16 W^T in UMMA layout), zeroed P buffers
   if (tid == 0) {
-    mbar_init(bar, 1);
+    mbar_init(bar, 2);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -83,6 +83,7 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
   constexpr uint32_t ID_O = make_idesc(1, 128, U, 0, 1);                // bf16, B = V MN-major, N = 16
 
   const int s_loc = tid / FP, f_loc = tid - s_loc * FP;
+  const int issuer = tid == 0 ? 0 : (tid == 32 ? 1 : -1);   // one MMA issuer per head; both commit every phase
   const int ntiles = (B + SPT - 1) / SPT;
   const float scale_log2 = ITC_LOG2E / sqrtf((float)DH);
   uint32_t phase = 0;
@@ -112,9 +113,9 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (issuer >= 0) {
         tc_fence_after();
-        issue_proj_3xtf32(tmem + TM_Z, sbase + OFF_X, sbase + OFF_W, ID_Z);
+        if (issuer == 0) issue_proj_3xtf32(tmem + TM_Z, sbase + OFF_X, sbase + OFF_W, ID_Z);
         tc_commit(bar);
       }
       mbar_wait(bar, phase); phase ^= 1u;
@@ -157,12 +158,11 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (issuer >= 0) {
         tc_fence_after();
-#pragma unroll
-        for (int h = 0; h < H; ++h)
-          tc_mma_tf32(tmem + (h == 0 ? TM_S0 : TM_S1), make_nosw_desc(sbase + OFF_Q + h * 4096, 128, 256),
-                      make_nosw_desc(sbase + OFF_K + h * 4096, 128, 256), ID_S, 0u);
+        const int h = issuer;
+        tc_mma_tf32(tmem + (h == 0 ? TM_S0 : TM_S1), make_nosw_desc(sbase + OFF_Q + h * 4096, 128, 256),
+                    make_nosw_desc(sbase + OFF_K + h * 4096, 128, 256), ID_S, 0u);
         tc_commit(bar);
       }
       mbar_wait(bar, phase); phase ^= 1u;
@@ -186,18 +186,22 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
               if (mine && c0 + j < F) p[c0 + j] = __uint_as_float(t8[j]);
           }
         }
-        float m = p[0];
+        float m4[4] = {p[0], p[1], p[2], p[3]};
 #pragma unroll
-        for (int j = 1; j < FP; ++j) m = fmaxf(m, p[j]);
+        for (int j = 4; j < FP; ++j) m4[j & 3] = fmaxf(m4[j & 3], p[j]);
+        float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         if (!active) m = 0.f;
-        float l = 0.f;
+        const float mb = m * scale_log2;
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < FP; ++j) {
           // -inf -> 0 for padded keys; round to the bf16 value the MMA will see, so that the
-          // normaliser l is the sum of exactly the weights used (a true convex combination)
-          p[j] = bf16_round(exp2f((p[j] - m) * scale_log2));
-          l += p[j];
+          // normaliser l is the sum of exactly the weights used (a true convex combination).
+          // (same expression as the backward's recomputation: interacting_tc_bwd.cu)
+          p[j] = bf16_round(ex2_approx(fmaf(p[j], scale_log2, -mb)));
+          l4[j & 3] += p[j];
         }
+        const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
         linv[h] = active ? 1.f / l : 0.f;
         // P row: chunks [s_loc*NCHF, +NCHF) of the 16 chunks, SWIZZLE_128B (chunk ^= row & 7)
         if (s_loc < SPT) {
@@ -217,17 +221,15 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       fence_async_smem();
       tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
+      if (issuer >= 0) {
         tc_fence_after();
+        const int h = issuer;
 #pragma unroll
-        for (int h = 0; h < H; ++h) {
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t pa = sbase + OFF_P + h * P_BYTES + (ks >> 2) * 16384 + (ks & 3) * 32;
-            // V advances 16 keys = 2 K-groups of 256 B per step
-            tc_mma_bf16(tmem + (h == 0 ? TM_O0 : TM_O1), make_sw128_kmajor_desc(pa),
-                        make_nosw_desc(sbase + OFF_V + ks * 512, 256, 128), ID_O, ks ? 1u : 0u);
-          }
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t pa = sbase + OFF_P + h * P_BYTES + (ks >> 2) * 16384 + (ks & 3) * 32;
+          // V advances 16 keys = 2 K-groups of 256 B per step
+          tc_mma_bf16(tmem + (h == 0 ? TM_O0 : TM_O1), make_sw128_kmajor_desc(pa),
+                      make_nosw_desc(sbase + OFF_V + ks * 512, 256, 128), ID_O, ks ? 1u : 0u);
         }
         tc_commit(bar);
       }

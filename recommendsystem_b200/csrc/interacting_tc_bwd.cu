@@ -64,6 +64,18 @@ __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
 
 // element e of this thread's head inside a 16-wide register row (compile-time indices + select:
 // a runtime index would push the array to local memory)
+#ifdef RS_ITB_PROFILE
+__device__ unsigned long long itb_prof[32];
+#define PROF(i)                                         \
+  if (blockIdx.x == 0 && tid == 0) {                    \
+    const long long t_now = clock64();                  \
+    itb_prof[i] += (unsigned long long)(t_now - t_last); \
+    t_last = t_now;                                     \
+  }
+#else
+#define PROF(i)
+#endif
+
 #define HSEL(a, e) (wg ? (a)[8 + (e)] : (a)[(e)])
 #define HSELF(a, e) __uint_as_float(HSEL(a, e))
 
@@ -105,7 +117,7 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
   const int wg = tid >> 7;                  // warpgroup = head this thread works for
   const int row = tid & 127;                // tile row = TMEM lane
   if (tid == 0) {
-    mbar_init(bar, 1);
+    mbar_init(bar, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -140,9 +152,10 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
   constexpr uint32_t TM_DW = 464;     // 32, persistent
 
   const uint32_t sbase = smem_u32(smem);
+  const uint32_t b16 = sbase >> 4;                              // descriptor start-address unit
   constexpr uint32_t ID_Z = make_idesc(2, 128, N4, 0, 0);       // tf32
   constexpr uint32_t ID_S = make_idesc(2, 128, 128, 0, 0);      // tf32 (S and dP)
-  constexpr uint32_t ID_AK = make_idesc(1, 128, 16, 0, 1);      // bf16, A K-major, B MN-major (O, dQ)
+  constexpr uint32_t ID_AK = make_idesc(1, 128, 16, 0, 1);      // bf16, A K-major, B MN-major (dQ)
   constexpr uint32_t ID_AT = make_idesc(1, 128, 16, 1, 1);      // bf16, A MN-major (transposed), B MN-major (dV, dK)
   constexpr uint32_t ID_DX = make_idesc(1, 128, 16, 0, 0);      // bf16, both K-major
   constexpr uint32_t ID_DW = make_idesc(1, 128, 32, 1, 1);      // bf16, A = dZ^T, B = [X|1]
@@ -154,301 +167,378 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
   const int wq = warp & 3;
   const int ws_lo = (wq * 32) / FP, ws_hi = min((wq * 32 + 31) / FP, SPT - 1);
   const int64_t total_rows = (int64_t)B * F;
+  const bool row_ok = s_loc < SPT && f_loc < F;
+  const int hb = wg * DH;              // first column of this thread's head
+  // Four MMA issuers (lane 0 of warps 0, 1, 4, 5): independent accumulator chains are issued
+  // concurrently; every issuer commits to the one mbarrier each phase (count 4).
+  const int issuer = tid == 0 ? 0 : (tid == 32 ? 1 : (tid == 128 ? 2 : (tid == 160 ? 3 : -1)));
+#ifdef RS_ITB_PROFILE
+  long long t_last = clock64();
+#endif
   uint32_t phase = 0;
   uint32_t dw_acc = 0;                 // 0 until the first dW MMA of this CTA
-  const int hb = wg * DH;              // first column of this thread's head
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t smp = (int64_t)tile * SPT + s_loc;
-    const bool active = s_loc < SPT && f_loc < F && smp < B;
-    float g[U];
-    if (active) {
+  // x-source row of step (tile, it): the bf16 layer input (it == 0) or the stored activations of
+  // iteration it-1 (LayerNorm is applied when the row is staged)
+  auto load_xsrc = [&](int tile_, int it_, float (&dst)[U]) {
+    const int64_t smp_ = (int64_t)tile_ * SPT + s_loc;
+    if (row_ok && smp_ < B) {
+      if (it_ == 0) {
 #pragma unroll
-      for (int c = 0; c < U; c += 4) {
-        const float4 t4 = load4<T>(dy + smp * dy_bs + (int64_t)f_loc * dy_ld + c);
-        g[c] = t4.x; g[c + 1] = t4.y; g[c + 2] = t4.z; g[c + 3] = t4.w;
+        for (int c = 0; c < U; c += 4) {
+          const float4 t4 = load4<T>(x + smp_ * x_bs + (int64_t)f_loc * x_ld + c);
+          dst[c] = t4.x; dst[c + 1] = t4.y; dst[c + 2] = t4.z; dst[c + 3] = t4.w;
+        }
+      } else {
+        const float* sp = saved + ((int64_t)(it_ - 1) * total_rows + smp_ * F + f_loc) * U;
+#pragma unroll
+        for (int c = 0; c < U; c += 4) {
+          const float4 t4 = ldg_nc_f4(reinterpret_cast<const float4*>(sp + c));
+          dst[c] = t4.x; dst[c + 1] = t4.y; dst[c + 2] = t4.z; dst[c + 3] = t4.w;
+        }
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < U; ++c) g[c] = 0.f;
+      for (int c = 0; c < U; ++c) dst[c] = 0.f;
     }
-    for (int it = L - 1; it >= 0; --it) {
-      // ================= 1. X -> Z = X W
-      {
-        float xr[8];                   // this warpgroup's half of the row
-        if (active) {
-          if (it == 0) {
+  };
+  // first-step-of-a-tile rows: stored activations of the last iteration and the incoming gradient
+  auto load_tile_head = [&](int tile_, float (&a_)[U], float (&g_)[U]) {
+    const int64_t smp_ = (int64_t)tile_ * SPT + s_loc;
+    if (row_ok && smp_ < B) {
+      const float* sp = saved + ((int64_t)(L - 1) * total_rows + smp_ * F + f_loc) * U;
 #pragma unroll
-            for (int c = 0; c < 8; c += 4) {
-              const float4 t4 = load4<T>(x + smp * x_bs + (int64_t)f_loc * x_ld + hb + c);
-              xr[c] = t4.x; xr[c + 1] = t4.y; xr[c + 2] = t4.z; xr[c + 3] = t4.w;
-            }
-          } else {
-            // iteration input = LayerNorm(saved activations of the previous iteration), bit-identical
-            // to what the forward computed (ln_row_stats / ln_apply)
-            float ap[U], mean, rstd;
-            const float* sp = saved + ((int64_t)(it - 1) * total_rows + smp * F + f_loc) * U;
-#pragma unroll
-            for (int c = 0; c < U; c += 4) {
-              const float4 t4 = *reinterpret_cast<const float4*>(sp + c);
-              ap[c] = t4.x; ap[c + 1] = t4.y; ap[c + 2] = t4.z; ap[c + 3] = t4.w;
-            }
-            ln_row_stats<U>(ap, eps, mean, rstd);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) xr[e] = ln_apply(HSEL(ap, e), mean, rstd, gs[hb + e], be[hb + e]);
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) xr[c] = 0.f;
-        }
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-          stage_x4_3xtf32(smem + OFF_X, row, wg * 2 + c, xr[c * 4], xr[c * 4 + 1], xr[c * 4 + 2], xr[c * 4 + 3]);
-        *reinterpret_cast<uint4*>(smem + OFF_XB + nosw_off<4>(row, wg)) = pack8_bf16(xr);
+      for (int c = 0; c < U; c += 4) {
+        const float4 t4 = ldg_nc_f4(reinterpret_cast<const float4*>(sp + c));
+        a_[c] = t4.x; a_[c + 1] = t4.y; a_[c + 2] = t4.z; a_[c + 3] = t4.w;
+        const float4 d4 = load4<T>(dy + smp_ * dy_bs + (int64_t)f_loc * dy_ld + c);
+        g_[c] = d4.x; g_[c + 1] = d4.y; g_[c + 2] = d4.z; g_[c + 3] = d4.w;
       }
-      fence_async_smem();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        issue_proj_3xtf32(tmem + TM_Z, sbase + OFF_X, sbase + OFF_W32, ID_Z);
-        tc_commit(bar);
-      }
-      // while the MMA runs: the stored pre-LayerNorm activations of THIS iteration
-      float a[U];
-      if (active) {
-        const float* sp = saved + ((int64_t)it * total_rows + smp * F + f_loc) * U;
+    } else {
 #pragma unroll
-        for (int c = 0; c < U; c += 4) {
-          const float4 t4 = *reinterpret_cast<const float4*>(sp + c);
-          a[c] = t4.x; a[c + 1] = t4.y; a[c + 2] = t4.z; a[c + 3] = t4.w;
-        }
+      for (int c = 0; c < U; ++c) { a_[c] = 0.f; g_[c] = 0.f; }
+    }
+  };
+  // stage this warpgroup's half of the step input: X tile (3xTF32 split); returns the half row
+  auto stage_x = [&](const float (&src)[U], int it_, bool act_, float (&xh)[8]) {
+    if (act_ && it_ > 0) {
+      float mean, rstd;
+      ln_row_stats<U>(src, eps, mean, rstd);      // bit-identical to the forward's LayerNorm
+#pragma unroll
+      for (int e = 0; e < 8; ++e) xh[e] = ln_apply(HSEL(src, e), mean, rstd, gs[hb + e], be[hb + e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) xh[e] = act_ ? HSEL(src, e) : 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+      stage_x4_3xtf32(smem + OFF_X, row, wg * 2 + c, xh[c * 4], xh[c * 4 + 1], xh[c * 4 + 2], xh[c * 4 + 3]);
+  };
+
+  // ---- prologue: first step's rows, X tile, Z MMA
+  int tile = blockIdx.x, it = L - 1;
+  const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int nsteps = my_tiles * L;
+  bool active = row_ok && (int64_t)tile * SPT + s_loc < B;
+  float a[U], g[U], xs[U];
+  load_tile_head(tile, a, g);
+  load_xsrc(tile, it, xs);
+  {
+    float xh[8];
+    stage_x(xs, it, active, xh);
+    *reinterpret_cast<uint4*>(smem + OFF_XB + nosw_off<4>(row, wg)) = pack8_bf16(xh);
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (issuer >= 0) {
+    tc_fence_after();
+    if (issuer == 0) issue_proj_3xtf32(tmem + TM_Z, sbase + OFF_X, sbase + OFF_W32, ID_Z);
+    tc_commit(bar);
+  }
+  mbar_wait(bar, phase); phase ^= 1u;
+  tc_fence_after();
+
+  for (int step = 0; step < nsteps; ++step) {
+    const bool last = step + 1 == nsteps;
+    const bool new_tile = it == 0;                 // the next step starts another tile
+    const int ntile = new_tile ? tile + (int)gridDim.x : tile;
+    const int nit = new_tile ? L - 1 : it - 1;
+    const bool nactive = !last && row_ok && (int64_t)ntile * SPT + s_loc < B;
+    const int64_t smp = (int64_t)tile * SPT + s_loc;
+    // ================= E1a. Z -> q k (the operands of S) ; v, r pre-activations stay in registers
+    uint32_t qmask = 0, kmask = 0, vmask = 0;
+    uint32_t zv[8], zr[16];
+    {
+      uint32_t zq[8], zk[8];
+      tc_ld_32x8(tl + TM_Z + hb, zq);
+      tc_ld_32x8(tl + TM_Z + U + hb, zk);
+      tc_ld_32x8(tl + TM_Z + 2 * U + hb, zv);
+      tc_ld_32x16(tl + TM_Z + 3 * U, zr);
+      tc_wait_ld();
+      float q[DH], kk[DH];
+#pragma unroll
+      for (int e = 0; e < DH; ++e) {
+        q[e] = fmaxf(__uint_as_float(zq[e]) + bs[hb + e], 0.f);
+        kk[e] = fmaxf(__uint_as_float(zk[e]) + bs[U + hb + e], 0.f);
+        qmask |= (q[e] > 0.f ? 1u : 0u) << e;
+        kmask |= (kk[e] > 0.f ? 1u : 0u) << e;
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        *reinterpret_cast<float4*>(smem + OFF_Q32 + wg * 4096 + nosw_off<2>(row, c)) =
+            make_float4(q[c * 4], q[c * 4 + 1], q[c * 4 + 2], q[c * 4 + 3]);
+        *reinterpret_cast<float4*>(smem + OFF_K32 + wg * 4096 + nosw_off<2>(row, c)) =
+            make_float4(kk[c * 4], kk[c * 4 + 1], kk[c * 4 + 2], kk[c * 4 + 3]);
+      }
+      *reinterpret_cast<uint4*>(smem + OFF_Q16 + nosw_off<2>(row, wg)) = pack8_bf16(q);
+      *reinterpret_cast<uint4*>(smem + OFF_K16 + nosw_off<2>(row, wg)) = pack8_bf16(kk);
+    }
+    // ================= 2. S_h = Q_h K_h^T
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    PROF(0)
+    if (issuer >= 0) {
+      tc_fence_after();
+      if ((issuer & 1) == 0) {
+        const int h = issuer >> 1;
+        tc_mma_tf32(tmem + TM_S + h * 128, mk_desc(b16, OFF_Q32 + h * 4096, 128, 256),
+                    mk_desc(b16, OFF_K32 + h * 4096, 128, 256), ID_S, 0u);
+      }
+      tc_commit(bar);
+    }
+    PROF(1)
+    // ================= E1b (under the S MMA). v ; LayerNorm / ReLU backward at the stored a
+    {
+      float vv[DH];
+      uint32_t rmask = 0;
+#pragma unroll
+      for (int e = 0; e < DH; ++e) {
+        vv[e] = fmaxf(__uint_as_float(zv[e]) + bs[2 * U + hb + e], 0.f);
+        vmask |= (vv[e] > 0.f ? 1u : 0u) << e;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) rmask |= (__uint_as_float(zr[u]) + bs[3 * U + u] > 0.f ? 1u : 0u) << u;
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+        *reinterpret_cast<float4*>(smem + OFF_V32 + wg * 4096 + nosw_off<2>(row, c)) =
+            make_float4(vv[c * 4], vv[c * 4 + 1], vv[c * 4 + 2], vv[c * 4 + 3]);
+      // ---- LayerNorm + ReLU backward at the stored activations a (InteractingLayer.py:59-60)
+      float mean, rstd;
+      ln_row_stats<U>(a, eps, mean, rstd);
+      float xhat[U], s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll
+      for (int u = 0; u < U; u += 2) {
+        xhat[u] = (a[u] - mean) * rstd;
+        xhat[u + 1] = (a[u + 1] - mean) * rstd;
+        const float g0 = g[u] * gs[u], g1 = g[u + 1] * gs[u + 1];
+        s1a += g0; s1b += g1;
+        s2a = fmaf(g0, xhat[u], s2a); s2b = fmaf(g1, xhat[u + 1], s2b);
+      }
+      const float s1 = (s1a + s1b) * (1.f / U), s2 = (s2a + s2b) * (1.f / U);
+      // this head's 8 columns of dT = dO = dR
+      float dTh[8], t8[8];
+#pragma unroll
+      for (int e = 0; e < DH; ++e) {
+        const float ae = HSEL(a, e), xe = HSEL(xhat, e);
+        const float dA = (HSEL(g, e) * gs[hb + e] - s1 - xe * s2) * rstd;
+        dTh[e] = (active && ae > 0.f) ? dA : 0.f;
+      }
+      // operands: dO_h (tf32 A of dP; bf16 B of dV), and the dR, g*xhat, g columns of dZ
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+        *reinterpret_cast<float4*>(smem + OFF_DO32 + wg * 4096 + nosw_off<2>(row, c)) =
+            make_float4(dTh[c * 4], dTh[c * 4 + 1], dTh[c * 4 + 2], dTh[c * 4 + 3]);
+      *reinterpret_cast<uint4*>(smem + OFF_DO16 + nosw_off<2>(row, wg)) = pack8_bf16(dTh);
+      const uint32_t rm = rmask >> hb;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t8[e] = (use_res && ((rm >> e) & 1u)) ? dTh[e] : 0.f;
+      *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, 6 + wg)) = pack8_bf16(t8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t8[e] = HSEL(g, e) * HSEL(xhat, e);
+      *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, 8 + wg)) = pack8_bf16(t8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t8[e] = HSEL(g, e);
+      *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, 10 + wg)) = pack8_bf16(t8);
+    }
+    // ---- prefetch the next step's rows: a whole step of latency cover
+    float xs_n[U], a_n[U], g_n[U];
+    if (!last) load_xsrc(ntile, nit, xs_n);
+    if (!last && new_tile) load_tile_head(ntile, a_n, g_n);
+    mbar_wait(bar, phase); phase ^= 1u;
+    PROF(2)
+    tc_fence_after();
+    float p[FP];                     // normalised attention row of this head
+    {
+      ld_window<FP>(tl + TM_S + wg * 128, ws_lo, ws_hi, s_loc, F, -INFINITY, p);
+      float m4[4] = {p[0], p[1], p[2], p[3]};
+#pragma unroll
+      for (int j = 4; j < FP; ++j) m4[j & 3] = fmaxf(m4[j & 3], p[j]);
+      float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      if (!active) m = 0.f;
+      const float mb = m * scale_log2;
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < FP; ++j) {
+        p[j] = bf16_round(ex2_approx(fmaf(p[j], scale_log2, -mb)));   // the forward's P
+        l4[j & 3] += p[j];
+      }
+      const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      const float linv = active ? 1.f / l : 0.f;
+#pragma unroll
+      for (int j = 0; j < FP; ++j) p[j] = active ? p[j] * linv : 0.f;
+      if (s_loc < SPT) {
+#pragma unroll
+        for (int c = 0; c < NCHF; ++c)
+          *reinterpret_cast<uint4*>(smem + OFF_P + wg * 32768 + nosw_off<16>(row, s_loc * NCHF + c)) = pack8_bf16(p + c * 8);
+      }
+    }
+    // ================= 3. dP_h = dO_h V_h^T ; dV_h = P_h^T dO_h
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    PROF(3)
+    if (issuer >= 0) {
+      tc_fence_after();
+      const int h = issuer >> 1;
+      if ((issuer & 1) == 0) {
+        tc_mma_tf32(tmem + TM_S + h * 128, mk_desc(b16, OFF_DO32 + h * 4096, 128, 256),
+                    mk_desc(b16, OFF_V32 + h * 4096, 128, 256), ID_S, 0u);
       } else {
 #pragma unroll
-        for (int c = 0; c < U; ++c) a[c] = 0.f;
+        for (int ks = 0; ks < 8; ++ks)   // K = tile rows, 16 per step = 2 row groups of the P tile
+          tc_mma_bf16(tmem + TM_DV + h * 16, mk_desc(b16, OFF_P + h * 32768 + ks * 4096, 2048, 128),
+                      mk_desc(b16, OFF_DO16 + ks * 512, 256, 128), ID_AT, ks ? 1u : 0u);
       }
-      mbar_wait(bar, phase); phase ^= 1u;
+      tc_commit(bar);
+    }
+    PROF(4)
+    mbar_wait(bar, phase); phase ^= 1u;
+    PROF(5)
+    tc_fence_after();
+    {
+      float dp[FP];
+      ld_window<FP>(tl + TM_S + wg * 128, ws_lo, ws_hi, s_loc, F, 0.f, dp);
+      // delta = sum_j P_ij dP_ij from the very P and dP used (not dO.o): the softmax Jacobian then
+      // annihilates any common-mode error of dP exactly (sum_j dS_ij = 0)
+      float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < FP; ++j) d4[j & 3] = fmaf(p[j], dp[j], d4[j & 3]);
+      const float delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
+#pragma unroll
+      for (int j = 0; j < FP; ++j) dp[j] = p[j] * scale * (dp[j] - delta);     // dS (1/sqrt(dh) folded in)
+      if (s_loc < SPT) {
+#pragma unroll
+        for (int cc = 0; cc < NCHF; ++cc)
+          *reinterpret_cast<uint4*>(smem + OFF_P + wg * 32768 + nosw_off<16>(row, s_loc * NCHF + cc)) = pack8_bf16(dp + cc * 8);
+      }
+      uint32_t dv[16];
+      tc_ld_32x16(tl + TM_DV + wg * 16, dv);
+      tc_wait_ld();
+      float t8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t8[e] = ((vmask >> e) & 1u) ? HSELF(dv, e) : 0.f;
+      *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, 4 + wg)) = pack8_bf16(t8);
+    }
+    // ================= 4. dQ_h = dS_h K_h ; dK_h = dS_h^T Q_h
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    PROF(6)
+    if (issuer >= 0) {
       tc_fence_after();
-      uint32_t qmask = 0, kmask = 0, vmask = 0;
-      {
-        uint32_t zq[8], zk[8], zv[8], zr[16];
-        tc_ld_32x8(tl + TM_Z + hb, zq);
-        tc_ld_32x8(tl + TM_Z + U + hb, zk);
-        tc_ld_32x8(tl + TM_Z + 2 * U + hb, zv);
-        tc_ld_32x16(tl + TM_Z + 3 * U, zr);
-        tc_wait_ld();
-        float q[DH], kk[DH], vv[DH], r[U];
-        uint32_t rmask = 0;
-#pragma unroll
-        for (int e = 0; e < DH; ++e) {
-          q[e] = fmaxf(__uint_as_float(zq[e]) + bs[hb + e], 0.f);
-          kk[e] = fmaxf(__uint_as_float(zk[e]) + bs[U + hb + e], 0.f);
-          vv[e] = fmaxf(__uint_as_float(zv[e]) + bs[2 * U + hb + e], 0.f);
-          qmask |= (q[e] > 0.f ? 1u : 0u) << e;
-          kmask |= (kk[e] > 0.f ? 1u : 0u) << e;
-          vmask |= (vv[e] > 0.f ? 1u : 0u) << e;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          r[u] = fmaxf(__uint_as_float(zr[u]) + bs[3 * U + u], 0.f);
-          rmask |= (r[u] > 0.f ? 1u : 0u) << u;
-        }
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          *reinterpret_cast<float4*>(smem + OFF_Q32 + wg * 4096 + nosw_off<2>(row, c)) =
-              make_float4(q[c * 4], q[c * 4 + 1], q[c * 4 + 2], q[c * 4 + 3]);
-          *reinterpret_cast<float4*>(smem + OFF_K32 + wg * 4096 + nosw_off<2>(row, c)) =
-              make_float4(kk[c * 4], kk[c * 4 + 1], kk[c * 4 + 2], kk[c * 4 + 3]);
-          *reinterpret_cast<float4*>(smem + OFF_V32 + wg * 4096 + nosw_off<2>(row, c)) =
-              make_float4(vv[c * 4], vv[c * 4 + 1], vv[c * 4 + 2], vv[c * 4 + 3]);
-        }
-        *reinterpret_cast<uint4*>(smem + OFF_Q16 + nosw_off<2>(row, wg)) = pack8_bf16(q);
-        *reinterpret_cast<uint4*>(smem + OFF_K16 + nosw_off<2>(row, wg)) = pack8_bf16(kk);
-        // ---- LayerNorm + ReLU backward at the stored activations a (InteractingLayer.py:59-60)
-        float mean, rstd;
-        ln_row_stats<U>(a, eps, mean, rstd);
-        float xhat[U], s1 = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          xhat[u] = (a[u] - mean) * rstd;
-          const float gg = g[u] * gs[u];
-          s1 += gg;
-          s2 = fmaf(gg, xhat[u], s2);
-        }
-        s1 *= (1.f / U);
-        s2 *= (1.f / U);
-        // this head's 8 columns of dT = dO = dR
-        float dTh[8], t8[8];
-#pragma unroll
-        for (int e = 0; e < DH; ++e) {
-          const float ae = HSEL(a, e), xe = HSEL(xhat, e);
-          const float dA = (HSEL(g, e) * gs[hb + e] - s1 - xe * s2) * rstd;
-          dTh[e] = (active && ae > 0.f) ? dA : 0.f;
-        }
-        // operands: dO_h (tf32 A of dP; bf16 B of dV), and the dR, g*xhat, g columns of dZ
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-          *reinterpret_cast<float4*>(smem + OFF_DO32 + wg * 4096 + nosw_off<2>(row, c)) =
-              make_float4(dTh[c * 4], dTh[c * 4 + 1], dTh[c * 4 + 2], dTh[c * 4 + 3]);
-        *reinterpret_cast<uint4*>(smem + OFF_DO16 + nosw_off<2>(row, wg)) = pack8_bf16(dTh);
-        const uint32_t rm = rmask >> hb;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) t8[e] = (use_res && ((rm >> e) & 1u)) ? dTh[e] : 0.f;
-        *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, 6 + wg)) = pack8_bf16(t8);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) t8[e] = HSEL(g, e) * HSEL(xhat, e);
-        *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, 8 + wg)) = pack8_bf16(t8);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) t8[e] = HSEL(g, e);
-        *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, 10 + wg)) = pack8_bf16(t8);
-      }
-      // ================= 2. S_h = Q_h K_h^T
-      fence_async_smem();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-#pragma unroll
-        for (int h = 0; h < H; ++h)
-          tc_mma_tf32(tmem + TM_S + h * 128, make_nosw_desc(sbase + OFF_Q32 + h * 4096, 128, 256),
-                      make_nosw_desc(sbase + OFF_K32 + h * 4096, 128, 256), ID_S, 0u);
-        tc_commit(bar);
-      }
-      mbar_wait(bar, phase); phase ^= 1u;
-      tc_fence_after();
-      float p[FP];                     // normalised attention row of this head
-      {
-        ld_window<FP>(tl + TM_S + wg * 128, ws_lo, ws_hi, s_loc, F, -INFINITY, p);
-        float m = p[0];
-#pragma unroll
-        for (int j = 1; j < FP; ++j) m = fmaxf(m, p[j]);
-        if (!active) m = 0.f;
-        float l = 0.f;
-#pragma unroll
-        for (int j = 0; j < FP; ++j) {
-          p[j] = bf16_round(exp2f((p[j] - m) * scale_log2));   // the forward's P, bit for bit
-          l += p[j];
-        }
-        const float linv = active ? 1.f / l : 0.f;
-#pragma unroll
-        for (int j = 0; j < FP; ++j) p[j] = active ? p[j] * linv : 0.f;
-        if (s_loc < SPT) {
-#pragma unroll
-          for (int c = 0; c < NCHF; ++c)
-            *reinterpret_cast<uint4*>(smem + OFF_P + wg * 32768 + nosw_off<16>(row, s_loc * NCHF + c)) = pack8_bf16(p + c * 8);
-        }
-      }
-      // ================= 3. dP_h = dO_h V_h^T ; dV_h = P_h^T dO_h
-      fence_async_smem();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-#pragma unroll
-        for (int h = 0; h < H; ++h)
-          tc_mma_tf32(tmem + TM_S + h * 128, make_nosw_desc(sbase + OFF_DO32 + h * 4096, 128, 256),
-                      make_nosw_desc(sbase + OFF_V32 + h * 4096, 128, 256), ID_S, 0u);
-#pragma unroll
-        for (int h = 0; h < H; ++h) {
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)   // K = tile rows, 16 per step = 2 row groups of the P tile
-            tc_mma_bf16(tmem + TM_DV + h * 16, make_nosw_desc(sbase + OFF_P + h * 32768 + ks * 4096, 2048, 128),
-                        make_nosw_desc(sbase + OFF_DO16 + ks * 512, 256, 128), ID_AT, ks ? 1u : 0u);
-        }
-        tc_commit(bar);
-      }
-      mbar_wait(bar, phase); phase ^= 1u;
-      tc_fence_after();
-      {
-        float dp[FP];
-        ld_window<FP>(tl + TM_S + wg * 128, ws_lo, ws_hi, s_loc, F, 0.f, dp);
-        // delta = sum_j P_ij dP_ij from the very P and dP used (not dO.o): the softmax Jacobian then
-        // annihilates any common-mode error of dP exactly (sum_j dS_ij = 0)
-        float delta = 0.f;
-#pragma unroll
-        for (int j = 0; j < FP; ++j) delta = fmaf(p[j], dp[j], delta);
-#pragma unroll
-        for (int j = 0; j < FP; ++j) dp[j] = p[j] * scale * (dp[j] - delta);     // dS (1/sqrt(dh) folded in)
-        if (s_loc < SPT) {
-#pragma unroll
-          for (int cc = 0; cc < NCHF; ++cc)
-            *reinterpret_cast<uint4*>(smem + OFF_P + wg * 32768 + nosw_off<16>(row, s_loc * NCHF + cc)) = pack8_bf16(dp + cc * 8);
-        }
-        uint32_t dv[16];
-        tc_ld_32x16(tl + TM_DV + wg * 16, dv);
-        tc_wait_ld();
-        float t8[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) t8[e] = ((vmask >> e) & 1u) ? HSELF(dv, e) : 0.f;
-        *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, 4 + wg)) = pack8_bf16(t8);
-      }
-      // ================= 4. dQ_h = dS_h K_h ; dK_h = dS_h^T Q_h
-      fence_async_smem();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-#pragma unroll
-        for (int h = 0; h < H; ++h) {
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            tc_mma_bf16(tmem + TM_DQ + h * 16, make_nosw_desc(sbase + OFF_P + h * 32768 + ks * 256, 128, 2048),
-                        make_nosw_desc(sbase + OFF_K16 + ks * 512, 256, 128), ID_AK, ks ? 1u : 0u);
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            tc_mma_bf16(tmem + TM_DK + h * 16, make_nosw_desc(sbase + OFF_P + h * 32768 + ks * 4096, 2048, 128),
-                        make_nosw_desc(sbase + OFF_Q16 + ks * 512, 256, 128), ID_AT, ks ? 1u : 0u);
-        }
-        tc_commit(bar);
-      }
-      mbar_wait(bar, phase); phase ^= 1u;
-      tc_fence_after();
-      {
-        uint32_t dq[16], dk[16];
-        tc_ld_32x16(tl + TM_DQ + wg * 16, dq);
-        tc_ld_32x16(tl + TM_DK + wg * 16, dk);
-        tc_wait_ld();
-        float t8[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) t8[e] = ((qmask >> e) & 1u) ? HSELF(dq, e) : 0.f;
-        *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, wg)) = pack8_bf16(t8);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) t8[e] = ((kmask >> e) & 1u) ? HSELF(dk, e) : 0.f;
-        *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, 2 + wg)) = pack8_bf16(t8);
-      }
-      // ================= 5. dX = dZ W^T ; [dW^T | db ; dgamma ; dbeta] += [dZ | g*xhat | g]^T [X | 1]
-      fence_async_smem();
-      tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          tc_mma_bf16(tmem + TM_DX, make_nosw_desc(sbase + OFF_DZ + ks * 256, 128, 2048),
-                      make_nosw_desc(sbase + OFF_WT + ks * 256, 128, 1024), ID_DX, ks ? 1u : 0u);
+      const int h = issuer >> 1;
+      if ((issuer & 1) == 0) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
-          tc_mma_bf16(tmem + TM_DW, make_nosw_desc(sbase + OFF_DZ + ks * 4096, 2048, 128),
-                      make_nosw_desc(sbase + OFF_XB + ks * 1024, 512, 128), ID_DW, ks ? 1u : dw_acc);
-        tc_commit(bar);
-      }
-      dw_acc = 1u;
-      mbar_wait(bar, phase); phase ^= 1u;
-      tc_fence_after();
-      {
-        uint32_t dxr[16];
-        tc_ld_32x16(tl + TM_DX, dxr);
-        tc_wait_ld();
-        if (it > 0) {
+          tc_mma_bf16(tmem + TM_DQ + h * 16, mk_desc(b16, OFF_P + h * 32768 + ks * 256, 128, 2048),
+                      mk_desc(b16, OFF_K16 + ks * 512, 256, 128), ID_AK, ks ? 1u : 0u);
+      } else {
 #pragma unroll
-          for (int u = 0; u < U; ++u) g[u] = active ? __uint_as_float(dxr[u]) : 0.f;   // stays fp32 between iterations
-        } else if (active) {
+        for (int ks = 0; ks < 8; ++ks)
+          tc_mma_bf16(tmem + TM_DK + h * 16, mk_desc(b16, OFF_P + h * 32768 + ks * 4096, 2048, 128),
+                      mk_desc(b16, OFF_Q16 + ks * 512, 256, 128), ID_AT, ks ? 1u : 0u);
+      }
+      tc_commit(bar);
+    }
+    PROF(7)
+    // under the dQ / dK MMAs: the NEXT step's X tile (its Z MMA rides in the same phase as this
+    // step's dX / dW)
+    float xh_n[8];
+    if (!last) stage_x(xs_n, nit, nactive, xh_n);
+    mbar_wait(bar, phase); phase ^= 1u;
+    PROF(8)
+    tc_fence_after();
+    {
+      uint32_t dq[16], dk[16];
+      tc_ld_32x16(tl + TM_DQ + wg * 16, dq);
+      tc_ld_32x16(tl + TM_DK + wg * 16, dk);
+      tc_wait_ld();
+      float t8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t8[e] = ((qmask >> e) & 1u) ? HSELF(dq, e) : 0.f;
+      *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, wg)) = pack8_bf16(t8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t8[e] = ((kmask >> e) & 1u) ? HSELF(dk, e) : 0.f;
+      *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, 2 + wg)) = pack8_bf16(t8);
+    }
+    // ================= 5. dX = dZ W^T ; [dW^T | db ; dgamma ; dbeta] += [dZ | g*xhat | g]^T [X | 1] ; Z(next)
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    PROF(9)
+    if (issuer >= 0) {
+      tc_fence_after();
+      if (issuer == 0) {
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          tc_mma_bf16(tmem + TM_DX, mk_desc(b16, OFF_DZ + ks * 256, 128, 2048),
+                      mk_desc(b16, OFF_WT + ks * 256, 128, 1024), ID_DX, ks ? 1u : 0u);
+      } else if (issuer == 1) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          tc_mma_bf16(tmem + TM_DW, mk_desc(b16, OFF_DZ + ks * 4096, 2048, 128),
+                      mk_desc(b16, OFF_XB + ks * 1024, 512, 128), ID_DW, ks ? 1u : dw_acc);
+      } else if (issuer == 2 && !last) {
+        issue_proj_3xtf32(tmem + TM_Z, sbase + OFF_X, sbase + OFF_W32, ID_Z);
+      }
+      tc_commit(bar);
+    }
+    dw_acc = 1u;
+    PROF(10)
+    mbar_wait(bar, phase); phase ^= 1u;
+    PROF(11)
+    tc_fence_after();
+    {
+      uint32_t dxr[16];
+      tc_ld_32x16(tl + TM_DX, dxr);
+      tc_wait_ld();
+      if (it > 0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) g[u] = active ? __uint_as_float(dxr[u]) : 0.f;   // stays fp32 between iterations
+      } else {
+        if (active) {
           T* dp = dx + smp * dx_bs + (int64_t)f_loc * dx_ld + hb;
           store4<T>(dp, make_float4(HSELF(dxr, 0), HSELF(dxr, 1), HSELF(dxr, 2), HSELF(dxr, 3)));
           store4<T>(dp + 4, make_float4(HSELF(dxr, 4), HSELF(dxr, 5), HSELF(dxr, 6), HSELF(dxr, 7)));
         }
+        if (!last) {
+#pragma unroll
+          for (int u = 0; u < U; ++u) g[u] = g_n[u];
+        }
+      }
+      if (!last) {
+        // dW of this step has consumed XB: the next step's bf16 x row may land now
+        *reinterpret_cast<uint4*>(smem + OFF_XB + nosw_off<4>(row, wg)) = pack8_bf16(xh_n);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          a[u] = new_tile ? a_n[u] : xs[u];      // same tile: a of iteration it-1 = this step's x-source
+          xs[u] = xs_n[u];
+        }
       }
     }
+    tile = ntile; it = nit; active = nactive;
   }
   // ---- per-CTA partials in the layout of the FFMA kernel: dW[D][4U] | db[4U] | dgamma[U] | dbeta[U]
   if (wg == 0) {
@@ -505,5 +595,17 @@ static int launch_itc_bwd(const IBwdArgs& a) {
 }
 
 int interacting_tc_bwd(const IBwdArgs& a) { return launch_itc_bwd<5, __nv_bfloat16>(a); }
+
+#ifdef RS_ITB_PROFILE
+extern "C" int rs_debug_itb_profile(unsigned long long* out32, int reset) {
+  cudaDeviceSynchronize();
+  if (out32) cudaMemcpyFromSymbol(out32, itb_prof, sizeof(unsigned long long) * 32);
+  if (reset) {
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(itb_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 }  // namespace rs

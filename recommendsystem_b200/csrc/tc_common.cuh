@@ -188,4 +188,17 @@ __device__ __forceinline__ void stage_x4_3xtf32(uint8_t* x_smem, int row, int c,
   *reinterpret_cast<float4*>(x_smem + nosw_off<8>(row, 4 + c)) = make_float4(a - ha, b - hb, cc - hc, d - hd);
 }
 
+// No-swizzle descriptor from the tile base in 16-byte units (smem addresses are < 2^18, so the
+// 14-bit start-address field needs no mask): one integer add per MMA operand.
+__device__ __forceinline__ uint64_t mk_desc(uint32_t base16, uint32_t off_bytes, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  const uint32_t lo = (base16 + (off_bytes >> 4)) | ((lbo_bytes >> 4) << 16);
+  const uint32_t hi = (sbo_bytes >> 4) | (1u << 14);
+  return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 }  // namespace rs
