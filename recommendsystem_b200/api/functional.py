@@ -112,13 +112,17 @@ class DenseFn(torch.autograd.Function):
         if ctx.tc:
             w16 = kernel.to(torch.bfloat16).contiguous()                         # [in,out]: K-major B for dgrad
             dx = ops.gemm(dy2, w16, transB=True) if ctx.needs_input_grad[0] else None
-            M = x2.shape[0]
-            Mp = (M + 7) // 8 * 8                                                # 16-byte rows for TMA
-            xT = torch.zeros(x2.shape[1], Mp, dtype=x2.dtype, device=x2.device)
-            dyT = torch.zeros(dy2.shape[1], Mp, dtype=x2.dtype, device=x2.device)
-            ops.transpose2d(x2, xT[:, :M])
-            ops.transpose2d(dy2, dyT[:, :M])
-            dW = ops.gemm(xT[:, :M], dyT[:, :M], transB=True, out_dtype=torch.float32)
+            if dy2.shape[1] > 32:
+                # MN-major TMA/UMMA operands: x [B,in] and dy [B,out] are read as they lie
+                dW = ops.gemm(x2, dy2, transA=True, out_dtype=torch.float32)
+            else:
+                M = x2.shape[0]
+                Mp = (M + 7) // 8 * 8                                            # 16-byte rows for TMA
+                xT = torch.zeros(x2.shape[1], Mp, dtype=x2.dtype, device=x2.device)
+                dyT = torch.zeros(dy2.shape[1], Mp, dtype=x2.dtype, device=x2.device)
+                ops.transpose2d(x2, xT[:, :M])
+                ops.transpose2d(dy2, dyT[:, :M])
+                dW = ops.gemm(xT[:, :M], dyT[:, :M], transB=True, out_dtype=torch.float32)
         else:
             dx = ops.gemm(dy2, kernel.contiguous(), transB=True) if ctx.needs_input_grad[0] else None
             dW = ops.gemm(x2, dy2, transA=True)

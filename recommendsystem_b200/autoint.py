@@ -158,13 +158,10 @@ class AutoIntTrainer:
         self.dX = e(B, F, d)
         self.bf16 = self.act_dtype == torch.bfloat16
         if self.bf16:
-            # tensor-core GEMMs take K-major operands: [out,in] weight shadows for the forward,
-            # transposed activations / gradients ([features, batch]) for the weight gradients
+            # forward GEMMs take K-major operands: [out,in] bf16 weight shadows (weight gradients read
+            # activations / gradients MN-major as they lie: no transposed copies)
             self.WT16 = {f"mlp_W{i}": torch.zeros(widths[i + 1], widths[i], dtype=torch.bfloat16, device=self.dev)
                          for i in range(len(cfg.mlp_hidden))}
-            wmax = max(widths)
-            self.xT = torch.zeros(wmax, B, dtype=torch.bfloat16, device=self.dev)
-            self.dyT = torch.zeros(wmax, B, dtype=torch.bfloat16, device=self.dev)
             self._refresh_wt()
         self.side = torch.cuda.Stream(device=self.dev)
         self.graph = None
@@ -334,12 +331,8 @@ class AutoIntTrainer:
     def _wgrad(self, x, dy, wname, bname):
         """G[w] = x^T dy ; G[b] = colsum(dy)."""
         if self.bf16:
-            B = x.shape[0]
-            xT = self.xT[:x.shape[1]]
-            dyT = self.dyT[:dy.shape[1]]
-            ops.transpose2d(x, xT)
-            ops.transpose2d(dy, dyT)
-            ops.gemm(xT, dyT, self.G[wname], transB=True)
+            # MN-major TMA/UMMA operands: x [B,in] and dy [B,out] are read as they lie (no transposes)
+            ops.gemm(x, dy, self.G[wname], transA=True)
         else:
             ops.gemm(x, dy, self.G[wname], transA=True)
         ops.colsum(dy, out=self.G[bname])

@@ -3,7 +3,7 @@
 //
 // One CTA computes one 128 x BN output tile (optionally one K-split of it):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D tiles (64-element = 128-byte K slabs,
-//               SWIZZLE_128B) of A and B into a 4-stage shared-memory ring, mbarrier expect_tx
+//               SWIZZLE_128B) of A and B into a 2-stage shared-memory ring (3 CTAs per SM), mbarrier expect_tx
 //   warp 1      TMEM allocator + MMA issuer: one elected thread issues tcgen05.mma
 //               (cta_group::1, kind::f16, M=128, N=BN, K=16) four times per stage and
 //               tcgen05.commit's the stage back to the producer / the accumulator to the epilogue
@@ -17,7 +17,6 @@ namespace rs {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;          // bf16 elements per stage along K = one 128-byte swizzle row
-constexpr int TC_STAGES = 4;
 constexpr int TC_THREADS = 192;
 
 template <typename CT>
@@ -33,21 +32,25 @@ __device__ __forceinline__ float tc_epi(float acc, int epi, const float* bias, f
   }
 }
 
-template <int BN>
+// STAGES: 6 (one CTA per SM, every K slab of a short-K GEMM in flight at once: the tile's time is ~2
+// TMA round trips) when the grid is at most one wave; 2 (three CTAs per SM overlap each other's
+// prologue / epilogue) when there are more tiles than SMs.
+template <int BN, int STAGES>
 struct TcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = TC_STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, typename CT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int BN, int STAGES, bool MN, typename CT>
+__global__ void __launch_bounds__(TC_THREADS, STAGES <= 2 ? 3 : 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                CT* __restrict__ C, int64_t ldc, const float* __restrict__ bias,
                const CT* __restrict__ aux, int64_t ldaux, int epi, int M, int N, int K,
                int kb_per_split, float* __restrict__ partial, int vec_ok) {
-  using S = TcSmem<BN>;
+  using S = TcSmem<BN, STAGES>;
+  constexpr int TC_STAGES = STAGES;
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * S::STAGE_BYTES);
@@ -87,24 +90,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&empty_bar[s], ph ^ 1u);            // first pass through the ring falls through
         mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
         uint8_t* a_dst = smem + s * S::STAGE_BYTES;
-        tma_load_2d(a_dst, &tmA, &full_bar[s], (kb0 + i) * TC_BK, m0);
-        tma_load_2d(a_dst + S::A_BYTES, &tmB, &full_bar[s], (kb0 + i) * TC_BK, n0);
+        if constexpr (!MN) {
+          tma_load_2d(a_dst, &tmA, &full_bar[s], (kb0 + i) * TC_BK, m0);
+          tma_load_2d(a_dst + S::A_BYTES, &tmB, &full_bar[s], (kb0 + i) * TC_BK, n0);
+        } else {
+          // MN-major operands (A stored [K, M], B stored [K, N]: weight gradients x^T dy with no
+          // transposed copies): one box = 64 K rows x 64 M|N elements (128 B, SWIZZLE_128B) = one
+          // canonical MN-major swizzle atom column of 8 KB
+#pragma unroll
+          for (int at = 0; at < TC_BM / 64; ++at)
+            tma_load_2d(a_dst + at * 8192, &tmA, &full_bar[s], m0 + at * 64, (kb0 + i) * TC_BK);
+#pragma unroll
+          for (int at = 0; at < BN / 64; ++at)
+            tma_load_2d(a_dst + S::A_BYTES + at * 8192, &tmB, &full_bar[s], n0 + at * 64, (kb0 + i) * TC_BK);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(TC_BM, BN);
+      constexpr uint32_t idesc = MN ? make_idesc(1, TC_BM, BN, 1, 1) : make_idesc_bf16(TC_BM, BN);
       for (int i = 0; i < nkb; ++i) {
         const int s = i % TC_STAGES;
         const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
-        const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
-        const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + S::A_BYTES);
+        if constexpr (!MN) {
+          const uint64_t adesc = make_sw128_kmajor_desc(a_addr);
+          const uint64_t bdesc = make_sw128_kmajor_desc(a_addr + S::A_BYTES);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k)      // +32 B (>>4 = 2) per K=16 step inside the swizzle row
-          tc_mma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+          for (int k = 0; k < TC_BK / 16; ++k)      // +32 B (>>4 = 2) per K=16 step inside the swizzle row
+            tc_mma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (i | k) ? 1u : 0u);
+        } else {
+          // MN-major SWIZZLE_128B: LBO = 8192 B between 64-element M|N atoms, SBO = 1024 B between
+          // 8-row K groups; a K = 16 step is two K groups = +2048 B (>>4 = 128)
+          const uint64_t adesc = make_sw128_desc(a_addr, 8192, 1024);
+          const uint64_t bdesc = make_sw128_desc(a_addr + S::A_BYTES, 8192, 1024);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            tc_mma_bf16(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (i | k) ? 1u : 0u);
+        }
         tc_commit(&empty_bar[s]);                  // stage free once these MMAs have read it
       }
       tc_commit(acc_bar);                          // accumulator complete
@@ -235,12 +260,12 @@ static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
   return 0;
 }
 
-template <int BN, typename CT>
+template <int BN, int STAGES, bool MN, typename CT>
 static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int64_t ldc, const float* bias,
                      const void* aux, int64_t ldaux, int epi, int M, int N, int K, int splits, int kbps,
                      float* partial, int vec_ok, cudaStream_t st) {
-  auto kern = gemm_tc_kernel<BN, CT>;
-  const int smem = TcSmem<BN>::TOTAL;
+  auto kern = gemm_tc_kernel<BN, STAGES, MN, CT>;
+  const int smem = TcSmem<BN, STAGES>::TOTAL;
   RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   dim3 grid((unsigned)cdiv(N, BN), (unsigned)cdiv(M, TC_BM), (unsigned)splits);
   kern<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, (CT*)C, ldc, bias, (const CT*)aux, ldaux, epi, M, N, K, kbps,
@@ -254,9 +279,10 @@ size_t gemm_tc_workspace_bytes() { return (size_t)sm_count() * TC_BM * 128 * siz
 int gemm_bf16_tc(const void* A, int64_t lda, int transA, const void* B, int64_t ldb, int transB, void* C,
                  int64_t ldc, const float* bias, const void* aux, int64_t ldaux, int epilogue, int M, int N,
                  int K, int dtype_c, void* ws, size_t ws_bytes, cudaStream_t st) {
-  RS_REQUIRE(!transA && transB,
-             "gemm(bf16): tensor-core path needs K-major operands: A stored [M,K] (transA=0) and B stored "
-             "[N,K] (transB=1); transpose with rs_transpose2d first");
+  RS_REQUIRE((!transA && transB) || (transA && !transB),
+             "gemm(bf16): tensor-core path takes both operands K-major (A stored [M,K], transA=0; B stored [N,K], "
+             "transB=1) or both MN-major (A stored [K,M], transA=1; B stored [K,N], transB=0)");
+  const bool mn = transA != 0;
   RS_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm(bf16): lda/ldb must be multiples of 8 elements (16-byte TMA strides)");
   RS_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0), "gemm(bf16): A/B must be 16-byte aligned");
   RS_REQUIRE(dtype_c == RS_F32 || dtype_c == RS_BF16, "gemm(bf16): bad C dtype");
@@ -265,6 +291,7 @@ int gemm_bf16_tc(const void* A, int64_t lda, int transA, const void* B, int64_t 
   int BN = 128;
   if (N <= 32) BN = 32;
   else if (N <= 64) BN = 64;
+  else if (mn && N % 128 != 0 && N % 128 <= 64) BN = 64;   // MN-major boxes are 64 wide: no half-empty 128 tile
   else if ((int64_t)cdiv(M, TC_BM) * cdiv(N, 128) < sms && N % 128 != 0) BN = 64;
   else if ((int64_t)cdiv(M, TC_BM) * cdiv(N, 128) * 2 <= sms) BN = 64;
   const int tiles = (int)(cdiv(M, TC_BM) * cdiv(N, BN));
@@ -288,21 +315,34 @@ int gemm_bf16_tc(const void* A, int64_t lda, int transA, const void* B, int64_t 
     partial = (float*)ws;
   }
   CUtensorMap tmA, tmB;
-  if (int e = make_map(&tmA, A, M, K, lda, TC_BM)) return e;
-  if (int e = make_map(&tmB, B, N, K, ldb, BN)) return e;
+  if (!mn) {
+    if (int e = make_map(&tmA, A, M, K, lda, TC_BM)) return e;
+    if (int e = make_map(&tmB, B, N, K, ldb, BN)) return e;
+  } else {
+    RS_REQUIRE(BN >= 64, "gemm(bf16): MN-major operands need N > 32");
+    if (int e = make_map(&tmA, A, K, M, lda, TC_BK)) return e;     // [K rows, M cols], box 64 x 64
+    if (int e = make_map(&tmB, B, K, N, ldb, TC_BK)) return e;
+  }
   const int esz = dtype_c == RS_F32 ? 4 : 2;
   int vec_ok = ((uintptr_t)C % 16 == 0) && ((ldc * esz) % 16 == 0);
   if (aux) vec_ok = vec_ok && ((uintptr_t)aux % 16 == 0) && ((ldaux * esz) % 16 == 0);
   int rc;
-#define RS_TC_GO(BNV)                                                                                   \
-  rc = dtype_c == RS_F32                                                                                \
-           ? launch_tc<BNV, float>(tmA, tmB, C, ldc, bias, aux, ldaux, epilogue, M, N, K, splits, kbps, \
-                                   partial, vec_ok, st)                                                 \
-           : launch_tc<BNV, __nv_bfloat16>(tmA, tmB, C, ldc, bias, aux, ldaux, epilogue, M, N, K,      \
-                                           splits, kbps, partial, vec_ok, st)
-  if (BN == 32) RS_TC_GO(32);
-  else if (BN == 64) RS_TC_GO(64);
-  else RS_TC_GO(128);
+  const bool deep = (int64_t)tiles * splits <= sms;
+#define RS_TC_GO3(BNV, ST, MNV)                                                                                  \
+  rc = dtype_c == RS_F32                                                                                         \
+           ? launch_tc<BNV, ST, MNV, float>(tmA, tmB, C, ldc, bias, aux, ldaux, epilogue, M, N, K, splits, kbps, \
+                                            partial, vec_ok, st)                                                 \
+           : launch_tc<BNV, ST, MNV, __nv_bfloat16>(tmA, tmB, C, ldc, bias, aux, ldaux, epilogue, M, N, K,      \
+                                                    splits, kbps, partial, vec_ok, st)
+#define RS_TC_GO2(BNV, ST) \
+  if (mn) { RS_TC_GO3(BNV, ST, true); } else { RS_TC_GO3(BNV, ST, false); }
+#define RS_TC_GO(BNV) \
+  if (deep) { RS_TC_GO2(BNV, 6) } else { RS_TC_GO2(BNV, 2) }
+  if (BN == 32) { RS_TC_GO3(32, 2, false); }
+  else if (BN == 64) { RS_TC_GO(64) }
+  else { RS_TC_GO(128) }
+#undef RS_TC_GO3
+#undef RS_TC_GO2
 #undef RS_TC_GO
   if (rc) return rc;
   if (splits > 1)

@@ -66,6 +66,12 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// General SWIZZLE_128B descriptor (K-major: LBO ignored, SBO = 1024; MN-major: LBO = byte stride
+// between 64-element M|N atoms, SBO = byte stride between 8-row K groups).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c=f32 (1<<4), a=b=bf16 (1<<7, 1<<10),
 // both K-major, N>>3 at bit 17, M>>4 at bit 24.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {

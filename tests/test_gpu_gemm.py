@@ -141,11 +141,32 @@ def test_gemm_bf16_tc_splitk_wgrad(cuda_dev, M, N, K):
     assert_close(acc0.cpu().numpy(), ref + 1.0, REL_F32, "wgrad split-K accumulate")
 
 
+@pytest.mark.parametrize("M,N,K", [(624, 256, 8192), (256, 128, 8192), (752, 128, 4096), (128, 64, 64), (200, 72, 10000),
+                                   (624, 40, 1000)])
+def test_gemm_bf16_tc_mnmajor_wgrad(cuda_dev, M, N, K):
+    """Weight gradient with NO transposed copies: dW[M,N] = X^T dY with X stored [K=batch, M] and dY stored
+    [K, N] (transA=1, transB=0): both operands are MN-major TMA tiles / UMMA descriptors."""
+    from recommendsystem_b200 import ops
+    rng = np.random.default_rng(M + N + 1)
+    X = _t(rng.standard_normal((K, M)).astype(np.float32), cuda_dev, torch.bfloat16)       # [batch, in]
+    dY = _t(rng.standard_normal((K, N)).astype(np.float32) / 64, cuda_dev, torch.bfloat16)  # [batch, out]
+    dW = ops.gemm(X, dY, transA=True, out_dtype=torch.float32)
+    dW2 = ops.gemm(X, dY, transA=True, out_dtype=torch.float32)
+    ref = X.double().cpu().numpy().T @ dY.double().cpu().numpy()
+    assert_close(dW.cpu().numpy(), ref, REL_F32, "wgrad MN-major")
+    assert torch.equal(dW, dW2)
+    # strided views (columns of a wider buffer), as the trainer passes them
+    big = torch.zeros(K, M + 16, dtype=torch.bfloat16, device=cuda_dev)
+    big[:, 8:8 + M] = X
+    dW3 = ops.gemm(big[:, 8:8 + M], dY, transA=True, out_dtype=torch.float32)
+    assert torch.equal(dW, dW3)
+
+
 def test_gemm_bf16_rejects_non_kmajor(cuda_dev):
     from recommendsystem_b200 import cabi, ops
     A = torch.zeros(64, 64, dtype=torch.bfloat16, device=cuda_dev)
     with pytest.raises(cabi.RsError):
-        ops.gemm(A, A)            # transB=0: B stored [K,N] is not K-major
+        ops.gemm(A, A)            # A K-major with B MN-major: mixed majors are not built
 
 
 @pytest.mark.parametrize("M,N,dt", [(1, 1, "f32"), (100, 37, "f32"), (8192, 624, "bf16"), (33, 65, "bf16")])
