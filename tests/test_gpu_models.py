@@ -1,0 +1,135 @@
+"""GPU parity of the two composed model graphs against oracle/oracle_models.py on
+identical inputs and weights: forward outputs (fp32, 1e-5 norm-wise) and gradients w.r.t. the embeddings and
+representative weights (the torch float64 twin of the same restatement, autograd)."""
+import numpy as np
+import pytest
+
+from util import REL_F32, assert_close
+import util_models as um
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _load(module, P, dev):
+    sd = module.state_dict()
+    missing = set(k for k in sd if k != "wt_bins") ^ set(P)
+    assert not missing, sorted(missing)[:10]
+    module.load_state_dict({**{k: torch.from_numpy(np.asarray(v)).to(dev) for k, v in P.items()},
+                            **({"wt_bins": sd["wt_bins"]} if "wt_bins" in sd else {})})
+
+
+def _f64(d):
+    return {k: np.asarray(v, np.float64) for k, v in d.items()}
+
+
+@pytest.mark.parametrize("B,T,units", [(5, 7, (32, 16)), (64, 50, (256, 128))])
+def test_video_dnn_sub_model(cuda_dev, B, T, units):
+    from oracle import oracle_models as om
+    from recommendsystem_b200.api.staytime_config import Config as C
+    from recommendsystem_b200.api.video_dnn import TASK_KEYS, VideoDnnSubModel
+    rng = np.random.default_rng(B + T)
+    slots, seq = C.SLOTS, C.SEQ_SLOTS
+    P = um.video_dnn_params(rng, slots, seq, units)
+    embs, seqs = um.video_dnn_inputs(rng, B, T, slots, seq)
+    model = VideoDnnSubModel(slots, seq, units).to(cuda_dev)
+    te = {k: torch.from_numpy(v).to(cuda_dev).requires_grad_(True) for k, v in embs.items()}
+    ts = {k: (torch.from_numpy(v[0]).to(cuda_dev).requires_grad_(True), torch.from_numpy(v[1]).to(cuda_dev))
+          for k, v in seqs.items()}
+    model(te, ts)                       # lazy build
+    _load(model, P, cuda_dev)
+    train, predict = model(te, ts)
+    ref = om.video_dnn_fwd(om.NP, _f64(embs), {k: (v[0].astype(np.float64), v[1]) for k, v in seqs.items()}, _f64(P),
+                           slots, seq, units)
+    assert_close(train[TASK_KEYS[0]].detach().cpu().numpy(), ref["staytime"], REL_F32, "staytime [B,401]")
+    assert_close(predict[TASK_KEYS[0]].detach().cpu().numpy(), ref["staytime_pred"], REL_F32, "staytime_pred")
+    assert_close(train[TASK_KEYS[1]].detach().cpu().numpy(), ref["shortplay"], REL_F32, "shortplay")
+    assert_close(train[TASK_KEYS[2]].detach().cpu().numpy(), ref["longplay"], REL_F32, "longplay")
+    # gradients of a scalar mixing the three heads
+    wv = torch.from_numpy(rng.standard_normal(401)).to(cuda_dev, torch.float32)
+    loss = (train[TASK_KEYS[0]] * wv).sum() + 3.0 * train[TASK_KEYS[1]].sum() - 2.0 * train[TASK_KEYS[2]].sum()
+    loss.backward()
+    tP = {k: torch.from_numpy(v).requires_grad_(True) for k, v in _f64(P).items()}
+    re = {k: torch.from_numpy(v.astype(np.float64)).requires_grad_(True) for k, v in embs.items()}
+    rs = {k: (torch.from_numpy(v[0].astype(np.float64)).requires_grad_(True), torch.from_numpy(v[1])) for k, v in seqs.items()}
+    ro = om.video_dnn_fwd(om.TH, re, rs, tP, slots, seq, units)
+    rl = (ro["staytime"] * wv.double().cpu()).sum() + 3.0 * ro["shortplay"].sum() - 2.0 * ro["longplay"].sum()
+    rl.backward()
+    g_emb = np.stack([te[k].grad.cpu().numpy() for k in sorted(te)])
+    r_emb = np.stack([re[k].grad.numpy() for k in sorted(re)])
+    assert_close(g_emb, r_emb, 5 * REL_F32, "d/d embeddings")
+    for s in seq:
+        assert_close(ts[s][0].grad.cpu().numpy(), rs[s][0].grad.numpy(), 5 * REL_F32, "d/d seq " + s)
+    sd = dict(model.named_parameters())
+    for name in ("senet_squeeze_layer1.kernel", "experts.expert_output_0_0.kernel", "experts.gate_1_1_2.kernel",
+                 "task_gates.gate_output_2.kernel", "staytime_output.kernel", "din.din_2125.layer_1_kernel",
+                 "cross.W.1", "ffm.ffm_x_1568_1591_8.kernel", "tower_out.longplay_pred.bias"):
+        assert_close(sd[name].grad.cpu().numpy(), tP[name].grad.numpy(), 5 * REL_F32, "d/d " + name)
+
+
+def test_dssm_sub_model(cuda_dev):
+    from oracle import oracle_models as om
+    from recommendsystem_b200.api.rough_rank_model import DssmSubModel, config as C
+    rng = np.random.default_rng(11)
+    B = 96
+    uid, iid = C.USER_FEATURE_IDS, C.ITEM_FEATURE_IDS
+    P = um.dssm_params(rng, uid, iid)
+    embs = {k: (0.3 * rng.standard_normal((B, 16))).astype(np.float32) for k in uid + iid}
+    mask = (rng.random((B, 1)) < 0.5).astype(np.float32)
+    model = DssmSubModel(uid, iid).to(cuda_dev)
+    te = {k: torch.from_numpy(v).to(cuda_dev).requires_grad_(True) for k, v in embs.items()}
+    tm = torch.from_numpy(mask).to(cuda_dev)
+    model(te, tm)
+    _load(model, P, cuda_dev)
+    out = model(te, tm)
+    ref = om.dssm_fwd(om.NP, _f64(embs), mask.astype(np.float64), _f64(P), uid, iid)
+    for k in ("student", "teacher", "distill"):
+        assert_close(out[k].detach().cpu().numpy(), ref[k], REL_F32, k)
+    (out["student"].sum() + 2.0 * out["teacher"].sum() + out["distill"].sum()).backward()
+    tP = {k: torch.from_numpy(v).requires_grad_(True) for k, v in _f64(P).items()}
+    re = {k: torch.from_numpy(v.astype(np.float64)).requires_grad_(True) for k, v in embs.items()}
+    ro = om.dssm_fwd(om.TH, re, torch.from_numpy(mask.astype(np.float64)), tP, uid, iid)
+    (ro["student"].sum() + 2.0 * ro["teacher"].sum() + ro["distill"].sum()).backward()
+    g = np.stack([te[k].grad.cpu().numpy() for k in sorted(te)])
+    r = np.stack([re[k].grad.numpy() for k in sorted(re)])
+    assert_close(g, r, 5 * REL_F32, "d/d embeddings")
+    sd = dict(model.named_parameters())
+    for name in ("user.ple.shared_expert_nets.0.kernels.0", "user.ple.gate_nets.1.kernels.0", "item.heads.0.kernels.0",
+                 "teacher.cross.kernels.1", "teacher.dense2.kernel", "shallow.logit_shallow.kernel"):
+        assert_close(sd[name].grad.cpu().numpy(), tP[name].grad.numpy(), 5 * REL_F32, "d/d " + name)
+
+
+def test_mtl_net_and_dssm_train_steps(cuda_dev):
+    """End to end through EmbeddingFeatures (gather, sorted-segment AdaGrad / Adam push): shapes, finite
+    losses, and the loss of a repeated batch goes down."""
+    from recommendsystem_b200.api.rough_rank_model import DSSM, config as RC
+    from recommendsystem_b200.api.staytime_config import Config as C
+    from recommendsystem_b200.api.video_dnn import TASK_KEYS, mtl_net
+    g = torch.Generator().manual_seed(0)
+    B, T = 32, 50
+    net = mtl_net(C.SLOTS, C.SEQ_SLOTS, T, dnn_hidden_units=(64, 32), bucket_size=1000, device=str(cuda_dev))["net"]
+    inputs = {s: torch.randint(0, 10 ** 9, (B,), generator=g) for s in C.SLOTS}
+    for s in C.SEQ_SLOTS:
+        ids = torch.randint(0, 10 ** 9, (B, T), generator=g)
+        lens = torch.randint(0, T + 1, (B,), generator=g)
+        ids[torch.arange(T)[None, :] >= lens[:, None]] = -1
+        inputs[s] = ids        # one id bag per slot feeds both its mean column and its sequence column (VideoDnn.py:224-231)
+    seq_inputs = dict(inputs)
+    y0 = torch.softmax(torch.randn(B, 400, generator=g), -1)
+    labels = {TASK_KEYS[0]: torch.cat([y0, torch.zeros(B, 1)], 1).to(cuda_dev),
+              TASK_KEYS[1]: (torch.rand(B, 1, generator=g) < 0.3).float().to(cuda_dev),
+              TASK_KEYS[2]: (torch.rand(B, 1, generator=g) < 0.3).float().to(cuda_dev)}
+    pred = net.predict(seq_inputs)
+    assert pred[TASK_KEYS[0]].shape == (B, 1) and pred[TASK_KEYS[1]].shape == (B, 1)
+    losses = [float(net.train_step(seq_inputs, labels)[0]) for _ in range(6)]
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+
+    dnet = DSSM(bucket_size=1000, device=str(cuda_dev))["net"]
+    din = {f: torch.randint(0, 10 ** 9, (B,), generator=g) for f in RC.USER_FEATURE_IDS + RC.ITEM_FEATURE_IDS}
+    din[RC.DENSE_MASK_ID] = (torch.rand(B, 1, generator=g) < 0.5).float()
+    dl = {"student": (torch.rand(B, 1, generator=g) < 0.3).float().to(cuda_dev),
+          "teacher": (torch.rand(B, 1, generator=g) < 0.3).float().to(cuda_dev)}
+    out = dnet.predict(din)
+    assert out["student"].shape == (B, 1) and out["distill"].shape == (B,)
+    dlosses = [float(dnet.train_step(din, dl)[0]) for _ in range(6)]
+    assert all(np.isfinite(dlosses)) and dlosses[-1] < dlosses[0], dlosses
