@@ -99,7 +99,24 @@ class EmbeddingFeatures:
 
     def __call__(self, inputs: Dict[str, torch.Tensor]):
         out, plan = {}, []
+        # single-valued mean columns (ids [B] / [B,1], the Criteo-shaped case) share ONE gather launch over
+        # the stacked ids [B, F'] (per-column row_base / bucket size) and one sorted-segment push
+        single = [ci for ci, c in enumerate(self.cols) if c.combiner is not None and
+                  (inputs[c.categorical_column.key].dim() == 1 or inputs[c.categorical_column.key].shape[1] == 1)]
+        if len(single) > 1:
+            ids = torch.stack([inputs[self.cols[ci].categorical_column.key].reshape(-1) for ci in single], dim=1)
+            ids = ids.to(self.dev, torch.int64).contiguous()
+            base = torch.as_tensor(self.base[single], device=self.dev)
+            rows = torch.as_tensor(self.rows[single], device=self.dev)
+            emb, keys, _ = ops.embed_gather(self.table, ids, base, rows, torch.float32, want_keys=True)
+            for j, ci in enumerate(single):
+                out[self.cols[ci].key] = emb[:, j, :].to(self.out_dtype)
+            plan.append(([self.cols[ci].key for ci in single], keys, 1.0, None))
+        else:
+            single = []
         for ci, c in enumerate(self.cols):
+            if ci in single:
+                continue
             ids = inputs[c.categorical_column.key].to(self.dev, torch.int64)
             base = torch.tensor([int(self.base[ci])], device=self.dev)
             rows = torch.tensor([int(self.rows[ci])], device=self.dev)
@@ -134,7 +151,10 @@ class EmbeddingFeatures:
         if isinstance(self.opt, Adam):
             ops.adam_advance(self.scalars, self.opt.beta1, self.opt.beta2)
         for key, keys, scale, bag in self._last:
-            g = grads[key]
+            if isinstance(key, list):                             # stacked single-valued columns: [B, F', d]
+                g = torch.stack([grads[k] for k in key], dim=1)
+            else:
+                g = grads[key]
             if isinstance(g, tuple):
                 g = g[0]
             g = g.reshape(-1, self.d)
