@@ -162,8 +162,10 @@ def algorithmic(phase, B, act_bytes, n_unique):
     inter_f = L * (2 * 4 * F * D * U + 2 * 2 * H * F * F * (U // H)) * B
     t = {
         "embed_gather": (n * (8 + D * 4 + D * act_bytes + 8), 0),          # + 8 B sort key written
-        "interacting_fwd": (n * (D + U) * act_bytes + (L - 1) * n * U * 4, inter_f),
-        "interacting_bwd": (n * (2 * U + 2 * D) * act_bytes + (L - 1) * n * U * 4, 3 * inter_f),
+        "embed_gather_peer": (n * (8 + D * 4 + D * act_bytes), 0),          # rows read over NVLink (W-1)/W of them
+        # x in, y out, + the L saved pre-LayerNorm rows (fp32) the tcgen05 forward writes / backward reads
+        "interacting_fwd": (n * (D + U) * act_bytes + L * n * U * 4, inter_f),
+        "interacting_bwd": (n * (U + 2 * D) * act_bytes + L * n * U * 4, 3 * inter_f),
         "mlp_fwd": (B * (F * D + 2 * MLP[0] + MLP[1]) * act_bytes, gemm),
         "mlp_bwd": (B * (F * D + 3 * MLP[0] + 3 * MLP[1]) * act_bytes, gemm + 2 * B * MLP[0] * MLP[1]),
         "mlp_dgrad_x": (B * (MLP[0] + 2 * F * D) * act_bytes, 2 * B * F * D * MLP[0]),
@@ -290,11 +292,12 @@ def run_own(args):
                 "frac": (top["GBps"] or 0) / pk["hbm_gbs"], "traffic": None}
     roof.update({"kernel": top["phase"], "peak_source": pk["source"] + " (sustained: kernel timed inside the step)",
                  "share_of_step": top["share"]})
-    gk = next(k for k in kernels if k["phase"] == "embed_gather")
+    gk = next(k for k in kernels if k["phase"] in ("embed_gather", "embed_gather_peer"))
     sk = next(k for k in kernels if k["phase"] == "embed_segsum_adam")
     embed = {"gather_GBps": gk["GBps"], "gather_frac_of_measured_hbm": gk["GBps"] / pk["hbm_gbs"],
              "gather_frac_of_8TBps": gk["GBps"] / 8000.0, "scatter_adam_GBps": sk["GBps"],
-             "scatter_adam_frac_of_measured_hbm": sk["GBps"] / pk["hbm_gbs"], "unique_rows": n_unique}
+             "scatter_adam_frac_of_measured_hbm": sk["GBps"] / pk["hbm_gbs"], "unique_rows": n_unique,
+             "gather_kernel": gk["phase"]}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -92,10 +92,28 @@ int rs_embed_gather_fwd(const float* table, const int64_t* ids,
 /* Gather by precomputed arena rows (used by the row-sharded multi-GPU path
  * after id routing, and for sequence slots: staytime/VideoDnn.py:228-231
  * `combiner=None, seq_max_len=N` -> ([B,T,d], mask[B,T])).
- * rowidx[i] < 0 -> zeros and mask 0.  `mask_out` nullable (uint8). */
+ * rowidx[i] < 0 -> zeros and mask 0.  `mask_out` nullable (uint8).  out == NULL: no rows are
+ * read, only `sort_keys` / `mask_out` are produced (the owner side of the peer-gather path). */
 int rs_embed_gather_rows(const float* table, const int32_t* rowidx, int64_t n,
                          int d, void* out, int out_dtype, uint8_t* mask_out,
                          uint64_t* sort_keys, void* stream);
+
+/* Row-sharded tables read IN PLACE over NVLink (one process per GPU; replaces the id all-to-all +
+ * owner gather + row all-to-all of the sharded path — the only trace of sharding in the reference is
+ * tn.core.shard_num() / self_shard_id(), staytime/parse.py:78-79).  peer_tables[r] (HOST array of
+ * `world` DEVICE pointers) is rank r's shard, mapped into this process with rs_ipc_import; lookup i reads
+ *   r = ids[i] mod rows[f] ; owner = r mod world ; peer_tables[owner][local_base[f] + r div world]
+ * (ids[i] < 0 -> zeros).  Bit-exact with rs_embed_gather_fwd on the unsharded arena.  The caller orders
+ * the owners' sparse update of the previous step before this call (cross-rank barrier). */
+#define RS_MAX_PEERS 8
+int rs_embed_gather_peer_fwd(const float* const* peer_tables, int world, const int64_t* ids,
+                             const int64_t* local_base, const int64_t* rows, int64_t n, int F, int d,
+                             void* out, int out_dtype, void* stream);
+/* CUDA-IPC plumbing for the above: export the allocation containing `ptr` (64-byte handle + byte offset
+ * of ptr inside it); import maps a peer's allocation (peer access enabled lazily) and returns
+ * base + offset. */
+int rs_ipc_export(const void* ptr, unsigned char* handle64, unsigned long long* offset);
+int rs_ipc_import(const unsigned char* handle64, unsigned long long offset, void** mapped);
 
 /* Multi-valued slots: `combiner='mean'` over a CSR bag
  * (staytime/VideoDnn.py:224-226 with VarLenFeature ids, staytime/parse.py:22-23).

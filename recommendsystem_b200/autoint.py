@@ -239,10 +239,7 @@ class AutoIntTrainer:
         # the key sort only needs the forward's keys: run it on the side stream, hidden behind the
         # dense forward/backward (a parallel branch of the captured graph)
         main = torch.cuda.current_stream(self.dev)
-        self.side.wait_stream(main)
-        with torch.cuda.stream(self.side):
-            with ph("sort_keys"):
-                ops.sort_keys(self.keys, self.row_bits, out=self.keys_sorted)
+        self._sort_keys(ph)
         # K4: InteractingLayer forward
         with ph("interacting_fwd"):
             # writes Flatten(A) straight into its columns of the concat buffer Z (autoint:36,45)
@@ -290,6 +287,15 @@ class AutoIntTrainer:
                            self.adam_scalars, self.flat_bf16)
             if self.bf16:
                 self._refresh_wt()
+        if getattr(self, "_join_side2", False):      # peer-gather barrier stream joins the step
+            main.wait_stream(self.side2)
+
+    def _sort_keys(self, ph):
+        main = torch.cuda.current_stream(self.dev)
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            with ph("sort_keys"):
+                ops.sort_keys(self.keys, self.row_bits, out=self.keys_sorted)
 
     # ---- embedding halves of the step (overridden by the row-sharded multi-GPU trainer)
     def _embed_forward(self, ph, st, T):

@@ -1,6 +1,8 @@
 // core.cu — error reporting, launch accounting and the small glue kernels
 // (2-D copy/cast, add, activation backward, column sums, BCE loss).
 #include "common.cuh"
+#include <cuda.h>
+#include <string.h>
 #include <mutex>
 #include <string.h>
 
@@ -277,6 +279,45 @@ int rs_bce_sigmoid_fwd_bwd(const void* p_raw, int dtype, const float* y, float a
     bce_kernel<__nv_bfloat16><<<1, 1024, 0, st>>>((const __nv_bfloat16*)p_raw, y, a, loss_out, (__nv_bfloat16*)dz, B, k);
   else { set_error("bce: bad dtype"); return RS_ERR_INVALID; }
   return check_launch("bce");
+}
+
+// ---- CUDA IPC: peer mappings of row-sharded embedding tables (rs_embed_gather_peer_fwd) ----
+int rs_ipc_export(const void* ptr, unsigned char* handle64, unsigned long long* offset) {
+  RS_REQUIRE(ptr && handle64 && offset, "ipc_export: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  typedef CUresult (*RangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  static RangeFn range_fn = nullptr;
+  if (!range_fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      set_error("ipc_export: cuMemGetAddressRange unavailable");
+      return RS_ERR_UNSUPPORTED;
+    }
+    range_fn = (RangeFn)p;
+  }
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (range_fn(&base, &size, (CUdeviceptr)ptr) != CUDA_SUCCESS) {
+    set_error("ipc_export: %p is not inside a device allocation", ptr);
+    return RS_ERR_INVALID;
+  }
+  cudaIpcMemHandle_t h;
+  RS_CUDA(cudaIpcGetMemHandle(&h, (void*)base));
+  memcpy(handle64, &h, 64);
+  *offset = (unsigned long long)((CUdeviceptr)ptr - base);
+  return 0;
+}
+
+int rs_ipc_import(const unsigned char* handle64, unsigned long long offset, void** mapped) {
+  RS_REQUIRE(handle64 && mapped, "ipc_import: null argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* base = nullptr;
+  RS_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+  *mapped = (char*)base + offset;
+  return 0;
 }
 
 }  // extern "C"

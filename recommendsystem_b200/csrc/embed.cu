@@ -70,7 +70,7 @@ embed_gather_kernel(const float* __restrict__ table, const int64_t* __restrict__
         const int src = s * GROUPS + gj;
         const int32_t r = __shfl_sync(0xffffffffu, myrow[k], src);
         v[k][s] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r >= 0 && col_ok)
+        if (r >= 0 && col_ok && out)
           v[k][s] = ldg_row_f4(reinterpret_cast<const float4*>(table + (int64_t)r * d) + gl);
       }
     }
@@ -79,7 +79,7 @@ embed_gather_kernel(const float* __restrict__ table, const int64_t* __restrict__
 #pragma unroll
       for (int s = 0; s < G; ++s) {
         const int64_t i = base + k * 32 + s * GROUPS + gj;
-        if (i < n && col_ok) store4<OutT>(out + i * d + gl * 4, v[k][s]);
+        if (i < n && col_ok && out) store4<OutT>(out + i * d + gl * 4, v[k][s]);
       }
     }
   }
@@ -126,6 +126,96 @@ static int dispatch_gather(const float* table, const int64_t* ids, const int32_t
   if (g <= 16) RS_GATHER_CASE(16, 1);
   RS_GATHER_CASE(32, 1);
 #undef RS_GATHER_CASE
+}
+
+// ------------------------------------------------ gather over peer memory ----
+// Row-sharded tables, one process per GPU: owner(row) = row mod W, local row = local_base[f] + row div W
+// (SURVEY §8e).  Instead of routing ids to the owners and shipping rows back with two all-to-alls,
+// every rank reads the rows it needs straight out of the owners' HBM over NVLink / NVSwitch: the W
+// shard base pointers are CUDA-IPC mappings (rs_ipc_export / rs_ipc_import) and a lookup is one
+// 64-byte peer load.  Same warp shape as embed_gather_kernel (G lanes x 16 B per row, G*LPL loads in
+// flight per lane).  Peer rows are written only by their owner's sparse update of the PREVIOUS step,
+// which a cross-rank barrier orders before this kernel; plain (coherent) loads, no .nc.
+struct PeerTables { const float* p[RS_MAX_PEERS]; };
+
+__device__ __forceinline__ float4 ld_peer_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p) : "memory");
+  return r;
+}
+
+template <int G, int LPL, typename OutT>
+__global__ void __launch_bounds__(128)
+embed_gather_peer_kernel(PeerTables tabs, const int64_t* __restrict__ ids, const int64_t* __restrict__ local_base,
+                         const int64_t* __restrict__ rows, int64_t n, int F, int d, int W, OutT* __restrict__ out) {
+  constexpr int GROUPS = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G, gj = lane / G;
+  const int64_t warp_global = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const bool col_ok = gl * 4 < d;
+  for (int64_t base = warp_global * (32 * LPL); base < n; base += nwarps * (32 * LPL)) {
+    const float* myptr[LPL];
+#pragma unroll
+    for (int k = 0; k < LPL; ++k) {
+      const int64_t i = base + k * 32 + lane;
+      const float* ptr = nullptr;
+      if (i < n) {
+        const int64_t id = ids[i];
+        if (id >= 0) {
+          const int f = (int)(i % F);
+          const uint64_t R = (uint64_t)__ldg(rows + f);
+          uint64_t rr;
+          if (((uint64_t)id | R) >> 32) rr = (uint64_t)id % R;
+          else rr = (uint32_t)id % (uint32_t)R;
+          const uint32_t owner = (uint32_t)(rr % (uint64_t)W);
+          const int64_t lrow = __ldg(local_base + f) + (int64_t)(rr / (uint64_t)W);
+          ptr = tabs.p[owner] + lrow * d;
+        }
+      }
+      myptr[k] = ptr;
+    }
+    float4 v[LPL][G];
+#pragma unroll
+    for (int k = 0; k < LPL; ++k) {
+#pragma unroll
+      for (int s = 0; s < G; ++s) {
+        const int src = s * GROUPS + gj;
+        const float* r = reinterpret_cast<const float*>(
+            __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)myptr[k], src));
+        v[k][s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r != nullptr && col_ok) v[k][s] = ld_peer_f4(reinterpret_cast<const float4*>(r) + gl);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < LPL; ++k) {
+#pragma unroll
+      for (int s = 0; s < G; ++s) {
+        const int64_t i = base + k * 32 + s * GROUPS + gj;
+        if (i < n && col_ok) store4<OutT>(out + i * d + gl * 4, v[k][s]);
+      }
+    }
+  }
+}
+
+template <int G, int LPL>
+static int launch_gather_peer(const PeerTables& tabs, const int64_t* ids, const int64_t* local_base,
+                              const int64_t* rows, int64_t n, int F, int d, int W, void* out, int out_dtype,
+                              cudaStream_t st) {
+  const int threads = 128;
+  const int64_t per_block = (int64_t)(threads / 32) * 32 * LPL;
+  int64_t blocks = cdiv(n, per_block);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (out_dtype == RS_F32)
+    embed_gather_peer_kernel<G, LPL, float><<<(unsigned)blocks, threads, 0, st>>>(tabs, ids, local_base, rows, n, F, d,
+                                                                                  W, (float*)out);
+  else
+    embed_gather_peer_kernel<G, LPL, __nv_bfloat16><<<(unsigned)blocks, threads, 0, st>>>(
+        tabs, ids, local_base, rows, n, F, d, W, (__nv_bfloat16*)out);
+  return check_launch("embed_gather_peer");
 }
 
 // ------------------------------------------------------------- bag mean ----
@@ -556,6 +646,27 @@ int rs_embed_gather_rows(const float* table, const int32_t* rowidx, int64_t n, i
                          int out_dtype, uint8_t* mask_out, uint64_t* sort_keys, void* stream) {
   return dispatch_gather<false>(table, nullptr, rowidx, nullptr, nullptr, n, 1, d, out, out_dtype,
                                 sort_keys, nullptr, mask_out, as_stream(stream));
+}
+
+int rs_embed_gather_peer_fwd(const float* const* peer_tables, int world, const int64_t* ids,
+                             const int64_t* local_base, const int64_t* rows, int64_t n, int F, int d, void* out,
+                             int out_dtype, void* stream) {
+  RS_REQUIRE(world >= 1 && world <= RS_MAX_PEERS, "embed_gather_peer: world=%d (max %d)", world, RS_MAX_PEERS);
+  RS_REQUIRE(F > 0 && d > 0 && d % 4 == 0 && d <= 128, "embed_gather_peer: F=%d d=%d", F, d);
+  RS_REQUIRE(out_dtype == RS_F32 || out_dtype == RS_BF16, "embed_gather_peer: bad out dtype %d", out_dtype);
+  if (n == 0) return 0;
+  PeerTables tabs;
+  for (int r = 0; r < RS_MAX_PEERS; ++r) tabs.p[r] = r < world ? peer_tables[r] : nullptr;
+  const int g = d / 4;
+  cudaStream_t st = as_stream(stream);
+  if (g <= 1) return launch_gather_peer<1, 4>(tabs, ids, local_base, rows, n, F, d, world, out, out_dtype, st);
+  if (g <= 2) return launch_gather_peer<2, 4>(tabs, ids, local_base, rows, n, F, d, world, out, out_dtype, st);
+  // (measured at W = 2: 4 lookups per lane is slower than 2 — fewer, fatter CTAs; the NVLink request rate,
+  //  not the loads in flight per lane, bounds the kernel)
+  if (g <= 4) return launch_gather_peer<4, 2>(tabs, ids, local_base, rows, n, F, d, world, out, out_dtype, st);
+  if (g <= 8) return launch_gather_peer<8, 1>(tabs, ids, local_base, rows, n, F, d, world, out, out_dtype, st);
+  if (g <= 16) return launch_gather_peer<16, 1>(tabs, ids, local_base, rows, n, F, d, world, out, out_dtype, st);
+  return launch_gather_peer<32, 1>(tabs, ids, local_base, rows, n, F, d, world, out, out_dtype, st);
 }
 
 int rs_embed_gather_bag_mean(const float* table, const int64_t* ids, const int64_t* offsets,

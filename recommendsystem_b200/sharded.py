@@ -8,6 +8,14 @@ ids / rows / gradients exchanged by NCCL all-to-all over NVLink (one process per
         --> permute --> all-to-all(grads) --> owner: sort + segment-sum + sparse Adam (K3)
     dense gradients: one flat all-reduce (average) before the dense Adam.
 
+`peer_gather=True` (default on NCCL) replaces the forward half by ONE kernel that reads the rows it
+needs straight out of the owners' HBM over NVLink / NVSwitch (CUDA-IPC mappings of every rank's shard,
+rs_embed_gather_peer_fwd): no id all-to-all, owner gather, row all-to-all or un-permute on the critical
+path.  The routing + id all-to-all still run — on a side stream, hidden behind the dense forward — because
+the owners need the (row, position) keys for the backward's sorted-segment update; a one-element
+all-reduce after the sparse update is the cross-rank barrier that orders every owner's update before the
+next step's peer reads.
+
 Buckets have a fixed capacity, so there is no host round trip for the counts and the whole
 step — collectives included — is one CUDA graph.  A bucket overflow (skewed ids) sets a device
 flag that `check_overflow()` turns into an exception; nothing is silently dropped.
@@ -18,6 +26,7 @@ is device-agnostic so that the protocol is tested on CPU with the gloo backend.
 """
 from __future__ import annotations
 
+import ctypes
 import math
 
 import numpy as np
@@ -74,7 +83,8 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
     gradients are averaged over ranks, i.e. the update is that of the global batch W * batch."""
 
     def __init__(self, cfg: AutoIntConfig, device, group=None, global_tables: torch.Tensor | None = None,
-                 dense_init: dict | None = None, capacity_factor: float | None = None):
+                 dense_init: dict | None = None, capacity_factor: float | None = None,
+                 peer_gather: bool | None = None):
         self.ex = Exchange(group)
         self.world, self.rank = self.ex.world, self.ex.rank
         self._global_tables = global_tables
@@ -96,6 +106,34 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
         self.keys = torch.empty(W * self.cap, dtype=torch.int64, device=dev)
         self.keys_sorted = torch.empty_like(self.keys)
         self.lbase_t = torch.from_numpy(self.local_base).to(dev)
+        if peer_gather is None:
+            peer_gather = dist.get_backend(group) == "nccl" and W <= 8
+        self.peer_gather = bool(peer_gather)
+        if self.peer_gather:
+            self._map_peer_tables(group)
+            self.side2 = torch.cuda.Stream(device=dev)
+            self.route_done = torch.cuda.Event()
+            self.barrier_buf = torch.zeros(1, device=dev)
+
+    def _map_peer_tables(self, group):
+        """Exchange CUDA-IPC handles of every rank's table shard and map them into this process."""
+        handle = (ctypes.c_ubyte * 64)()
+        off = ctypes.c_ulonglong(0)
+        cabi.call("rs_ipc_export", self.table.data_ptr(), ctypes.addressof(handle), ctypes.addressof(off))
+        mine = (bytes(handle), int(off.value))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=group)
+        ptrs = (ctypes.c_void_p * self.world)()
+        for r, (h, o) in enumerate(everyone):
+            if r == self.rank:
+                ptrs[r] = self.table.data_ptr()
+                continue
+            hb = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+            out = ctypes.c_void_p(0)
+            cabi.call("rs_ipc_import", ctypes.addressof(hb), o, ctypes.addressof(out))
+            ptrs[r] = out.value
+        self.peer_ptrs = ptrs               # host array of W device pointers (kernel argument)
+        dist.barrier(group=group)
 
     def _alloc_tables(self, tables):
         cfg, d, W = self.cfg, self.cfg.embed_dim, self.world
@@ -121,6 +159,27 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
     def _embed_forward(self, ph, st, T):
         c = self.cfg
         F, d = c.num_fields, c.embed_dim
+        if self.peer_gather:
+            main = torch.cuda.current_stream(self.dev)
+            # owners' view of the step (keys for the backward): routing, id all-to-all, key sort — all on a
+            # side stream; the peer reads below need none of it
+            self.side2.wait_stream(main)
+            with torch.cuda.stream(self.side2):
+                with ph("route_ids"):
+                    ops.route_ids_padded(self.ids, F, self.rows_t, self.lbase_t, self.world, self.cap, self.send_rows,
+                                         self.inverse, self.send_counts, self.overflow)
+                with ph("a2a_ids"):
+                    self.ex.all_to_all(self.recv_rows, self.send_rows)
+                with ph("sort_keys"):
+                    cabi.call("rs_embed_gather_rows", self.table.data_ptr(), self.recv_rows.data_ptr(),
+                              self.recv_rows.numel(), d, None, T, None, self.keys.data_ptr(), ops._stream())
+                    ops.sort_keys(self.keys, self.row_bits, out=self.keys_sorted)
+                self.route_done.record(self.side2)
+            with ph("embed_gather_peer"):
+                cabi.call("rs_embed_gather_peer_fwd", ctypes.addressof(self.peer_ptrs), self.world,
+                          self.ids.data_ptr(), self.lbase_t.data_ptr(), self.rows_t.data_ptr(),
+                          c.batch * F, F, d, self.X.data_ptr(), T, st)
+            return
         with ph("route_ids"):
             ops.route_ids_padded(self.ids, F, self.rows_t, self.lbase_t, self.world, self.cap, self.send_rows,
                                  self.inverse, self.send_counts, self.overflow)
@@ -134,9 +193,15 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
         with ph("unpermute"):
             ops.permute_rows(self.rows_in, self.inverse, scatter=False, out=self.X.view(-1, d))
 
+    def _sort_keys(self, ph):
+        if not self.peer_gather:            # peer mode sorts on its own side stream (see _embed_forward)
+            super()._sort_keys(ph)
+
     def _embed_backward(self, ph, st, T, main):
         c = self.cfg
         d = c.embed_dim
+        if self.peer_gather:
+            main.wait_event(self.route_done)   # inverse permutation + sorted keys of this step
         with ph("permute_grads"):
             self.g_send.zero_()
             ops.permute_rows(self.dX.view(-1, d), self.inverse, scatter=True, out=self.g_send)
@@ -147,6 +212,14 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
             # local losses are means over the local batch: 1/W makes it the global-batch mean
             ops.segsum_adam(self.table, self.table_m, self.table_v, self.g_recv, self.keys_sorted, c.lr_sparse,
                             c.beta1, c.beta2, c.eps, self.adam_scalars, grad_scale=1.0 / self.world)
+        if self.peer_gather:
+            # cross-rank barrier: every owner's update is complete before any rank's next peer gather;
+            # runs beside the dense Adam
+            self.side2.wait_stream(main)
+            with torch.cuda.stream(self.side2):
+                with ph("peer_barrier"):
+                    dist.all_reduce(self.barrier_buf, group=self.ex.group)
+            self._join_side2 = True
 
     def _dense_sync(self, ph):
         with ph("allreduce_dense"):
