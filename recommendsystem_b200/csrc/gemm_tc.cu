@@ -19,16 +19,101 @@ constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;          // bf16 elements per stage along K = one 128-byte swizzle row
 constexpr int TC_THREADS = 192;
 
-template <typename CT>
-__device__ __forceinline__ float tc_epi(float acc, int epi, const float* bias, float auxv, float cold, int n) {
-  switch (epi) {
-    case RS_EPI_BIAS: return acc + bias[n];
-    case RS_EPI_BIAS_RELU: return fmaxf(acc + bias[n], 0.f);
-    case RS_EPI_BIAS_SIGMOID: return 1.f / (1.f + __expf(-(acc + bias[n])));
-    case RS_EPI_MUL_RELU_MASK: return auxv > 0.f ? acc : 0.f;
-    case RS_EPI_MUL_DSIGMOID: return acc * auxv * (1.f - auxv);
-    case RS_EPI_ACCUM: return acc + cold;
-    default: return acc;
+#ifdef RS_GEMM_PROFILE
+__device__ long long gemm_prof[16];
+#define GPROF(i) if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) gemm_prof[i] = clock64();
+#else
+#define GPROF(i)
+#endif
+
+
+// ---- epilogue phase B: lane = column group of a staged [32 rows][BN] fp32 block; every warp instruction
+// touches one contiguous row segment of C / aux.  Rows are unrolled by 4 so that the shared-memory and
+// aux loads of four rows are in flight together; EPI is a compile-time constant here.
+template <int BN, int EPI, typename CT>
+__device__ __forceinline__ void epilogue_rows(const float* stg, int rows_here, int lane, int ncols, int N, CT* c_rows,
+                                              int64_t ldc, const CT* a_rows, int64_t ldaux, const float* bias,
+                                              int vec_ok) {
+  constexpr int PITCH = BN + 4;
+  constexpr int CPL = BN / 32;
+  constexpr bool NEED_AUX = EPI == RS_EPI_MUL_RELU_MASK || EPI == RS_EPI_MUL_DSIGMOID;
+  constexpr bool NEED_BIAS = EPI == RS_EPI_BIAS || EPI == RS_EPI_BIAS_RELU || EPI == RS_EPI_BIAS_SIGMOID;
+  const int col = lane * CPL;
+  if (col >= ncols) return;
+  const bool lane_full = col + CPL <= ncols;
+  const bool vec = vec_ok && lane_full && CPL == 4;
+  float bv[CPL];
+#pragma unroll
+  for (int e = 0; e < CPL; ++e) bv[e] = (NEED_BIAS && col + e < ncols) ? bias[col + e] : 0.f;
+  constexpr int RU = 4;
+  for (int r0 = 0; r0 < rows_here; r0 += RU) {
+    float acc[RU][CPL], av[RU][CPL];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      const int rr = min(r0 + u, rows_here - 1);
+#pragma unroll
+      for (int e = 0; e < CPL; ++e) { acc[u][e] = stg[rr * PITCH + col + e]; av[u][e] = 0.f; }
+      if (NEED_AUX || EPI == RS_EPI_ACCUM) {
+        const CT* src = (NEED_AUX ? a_rows + (int64_t)rr * ldaux : c_rows + (int64_t)rr * ldc) + col;
+        if (vec) {
+          const float4 a4 = load4<CT>(src);
+          av[u][0] = a4.x;
+          if constexpr (CPL == 4) { av[u][1] = a4.y; av[u][2] = a4.z; av[u][3] = a4.w; }
+        } else {
+#pragma unroll
+          for (int e = 0; e < CPL; ++e)
+            if (col + e < ncols) av[u][e] = to_f<CT>(src[e]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+      if (r0 + u >= rows_here) break;
+      float v[CPL];
+#pragma unroll
+      for (int e = 0; e < CPL; ++e) {
+        const float a = acc[u][e];
+        if (EPI == RS_EPI_BIAS) v[e] = a + bv[e];
+        else if (EPI == RS_EPI_BIAS_RELU) v[e] = fmaxf(a + bv[e], 0.f);
+        else if (EPI == RS_EPI_BIAS_SIGMOID) v[e] = 1.f / (1.f + __expf(-(a + bv[e])));
+        else if (EPI == RS_EPI_MUL_RELU_MASK) v[e] = av[u][e] > 0.f ? a : 0.f;
+        else if (EPI == RS_EPI_MUL_DSIGMOID) v[e] = a * av[u][e] * (1.f - av[u][e]);
+        else if (EPI == RS_EPI_ACCUM) v[e] = a + av[u][e];
+        else v[e] = a;
+      }
+      CT* crow = c_rows + (int64_t)(r0 + u) * ldc + col;
+      if (vec) {
+        if constexpr (CPL == 4) store4<CT>(crow, make_float4(v[0], v[1], v[2], v[3]));
+      } else {
+#pragma unroll
+        for (int e = 0; e < CPL; ++e)
+          if (col + e < ncols) crow[e] = from_f<CT>(v[e]);
+      }
+    }
+  }
+}
+
+// split-K partial tile rows (fp32, [splits][M][N])
+template <int BN>
+__device__ __forceinline__ void epilogue_partial(const float* stg, int rows_here, int lane, int ncols, int N, float* dst_rows) {
+  constexpr int PITCH = BN + 4;
+  constexpr int CPL = BN / 32;
+  const int col = lane * CPL;
+  if (col >= ncols) return;
+  const bool vec = (col + CPL <= ncols) && (N % CPL) == 0;
+#pragma unroll 4
+  for (int rr = 0; rr < rows_here; ++rr) {
+    float* dst = dst_rows + (int64_t)rr * N + col;
+    const float* src = stg + rr * PITCH + col;
+    if (vec) {
+      if constexpr (CPL == 4) *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src);
+      else if constexpr (CPL == 2) *reinterpret_cast<float2*>(dst) = make_float2(src[0], src[1]);
+      else dst[0] = src[0];
+    } else {
+#pragma unroll
+      for (int e = 0; e < CPL; ++e)
+        if (col + e < ncols) dst[e] = src[e];
+    }
   }
 }
 
@@ -40,7 +125,10 @@ struct TcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int STG_PITCH = BN + 4;                      // epilogue staging row pitch (floats)
+  static constexpr int STG_BYTES = TC_BM * STG_PITCH * 4;       // [128 rows][BN + 4] fp32, reuses the stages
+  static constexpr int MAIN_BYTES = STAGES * STAGE_BYTES > STG_BYTES ? STAGES * STAGE_BYTES : STG_BYTES;
+  static constexpr int TOTAL = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BN, int STAGES, bool MN, typename CT>
@@ -53,12 +141,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int TC_STAGES = STAGES;
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * S::STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::MAIN_BYTES);
   uint64_t* empty_bar = full_bar + TC_STAGES;
   uint64_t* acc_bar = empty_bar + TC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { GPROF(0) }
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
   const int kb_total = (K + TC_BK - 1) / TC_BK;
   const int kb0 = blockIdx.z * kb_per_split;
@@ -79,6 +168,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) { GPROF(1) }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -113,6 +203,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int s = i % TC_STAGES;
         const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
         mbar_wait(&full_bar[s], ph);
+        if (i == 0) { GPROF(2) }
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * S::STAGE_BYTES);
         if constexpr (!MN) {
@@ -133,68 +224,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_commit(&empty_bar[s]);                  // stage free once these MMAs have read it
       }
       tc_commit(acc_bar);                          // accumulator complete
+      GPROF(3)
     }
   } else {
-    // ---- epilogue warps 2..5: TMEM lane group = warp % 4
+    // ---- epilogue warps 2..5 (TMEM lane group = warp % 4).  A thread owns an accumulator ROW, but a
+    // row-per-thread global access pattern costs one memory transaction per lane (measured: 22 k of the
+    // tile's 28 k cycles).  So: accumulators -> shared memory (the pipeline stages are idle now; each warp
+    // touches only its own 32 rows, __syncwarp suffices) -> lane = column group, and every warp
+    // instruction reads aux / writes C as ONE contiguous row segment.
     const int lg = warp & 3;
     mbar_wait(acc_bar, 0);
+    if (threadIdx.x == 64) { GPROF(4) }
     tc_fence_after();
-    const int row = m0 + lg * 32 + lane;
-    const bool row_ok = row < M;
+    constexpr int PITCH = S::STG_PITCH;            // floats; (BN + 4) mod 32 = 4: conflict-free 16-byte row writes
+    float* stg = reinterpret_cast<float*>(smem) + (size_t)lg * 32 * PITCH;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (n0 + c0 >= N) break;                     // warp-uniform
       uint32_t r[32];
       tc_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, r);
-      if (!row_ok) continue;
-      const int nbase = n0 + c0;
-      if (partial) {
-        float* dst = partial + ((int64_t)blockIdx.z * M + row) * N + nbase;
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (nbase + j < N) dst[j] = __uint_as_float(r[j]);
-        continue;
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(stg + lane * PITCH + c0 + j) =
+            make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+    }
+    __syncwarp();
+    const int rows_here = min(32, M - (m0 + lg * 32));      // warp-uniform
+    if (rows_here > 0) {
+      float* part_rows = partial ? partial + ((int64_t)blockIdx.z * M + m0 + lg * 32) * N + n0 : nullptr;
+      CT* c_rows = C + (int64_t)(m0 + lg * 32) * ldc + n0;
+      const CT* a_rows = aux ? aux + (int64_t)(m0 + lg * 32) * ldaux + n0 : nullptr;
+      const int ncols = N - n0;
+#define RS_EPI_GO(E) epilogue_rows<BN, E, CT>(stg, rows_here, lane, ncols, N, c_rows, ldc, a_rows, ldaux, bias ? bias + n0 : nullptr, vec_ok)
+      if (part_rows) epilogue_partial<BN>(stg, rows_here, lane, ncols, N, part_rows);
+      else switch (epi) {
+        case RS_EPI_BIAS: RS_EPI_GO(RS_EPI_BIAS); break;
+        case RS_EPI_BIAS_RELU: RS_EPI_GO(RS_EPI_BIAS_RELU); break;
+        case RS_EPI_BIAS_SIGMOID: RS_EPI_GO(RS_EPI_BIAS_SIGMOID); break;
+        case RS_EPI_MUL_RELU_MASK: RS_EPI_GO(RS_EPI_MUL_RELU_MASK); break;
+        case RS_EPI_MUL_DSIGMOID: RS_EPI_GO(RS_EPI_MUL_DSIGMOID); break;
+        case RS_EPI_ACCUM: RS_EPI_GO(RS_EPI_ACCUM); break;
+        default: RS_EPI_GO(RS_EPI_NONE);
       }
-      CT* crow = C + (int64_t)row * ldc + nbase;
-      const CT* arow = aux ? aux + (int64_t)row * ldaux + nbase : nullptr;
-      const bool full = vec_ok && (nbase + 32 <= N);
-      if (full) {
-        float v[32];
-        if (epi == RS_EPI_MUL_RELU_MASK || epi == RS_EPI_MUL_DSIGMOID) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 a4 = load4<CT>(arow + j);
-            v[j] = a4.x; v[j + 1] = a4.y; v[j + 2] = a4.z; v[j + 3] = a4.w;
-          }
-        } else if (epi == RS_EPI_ACCUM) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 a4 = load4<CT>(crow + j);
-            v[j] = a4.x; v[j + 1] = a4.y; v[j + 2] = a4.z; v[j + 3] = a4.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          v[j] = tc_epi<CT>(__uint_as_float(r[j]), epi, bias, v[j], v[j], nbase + j);
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) store4<CT>(crow + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (nbase + j < N) {
-            const float av = arow ? to_f<CT>(arow[j]) : 0.f;
-            const float cv = epi == RS_EPI_ACCUM ? to_f<CT>(crow[j]) : 0.f;
-            crow[j] = from_f<CT>(tc_epi<CT>(__uint_as_float(r[j]), epi, bias, av, cv, nbase + j));
-          }
-        }
-      }
+#undef RS_EPI_GO
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) { GPROF(5) }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN));
@@ -349,5 +426,13 @@ int gemm_bf16_tc(const void* A, int64_t lda, int transA, const void* B, int64_t 
     return splitk_reduce(partial, splits, C, ldc, M, N, epilogue == RS_EPI_ACCUM, dtype_c, st);
   return 0;
 }
+
+#ifdef RS_GEMM_PROFILE
+extern "C" int rs_debug_gemm_profile(long long* out16) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, gemm_prof, sizeof(long long) * 16);
+  return 0;
+}
+#endif
 
 }  // namespace rs

@@ -74,6 +74,20 @@ def embed_gather(table, ids, row_base, rows, out_dtype=torch.float32, want_keys=
     return out, keys, rws
 
 
+def embed_gather_peer(shards, ids, local_base, rows, out_dtype=torch.float32):
+    """Row-sharded gather over (peer) shard pointers: shards[r] is rank r's [local_rows, d] fp32 table (a
+    CUDA-IPC mapping in the multi-process trainer; plain local tensors in single-process tests)."""
+    import ctypes
+    W = len(shards)
+    F = ids.shape[-1]
+    n, d = ids.numel(), shards[0].shape[1]
+    ptrs = (ctypes.c_void_p * W)(*[t.data_ptr() for t in shards])
+    out = torch.empty(*ids.shape, d, dtype=out_dtype, device=ids.device)
+    call("rs_embed_gather_peer_fwd", ctypes.addressof(ptrs), W, _ptr(ids), _ptr(local_base), _ptr(rows), n, F, d,
+         _ptr(out), _DT[out_dtype], _stream())
+    return out
+
+
 def embed_gather_rows(table, rowidx, out_dtype=torch.float32, want_mask=False, want_keys=False):
     _need(rowidx.dtype == torch.int32 and rowidx.is_contiguous(), "rowidx must be contiguous int32")
     n, d = rowidx.numel(), table.shape[1]

@@ -230,3 +230,37 @@ def test_route_ids_padded_bit_exact(cuda_dev, n_b, F, world, cap):
     got = ops.permute_rows(src, g_inv, scatter=False).cpu().numpy()
     ref = np.where((inv >= 0)[:, None], src.cpu().numpy()[np.maximum(inv, 0)], 0)
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("W", [1, 2, 3, 8])
+@pytest.mark.parametrize("d,odt", [(16, "bf16"), (16, "f32"), (8, "f32"), (32, "bf16")])
+def test_embed_gather_peer_sharded_layout(cuda_dev, W, d, odt):
+    """rs_embed_gather_peer_fwd on W shards (all resident on this GPU here; CUDA-IPC peer mappings in the
+    multi-process trainer): owner = row mod W, local row = local_base[f] + row div W must reproduce the
+    unsharded gather BIT-EXACTLY, padding ids included."""
+    from recommendsystem_b200 import ops
+    from recommendsystem_b200.sharded import shard_layout
+    rng = np.random.default_rng(W * 100 + d)
+    F, B = 7, 333
+    rows = rng.integers(1, 300, size=F).astype(np.int64)
+    base = np.concatenate([[0], np.cumsum(rows)[:-1]]).astype(np.int64)
+    table = rng.standard_normal((int(rows.sum()), d)).astype(np.float32)
+    ids = rng.integers(0, 2 ** 45, size=(B, F)).astype(np.int64)
+    ids[5, 2] = -1
+    ids[0, 0] = -7
+    local_rows, local_base = shard_layout(rows, W)
+    shards = []
+    for r in range(W):
+        sh = np.zeros((int(local_rows.sum()), d), np.float32)
+        for f in range(F):
+            src = table[base[f] + r: base[f] + rows[f]: W]
+            sh[local_base[f]: local_base[f] + len(src)] = src
+        shards.append(torch.from_numpy(sh).to(cuda_dev))
+    dt = torch.bfloat16 if odt == "bf16" else torch.float32
+    tids = torch.from_numpy(ids).to(cuda_dev)
+    got = ops.embed_gather_peer(shards, tids, torch.from_numpy(local_base).to(cuda_dev),
+                                torch.from_numpy(rows).to(cuda_dev), dt)
+    ref, _, _ = ops.embed_gather(torch.from_numpy(table).to(cuda_dev), tids, torch.from_numpy(base).to(cuda_dev),
+                                 torch.from_numpy(rows).to(cuda_dev), dt)
+    assert torch.equal(got, ref)
+    assert float(got[5, 2].abs().sum()) == 0.0
