@@ -9,8 +9,9 @@ forward + backward + sparse Adam on touched rows + dense Adam.  A "step" is one 
 one fresh batch of uniform ids.
 
 Own arm: `value` = samples/s with ids/labels already resident in HBM (CUDA-graph replay per
-step, CUDA events, max over ranks); `e2e` = the same through AutoIntTrainer.step_from_host with
-pinned HOST ids/labels (H2D every step, loss read back every step).  `roofline` is the phase
+step, CUDA events, max over ranks); `e2e` = the same through the public host loop
+AutoIntTrainer.fit_host with pinned HOST ids/labels (every step's inputs go H2D and every step's loss
+comes back D2H inside the timed region; the loop double-buffers them beside the compute).  `roofline` is the phase
 with the largest share of the step; `kernels` lists every phase with its algorithmic
 bytes/FLOPs.  `cpu_baseline` / `--impl reference`: the op-for-op torch-CPU restatement of the
 reference TF graph (oracle/oracle_torch.py — TensorFlow is not installable offline) on the
@@ -255,13 +256,15 @@ def run_own(args):
     # ---- end to end: pinned host inputs, H2D + step + loss D2H every step
     ids_host = ids_dev.cpu().pin_memory()
     y_host = y_dev.cpu().pin_memory()
-    for i in range(W):
-        tr.step_from_host(ids_host[i], y_host[i])
+    for _ in tr.fit_host((ids_host[i], y_host[i]) for i in range(W)):
+        pass
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    for i in range(W, W + K):
-        last = tr.step_from_host(ids_host[i], y_host[i])
+    # the public end-to-end loop: every step uploads its own pinned-host batch and returns its own loss
+    # to the host; the loader overlaps batch n+1's H2D and step n-1's loss D2H with step n's compute
+    for last in tr.fit_host((ids_host[i], y_host[i]) for i in range(W, W + K)):
+        pass
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)

@@ -378,6 +378,65 @@ class AutoIntTrainer:
         self.run()
         return float(self.loss.item())
 
+    def fit_host(self, batches):
+        """End-to-end training loop over an iterable of (ids_pinned [B,F] int64, labels_pinned [B,1] f32) host
+        batches; yields one loss (python float) per batch, in order.
+
+        Input pipeline: batch n+1's host->device copy runs on a copy stream into the other half of a
+        double buffer while step n computes; step n's loss is copied device->host asynchronously into
+        pinned memory and handed out one step later, when it has long arrived.  Every step still moves
+        its own inputs H2D and its own loss D2H — they just do not serialise with the compute."""
+        dev = self.dev
+        if not hasattr(self, "_pipe"):
+            self._pipe = {
+                "copy": torch.cuda.Stream(device=dev),
+                "ids": [torch.empty_like(self.ids) for _ in range(2)],
+                "lab": [torch.empty_like(self.labels) for _ in range(2)],
+                "ready": [torch.cuda.Event() for _ in range(2)],       # H2D of slot k finished
+                "free": [torch.cuda.Event() for _ in range(2)],        # slot k consumed by the step
+                "loss": [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)],
+                "done": [torch.cuda.Event() for _ in range(2)],        # loss of slot k is on the host
+            }
+        p = self._pipe
+        main = torch.cuda.current_stream(dev)
+        it = iter(batches)
+
+        def upload(k, batch):
+            ids_h, lab_h = batch
+            with torch.cuda.stream(p["copy"]):
+                p["copy"].wait_event(p["free"][k])
+                p["ids"][k].copy_(ids_h, non_blocking=True)
+                p["lab"][k].copy_(lab_h, non_blocking=True)
+                p["ready"][k].record(p["copy"])
+
+        for k in range(2):
+            p["free"][k].record(main)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        upload(0, nxt)
+        n = 0
+        pending = None
+        while nxt is not None:
+            k = n & 1
+            cur, nxt = nxt, next(it, None)
+            main.wait_event(p["ready"][k])
+            self.ids.copy_(p["ids"][k], non_blocking=True)          # device-to-device, a few microseconds
+            self.labels.copy_(p["lab"][k], non_blocking=True)
+            p["free"][k].record(main)
+            if nxt is not None:
+                upload(k ^ 1, nxt)                                   # overlaps the step below
+            self.run()
+            p["loss"][k].copy_(self.loss.reshape(1), non_blocking=True)
+            p["done"][k].record(main)
+            if pending is not None:
+                p["done"][pending].synchronize()
+                yield float(p["loss"][pending][0])
+            pending = k
+            n += 1
+        p["done"][pending].synchronize()
+        yield float(p["loss"][pending][0])
+
     @torch.no_grad()
     def predict(self, ids: torch.Tensor) -> torch.Tensor:
         """Forward only (clip(sigmoid) probabilities), eager launches."""
