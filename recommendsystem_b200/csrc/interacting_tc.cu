@@ -194,12 +194,15 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
         const float mb = m * scale_log2;
         float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < FP; ++j) {
+        for (int j = 0; j < FP; j += 2) {
           // -inf -> 0 for padded keys; round to the bf16 value the MMA will see, so that the
           // normaliser l is the sum of exactly the weights used (a true convex combination).
           // (same expression as the backward's recomputation: interacting_tc_bwd.cu)
-          p[j] = bf16_round(ex2_approx(fmaf(p[j], scale_log2, -mb)));
+          p[j] = ex2_approx(fmaf(p[j], scale_log2, -mb));
+          p[j + 1] = ex2_approx(fmaf(p[j + 1], scale_log2, -mb));
+          bf16_round2(p[j], p[j + 1]);
           l4[j & 3] += p[j];
+          l4[(j + 1) & 3] += p[j + 1];
         }
         const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
         linv[h] = active ? 1.f / l : 0.f;

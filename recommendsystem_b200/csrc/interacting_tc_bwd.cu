@@ -72,8 +72,15 @@ __device__ unsigned long long itb_prof[32];
     itb_prof[i] += (unsigned long long)(t_now - t_last); \
     t_last = t_now;                                     \
   }
+#define PROFW(i)                                                                     \
+  if (blockIdx.x == 0 && (tid == 0 || tid == 32)) {                                   \
+    const long long t_now = clock64();                                               \
+    itb_prof[(tid == 0 ? 16 : 24) + (i)] += (unsigned long long)(t_now - t_w);        \
+    t_w = t_now;                                                                     \
+  }
 #else
 #define PROF(i)
+#define PROFW(i)
 #endif
 
 #define HSEL(a, e) (wg ? (a)[8 + (e)] : (a)[(e)])
@@ -174,6 +181,7 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
   const int issuer = tid == 0 ? 0 : (tid == 32 ? 1 : (tid == 128 ? 2 : (tid == 160 ? 3 : -1)));
 #ifdef RS_ITB_PROFILE
   long long t_last = clock64();
+  long long t_w = clock64();
 #endif
   uint32_t phase = 0;
   uint32_t dw_acc = 0;                 // 0 until the first dW MMA of this CTA
@@ -371,7 +379,11 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
     tc_fence_after();
     float p[FP];                     // normalised attention row of this head
     {
+#ifdef RS_ITB_PROFILE
+      t_w = clock64();
+#endif
       ld_window<FP>(tl + TM_S + wg * 128, ws_lo, ws_hi, s_loc, F, -INFINITY, p);
+      PROFW(0)
       float m4[4] = {p[0], p[1], p[2], p[3]};
 #pragma unroll
       for (int j = 4; j < FP; ++j) m4[j & 3] = fmaxf(m4[j & 3], p[j]);
@@ -380,14 +392,18 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       const float mb = m * scale_log2;
       float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int j = 0; j < FP; ++j) {
-        p[j] = bf16_round(ex2_approx(fmaf(p[j], scale_log2, -mb)));   // the forward's P
+      for (int j = 0; j < FP; j += 2) {                                // the forward's P, bit for bit
+        p[j] = ex2_approx(fmaf(p[j], scale_log2, -mb));
+        p[j + 1] = ex2_approx(fmaf(p[j + 1], scale_log2, -mb));
+        bf16_round2(p[j], p[j + 1]);
         l4[j & 3] += p[j];
+        l4[(j + 1) & 3] += p[j + 1];
       }
       const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
       const float linv = active ? 1.f / l : 0.f;
 #pragma unroll
       for (int j = 0; j < FP; ++j) p[j] = active ? p[j] * linv : 0.f;
+      PROFW(1)
       if (s_loc < SPT) {
 #pragma unroll
         for (int c = 0; c < NCHF; ++c)
@@ -395,9 +411,12 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       }
     }
     // ================= 3. dP_h = dO_h V_h^T ; dV_h = P_h^T dO_h
+    PROFW(2)
     fence_async_smem();
+    PROFW(3)
     tc_fence_before();
     __syncthreads();
+    PROFW(4)
     PROF(3)
     if (issuer >= 0) {
       tc_fence_after();

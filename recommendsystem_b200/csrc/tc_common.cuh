@@ -207,4 +207,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Round two fp32 values to bf16 (RNE) and back.  ONE F2FP.PACK_AB (ALU pipe) + two integer unpacks; the
+// scalar __float2bfloat16_rn compiles to F2F.BF16.F32, which shares the quarter-rate XU pipe with MUFU.EX2
+// and made the softmax phases XU-bound (80 XU ops per 40 elements).
+__device__ __forceinline__ void bf16_round2(float& a, float& b) {
+  const uint32_t u = pack_bf16x2(a, b);
+  a = __uint_as_float(u << 16);
+  b = __uint_as_float(u & 0xFFFF0000u);
+}
+
 }  // namespace rs

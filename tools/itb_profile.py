@@ -29,3 +29,8 @@ print("kernel ms", e0.elapsed_time(e1), "cycles CTA0", tot)
 names = ["S", "dP+dV", "dQ+dK", "dX+dW+Z"]
 for p in range(4):
     print(f"phase {names[p]:6s} work+sync {v[3*p]:9d} ({v[3*p]/tot:5.1%})  issue {v[3*p+1]:9d} ({v[3*p+1]/tot:5.1%})  mma-wait {v[3*p+2]:9d} ({v[3*p+2]/tot:5.1%})")
+
+w = list(out)
+lab = ["ld_window", "max/exp/sum/normalise", "pack + smem store", "fence.proxy.async", "bar.sync wait"]
+for name, base in (("warp 0 (one window)", 16), ("warp 1 (two windows)", 24)):
+    print(name, {lab[i]: w[base + i] for i in range(5)})
