@@ -232,3 +232,117 @@ def dssm_fwd(xp, embs, dense_mask, P, user_ids, item_ids):
     kd = xp.mean((xp.detach(teacher_logit) - student_logit) ** 2, -1)            # KDLoss layer.py:277-279
     return {"student": xp.sigmoid(student_logit), "teacher": xp.sigmoid(teacher_logit), "distill": kd,
             "user_emb": user, "item_emb": item}
+
+
+# ------------------------------------------------------------------------------------- rank/ctr
+PPNET_SPLIT = [256, 64, 8, 256, 64, 8, 32, 16]
+GATE_FEATURE_LIST = ["1568", "1570", "1578", "1591", "1593", "1614", "1736", "1737", "2039", "2599", "3051", "3303",
+                     "3389", "1576", "1577", "1578"]
+
+
+def rank_ctr_layout(model_config):
+    """SingleSlot + BaseModel.__init__ bookkeeping (rank/ctr/base_model.py:14-27,35-86,132-158), restated with
+    the reference's own variable roles (last_start / last_end per slot).  Returns (max_embed_size, structure,
+    bias, gate) with slices as [slot, start, end]."""
+    fs = model_config["feature_slot"]
+    slot = {}          # slot -> dict(intervals, last_start, last_end, total)
+    bias = {}
+
+    def update(s, emb_size, is_single):                                  # SingleSlot.update_intervals :22-27
+        st = slot.setdefault(s, dict(intervals=[], last_start=-1, last_end=-1, total=0))
+        st["last_start"] = st["last_end"] + 1
+        st["last_end"] = st["last_start"] + emb_size - 1
+        if is_single:
+            st["intervals"].append([st["last_start"], st["last_end"] + 1])
+        st["total"] += emb_size
+
+    for k, ft in fs["sparse_feature"].items():                           # :40-56
+        s = ft["slot_id"][0]
+        update(s, ft["emb_size"], "bias" not in ft)
+        if "bias" in ft:
+            if "bias_type" not in ft:
+                raise Exception("bias_type could not be null")
+            bias.setdefault(s, {})[ft["bias_type"]] = [slot[s]["last_start"], slot[s]["last_end"] + 1]
+    for k, ft in fs["sequence_feature"].items():                         # :63-71
+        s = ft["slot_id"][0]
+        if s in slot:
+            raise Exception("sequence feature " + s + "has been defined more than once")
+        update(s, ft["emb_size"], True)
+    max_embed = max(st["total"] for st in slot.values())                 # :82-86
+    structure, gate = [], []
+    for s, st in slot.items():                                           # :136-143
+        for iv in st["intervals"]:
+            structure.append([s, iv[0], iv[1]])
+            if s in GATE_FEATURE_LIST:
+                gate.append([s, iv[0], iv[1]])
+    b = {}
+    for s in sorted(bias):                                               # :146-154
+        for t, iv in bias[s].items():
+            b.setdefault(t, []).append([s, iv[0], iv[1]])
+    return max_embed, structure, b, gate
+
+
+def _interacting(xp, x, P, name, H, L, eps=1e-3):
+    """InteractingLayer.call (InteractingLayer.py:37-61) with the layer's own Dense / LayerNorm parameters."""
+    g = lambda k: P["%s.%s" % (name, k)]
+    if xp is NP:
+        from . import oracle_np as onp
+        W = np.concatenate([g("query_dense_kernel"), g("key_dense_kernel"), g("value_dense_kernel"), g("res_dense_kernel")], 1)
+        b = np.concatenate([g("query_dense_bias"), g("key_dense_bias"), g("value_dense_bias"), g("res_dense_bias")])
+        return onp.interacting_fwd(x, W, b, g("layer_norm_gamma"), g("layer_norm_beta"), eps, H, L, True)
+    from . import oracle_torch as ot
+    return ot.interacting_layer(x, g("query_dense_kernel"), g("query_dense_bias"), g("key_dense_kernel"), g("key_dense_bias"),
+                                g("value_dense_kernel"), g("value_dense_bias"), g("res_dense_kernel"), g("res_dense_bias"),
+                                g("layer_norm_gamma"), g("layer_norm_beta"), eps, H, L, True)
+
+
+def rank_ctr_fwd(xp, emb, P, structure, bias, gate):
+    """Model.model_layer (rank/ctr/model_init.py:19-162).  emb: slot -> [B, max_embed_size]."""
+    take = lambda sl: emb[sl[0]][:, sl[1]:sl[2]]
+    st = [take(s) for s in structure]
+    n = len(st)
+    squeeze = xp.detach(xp.cat([xp.sum(e, 1, keepdims=True) / e.shape[1] for e in st], 1))       # :22-31
+    w = 2 * _dense(xp, _dense(xp, squeeze, P, "senet_squeeze_layer", "relu"), P, "senet_extract_layer", "sigmoid")
+    rw = [e * w[:, i:i + 1] for i, e in enumerate(st)]                                            # :39-41
+    fields = xp.stack([_dense(xp, e, P, "emb_linear_map.%d" % i) for i, e in enumerate(rw)], 1)   # :44-49
+    auto = _interacting(xp, fields, P, "interact", 2, 1)                                          # :54-59
+    auto = auto.reshape(auto.shape[0], -1)                                                        # :60
+    ppnet = 2 * _dense(xp, xp.cat([take(s) for s in bias["ppnet"]], 1), P, "dnn_ppnet_gate", "sigmoid")   # :63-65
+    offs = np.cumsum([0] + PPNET_SPLIT)
+    gates = [ppnet[:, offs[i]:offs[i + 1]] for i in range(len(PPNET_SPLIT))]                      # :66
+    deep = xp.cat(rw, 1)                                                                          # :70
+    for i in range(2):                                                                            # :72-77
+        deep = xp.relu(_dense(xp, deep, P, "dnn.%d" % i) * gates[i + 6])
+    mult = xp.relu(xp.cat([take(s) for s in bias["multiply_user"]], 1) *
+                   xp.cat([take(s) for s in bias["multiply_item"]], 1))                           # :80-84
+    result = xp.cat([deep, auto, mult], 1)                                                        # :88
+    can = _dense(xp, xp.cat([take(s) for s in bias["can"]], 1), P, "dnn_can")                     # :92-93
+    B = can.shape[0]
+    w1, b1 = can[:, 0:48].reshape(B, 8, 6), can[:, 48:54].reshape(B, 1, 6)                        # :94-98
+    w2, b2 = can[:, 54:78].reshape(B, 6, 4), can[:, 78:82].reshape(B, 1, 4)
+    gate_input = xp.cat([take(s) for s in gate], 1)                                               # :105
+    ex = []
+    for i in range(3):                                                                            # :106-115
+        x = result
+        for j in range(2):
+            g = 2 * _dense(xp, _dense(xp, gate_input, P, "experts.gate_%d_%d_1" % (i, j), "relu"), P,
+                           "experts.gate_%d_%d_2" % (i, j), "sigmoid")
+            x = g * _dense(xp, x, P, "experts.expert_output_%d_%d" % (i, j), "relu")
+        ex.append(x)
+    ec = xp.stack(ex, 1)
+    out = {}
+    for i in range(2):                                                                            # :123-161
+        go = result
+        for j in range(2):
+            go = _dense(xp, go, P, "task_gates.gate_%d_%d" % (i, j), "relu")
+        go = _dense(xp, go, P, "task_gates.gate_output_%d" % i, "softmax")
+        r = xp.sum(ec * xp.expand(go, -1), 1)
+        for j in range(2):
+            if j == 0:
+                r = xp.relu(r * gates[i * 3])
+            r = xp.relu(_dense(xp, r, P, "task_dnn2.task%d_dnn2_%d" % (i, j)) * gates[i * 3 + j + 1])
+        c = xp.relu(xp.expand(r, 1) @ w1 + b1)
+        c = xp.relu(c @ w2 + b2)[:, 0, :]
+        p = _dense(xp, xp.cat([r, c], 1), P, "task_out.%d" % i, "sigmoid")
+        out["task%d" % i] = xp.where(p < 1e-6, p * 0 + 1e-6, p)                                    # clip_by_value(1e-6, 1.0)
+    return out

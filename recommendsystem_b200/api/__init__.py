@@ -13,6 +13,7 @@ forward/backward run the hand-written sm_100a kernels through the C-ABI.
     autoint, rank/multi_head/multidnn.py  ->  api.builders.{AutoInt, AUTOINT}
     staytime/VideoDnn.py, model.py, config.py -> api.video_dnn.{create_moe_sub_model, mtl_net, create_model_func,
                                                custom_kl_loss, cross_entropy, mse_loss, huber_loss}, api.staytime_config
+    rank/ctr/base_model.py, model_init.py ->  api.rank_ctr.{parse_feature_slots, RankCtrSubModel, Model}
     rough_rank/model.py, config/config.py ->  api.rough_rank_model.{create_tower, create_tower_teacher,
                                                create_shallow_tower, DSSM, create_model, mse_loss, y_pred_loss, config}
 """

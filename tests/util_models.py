@@ -89,3 +89,62 @@ def dssm_params(rng, user_ids, item_ids, d=16):
     _dense(P, rng, "shallow.shallow_dnn_0", 32, 32)
     _dense(P, rng, "shallow.logit_shallow", 32, 1)
     return P
+
+
+def rank_ctr_config(rng, n_common=14, n_extra_slots=3):
+    """A small synthetic model_config with the structure of rank/ctr/model_parameter.json: common features of
+    width 8 / 16, slots shared by several features, all four bias types, gate slots, a sequence feature."""
+    sparse = {}
+    gate_slots = ["1568", "1570", "1578", "1591"]
+    slots = gate_slots + [str(5000 + i) for i in range(n_common - len(gate_slots))]
+    for i, s in enumerate(slots):
+        sparse["f_common_%d" % i] = {"emb_size": int(rng.choice([8, 16])), "slot_id": [s]}
+    for i in range(n_extra_slots):                      # a second common feature on an existing slot
+        sparse["f_second_%d" % i] = {"emb_size": 8, "slot_id": [slots[i]]}
+    for i in range(4):
+        sparse["f_ppnet_%d" % i] = {"emb_size": 8, "bias": True, "bias_type": "ppnet", "slot_id": [slots[i]]}
+        sparse["f_can_%d" % i] = {"emb_size": 8, "bias": True, "bias_type": "can", "slot_id": [slots[i + 2]]}
+    for i in range(2):
+        sparse["f_mu_%d" % i] = {"emb_size": 16, "bias": True, "bias_type": "multiply_user", "slot_id": [slots[i + 5]]}
+        sparse["f_mi_%d" % i] = {"emb_size": 16, "bias": True, "bias_type": "multiply_item", "slot_id": [slots[i + 7]]}
+    sparse["f_bias_only"] = {"emb_size": 8, "bias": True, "bias_type": "ppnet", "slot_id": ["7000"]}
+    return {"feature_slot": {"sparse_feature": sparse,
+                             "sequence_feature": {"seq_0": {"emb_size": 16, "slot_id": ["8000"]}},
+                             "dense_feature": {}}}
+
+
+def rank_ctr_params(rng, structure, bias, gate):
+    n = len(structure)
+    w = lambda sl: sl[2] - sl[1]
+    P = {}
+    _dense(P, rng, "senet_squeeze_layer", n, n // 4)
+    _dense(P, rng, "senet_extract_layer", n // 4, n)
+    for i, sl in enumerate(structure):
+        _dense(P, rng, "emb_linear_map.%d" % i, w(sl), 8)
+    for nm in ("query", "key", "value", "res"):
+        P["interact.%s_dense_kernel" % nm] = glorot_uniform(rng, 8, 8)
+        P["interact.%s_dense_bias" % nm] = (0.1 * rng.standard_normal(8)).astype(np.float32)
+    P["interact.layer_norm_gamma"] = (1 + 0.1 * rng.standard_normal(8)).astype(np.float32)
+    P["interact.layer_norm_beta"] = (0.1 * rng.standard_normal(8)).astype(np.float32)
+    _dense(P, rng, "dnn_ppnet_gate", sum(w(s) for s in bias["ppnet"]), 704)
+    tot = sum(w(s) for s in structure)
+    _dense(P, rng, "dnn.0", tot, 32)
+    _dense(P, rng, "dnn.1", 32, 16)
+    _dense(P, rng, "dnn_can", sum(w(s) for s in bias["can"]), 82)
+    res_w = 16 + 8 * n + sum(w(s) for s in bias["multiply_user"])
+    gw = sum(w(s) for s in gate)
+    for i in range(3):
+        x = res_w
+        for j, u in enumerate((512, 256)):
+            _dense(P, rng, "experts.gate_%d_%d_1" % (i, j), gw, u)
+            _dense(P, rng, "experts.gate_%d_%d_2" % (i, j), u, u)
+            _dense(P, rng, "experts.expert_output_%d_%d" % (i, j), x, u)
+            x = u
+    for i in range(2):
+        _dense(P, rng, "task_gates.gate_%d_0" % i, res_w, 256)
+        _dense(P, rng, "task_gates.gate_%d_1" % i, 256, 32)
+        _dense(P, rng, "task_gates.gate_output_%d" % i, 32, 3)
+        _dense(P, rng, "task_dnn2.task%d_dnn2_0" % i, 256, 64)
+        _dense(P, rng, "task_dnn2.task%d_dnn2_1" % i, 64, 8)
+        _dense(P, rng, "task_out.%d" % i, 12, 1)
+    return P
