@@ -168,7 +168,8 @@ def algorithmic(phase, B, act_bytes, n_unique):
         "interacting_fwd": (n * (D + U) * act_bytes + L * n * U * 4, inter_f),
         "interacting_bwd": (n * (U + 2 * D) * act_bytes + L * n * U * 4, 3 * inter_f),
         "mlp_fwd": (B * (F * D + 2 * MLP[0] + MLP[1]) * act_bytes, gemm),
-        "mlp_bwd": (B * (F * D + 3 * MLP[0] + 3 * MLP[1]) * act_bytes, gemm + 2 * B * MLP[0] * MLP[1]),
+        "mlp_bwd": (B * (2 * MLP[0] + 3 * MLP[1]) * act_bytes, 2 * B * MLP[0] * MLP[1]),     # act_bwd + dgrad (main stream)
+        "mlp_wgrad": (B * (F * D + 2 * MLP[0] + MLP[1]) * act_bytes, gemm),                  # x^T dy + colsums (side stream)
         "mlp_dgrad_x": (B * (MLP[0] + 2 * F * D) * act_bytes, 2 * B * F * D * MLP[0]),
         "logits_loss": (B * zw * act_bytes * 5, 6 * B * zw),
         "sort_keys": (n * 8 * 2, 0),

@@ -262,7 +262,12 @@ class AutoIntTrainer:
         with ph("mlp_bwd"):
             ops.act_bwd(self.dZ[:, :self.n_deep], acts[nmlp], 0, out=self.dH[nmlp - 1])
             for i in reversed(range(nmlp)):
-                self._wgrad(acts[i], self.dH[i], f"mlp_W{i}", f"mlp_b{i}")
+                # weight / bias gradients are only consumed by the dense Adam at the end of the step: they run
+                # on the side stream (after the key sort), off the dgrad -> InteractingLayer-backward chain
+                self.side.wait_stream(main)
+                with torch.cuda.stream(self.side):
+                    with ph("mlp_wgrad"):
+                        self._wgrad(acts[i], self.dH[i], f"mlp_W{i}", f"mlp_b{i}")
                 if i > 0:   # dH[i-1] = (dH[i] @ W_i^T) * relu'(h_{i-1}); W_i [in,out] is the K-major B operand
                     ops.gemm(self.dH[i], self._w(f"mlp_W{i}"), self.dH[i - 1], aux=acts[i],
                              epilogue=E.EPI_MUL_RELU_MASK, transB=True)
