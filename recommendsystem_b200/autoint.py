@@ -164,6 +164,7 @@ class AutoIntTrainer:
                          for i in range(len(cfg.mlp_hidden))}
             self._refresh_wt()
         self.side = torch.cuda.Stream(device=self.dev)
+        self.sort_done = torch.cuda.Event()
         self.graph = None
         self.timer = None               # set to a PhaseTimer for an instrumented (eager) step
         n_ws = max(cabi.load().rs_interacting_workspace_bytes(B, F, d, U),
@@ -277,21 +278,24 @@ class AutoIntTrainer:
         assert self.spec[1][2] == nW and self.spec[2][2] == nW + 4 * U and self.spec[3][2] == nW + 5 * U
         with ph("interacting_bwd"):
             self._interacting_bwd(dparams, st, T)
-        # all dense gradients exist now: their all-reduce (multi-GPU) overlaps the embedding backward
+        # all dense gradients exist now: their all-reduce (multi-GPU) and then the dense Adam run on the side
+        # stream beside the embedding backward
+        ops.adam_advance(self.adam_scalars, c.beta1, c.beta2)
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
             self._dense_sync(ph)
         with ph("mlp_dgrad_x"):
             ops.gemm(self.dH[0], self._w("mlp_W0"), self.dX.view(B, F * d), epilogue=E.EPI_ACCUM, transB=True)
-        # K3: sparse Adam on touched rows; dense Adam on the flat buffer
-        ops.adam_advance(self.adam_scalars, c.beta1, c.beta2)
+        self.side.wait_stream(main)          # the last reader of the bf16 weight shadows is done
+        with torch.cuda.stream(self.side):
+            with ph("dense_adam"):
+                ops.dense_adam(self.flat, self.flat_m, self.flat_v, self.flat_g, c.lr_dense, c.beta1, c.beta2, c.eps,
+                               self.adam_scalars, self.flat_bf16)
+                if self.bf16:
+                    self._refresh_wt()
+        # K3: sparse Adam on touched rows
         self._embed_backward(ph, st, T, main)
         main.wait_stream(self.side)
-        with ph("dense_adam"):
-            ops.dense_adam(self.flat, self.flat_m, self.flat_v, self.flat_g, c.lr_dense, c.beta1, c.beta2, c.eps,
-                           self.adam_scalars, self.flat_bf16)
-            if self.bf16:
-                self._refresh_wt()
         if getattr(self, "_join_side2", False):      # peer-gather barrier stream joins the step
             main.wait_stream(self.side2)
 
@@ -301,6 +305,7 @@ class AutoIntTrainer:
         with torch.cuda.stream(self.side):
             with ph("sort_keys"):
                 ops.sort_keys(self.keys, self.row_bits, out=self.keys_sorted)
+            self.sort_done.record(self.side)
 
     # ---- embedding halves of the step (overridden by the row-sharded multi-GPU trainer)
     def _embed_forward(self, ph, st, T):
@@ -313,7 +318,7 @@ class AutoIntTrainer:
 
     def _embed_backward(self, ph, st, T, main):
         c = self.cfg
-        main.wait_stream(self.side)            # sorted keys
+        main.wait_event(self.sort_done)        # sorted keys (not the dense work queued behind them)
         with ph("embed_segsum_adam"):
             ops.segsum_adam(self.table, self.table_m, self.table_v, self.dX.view(-1, c.embed_dim), self.keys_sorted,
                             c.lr_sparse, c.beta1, c.beta2, c.eps, self.adam_scalars)

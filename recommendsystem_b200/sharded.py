@@ -207,7 +207,8 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
             ops.permute_rows(self.dX.view(-1, d), self.inverse, scatter=True, out=self.g_send)
         with ph("a2a_grads"):
             self.ex.all_to_all(self.g_recv, self.g_send)
-        main.wait_stream(self.side)            # sorted keys + dense all-reduce (side stream)
+        if not self.peer_gather:
+            main.wait_event(self.sort_done)    # sorted keys (the dense all-reduce / Adam stay on the side stream)
         with ph("embed_segsum_adam"):
             # local losses are means over the local batch: 1/W makes it the global-batch mean
             ops.segsum_adam(self.table, self.table_m, self.table_v, self.g_recv, self.keys_sorted, c.lr_sparse,
