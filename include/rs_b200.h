@@ -247,6 +247,27 @@ int rs_interacting_fwd(const void* x, int64_t x_ld, int64_t x_bs, int dtype,
                        void* y, int64_t y_ld, int64_t y_bs, void* saved,
                        int B, int F, int D, int U, int H, int L, int use_res,
                        int compute_bf16, void* stream);
+/* Training-mode attention-weight dropout (InteractingLayer.py:53-54; use_dropout=True at
+ * rank/multi_head/multidnn.py:54 and rank/ctr/model_init.py:54-59): the softmax weights are multiplied by an
+ * inverted-dropout mask before P.V.  The mask is a pure function of (dropout_seed, iteration, sample, head,
+ * query, key) — a splitmix64 hash of the element's linear index, kept iff its top 24 bits >= rate * 2^24 — so
+ * the backward regenerates it; pass the SAME rate and seed to both, and a fresh seed every step.
+ * dropout_rate == 0 is exactly rs_interacting_fwd / _bwd.  Built into the FFMA kernels (any shape). */
+int rs_interacting_fwd_dropout(const void* x, int64_t x_ld, int64_t x_bs, int dtype,
+                               const float* Wqkvr, const float* bqkvr,
+                               const float* ln_gamma, const float* ln_beta, float ln_eps,
+                               void* y, int64_t y_ld, int64_t y_bs, void* saved,
+                               int B, int F, int D, int U, int H, int L, int use_res,
+                               int compute_bf16, float dropout_rate, unsigned long long dropout_seed,
+                               void* stream);
+int rs_interacting_bwd_dropout(const void* x, int64_t x_ld, int64_t x_bs, const void* saved, int dtype,
+                               const float* Wqkvr, const float* bqkvr,
+                               const float* ln_gamma, const float* ln_beta, float ln_eps,
+                               const void* dy, int64_t dy_ld, int64_t dy_bs,
+                               void* dx, int64_t dx_ld, int64_t dx_bs, float* dparams,
+                               int B, int F, int D, int U, int H, int L, int use_res,
+                               int compute_bf16, float dropout_rate, unsigned long long dropout_seed,
+                               void* ws, size_t ws_bytes, void* stream);
 /* dx [B,F,D] (ld dx_ld), dparams: fp32 [D*4U + 4U + U + U] = dW | db | dgamma |
  * dbeta, OVERWRITTEN.  ws >= rs_interacting_workspace_bytes. */
 int rs_interacting_bwd(const void* x, int64_t x_ld, int64_t x_bs, const void* saved, int dtype,

@@ -263,8 +263,26 @@ def route_ids_padded(ids, F, rows, local_base, world, capacity):
 # ------------------------------------------------------- K4 InteractingLayer
 
 
+def dropout_scale(seed, it, B, H, F, rate):
+    """Inverted-dropout scale [H,B,F,F] of the attention weights of iteration `it` (InteractingLayer.py:53-54).
+    TensorFlow's random stream cannot be reproduced; the kernels use a counter-based mask instead
+    (include/rs_b200.h, rs_interacting_fwd_dropout): element (it, b, h, i, j) is kept iff the top 24 bits of
+    splitmix64(linear index + seed) are >= rate * 2^24, kept weights scale by 1 / (1 - rate)."""
+    h, b, i, j = np.meshgrid(np.arange(H, dtype=np.uint64), np.arange(B, dtype=np.uint64),
+                             np.arange(F, dtype=np.uint64), np.arange(F, dtype=np.uint64), indexing="ij")
+    with np.errstate(over="ignore"):
+        idx = ((((np.uint64(it) * np.uint64(B) + b) * np.uint64(H) + h) * np.uint64(F) + i) * np.uint64(F)) + j
+        z = idx + np.uint64(seed & 0xFFFFFFFFFFFFFFFF)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = (z >> np.uint64(40)).astype(np.float32) * np.float32(1.0 / 16777216.0)
+    keep = u >= np.float32(rate)
+    return np.where(keep, np.float32(1.0) / (np.float32(1.0) - np.float32(rate)), np.float32(0.0)).astype(np.float64)
+
+
 def interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res=True, keep_cache=False,
-                    iter_inputs=None, stored_act=None):
+                    iter_inputs=None, stored_act=None, dropout=None):
     """InteractingLayer.call (InteractingLayer.py:37-61; duplicate at
     rank/multi_head/interacting_layer.py).  Wqkvr = [Wq|Wk|Wv|Wr] ([D,4U], Keras
     [in,out] kernels side by side).  The four Dense(relu) layers and the
@@ -295,7 +313,10 @@ def interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res=True, ke
         vh = v.reshape(B, F, H, dh).transpose(2, 0, 1, 3)
         s = qh @ kh.transpose(0, 1, 3, 2) / (dh ** 0.5)     # :50-51
         p = softmax(s)                                      # :52
-        o = (p @ vh).transpose(1, 2, 0, 3).reshape(B, F, U)  # :55-56
+        pm = p
+        if dropout is not None and dropout[0] > 0:          # :53-54 (training): dropout = (rate, seed)
+            pm = p * dropout_scale(dropout[1], it, B, H, F, dropout[0])
+        o = (pm @ vh).transpose(1, 2, 0, 3).reshape(B, F, U)  # :55-56
         t = o + r if use_res else o                         # :57-58
         act = relu(t)                                       # :59
         if stored_act is not None:
@@ -304,13 +325,13 @@ def interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res=True, ke
             t = act
         y = layer_norm(act, gamma, beta, ln_eps)            # :60
         if keep_cache:
-            cache.append(dict(x=out, z=z, p=p, qh=qh, kh=kh, vh=vh, t=t, act=act))
+            cache.append(dict(x=out, z=z, p=p, pm=pm, it=it, qh=qh, kh=kh, vh=vh, t=t, act=act))
         out = y
     return (out, cache) if keep_cache else out
 
 
 def interacting_bwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, dy, use_res=True, iter_inputs=None,
-                    stored_act=None):
+                    stored_act=None, dropout=None):
     """Manual backward of interacting_fwd.  Returns dx, dW[D,4U], db[4U], dgamma, dbeta.
     iter_inputs: optional stored inputs of iterations 1..L-1; stored_act: optional stored
     pre-LayerNorm activations of iterations 0..L-1 (see interacting_fwd)."""
@@ -318,7 +339,7 @@ def interacting_bwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, dy, use_res=True
     dh = U // H
     B, F, _ = x.shape
     _, cache = interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res, keep_cache=True,
-                               iter_inputs=iter_inputs, stored_act=stored_act)
+                               iter_inputs=iter_inputs, stored_act=stored_act, dropout=dropout)
     dW = np.zeros_like(Wqkvr)
     db = np.zeros_like(bqkvr)
     dgamma = np.zeros_like(gamma)
@@ -338,8 +359,10 @@ def interacting_bwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, dy, use_res=True
         dr = dt if use_res else np.zeros_like(dt)
         do = dt.reshape(B, F, H, dh).transpose(2, 0, 1, 3)          # [H,B,F,dh]
         p, qh, kh, vh = c["p"], c["qh"], c["kh"], c["vh"]
-        dv = p.transpose(0, 1, 3, 2) @ do
+        dv = c["pm"].transpose(0, 1, 3, 2) @ do
         dp = do @ vh.transpose(0, 1, 3, 2)
+        if dropout is not None and dropout[0] > 0:                  # chain rule through p -> p * scale
+            dp = dp * dropout_scale(dropout[1], c["it"], B, H, F, dropout[0])
         ds = p * (dp - (dp * p).sum(-1, keepdims=True)) / (dh ** 0.5)
         dq = ds @ kh
         dk = ds.transpose(0, 1, 3, 2) @ qh

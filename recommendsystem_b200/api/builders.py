@@ -47,7 +47,8 @@ class AutoInt:
         if list(lg["hidden_units"]) != [1] or lg["activation"] != "sigmoid":
             raise NotImplementedError("logits head: Dense(1, sigmoid) (autoint:49-52 clips to a probability)")
         if it.get("use_dropout", False):
-            raise NotImplementedError("attention dropout is not built into the fused kernel yet")
+            raise NotImplementedError("the captured AutoInt engine runs without attention dropout; use "
+                                      "api.InteractingLayer(use_dropout=True) in a module graph")
         self.cfg = AutoIntConfig(num_fields=ft["num_fields"], rows_per_field=ft["rows_per_field"],
                                  embed_dim=ft["embed_dim"], layer_num=it["layer_num"], unit_num=it["unit_num"],
                                  head_num=it["head_num"], use_res=it.get("use_res", True),
@@ -88,8 +89,9 @@ class AutoIntSubModel(nn.Module):
 
     def __init__(self, deep_hidden_units: Sequence[int] = (32, 16), expert_num=7, expert_units=32):
         super().__init__()
-        # multidnn.py:54 (use_dropout=True there; dropout is applied only in training and is not built yet)
-        self.interact = InteractingLayer(layer_num=1, unit_num=8, head_num=2, use_dropout=False, use_res=True)
+        # multidnn.py:54: attention dropout 0.2 in training (fused into the kernel, counter-based mask)
+        self.interact = InteractingLayer(layer_num=1, unit_num=8, head_num=2, use_dropout=True, dropout_rate=0.2,
+                                         use_res=True)
         self.deep = nn.ModuleList([_KerasDense(u, "relu") for u in deep_hidden_units])
         self.experts = nn.ModuleList([_KerasDense(expert_units, "relu", 0.001) for _ in range(expert_num + 1)])
         self.gates = nn.ModuleList([_KerasDense(expert_num, "softmax", 0.001) for _ in range(self.NUM_LABELS)])

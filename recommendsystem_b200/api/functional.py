@@ -17,21 +17,23 @@ class InteractingFn(torch.autograd.Function):
     """InteractingLayer.call (InteractingLayer.py:37-61) fused forward / backward."""
 
     @staticmethod
-    def forward(ctx, x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res):
+    def forward(ctx, x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res, dropout_rate=0.0, dropout_seed=0):
         _require_cuda(x, Wqkvr)
         x = x.contiguous()
-        y, saved = ops.interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res)
+        y, saved = ops.interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res,
+                                       dropout_rate=dropout_rate, dropout_seed=dropout_seed)
         ctx.save_for_backward(x, saved if saved is not None else x.new_empty(0), Wqkvr, bqkvr, gamma, beta)
-        ctx.cfg = (ln_eps, H, L, use_res)
+        ctx.cfg = (ln_eps, H, L, use_res, dropout_rate, dropout_seed)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, saved, Wqkvr, bqkvr, gamma, beta = ctx.saved_tensors
-        ln_eps, H, L, use_res = ctx.cfg
+        ln_eps, H, L, use_res, rate, seed = ctx.cfg
         dx, dW, db, dg, dbt = ops.interacting_bwd(x, saved if saved.numel() else None, Wqkvr, bqkvr, gamma, beta,
-                                                  ln_eps, H, L, dy.contiguous().to(x.dtype), use_res)
-        return dx, dW, db, dg, dbt, None, None, None, None
+                                                  ln_eps, H, L, dy.contiguous().to(x.dtype), use_res,
+                                                  dropout_rate=rate, dropout_seed=seed)
+        return dx, dW, db, dg, dbt, None, None, None, None, None, None
 
 
 class DinFn(torch.autograd.Function):

@@ -18,6 +18,9 @@ class InteractingLayer(nn.Module):
 
     Extra keyword `ln_eps` pins the epsilon of the LayerNormalization whose source is missing from
     the reference (InteractingLayer.py:4); default 1e-3 = tf.keras.layers.LayerNormalization.
+    `use_dropout=True` applies inverted dropout to the attention weights in training mode (:53-54) inside the
+    fused kernels (counter-based mask, seed `dropout_seed` + call counter; TF's own random stream cannot be
+    reproduced, the distribution can).
     Weights are created on the first call (Keras `build`), Keras layout and names:
     query_dense/key_dense/value_dense/res_dense .kernel [in, unit_num] and .bias, layer_norm.gamma/.beta.
     """
@@ -28,6 +31,9 @@ class InteractingLayer(nn.Module):
         self.layer_num, self.unit_num, self.head_num = int(layer_num), int(unit_num), int(head_num)
         self.use_dropout, self.dropout_rate, self.use_res = bool(use_dropout), float(dropout_rate), bool(use_res)
         self.ln_eps = float(ln_eps)
+        self.dropout_seed = int(kwargs.get("dropout_seed", 0x5DEECE66D))     # masks = f(seed, call counter)
+        self._dropout_calls = 0
+        self.last_dropout_seed = None
         if self.unit_num % self.head_num != 0:
             raise ValueError("head_num must divide unit_num (tf.split, InteractingLayer.py:47)")
         self.built = False
@@ -63,13 +69,17 @@ class InteractingLayer(nn.Module):
             raise ValueError('The rank of input of InteractingLayer must be 3, but now is %d' % inputs.dim())
         if not self.built:
             self.build(inputs.shape, device=inputs.device)
+        rate, seed = 0.0, 0
         if self.use_dropout and self.training:
-            raise NotImplementedError(
-                "attention-weight dropout (InteractingLayer.py:53-54) is not built into the fused kernel yet; "
-                "call .eval() or construct with use_dropout=False")
+            # tf.keras Dropout on the attention weights (InteractingLayer.py:53-54): a fresh counter-based mask
+            # per call, reproducible from (dropout_seed, call counter)
+            rate = float(self.dropout_rate)
+            seed = (self.dropout_seed + 0x9E3779B97F4A7C15 * self._dropout_calls) & 0xFFFFFFFFFFFFFFFF
+            self._dropout_calls += 1
+            self.last_dropout_seed = seed
         W, b = self.packed()
         return InteractingFn.apply(inputs, W, b, self.layer_norm_gamma, self.layer_norm_beta, self.ln_eps,
-                                   self.head_num, self.layer_num, self.use_res)
+                                   self.head_num, self.layer_num, self.use_res, rate, seed)
 
     def get_config(self):
         return dict(layer_num=self.layer_num, unit_num=self.unit_num, head_num=self.head_num,

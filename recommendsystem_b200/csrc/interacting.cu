@@ -30,10 +30,12 @@ size_t rs_interacting_saved_bytes(int B, int F, int U, int L) {
   return (size_t)L * (size_t)B * (size_t)F * (size_t)U * sizeof(float);
 }
 
-int rs_interacting_fwd(const void* x, int64_t x_ld, int64_t x_bs, int dtype, const float* Wqkvr,
-                       const float* bqkvr, const float* ln_gamma, const float* ln_beta,
-                       float ln_eps, void* y, int64_t y_ld, int64_t y_bs, void* saved, int B, int F, int D, int U,
-                       int H, int L, int use_res, int compute_bf16, void* stream) {
+int rs_interacting_fwd_dropout(const void* x, int64_t x_ld, int64_t x_bs, int dtype, const float* Wqkvr,
+                               const float* bqkvr, const float* ln_gamma, const float* ln_beta,
+                               float ln_eps, void* y, int64_t y_ld, int64_t y_bs, void* saved, int B, int F, int D, int U,
+                               int H, int L, int use_res, int compute_bf16, float dropout_rate,
+                               unsigned long long dropout_seed, void* stream) {
+  RS_REQUIRE(dropout_rate >= 0.f && dropout_rate < 1.f, "interacting_fwd: dropout_rate %g not in [0, 1)", dropout_rate);
   RS_REQUIRE(B > 0 && F > 0 && L >= 1, "interacting_fwd: B=%d F=%d L=%d", B, F, L);
   RS_REQUIRE(H > 0 && U % H == 0, "interacting_fwd: head_num %d must divide unit_num %d", H, U);
   RS_REQUIRE(L == 1 || D == U, "interacting_fwd: layer_num>1 needs input dim %d == unit_num %d", D, U);
@@ -45,7 +47,10 @@ int rs_interacting_fwd(const void* x, int64_t x_ld, int64_t x_bs, int dtype, con
   RS_REQUIRE(x_bs % 4 == 0 && y_bs % 4 == 0, "interacting_fwd: batch strides must be multiples of 4");
   IFwdArgs a{x, x_ld, x_bs, Wqkvr, bqkvr, ln_gamma, ln_beta, ln_eps, y, y_ld, y_bs, saved, B, F, L, use_res,
              dtype, as_stream(stream)};
-  if (compute_bf16 && interacting_tc_supported(F, D, U, H, dtype)) return interacting_tc_fwd(a);
+  a.drop_rate = dropout_rate;
+  a.drop_seed = dropout_seed;
+  // attention dropout is built into the FFMA kernels only: the tensor-core path is taken without it
+  if (compute_bf16 && dropout_rate == 0.f && interacting_tc_supported(F, D, U, H, dtype)) return interacting_tc_fwd(a);
 #define RS_CASE(DD, UU, HH) \
   if (D == DD && U == UU && H == HH) return interacting_fwd_##DD##_##UU##_##HH(a);
   RS_INTERACT_SHAPES(RS_CASE)
@@ -54,11 +59,21 @@ int rs_interacting_fwd(const void* x, int64_t x_ld, int64_t x_bs, int dtype, con
   return RS_ERR_UNSUPPORTED;
 }
 
-int rs_interacting_bwd(const void* x, int64_t x_ld, int64_t x_bs, const void* saved, int dtype,
-                       const float* Wqkvr, const float* bqkvr, const float* ln_gamma,
-                       const float* ln_beta, float ln_eps, const void* dy, int64_t dy_ld,
-                       int64_t dy_bs, void* dx, int64_t dx_ld, int64_t dx_bs, float* dparams, int B, int F, int D, int U, int H, int L,
-                       int use_res, int compute_bf16, void* ws, size_t ws_bytes, void* stream) {
+int rs_interacting_fwd(const void* x, int64_t x_ld, int64_t x_bs, int dtype, const float* Wqkvr,
+                       const float* bqkvr, const float* ln_gamma, const float* ln_beta,
+                       float ln_eps, void* y, int64_t y_ld, int64_t y_bs, void* saved, int B, int F, int D, int U,
+                       int H, int L, int use_res, int compute_bf16, void* stream) {
+  return rs_interacting_fwd_dropout(x, x_ld, x_bs, dtype, Wqkvr, bqkvr, ln_gamma, ln_beta, ln_eps, y, y_ld, y_bs, saved,
+                                    B, F, D, U, H, L, use_res, compute_bf16, 0.f, 0ULL, stream);
+}
+
+int rs_interacting_bwd_dropout(const void* x, int64_t x_ld, int64_t x_bs, const void* saved, int dtype,
+                               const float* Wqkvr, const float* bqkvr, const float* ln_gamma,
+                               const float* ln_beta, float ln_eps, const void* dy, int64_t dy_ld,
+                               int64_t dy_bs, void* dx, int64_t dx_ld, int64_t dx_bs, float* dparams, int B, int F, int D,
+                               int U, int H, int L, int use_res, int compute_bf16, float dropout_rate,
+                               unsigned long long dropout_seed, void* ws, size_t ws_bytes, void* stream) {
+  RS_REQUIRE(dropout_rate >= 0.f && dropout_rate < 1.f, "interacting_bwd: dropout_rate %g not in [0, 1)", dropout_rate);
   RS_REQUIRE(B > 0 && F > 0 && L >= 1, "interacting_bwd: B=%d F=%d L=%d", B, F, L);
   RS_REQUIRE(H > 0 && U % H == 0, "interacting_bwd: head_num %d must divide unit_num %d", H, U);
   RS_REQUIRE(L == 1 || D == U, "interacting_bwd: layer_num>1 needs input dim == unit_num");
@@ -73,13 +88,25 @@ int rs_interacting_bwd(const void* x, int64_t x_ld, int64_t x_bs, const void* sa
   RS_REQUIRE(x_bs % 4 == 0 && dy_bs % 4 == 0 && dx_bs % 4 == 0, "interacting_bwd: batch strides must be multiples of 4");
   IBwdArgs a{x, x_ld, x_bs, saved, Wqkvr, bqkvr, ln_gamma, ln_beta, ln_eps, dy, dy_ld, dy_bs, dx, dx_ld, dx_bs, dparams,
              B, F, L, use_res, dtype, ws, ws_bytes, as_stream(stream)};
-  if (compute_bf16 && interacting_tc_supported(F, D, U, H, dtype)) return interacting_tc_bwd(a);
+  a.drop_rate = dropout_rate;
+  a.drop_seed = dropout_seed;
+  if (compute_bf16 && dropout_rate == 0.f && interacting_tc_supported(F, D, U, H, dtype)) return interacting_tc_bwd(a);
 #define RS_CASE(DD, UU, HH) \
   if (D == DD && U == UU && H == HH) return interacting_bwd_##DD##_##UU##_##HH(a);
   RS_INTERACT_SHAPES(RS_CASE)
 #undef RS_CASE
   set_error("interacting_bwd: (D=%d, U=%d, H=%d) not built", D, U, H);
   return RS_ERR_UNSUPPORTED;
+}
+
+int rs_interacting_bwd(const void* x, int64_t x_ld, int64_t x_bs, const void* saved, int dtype,
+                       const float* Wqkvr, const float* bqkvr, const float* ln_gamma,
+                       const float* ln_beta, float ln_eps, const void* dy, int64_t dy_ld,
+                       int64_t dy_bs, void* dx, int64_t dx_ld, int64_t dx_bs, float* dparams, int B, int F, int D, int U, int H, int L,
+                       int use_res, int compute_bf16, void* ws, size_t ws_bytes, void* stream) {
+  return rs_interacting_bwd_dropout(x, x_ld, x_bs, saved, dtype, Wqkvr, bqkvr, ln_gamma, ln_beta, ln_eps, dy, dy_ld, dy_bs,
+                                    dx, dx_ld, dx_bs, dparams, B, F, D, U, H, L, use_res, compute_bf16, 0.f, 0ULL, ws,
+                                    ws_bytes, stream);
 }
 
 }  // extern "C"

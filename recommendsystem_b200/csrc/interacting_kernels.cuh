@@ -55,6 +55,26 @@ __device__ __forceinline__ void project_row(const float* __restrict__ Ws,
   }
 }
 
+// Attention-weight dropout (InteractingLayer.py:53-54, tf.keras Dropout = inverted dropout): element
+// (iteration, sample, head, query i, key j) is kept iff the top 24 bits of a splitmix64 hash of its linear
+// index (+ seed) are >= rate * 2^24; kept weights are scaled by 1 / (1 - rate).  Counter-based, so the
+// backward (row pass AND column pass) regenerates any element's mask from its indices, and
+// oracle/oracle_np.py::dropout_scale reproduces it bit for bit.
+struct DropCfg { float rate; float inv_keep; unsigned long long seed; };
+
+__device__ __forceinline__ float drop_scale(const DropCfg& dc, unsigned long long idx) {
+  unsigned long long z = idx + dc.seed;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  const float u = (float)(unsigned int)(z >> 40) * (1.f / 16777216.f);
+  return u >= dc.rate ? dc.inv_keep : 0.f;
+}
+// linear index of attention element (it, b, h, i, j = 0): add j
+__device__ __forceinline__ unsigned long long drop_row_base(int it, long long B, long long b, int H, int h, int F, int i) {
+  return ((((unsigned long long)it * (unsigned long long)B + (unsigned long long)b) * H + h) * F + i) * (unsigned long long)F;
+}
+
 // Chunked online softmax attention for one query row and one head.
 // Krow0 points at K of the sample's first field (head offset applied), rows are
 // `stride` floats apart; V sits `voff` floats after K in the same row.
@@ -62,7 +82,8 @@ __device__ __forceinline__ void project_row(const float* __restrict__ Ws,
 template <int DH>
 __device__ __forceinline__ void attn_row_fwd(const float (&q)[DH], const float* __restrict__ Krow0,
                                              int stride, int voff, int F, float scale_log2,
-                                             float& m_out, float& l_out, float (&o)[DH]) {
+                                             float& m_out, float& l_out, float (&o)[DH],
+                                             const DropCfg& dc, unsigned long long drop_base) {
   float m = -INFINITY, l = 0.f;
 #pragma unroll
   for (int e = 0; e < DH; ++e) o[e] = 0.f;
@@ -94,8 +115,9 @@ __device__ __forceinline__ void attn_row_fwd(const float (&q)[DH], const float* 
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const int j = min(j0 + c, F - 1);
-      const float p = exp2f(s[c] - mn);
-      l += p;
+      float p = exp2f(s[c] - mn);
+      l += p;                                                       // the softmax normaliser ignores the mask
+      if (dc.rate > 0.f) p *= drop_scale(dc, drop_base + (unsigned long long)j);
       const float* vr = Krow0 + j * stride + voff;
 #pragma unroll
       for (int e = 0; e < DH; e += 4) {
@@ -174,7 +196,7 @@ __global__ void __launch_bounds__(NT)
 interacting_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, const float* __restrict__ W,
                        const float* __restrict__ bias, const float* __restrict__ gamma,
                        const float* __restrict__ beta, float eps, T* __restrict__ y, int64_t y_ld, int64_t y_bs,
-                       float* __restrict__ saved, int B, int F, int L, int use_res) {
+                       float* __restrict__ saved, int B, int F, int L, int use_res, DropCfg dc) {
   static_assert(U <= 32, "tmask is 32 bits");
   constexpr int DH = U / H;
   constexpr int N4 = 4 * U;
@@ -238,7 +260,8 @@ interacting_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, cons
           float qh[DH], oh[DH], m, linv;
 #pragma unroll
           for (int e = 0; e < DH; ++e) qh[e] = q[h * DH + e];
-          attn_row_fwd<DH>(qh, Ksample + h * DH, SK, U, F, scale_log2, m, linv, oh);
+          attn_row_fwd<DH>(qh, Ksample + h * DH, SK, U, F, scale_log2, m, linv, oh, dc,
+                           drop_row_base(it, B, smp, H, h, F, fld));
 #pragma unroll
           for (int e = 0; e < DH; ++e) o[h * DH + e] = oh[e];
         }
@@ -267,7 +290,7 @@ interacting_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, cons
                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                        const T* __restrict__ dy, int64_t dy_ld, int64_t dy_bs, T* __restrict__ dx, int64_t dx_ld,
                        int64_t dx_bs,
-                       float* __restrict__ part, int B, int F, int L, int use_res) {
+                       float* __restrict__ part, int B, int F, int L, int use_res, DropCfg dc) {
   constexpr int DH = U / H;
   constexpr int N4 = 4 * U;
   using S = ISmem<D, U>;
@@ -364,7 +387,8 @@ interacting_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, cons
             float qh[DH], oh[DH];
 #pragma unroll
             for (int e = 0; e < DH; ++e) qh[e] = q[h * DH + e];
-            attn_row_fwd<DH>(qh, A + sbase * SA + h * DH, SA, U, F, scale_log2, mh[h], lh[h], oh);
+            attn_row_fwd<DH>(qh, A + sbase * SA + h * DH, SA, U, F, scale_log2, mh[h], lh[h], oh, dc,
+                             drop_row_base(it, B, smp, H, h, F, fld));
 #pragma unroll
             for (int e = 0; e < DH; ++e) o[h * DH + e] = oh[e];
           }
@@ -449,6 +473,7 @@ interacting_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, cons
                 dp = fmaf(doh[e + 2], v4.z, dp); dp = fmaf(doh[e + 3], v4.w, dp);
               }
               const float p = exp2f(s * scale_log2 - m) * linv;
+              if (dc.rate > 0.f) dp *= drop_scale(dc, drop_row_base(it, B, smp, H, h, F, fld) + (unsigned long long)j);
               const float ds = p * (dp - delta);
 #pragma unroll
               for (int e = 0; e < DH; ++e) dq[e] = fmaf(ds, kk[e], dq[e]);
@@ -479,11 +504,14 @@ interacting_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, cons
                 dp = fmaf(d4.z, vh[e + 2], dp); dp = fmaf(d4.w, vh[e + 3], dp);
               }
               const float p = exp2f(s * scale_log2 - st[0]) * st[1];
-              const float ds = p * (dp - st[2]);
+              float ks = 1.f;                                          // mask of element (query i, key = this row)
+              if (dc.rate > 0.f) ks = drop_scale(dc, drop_row_base(it, B, smp, H, h, F, i) + (unsigned long long)fld);
+              const float ds = p * (ks * dp - st[2]);
+              const float pk = p * ks;
 #pragma unroll
               for (int e = 0; e < DH; ++e) {
                 dk[e] = fmaf(ds, qq[e], dk[e]);
-                dv[e] = fmaf(p, dd[e], dv[e]);
+                dv[e] = fmaf(pk, dd[e], dv[e]);
               }
             }
 #pragma unroll
@@ -573,6 +601,13 @@ static __global__ void reduce_partials_kernel(const float* __restrict__ part, fl
 }
 
 // ------------------------------------------------------------ host dispatch
+static inline DropCfg drop_cfg(float rate, unsigned long long seed) {
+  DropCfg dc;
+  dc.rate = rate;
+  dc.inv_keep = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
+  dc.seed = seed;
+  return dc;
+}
 
 template <int D, int U, int NT>
 static size_t fwd_smem_bytes() { return (size_t)(D * 4 * U + 4 * U + 2 * U + NT * (2 * U + 4)) * 4; }
@@ -601,7 +636,7 @@ static int launch_fwd(const IFwdArgs& a) {
   int grid = sm_count() * 4;
   if (grid > ntiles) grid = ntiles;
   kern<<<grid, NT, smem, a.st>>>((const T*)a.x, a.x_ld, a.x_bs, a.W, a.b, a.gm, a.bt, a.eps, (T*)a.y, a.y_ld, a.y_bs,
-                                 (float*)a.saved, a.B, a.F, a.L, a.use_res);
+                                 (float*)a.saved, a.B, a.F, a.L, a.use_res, drop_cfg(a.drop_rate, a.drop_seed));
   return check_launch("interacting_fwd");
 }
 
@@ -618,7 +653,7 @@ static int launch_bwd(const IBwdArgs& a) {
   }
   kern<<<grid, NT, smem, a.st>>>((const T*)a.x, a.x_ld, a.x_bs, (const float*)a.saved, a.W, a.b, a.gm, a.bt, a.eps,
                                  (const T*)a.dy, a.dy_ld, a.dy_bs, (T*)a.dx, a.dx_ld, a.dx_bs, (float*)a.ws, a.B, a.F,
-                                 a.L, a.use_res);
+                                 a.L, a.use_res, drop_cfg(a.drop_rate, a.drop_seed));
   if (int e = check_launch("interacting_bwd")) return e;
   reduce_partials_kernel<<<(np * 32 + 255) / 256, 256, 0, a.st>>>((const float*)a.ws, a.dparams, grid, np);
   return check_launch("interacting_bwd_reduce");

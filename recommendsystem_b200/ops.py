@@ -187,18 +187,21 @@ def permute_rows(src, index, scatter=False, out=None):
 # ------------------------------------------------------------- interacting
 
 
-def interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res=True, save=True, compute_bf16=False):
+def interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res=True, save=True, compute_bf16=False,
+                    dropout_rate=0.0, dropout_seed=0):
     B, F, D = x.shape
     U = Wqkvr.shape[1] // 4
     _need(x.is_contiguous(), "x must be contiguous")
     y = torch.empty(B, F, U, dtype=x.dtype, device=x.device)
     saved = torch.empty(L, B * F, U, dtype=torch.float32, device=x.device) if save else None   # rs_interacting_saved_bytes
-    call("rs_interacting_fwd", _ptr(x), D, 0, _dt(x), _ptr(Wqkvr), _ptr(bqkvr), _ptr(gamma), _ptr(beta),
-         ln_eps, _ptr(y), U, 0, _ptr(saved), B, F, D, U, H, L, int(use_res), int(compute_bf16), _stream())
+    call("rs_interacting_fwd_dropout", _ptr(x), D, 0, _dt(x), _ptr(Wqkvr), _ptr(bqkvr), _ptr(gamma), _ptr(beta),
+         ln_eps, _ptr(y), U, 0, _ptr(saved), B, F, D, U, H, L, int(use_res), int(compute_bf16),
+         float(dropout_rate), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _stream())
     return y, saved
 
 
-def interacting_bwd(x, saved, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, dy, use_res=True, compute_bf16=False):
+def interacting_bwd(x, saved, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, dy, use_res=True, compute_bf16=False,
+                    dropout_rate=0.0, dropout_seed=0):
     B, F, D = x.shape
     U = Wqkvr.shape[1] // 4
     dx = torch.empty_like(x)
@@ -206,9 +209,9 @@ def interacting_bwd(x, saved, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, dy, use_r
     nbytes = cabi.load().rs_interacting_workspace_bytes(B, F, D, U)
     ws = WS.get("interacting", nbytes, x.device)
     dy = dy.contiguous()
-    call("rs_interacting_bwd", _ptr(x), D, 0, _ptr(saved), _dt(x), _ptr(Wqkvr), _ptr(bqkvr), _ptr(gamma),
+    call("rs_interacting_bwd_dropout", _ptr(x), D, 0, _ptr(saved), _dt(x), _ptr(Wqkvr), _ptr(bqkvr), _ptr(gamma),
          _ptr(beta), ln_eps, _ptr(dy), U, 0, _ptr(dx), D, 0, _ptr(dparams), B, F, D, U, H, L, int(use_res),
-         int(compute_bf16), _ptr(ws), ws.numel(), _stream())
+         int(compute_bf16), float(dropout_rate), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _ptr(ws), ws.numel(), _stream())
     nW = D * 4 * U
     return dx, dparams[:nW].view(D, 4 * U), dparams[nW:nW + 4 * U], dparams[nW + 4 * U:nW + 5 * U], dparams[nW + 5 * U:]
 

@@ -148,3 +148,64 @@ def test_interacting_tc_bwd(cuda_dev, B, F, L, use_res):
         assert_close(a, r, 2 * REL_BF16, "tc " + n)
     dx2, dW2, *_ = ops.interacting_bwd(xt, saved, Wt, bt, gt, bet, 1e-3, H, L, dyt, use_res, compute_bf16=True)
     assert torch.equal(dx, dx2) and torch.equal(dW, dW2)
+
+
+@pytest.mark.parametrize("B,F,D,U,H,L", [(5, 39, 16, 16, 2, 3), (33, 7, 8, 8, 2, 1), (3, 175, 8, 8, 2, 1), (9, 40, 16, 16, 4, 2)])
+@pytest.mark.parametrize("rate", [0.2, 0.5])
+def test_interacting_attention_dropout(cuda_dev, B, F, D, U, H, L, rate):
+    """Training-mode attention-weight dropout (InteractingLayer.py:53-54; multidnn.py:54, model_init.py:54-59)
+    fused into forward and backward: the counter-based mask is regenerated by the oracle from the same seed, so
+    outputs and every gradient are compared at the fp32 bar; rate 0 reproduces the no-dropout kernels bit for bit."""
+    from oracle import oracle_np as onp
+    from recommendsystem_b200 import ops
+    rng = np.random.default_rng(B + F + int(rate * 10))
+    W, b, gamma, beta = interacting_params(rng, D, U)
+    x = rng.standard_normal((B, F, D)).astype(np.float32)
+    dy = rng.standard_normal((B, F, U)).astype(np.float32)
+    seed = 0x1234567890ABCDEF + B
+    f64 = lambda a: a.astype(np.float64)
+    drop = (rate, seed)
+    ref = onp.interacting_fwd(f64(x), f64(W), f64(b), f64(gamma), f64(beta), 1e-3, H, L, True, dropout=drop)
+    rdx, rdW, rdb, rdg, rdbt = onp.interacting_bwd(f64(x), f64(W), f64(b), f64(gamma), f64(beta), 1e-3, H, L, f64(dy), True,
+                                                   dropout=drop)
+    xt, dyt = _t(x, cuda_dev), _t(dy, cuda_dev)
+    Wt, bt, gt, bet = (_t(a, cuda_dev) for a in (W, b, gamma, beta))
+    y, saved = ops.interacting_fwd(xt, Wt, bt, gt, bet, 1e-3, H, L, True, dropout_rate=rate, dropout_seed=seed)
+    assert_close(y.cpu().numpy(), ref, REL_F32, "dropout fwd")
+    ref0 = onp.interacting_fwd(f64(x), f64(W), f64(b), f64(gamma), f64(beta), 1e-3, H, L, True)
+    assert np.abs(ref - ref0).max() > 1e-3            # the mask really changes the output
+    dx, dW, db, dg, dbt = ops.interacting_bwd(xt, saved, Wt, bt, gt, bet, 1e-3, H, L, dyt, True, dropout_rate=rate,
+                                              dropout_seed=seed)
+    for n, a, r in zip(["dx", "dW", "db", "dgamma", "dbeta"], [dx, dW, db, dg, dbt], [rdx, rdW, rdb, rdg, rdbt]):
+        assert_close(a.cpu().numpy(), r, REL_F32, "dropout " + n)
+    y0, s0 = ops.interacting_fwd(xt, Wt, bt, gt, bet, 1e-3, H, L, True, dropout_rate=0.0, dropout_seed=seed)
+    y1, s1 = ops.interacting_fwd(xt, Wt, bt, gt, bet, 1e-3, H, L, True)
+    assert torch.equal(y0, y1)
+    # a different seed gives a different mask
+    y2, _ = ops.interacting_fwd(xt, Wt, bt, gt, bet, 1e-3, H, L, True, dropout_rate=rate, dropout_seed=seed + 1)
+    assert not torch.equal(y, y2)
+
+
+def test_interacting_layer_module_dropout(cuda_dev):
+    """api.InteractingLayer(use_dropout=True): active in train mode (fresh mask per call, reproducible from
+    last_dropout_seed), inactive in eval mode; bf16 input with dropout falls back to the FFMA kernels."""
+    from oracle import oracle_np as onp
+    from recommendsystem_b200.api import InteractingLayer
+    torch.manual_seed(0)
+    layer = InteractingLayer(layer_num=1, unit_num=8, head_num=2, use_dropout=True, dropout_rate=0.2, use_res=True)
+    x = torch.randn(6, 11, 8, device=cuda_dev, requires_grad=True)
+    layer.train()
+    y_a = layer(x)
+    seed_a = layer.last_dropout_seed
+    y_b = layer(x)
+    assert not torch.equal(y_a, y_b) and layer.last_dropout_seed != seed_a
+    W, b = layer.packed()
+    f64 = lambda t: t.detach().cpu().numpy().astype(np.float64)
+    ref = onp.interacting_fwd(f64(x), f64(W), f64(b), f64(layer.layer_norm_gamma), f64(layer.layer_norm_beta), 1e-3, 2, 1,
+                              True, dropout=(0.2, seed_a))
+    assert_close(y_a.detach().cpu().numpy(), ref, REL_F32, "module dropout fwd")
+    y_a.sum().backward()
+    assert torch.isfinite(x.grad).all()
+    layer.eval()
+    ref0 = onp.interacting_fwd(f64(x), f64(W), f64(b), f64(layer.layer_norm_gamma), f64(layer.layer_norm_beta), 1e-3, 2, 1, True)
+    assert_close(layer(x).detach().cpu().numpy(), ref0, REL_F32, "module eval fwd")

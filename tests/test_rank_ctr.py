@@ -99,7 +99,7 @@ def test_rank_ctr_sub_model_gpu(cuda_dev):
     rng = np.random.default_rng(4)
     B = 48
     cfg, (me, st, b, gt), P, emb = _setup(rng, B)
-    model = RankCtrSubModel(parse_feature_slots(cfg)).to(cuda_dev)
+    model = RankCtrSubModel(parse_feature_slots(cfg)).to(cuda_dev).eval()       # eval: no attention dropout
     te = {k: torch.from_numpy(v).to(cuda_dev).requires_grad_(True) for k, v in emb.items()}
     model(te)
     sd = model.state_dict()
