@@ -139,21 +139,9 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
                 make_float4(kk[h * DH + c * 4], kk[h * DH + c * 4 + 1], kk[h * DH + c * 4 + 2], kk[h * DH + c * 4 + 3]);
           }
         }
-        tc_ld_32x32(tmem + lane_base + TM_Z + 32, z);                  // v | r pre-activations
-        float vv[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          vv[u] = fmaxf(__uint_as_float(z[u]) + bs[2 * U + u], 0.f);
-          r[u] = fmaxf(__uint_as_float(z[U + u]) + bs[3 * U + u], 0.f);
-        }
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {                                  // V: MN-major B, row = key
-          uint4 v;
-          v.x = pack_bf16x2(vv[c * 8 + 0], vv[c * 8 + 1]); v.y = pack_bf16x2(vv[c * 8 + 2], vv[c * 8 + 3]);
-          v.z = pack_bf16x2(vv[c * 8 + 4], vv[c * 8 + 5]); v.w = pack_bf16x2(vv[c * 8 + 6], vv[c * 8 + 7]);
-          *reinterpret_cast<uint4*>(smem + OFF_V + nosw_off<2>(tid, c)) = v;
-        }
       }
+      uint32_t zvr[32];                                                // v | r pre-activations: read now (S_1 aliases
+      tc_ld_32x32(tmem + lane_base + TM_Z + 32, zvr);                  // these columns), used under the S MMA
       // ---- 2. S_h = Q_h K_h^T (both heads), Z columns are dead now
       fence_async_smem();
       tc_fence_before();
@@ -164,6 +152,21 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
         tc_mma_tf32(tmem + (h == 0 ? TM_S0 : TM_S1), make_nosw_desc(sbase + OFF_Q + h * 4096, 128, 256),
                     make_nosw_desc(sbase + OFF_K + h * 4096, 128, 256), ID_S, 0u);
         tc_commit(bar);
+      }
+      {
+        float vv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          vv[u] = fmaxf(__uint_as_float(zvr[u]) + bs[2 * U + u], 0.f);
+          r[u] = fmaxf(__uint_as_float(zvr[U + u]) + bs[3 * U + u], 0.f);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {                                  // V: MN-major B, row = key (read by P.V, phase 3)
+          uint4 v;
+          v.x = pack_bf16x2(vv[c * 8 + 0], vv[c * 8 + 1]); v.y = pack_bf16x2(vv[c * 8 + 2], vv[c * 8 + 3]);
+          v.z = pack_bf16x2(vv[c * 8 + 4], vv[c * 8 + 5]); v.w = pack_bf16x2(vv[c * 8 + 6], vv[c * 8 + 7]);
+          *reinterpret_cast<uint4*>(smem + OFF_V + nosw_off<2>(tid, c)) = v;
+        }
       }
       mbar_wait(bar, phase); phase ^= 1u;
       tc_fence_after();
