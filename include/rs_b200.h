@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 1
+#define RS_ABI_VERSION 2
 
 enum rs_dtype { RS_F32 = 0, RS_BF16 = 1 };
 
@@ -89,6 +89,15 @@ int rs_embed_gather_fwd(const float* table, const int64_t* ids,
                         void* out, int out_dtype,
                         uint64_t* sort_keys, int32_t* rows_out, void* stream);
 
+/* Same with an explicit row stride `table_ld` (floats, >= d, multiple of 4; 0 = d): the trainer keeps each
+ * row's weights and its Adam moments in ONE 3d-float record [w | m | v] (table_ld = 3d) so that the sparse
+ * update touches one contiguous 12d-byte block per row instead of three scattered ones. */
+int rs_embed_gather_fwd_ld(const float* table, int64_t table_ld, const int64_t* ids,
+                           const int64_t* row_base, const int64_t* rows,
+                           int64_t n, int F, int d,
+                           void* out, int out_dtype,
+                           uint64_t* sort_keys, int32_t* rows_out, void* stream);
+
 /* Gather by precomputed arena rows (used by the row-sharded multi-GPU path
  * after id routing, and for sequence slots: staytime/VideoDnn.py:228-231
  * `combiner=None, seq_max_len=N` -> ([B,T,d], mask[B,T])).
@@ -98,15 +107,19 @@ int rs_embed_gather_rows(const float* table, const int32_t* rowidx, int64_t n,
                          int d, void* out, int out_dtype, uint8_t* mask_out,
                          uint64_t* sort_keys, void* stream);
 
+int rs_embed_gather_rows_ld(const float* table, int64_t table_ld, const int32_t* rowidx, int64_t n,
+                            int d, void* out, int out_dtype, uint8_t* mask_out,
+                            uint64_t* sort_keys, void* stream);
+
 /* Row-sharded tables read IN PLACE over NVLink (one process per GPU; replaces the id all-to-all +
  * owner gather + row all-to-all of the sharded path — the only trace of sharding in the reference is
  * tn.core.shard_num() / self_shard_id(), staytime/parse.py:78-79).  peer_tables[r] (HOST array of
  * `world` DEVICE pointers) is rank r's shard, mapped into this process with rs_ipc_import; lookup i reads
- *   r = ids[i] mod rows[f] ; owner = r mod world ; peer_tables[owner][local_base[f] + r div world]
+ *   r = ids[i] mod rows[f] ; owner = r mod world ; peer_tables[owner] + (local_base[f] + r div world) * table_ld
  * (ids[i] < 0 -> zeros).  Bit-exact with rs_embed_gather_fwd on the unsharded arena.  The caller orders
  * the owners' sparse update of the previous step before this call (cross-rank barrier). */
 #define RS_MAX_PEERS 8
-int rs_embed_gather_peer_fwd(const float* const* peer_tables, int world, const int64_t* ids,
+int rs_embed_gather_peer_fwd(const float* const* peer_tables, int64_t table_ld, int world, const int64_t* ids,
                              const int64_t* local_base, const int64_t* rows, int64_t n, int F, int d,
                              void* out, int out_dtype, void* stream);
 /* CUDA-IPC plumbing for the above: export the allocation containing `ptr` (64-byte handle + byte offset
@@ -151,6 +164,12 @@ int rs_embed_segsum_adam(float* w, float* m, float* v,
                          const uint64_t* keys_sorted, int64_t n, int d,
                          float lr, float beta1, float beta2, float eps,
                          const float* opt_scalars, float grad_scale, void* stream);
+/* Same with a common row stride `state_ld` (floats) of w, m, v — see rs_embed_gather_fwd_ld. */
+int rs_embed_segsum_adam_ld(float* w, float* m, float* v, int64_t state_ld,
+                            const void* grad, int grad_dtype,
+                            const uint64_t* keys_sorted, int64_t n, int d,
+                            float lr, float beta1, float beta2, float eps,
+                            const float* opt_scalars, float grad_scale, void* stream);
 
 /* TensorNet AdaGrad: g2sum is ONE scalar per row:
  *   g2sum += mean_d(g*g) ; w -= lr * g / (sqrt(g2sum) + eps)

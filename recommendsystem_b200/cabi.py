@@ -24,14 +24,17 @@ PROTOTYPES = {
     "rs_launch_count": (_u64, []),
     "rs_built_for_sm100a": (_i, []),
     "rs_embed_gather_fwd": (_i, [_p, _p, _p, _p, _i64, _i, _i, _p, _i, _p, _p, _p]),
+    "rs_embed_gather_fwd_ld": (_i, [_p, _i64, _p, _p, _p, _i64, _i, _i, _p, _i, _p, _p, _p]),
     "rs_embed_gather_rows": (_i, [_p, _p, _i64, _i, _p, _i, _p, _p, _p]),
+    "rs_embed_gather_rows_ld": (_i, [_p, _i64, _p, _i64, _i, _p, _i, _p, _p, _p]),
     "rs_embed_gather_bag_mean": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _p, _i, _p]),
     "rs_embed_sort_workspace_bytes": (_sz, [_i64]),
-    "rs_embed_gather_peer_fwd": (_i, [_p, _i, _p, _p, _p, _i64, _i, _i, _p, _i, _p]),
+    "rs_embed_gather_peer_fwd": (_i, [_p, _i64, _i, _p, _p, _p, _i64, _i, _i, _p, _i, _p]),
     "rs_ipc_export": (_i, [_p, _p, _p]),
     "rs_ipc_import": (_i, [_p, _u64, _p]),
     "rs_embed_sort_keys": (_i, [_p, _p, _i64, _i, _p, _sz, _p]),
     "rs_embed_segsum_adam": (_i, [_p, _p, _p, _p, _i, _p, _i64, _i, _f, _f, _f, _f, _p, _f, _p]),
+    "rs_embed_segsum_adam_ld": (_i, [_p, _p, _p, _i64, _p, _i, _p, _i64, _i, _f, _f, _f, _f, _p, _f, _p]),
     "rs_embed_segsum_adagrad": (_i, [_p, _p, _p, _i, _p, _i64, _i, _f, _f, _i, _f, _p]),
     "rs_embed_segsum": (_i, [_p, _i, _p, _i64, _i, _p, _p, _p]),
     "rs_adam_advance": (_i, [_p, _f, _f, _p]),

@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(128)
 embed_gather_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids,
                     const int32_t* __restrict__ rowidx,
                     const int64_t* __restrict__ row_base, const int64_t* __restrict__ rows,
-                    int64_t n, int F, int d, OutT* __restrict__ out,
+                    int64_t n, int F, int d, int64_t tld, OutT* __restrict__ out,
                     uint64_t* __restrict__ sort_keys, int32_t* __restrict__ rows_out,
                     uint8_t* __restrict__ mask_out) {
   constexpr int GROUPS = 32 / G;  // lookups served per step
@@ -71,7 +71,7 @@ embed_gather_kernel(const float* __restrict__ table, const int64_t* __restrict__
         const int32_t r = __shfl_sync(0xffffffffu, myrow[k], src);
         v[k][s] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (r >= 0 && col_ok && out)
-          v[k][s] = ldg_row_f4(reinterpret_cast<const float4*>(table + (int64_t)r * d) + gl);
+          v[k][s] = ldg_row_f4(reinterpret_cast<const float4*>(table + (int64_t)r * tld) + gl);
       }
     }
 #pragma unroll
@@ -86,7 +86,7 @@ embed_gather_kernel(const float* __restrict__ table, const int64_t* __restrict__
 }
 
 template <int G, int LPL, bool FROM_IDS>
-static int launch_gather(const float* table, const int64_t* ids, const int32_t* rowidx,
+static int launch_gather(const float* table, int64_t tld, const int64_t* ids, const int32_t* rowidx,
                          const int64_t* row_base, const int64_t* rows, int64_t n, int F,
                          int d, void* out, int out_dtype, uint64_t* sort_keys,
                          int32_t* rows_out, uint8_t* mask_out, cudaStream_t st) {
@@ -98,16 +98,16 @@ static int launch_gather(const float* table, const int64_t* ids, const int32_t* 
   if (blocks < 1) blocks = 1;
   if (out_dtype == RS_F32)
     embed_gather_kernel<G, LPL, float, FROM_IDS><<<(unsigned)blocks, threads, 0, st>>>(
-        table, ids, rowidx, row_base, rows, n, F, d, (float*)out, sort_keys, rows_out, mask_out);
+        table, ids, rowidx, row_base, rows, n, F, d, tld, (float*)out, sort_keys, rows_out, mask_out);
   else
     embed_gather_kernel<G, LPL, __nv_bfloat16, FROM_IDS><<<(unsigned)blocks, threads, 0, st>>>(
-        table, ids, rowidx, row_base, rows, n, F, d, (__nv_bfloat16*)out, sort_keys, rows_out,
+        table, ids, rowidx, row_base, rows, n, F, d, tld, (__nv_bfloat16*)out, sort_keys, rows_out,
         mask_out);
   return check_launch("embed_gather");
 }
 
 template <bool FROM_IDS>
-static int dispatch_gather(const float* table, const int64_t* ids, const int32_t* rowidx,
+static int dispatch_gather(const float* table, int64_t tld, const int64_t* ids, const int32_t* rowidx,
                            const int64_t* row_base, const int64_t* rows, int64_t n, int F,
                            int d, void* out, int out_dtype, uint64_t* sort_keys,
                            int32_t* rows_out, uint8_t* mask_out, cudaStream_t st) {
@@ -115,9 +115,11 @@ static int dispatch_gather(const float* table, const int64_t* ids, const int32_t
   RS_REQUIRE(out_dtype == RS_F32 || out_dtype == RS_BF16, "embed_gather: bad out dtype %d", out_dtype);
   RS_REQUIRE(n >= 0 && n < ((int64_t)1 << 32), "embed_gather: n=%lld out of range", (long long)n);
   if (n == 0) return 0;
+  if (tld == 0) tld = d;
+  RS_REQUIRE(tld >= d && tld % 4 == 0, "embed_gather: table row stride %lld (d = %d)", (long long)tld, d);
   const int g = d / 4;
 #define RS_GATHER_CASE(G, LPL)                                                                  \
-  return launch_gather<G, LPL, FROM_IDS>(table, ids, rowidx, row_base, rows, n, F, d, out,      \
+  return launch_gather<G, LPL, FROM_IDS>(table, tld, ids, rowidx, row_base, rows, n, F, d, out, \
                                          out_dtype, sort_keys, rows_out, mask_out, st)
   if (g <= 1) RS_GATHER_CASE(1, 4);
   if (g <= 2) RS_GATHER_CASE(2, 4);
@@ -149,7 +151,8 @@ __device__ __forceinline__ float4 ld_peer_f4(const float4* p) {
 template <int G, int LPL, typename OutT>
 __global__ void __launch_bounds__(128)
 embed_gather_peer_kernel(PeerTables tabs, const int64_t* __restrict__ ids, const int64_t* __restrict__ local_base,
-                         const int64_t* __restrict__ rows, int64_t n, int F, int d, int W, OutT* __restrict__ out) {
+                         const int64_t* __restrict__ rows, int64_t n, int F, int d, int64_t tld, int W,
+                         OutT* __restrict__ out) {
   constexpr int GROUPS = 32 / G;
   const int lane = threadIdx.x & 31;
   const int gl = lane % G, gj = lane / G;
@@ -172,7 +175,7 @@ embed_gather_peer_kernel(PeerTables tabs, const int64_t* __restrict__ ids, const
           else rr = (uint32_t)id % (uint32_t)R;
           const uint32_t owner = (uint32_t)(rr % (uint64_t)W);
           const int64_t lrow = __ldg(local_base + f) + (int64_t)(rr / (uint64_t)W);
-          ptr = tabs.p[owner] + lrow * d;
+          ptr = tabs.p[owner] + lrow * tld;
         }
       }
       myptr[k] = ptr;
@@ -202,8 +205,8 @@ embed_gather_peer_kernel(PeerTables tabs, const int64_t* __restrict__ ids, const
 
 template <int G, int LPL>
 static int launch_gather_peer(const PeerTables& tabs, const int64_t* ids, const int64_t* local_base,
-                              const int64_t* rows, int64_t n, int F, int d, int W, void* out, int out_dtype,
-                              cudaStream_t st) {
+                              const int64_t* rows, int64_t n, int F, int d, int64_t tld, int W, void* out,
+                              int out_dtype, cudaStream_t st) {
   const int threads = 128;
   const int64_t per_block = (int64_t)(threads / 32) * 32 * LPL;
   int64_t blocks = cdiv(n, per_block);
@@ -211,10 +214,10 @@ static int launch_gather_peer(const PeerTables& tabs, const int64_t* ids, const 
   if (blocks > cap) blocks = cap;
   if (out_dtype == RS_F32)
     embed_gather_peer_kernel<G, LPL, float><<<(unsigned)blocks, threads, 0, st>>>(tabs, ids, local_base, rows, n, F, d,
-                                                                                  W, (float*)out);
+                                                                                  tld, W, (float*)out);
   else
     embed_gather_peer_kernel<G, LPL, __nv_bfloat16><<<(unsigned)blocks, threads, 0, st>>>(
-        tabs, ids, local_base, rows, n, F, d, W, (__nv_bfloat16*)out);
+        tabs, ids, local_base, rows, n, F, d, tld, W, (__nv_bfloat16*)out);
   return check_launch("embed_gather_peer");
 }
 
@@ -260,6 +263,7 @@ enum { OPT_NONE = 0, OPT_ADAM = 1, OPT_ADAGRAD_ROW = 2, OPT_ADAGRAD_ELEM = 3 };
 struct OptArgs {
   float* w; float* s0; float* s1;   // adam: m, v ; adagrad: g2sum, -
   float lr, beta1, beta2, eps;
+  int64_t ld;                       // row stride of w / s0 / s1 in floats (d, or 3d for interleaved [w|m|v] rows)
   const float* scalars;             // device {step, b1^t, b2^t, corr}
   float grad_scale;
   int32_t* seg_rows; float* seg_sum; // OPT_NONE outputs
@@ -318,6 +322,20 @@ embed_segsum_kernel(const uint64_t* __restrict__ keys, const GT* __restrict__ gr
       acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (shead[s] && col_ok) acc[s] = load_grad<GT>(grad, pos, d, gl, a.grad_scale);
     }
+    // Adam: the state rows depend on the keys only — request them together with the gradient rows (two
+    // dependent DRAM round trips per warp instead of three)
+    float4 w[G], m[G], v[G];
+    if (OPT == OPT_ADAM) {
+#pragma unroll
+      for (int s = 0; s < G; ++s) {
+        if (shead[s] && col_ok) {
+          const int64_t off = (int64_t)srow[s] * a.ld + gl * 4;
+          w[s] = ld_row_f4(reinterpret_cast<const float4*>(a.w + off));
+          m[s] = ld_row_f4(reinterpret_cast<const float4*>(a.s0 + off));
+          v[s] = ld_row_f4(reinterpret_cast<const float4*>(a.s1 + off));
+        }
+      }
+    }
     // runs longer than one: walk the rest of the run in order.
 #pragma unroll
     for (int s = 0; s < G; ++s) {
@@ -345,21 +363,11 @@ embed_segsum_kernel(const uint64_t* __restrict__ keys, const GT* __restrict__ gr
         }
       }
     } else if (OPT == OPT_ADAM) {
-      float4 w[G], m[G], v[G];
-#pragma unroll
-      for (int s = 0; s < G; ++s) {
-        if (shead[s] && col_ok) {
-          const int64_t off = (int64_t)srow[s] * d + gl * 4;
-          w[s] = ld_row_f4(reinterpret_cast<const float4*>(a.w + off));
-          m[s] = ld_row_f4(reinterpret_cast<const float4*>(a.s0 + off));
-          v[s] = ld_row_f4(reinterpret_cast<const float4*>(a.s1 + off));
-        }
-      }
       const float b1 = a.beta1, b2 = a.beta2, eps = a.eps;
 #pragma unroll
       for (int s = 0; s < G; ++s) {
         if (shead[s] && col_ok) {
-          const int64_t off = (int64_t)srow[s] * d + gl * 4;
+          const int64_t off = (int64_t)srow[s] * a.ld + gl * 4;
           const float4 g = acc[s];
 #define RS_ADAM1(c)                                              \
   m[s].c = b1 * m[s].c + (1.f - b1) * g.c;                       \
@@ -634,23 +642,34 @@ using namespace rs;
 
 extern "C" {
 
+int rs_embed_gather_fwd_ld(const float* table, int64_t table_ld, const int64_t* ids, const int64_t* row_base,
+                           const int64_t* rows, int64_t n, int F, int d, void* out, int out_dtype,
+                           uint64_t* sort_keys, int32_t* rows_out, void* stream) {
+  RS_REQUIRE(F > 0, "embed_gather_fwd: F=%d", F);
+  return dispatch_gather<true>(table, table_ld, ids, nullptr, row_base, rows, n, F, d, out, out_dtype,
+                               sort_keys, rows_out, nullptr, as_stream(stream));
+}
 int rs_embed_gather_fwd(const float* table, const int64_t* ids, const int64_t* row_base,
                         const int64_t* rows, int64_t n, int F, int d, void* out, int out_dtype,
                         uint64_t* sort_keys, int32_t* rows_out, void* stream) {
-  RS_REQUIRE(F > 0, "embed_gather_fwd: F=%d", F);
-  return dispatch_gather<true>(table, ids, nullptr, row_base, rows, n, F, d, out, out_dtype,
-                               sort_keys, rows_out, nullptr, as_stream(stream));
+  return rs_embed_gather_fwd_ld(table, d, ids, row_base, rows, n, F, d, out, out_dtype, sort_keys, rows_out, stream);
 }
 
-int rs_embed_gather_rows(const float* table, const int32_t* rowidx, int64_t n, int d, void* out,
-                         int out_dtype, uint8_t* mask_out, uint64_t* sort_keys, void* stream) {
-  return dispatch_gather<false>(table, nullptr, rowidx, nullptr, nullptr, n, 1, d, out, out_dtype,
+int rs_embed_gather_rows_ld(const float* table, int64_t table_ld, const int32_t* rowidx, int64_t n, int d, void* out,
+                            int out_dtype, uint8_t* mask_out, uint64_t* sort_keys, void* stream) {
+  return dispatch_gather<false>(table, table_ld, nullptr, rowidx, nullptr, nullptr, n, 1, d, out, out_dtype,
                                 sort_keys, nullptr, mask_out, as_stream(stream));
 }
+int rs_embed_gather_rows(const float* table, const int32_t* rowidx, int64_t n, int d, void* out,
+                         int out_dtype, uint8_t* mask_out, uint64_t* sort_keys, void* stream) {
+  return rs_embed_gather_rows_ld(table, d, rowidx, n, d, out, out_dtype, mask_out, sort_keys, stream);
+}
 
-int rs_embed_gather_peer_fwd(const float* const* peer_tables, int world, const int64_t* ids,
+int rs_embed_gather_peer_fwd(const float* const* peer_tables, int64_t table_ld, int world, const int64_t* ids,
                              const int64_t* local_base, const int64_t* rows, int64_t n, int F, int d, void* out,
                              int out_dtype, void* stream) {
+  if (table_ld == 0) table_ld = d;
+  RS_REQUIRE(table_ld >= d && table_ld % 4 == 0, "embed_gather_peer: table row stride %lld", (long long)table_ld);
   RS_REQUIRE(world >= 1 && world <= RS_MAX_PEERS, "embed_gather_peer: world=%d (max %d)", world, RS_MAX_PEERS);
   RS_REQUIRE(F > 0 && d > 0 && d % 4 == 0 && d <= 128, "embed_gather_peer: F=%d d=%d", F, d);
   RS_REQUIRE(out_dtype == RS_F32 || out_dtype == RS_BF16, "embed_gather_peer: bad out dtype %d", out_dtype);
@@ -659,14 +678,14 @@ int rs_embed_gather_peer_fwd(const float* const* peer_tables, int world, const i
   for (int r = 0; r < RS_MAX_PEERS; ++r) tabs.p[r] = r < world ? peer_tables[r] : nullptr;
   const int g = d / 4;
   cudaStream_t st = as_stream(stream);
-  if (g <= 1) return launch_gather_peer<1, 4>(tabs, ids, local_base, rows, n, F, d, world, out, out_dtype, st);
-  if (g <= 2) return launch_gather_peer<2, 4>(tabs, ids, local_base, rows, n, F, d, world, out, out_dtype, st);
+  if (g <= 1) return launch_gather_peer<1, 4>(tabs, ids, local_base, rows, n, F, d, table_ld, world, out, out_dtype, st);
+  if (g <= 2) return launch_gather_peer<2, 4>(tabs, ids, local_base, rows, n, F, d, table_ld, world, out, out_dtype, st);
   // (measured at W = 2: 4 lookups per lane is slower than 2 — fewer, fatter CTAs; the NVLink request rate,
   //  not the loads in flight per lane, bounds the kernel)
-  if (g <= 4) return launch_gather_peer<4, 2>(tabs, ids, local_base, rows, n, F, d, world, out, out_dtype, st);
-  if (g <= 8) return launch_gather_peer<8, 1>(tabs, ids, local_base, rows, n, F, d, world, out, out_dtype, st);
-  if (g <= 16) return launch_gather_peer<16, 1>(tabs, ids, local_base, rows, n, F, d, world, out, out_dtype, st);
-  return launch_gather_peer<32, 1>(tabs, ids, local_base, rows, n, F, d, world, out, out_dtype, st);
+  if (g <= 4) return launch_gather_peer<4, 2>(tabs, ids, local_base, rows, n, F, d, table_ld, world, out, out_dtype, st);
+  if (g <= 8) return launch_gather_peer<8, 1>(tabs, ids, local_base, rows, n, F, d, table_ld, world, out, out_dtype, st);
+  if (g <= 16) return launch_gather_peer<16, 1>(tabs, ids, local_base, rows, n, F, d, table_ld, world, out, out_dtype, st);
+  return launch_gather_peer<32, 1>(tabs, ids, local_base, rows, n, F, d, table_ld, world, out, out_dtype, st);
 }
 
 int rs_embed_gather_bag_mean(const float* table, const int64_t* ids, const int64_t* offsets,
@@ -712,15 +731,25 @@ int rs_embed_sort_keys(const uint64_t* keys, uint64_t* keys_sorted, int64_t n, i
   return 0;
 }
 
+int rs_embed_segsum_adam_ld(float* w, float* m, float* v, int64_t state_ld, const void* grad, int grad_dtype,
+                            const uint64_t* keys_sorted, int64_t n, int d, float lr, float beta1,
+                            float beta2, float eps, const float* opt_scalars, float grad_scale,
+                            void* stream) {
+  RS_REQUIRE(opt_scalars != nullptr, "embed_segsum_adam: opt_scalars is NULL");
+  if (state_ld == 0) state_ld = d;
+  RS_REQUIRE(state_ld >= d && state_ld % 4 == 0, "embed_segsum_adam: state row stride %lld", (long long)state_ld);
+  OptArgs a{};
+  a.w = w; a.s0 = m; a.s1 = v; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
+  a.ld = state_ld;
+  a.scalars = opt_scalars; a.grad_scale = grad_scale;
+  return dispatch_segsum<OPT_ADAM>(keys_sorted, grad, grad_dtype, n, d, a, as_stream(stream));
+}
 int rs_embed_segsum_adam(float* w, float* m, float* v, const void* grad, int grad_dtype,
                          const uint64_t* keys_sorted, int64_t n, int d, float lr, float beta1,
                          float beta2, float eps, const float* opt_scalars, float grad_scale,
                          void* stream) {
-  RS_REQUIRE(opt_scalars != nullptr, "embed_segsum_adam: opt_scalars is NULL");
-  OptArgs a{};
-  a.w = w; a.s0 = m; a.s1 = v; a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps;
-  a.scalars = opt_scalars; a.grad_scale = grad_scale;
-  return dispatch_segsum<OPT_ADAM>(keys_sorted, grad, grad_dtype, n, d, a, as_stream(stream));
+  return rs_embed_segsum_adam_ld(w, m, v, d, grad, grad_dtype, keys_sorted, n, d, lr, beta1, beta2, eps, opt_scalars,
+                                 grad_scale, stream);
 }
 
 int rs_embed_segsum_adagrad(float* w, float* g2sum, const void* grad, int grad_dtype,

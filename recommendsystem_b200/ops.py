@@ -63,14 +63,15 @@ WS = _Workspace()
 def embed_gather(table, ids, row_base, rows, out_dtype=torch.float32, want_keys=False, want_rows=False):
     """ids int64 [..., F] -> out [..., F, d]; optional sort keys / arena rows."""
     _need(ids.dtype == torch.int64 and ids.is_contiguous(), "ids must be contiguous int64")
-    _need(table.dtype == torch.float32 and table.is_contiguous() and table.dim() == 2, "table must be fp32 [R,d]")
+    _need(table.dtype == torch.float32 and table.dim() == 2 and table.stride(1) == 1,
+          "table must be fp32 [R,d] with contiguous rows (a row stride > d is allowed)")
     F = ids.shape[-1]
     n, d = ids.numel(), table.shape[1]
     out = torch.empty(*ids.shape, d, dtype=out_dtype, device=table.device)
     keys = torch.empty(n, dtype=torch.int64, device=table.device) if want_keys else None
     rws = torch.empty(ids.shape, dtype=torch.int32, device=table.device) if want_rows else None
-    call("rs_embed_gather_fwd", _ptr(table), _ptr(ids), _ptr(row_base), _ptr(rows), n, F, d, _ptr(out),
-         _DT[out_dtype], _ptr(keys), _ptr(rws), _stream())
+    call("rs_embed_gather_fwd_ld", _ptr(table), table.stride(0), _ptr(ids), _ptr(row_base), _ptr(rows), n, F, d,
+         _ptr(out), _DT[out_dtype], _ptr(keys), _ptr(rws), _stream())
     return out, keys, rws
 
 
@@ -83,8 +84,9 @@ def embed_gather_peer(shards, ids, local_base, rows, out_dtype=torch.float32):
     n, d = ids.numel(), shards[0].shape[1]
     ptrs = (ctypes.c_void_p * W)(*[t.data_ptr() for t in shards])
     out = torch.empty(*ids.shape, d, dtype=out_dtype, device=ids.device)
-    call("rs_embed_gather_peer_fwd", ctypes.addressof(ptrs), W, _ptr(ids), _ptr(local_base), _ptr(rows), n, F, d,
-         _ptr(out), _DT[out_dtype], _stream())
+    _need(all(t.stride(1) == 1 and t.stride(0) == shards[0].stride(0) for t in shards), "shards: one common row stride")
+    call("rs_embed_gather_peer_fwd", ctypes.addressof(ptrs), shards[0].stride(0), W, _ptr(ids), _ptr(local_base),
+         _ptr(rows), n, F, d, _ptr(out), _DT[out_dtype], _stream())
     return out
 
 
@@ -94,8 +96,8 @@ def embed_gather_rows(table, rowidx, out_dtype=torch.float32, want_mask=False, w
     out = torch.empty(*rowidx.shape, d, dtype=out_dtype, device=table.device)
     mask = torch.empty(rowidx.shape, dtype=torch.uint8, device=table.device) if want_mask else None
     keys = torch.empty(n, dtype=torch.int64, device=table.device) if want_keys else None
-    call("rs_embed_gather_rows", _ptr(table), _ptr(rowidx), n, d, _ptr(out), _DT[out_dtype], _ptr(mask),
-         _ptr(keys), _stream())
+    call("rs_embed_gather_rows_ld", _ptr(table), table.stride(0), _ptr(rowidx), n, d, _ptr(out), _DT[out_dtype],
+         _ptr(mask), _ptr(keys), _stream())
     return out, mask, keys
 
 
@@ -130,7 +132,8 @@ def segsum(grad, keys_sorted):
 
 
 def segsum_adam(w, m, v, grad, keys_sorted, lr, beta1, beta2, eps, scalars, grad_scale=1.0):
-    call("rs_embed_segsum_adam", _ptr(w), _ptr(m), _ptr(v), _ptr(grad), _dt(grad), _ptr(keys_sorted),
+    _need(w.stride(1) == 1 and w.stride() == m.stride() == v.stride(), "w, m, v: one common row stride")
+    call("rs_embed_segsum_adam_ld", _ptr(w), _ptr(m), _ptr(v), w.stride(0), _ptr(grad), _dt(grad), _ptr(keys_sorted),
          keys_sorted.numel(), w.shape[1], lr, beta1, beta2, eps, _ptr(scalars), grad_scale, _stream())
 
 

@@ -139,20 +139,21 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
         cfg, d, W = self.cfg, self.cfg.embed_dim, self.world
         self.local_rows, self.local_base = shard_layout(self.rows_host, W)
         n_local = int(self.local_rows.sum())
+        self._alloc_arena(n_local, d)
         if self._global_tables is not None:
             # rows of field f owned by this rank: global rows rank, rank+W, ... (parity tests)
             g = self._global_tables.to(torch.float32)
-            self.table = torch.zeros(n_local, d, device=self.dev)
             for f in range(cfg.num_fields):
                 src = g[int(self.base_host[f]) + self.rank: int(self.base_host[f] + self.rows_host[f]): W]
                 self.table[int(self.local_base[f]): int(self.local_base[f]) + src.shape[0]] = src.to(self.dev)
             self._global_tables = None
         else:
             gen = torch.Generator(device=self.dev).manual_seed(cfg.seed + 7919 * self.rank)
-            self.table = torch.empty(n_local, d, device=self.dev)
-            self.table.normal_(0.0, cfg.table_init_scale, generator=gen)
-        self.table_m = torch.zeros_like(self.table)
-        self.table_v = torch.zeros_like(self.table)
+            chunk = 1 << 22
+            for r0 in range(0, n_local, chunk):
+                r1 = min(n_local, r0 + chunk)
+                self.table[r0:r1] = torch.empty(r1 - r0, d, device=self.dev).normal_(0.0, cfg.table_init_scale,
+                                                                                     generator=gen)
         self.row_bits = ops.row_bits(n_local)
 
     # ---- embedding halves of the step -----------------------------------------------------
@@ -171,12 +172,12 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
                 with ph("a2a_ids"):
                     self.ex.all_to_all(self.recv_rows, self.send_rows)
                 with ph("sort_keys"):
-                    cabi.call("rs_embed_gather_rows", self.table.data_ptr(), self.recv_rows.data_ptr(),
+                    cabi.call("rs_embed_gather_rows_ld", self.table.data_ptr(), self.table_ld, self.recv_rows.data_ptr(),
                               self.recv_rows.numel(), d, None, T, None, self.keys.data_ptr(), ops._stream())
                     ops.sort_keys(self.keys, self.row_bits, out=self.keys_sorted)
                 self.route_done.record(self.side2)
             with ph("embed_gather_peer"):
-                cabi.call("rs_embed_gather_peer_fwd", ctypes.addressof(self.peer_ptrs), self.world,
+                cabi.call("rs_embed_gather_peer_fwd", ctypes.addressof(self.peer_ptrs), self.table_ld, self.world,
                           self.ids.data_ptr(), self.lbase_t.data_ptr(), self.rows_t.data_ptr(),
                           c.batch * F, F, d, self.X.data_ptr(), T, st)
             return
@@ -186,8 +187,8 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
         with ph("a2a_ids"):
             self.ex.all_to_all(self.recv_rows, self.send_rows)
         with ph("embed_gather"):
-            cabi.call("rs_embed_gather_rows", self.table.data_ptr(), self.recv_rows.data_ptr(),
-                          self.recv_rows.numel(), d, self.rows_out.data_ptr(), T, None, self.keys.data_ptr(), st)
+            cabi.call("rs_embed_gather_rows_ld", self.table.data_ptr(), self.table_ld, self.recv_rows.data_ptr(),
+                      self.recv_rows.numel(), d, self.rows_out.data_ptr(), T, None, self.keys.data_ptr(), st)
         with ph("a2a_rows"):
             self.ex.all_to_all(self.rows_in, self.rows_out)
         with ph("unpermute"):

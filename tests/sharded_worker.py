@@ -50,8 +50,9 @@ def main():
     lt = torch.stack(losses).reshape(-1)
     dist.all_reduce(lt, op=dist.ReduceOp.AVG)
     # gather every rank's shard on rank 0
-    shards = [torch.empty_like(sh.table) for _ in range(world)] if rank == 0 else None
-    dist.gather(sh.table, shards, dst=0)
+    mine = sh.table.contiguous()                      # the shard is a strided view of the [w | m | v] arena
+    shards = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, shards, dst=0)
     ok = True
     if rank == 0:
         ref = AutoIntTrainer(AutoIntConfig(batch=world * b, **kw), dev, tables=torch.from_numpy(table),
