@@ -65,15 +65,20 @@ __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
 // element e of this thread's head inside a 16-wide register row (compile-time indices + select:
 // a runtime index would push the array to local memory)
 #ifdef RS_ITB_PROFILE
+// what-if timing experiments (WRONG results, profile builds only; tools/itb_whatif.py): bit 0 = no MMA issue,
+// bit 1 = no fence.proxy.async, bit 2 = no exponentials in the softmax, bit 3 = no P / dS tile stores;
+// bit 8 = clock64 phase hooks on (tools/itb_profile.py)
+__device__ int itb_exp_mode = 0;
+#define EXP(bit) (itb_exp_mode & (1 << (bit)))
 __device__ unsigned long long itb_prof[32];
 #define PROF(i)                                         \
-  if (blockIdx.x == 0 && tid == 0) {                    \
+  if (blockIdx.x == 0 && tid == 0 && EXP(8)) {          \
     const long long t_now = clock64();                  \
     itb_prof[i] += (unsigned long long)(t_now - t_last); \
     t_last = t_now;                                     \
   }
 #define PROFW(i)                                                                     \
-  if (blockIdx.x == 0 && (tid == 0 || tid == 32)) {                                   \
+  if (blockIdx.x == 0 && (tid == 0 || tid == 32) && EXP(8)) {                         \
     const long long t_now = clock64();                                               \
     itb_prof[(tid == 0 ? 16 : 24) + (i)] += (unsigned long long)(t_now - t_w);        \
     t_w = t_now;                                                                     \
@@ -81,6 +86,7 @@ __device__ unsigned long long itb_prof[32];
 #else
 #define PROF(i)
 #define PROFW(i)
+#define EXP(bit) 0
 #endif
 
 #define HSEL(a, e) (wg ? (a)[8 + (e)] : (a)[(e)])
@@ -303,16 +309,18 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       *reinterpret_cast<uint4*>(smem + OFF_K16 + nosw_off<2>(row, wg)) = pack8_bf16(kk);
     }
     // ================= 2. S_h = Q_h K_h^T
-    fence_async_smem();
+    if (!EXP(1)) fence_async_smem();
     tc_fence_before();
     __syncthreads();
     PROF(0)
     if (issuer >= 0) {
       tc_fence_after();
+      if (!EXP(0)) {
       if ((issuer & 1) == 0) {
         const int h = issuer >> 1;
         tc_mma_tf32(tmem + TM_S + h * 128, mk_desc(b16, OFF_Q32 + h * 4096, 128, 256),
                     mk_desc(b16, OFF_K32 + h * 4096, 128, 256), ID_S, 0u);
+      }
       }
       tc_commit(bar);
     }
@@ -393,8 +401,8 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int j = 0; j < FP; j += 2) {                                // the forward's P, bit for bit
-        p[j] = ex2_approx(fmaf(p[j], scale_log2, -mb));
-        p[j + 1] = ex2_approx(fmaf(p[j + 1], scale_log2, -mb));
+        p[j] = EXP(2) ? fmaf(p[j], scale_log2, -mb) : ex2_approx(fmaf(p[j], scale_log2, -mb));
+        p[j + 1] = EXP(2) ? fmaf(p[j + 1], scale_log2, -mb) : ex2_approx(fmaf(p[j + 1], scale_log2, -mb));
         bf16_round2(p[j], p[j + 1]);
         l4[j & 3] += p[j];
         l4[(j + 1) & 3] += p[j + 1];
@@ -404,7 +412,7 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
 #pragma unroll
       for (int j = 0; j < FP; ++j) p[j] = active ? p[j] * linv : 0.f;
       PROFW(1)
-      if (s_loc < SPT) {
+      if (s_loc < SPT && !EXP(3)) {
 #pragma unroll
         for (int c = 0; c < NCHF; ++c)
           *reinterpret_cast<uint4*>(smem + OFF_P + wg * 32768 + nosw_off<16>(row, s_loc * NCHF + c)) = pack8_bf16(p + c * 8);
@@ -412,7 +420,7 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
     }
     // ================= 3. dP_h = dO_h V_h^T ; dV_h = P_h^T dO_h
     PROFW(2)
-    fence_async_smem();
+    if (!EXP(1)) fence_async_smem();
     PROFW(3)
     tc_fence_before();
     __syncthreads();
@@ -420,6 +428,7 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
     PROF(3)
     if (issuer >= 0) {
       tc_fence_after();
+      if (!EXP(0)) {
       const int h = issuer >> 1;
       if ((issuer & 1) == 0) {
         tc_mma_tf32(tmem + TM_S + h * 128, mk_desc(b16, OFF_DO32 + h * 4096, 128, 256),
@@ -429,6 +438,7 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
         for (int ks = 0; ks < 8; ++ks)   // K = tile rows, 16 per step = 2 row groups of the P tile
           tc_mma_bf16(tmem + TM_DV + h * 16, mk_desc(b16, OFF_P + h * 32768 + ks * 4096, 2048, 128),
                       mk_desc(b16, OFF_DO16 + ks * 512, 256, 128), ID_AT, ks ? 1u : 0u);
+      }
       }
       tc_commit(bar);
     }
@@ -447,7 +457,7 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       const float delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
 #pragma unroll
       for (int j = 0; j < FP; ++j) dp[j] = p[j] * scale * (dp[j] - delta);     // dS (1/sqrt(dh) folded in)
-      if (s_loc < SPT) {
+      if (s_loc < SPT && !EXP(3)) {
 #pragma unroll
         for (int cc = 0; cc < NCHF; ++cc)
           *reinterpret_cast<uint4*>(smem + OFF_P + wg * 32768 + nosw_off<16>(row, s_loc * NCHF + cc)) = pack8_bf16(dp + cc * 8);
@@ -461,12 +471,13 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, 4 + wg)) = pack8_bf16(t8);
     }
     // ================= 4. dQ_h = dS_h K_h ; dK_h = dS_h^T Q_h
-    fence_async_smem();
+    if (!EXP(1)) fence_async_smem();
     tc_fence_before();
     __syncthreads();
     PROF(6)
     if (issuer >= 0) {
       tc_fence_after();
+      if (!EXP(0)) {
       const int h = issuer >> 1;
       if ((issuer & 1) == 0) {
 #pragma unroll
@@ -478,6 +489,7 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
         for (int ks = 0; ks < 8; ++ks)
           tc_mma_bf16(tmem + TM_DK + h * 16, mk_desc(b16, OFF_P + h * 32768 + ks * 4096, 2048, 128),
                       mk_desc(b16, OFF_Q16 + ks * 512, 256, 128), ID_AT, ks ? 1u : 0u);
+      }
       }
       tc_commit(bar);
     }
@@ -503,12 +515,13 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, 2 + wg)) = pack8_bf16(t8);
     }
     // ================= 5. dX = dZ W^T ; [dW^T | db ; dgamma ; dbeta] += [dZ | g*xhat | g]^T [X | 1] ; Z(next)
-    fence_async_smem();
+    if (!EXP(1)) fence_async_smem();
     tc_fence_before();
     __syncthreads();
     PROF(9)
     if (issuer >= 0) {
       tc_fence_after();
+      if (!EXP(0)) {
       if (issuer == 0) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
@@ -521,6 +534,7 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
                       mk_desc(b16, OFF_XB + ks * 1024, 512, 128), ID_DW, ks ? 1u : dw_acc);
       } else if (issuer == 2 && !last) {
         issue_proj_3xtf32(tmem + TM_Z, sbase + OFF_X, sbase + OFF_W32, ID_Z);
+      }
       }
       tc_commit(bar);
     }
@@ -616,6 +630,11 @@ static int launch_itc_bwd(const IBwdArgs& a) {
 int interacting_tc_bwd(const IBwdArgs& a) { return launch_itc_bwd<5, __nv_bfloat16>(a); }
 
 #ifdef RS_ITB_PROFILE
+extern "C" int rs_debug_itb_exp(int mode) {
+  cudaDeviceSynchronize();
+  cudaMemcpyToSymbol(itb_exp_mode, &mode, sizeof(int));
+  return 0;
+}
 extern "C" int rs_debug_itb_profile(unsigned long long* out32, int reset) {
   cudaDeviceSynchronize();
   if (out32) cudaMemcpyFromSymbol(out32, itb_prof, sizeof(unsigned long long) * 32);

@@ -14,6 +14,7 @@ W = (torch.rand(D, 64, device=dev, generator=g) - 0.5) * 0.8
 b = torch.zeros(64, device=dev); gm = torch.ones(D, device=dev); bt = torch.zeros(D, device=dev)
 y, saved = ops.interacting_fwd(x, W, b, gm, bt, 1e-3, 2, L, True, compute_bf16=True)
 lib = cabi.load()
+lib.rs_debug_itb_exp(256)          # clock64 hooks on
 out = (ctypes.c_ulonglong * 32)()
 for _ in range(3):
     ops.interacting_bwd(x, saved, W, b, gm, bt, 1e-3, 2, L, dy, True, compute_bf16=True)
