@@ -392,6 +392,12 @@ int rs_logit_head_fwd_bwd(const void* Z, int64_t ldz, int dtype, const float* w,
                           const float* bias, const float* y, float a, void* p_out,
                           float* loss_out, void* dZ, int64_t lddz, float* dw, float* db,
                           int B, int zw, void* ws, size_t ws_bytes, void* stream);
+/* Same, and columns [0, relu_cols) of dZ come out already multiplied by relu'(Z) (those columns of Z are the
+ * output of the tower's last Dense(relu), autoint:39-45): the MLP backward starts from dZ[:, :relu_cols] as is. */
+int rs_logit_head_fwd_bwd_relu(const void* Z, int64_t ldz, int dtype, const float* w,
+                          const float* bias, const float* y, float a, void* p_out,
+                          float* loss_out, void* dZ, int64_t lddz, float* dw, float* db,
+                          int B, int zw, int relu_cols, void* ws, size_t ws_bytes, void* stream);
 
 /* dst[n, m] = src[m, n] (2-D transpose with leading dims; bf16 or fp32).  Used to
  * present activations K-major to the tensor-core weight-gradient GEMMs. */

@@ -154,7 +154,8 @@ class AutoIntTrainer:
         self.p_raw = e(B, 1)
         self.loss = torch.zeros(1, device=self.dev)
         self.dZ = e(B, self.zw)
-        self.dH = [e(B, w) for w in cfg.mlp_hidden]
+        # gradient of the last hidden layer = the first n_deep columns of dZ (the head writes them relu-masked)
+        self.dH = [e(B, w) for w in cfg.mlp_hidden[:-1]] + [self.dZ[:, :cfg.mlp_hidden[-1]]]
         self.dX = e(B, F, d)
         self.bf16 = self.act_dtype == torch.bfloat16
         if self.bf16:
@@ -267,11 +268,11 @@ class AutoIntTrainer:
                 self._dense_fwd(acts[i], f"mlp_W{i}", f"mlp_b{i}", acts[i + 1])
         with ph("logits_loss"):
             # final Dense(1, sigmoid) + clip + BCE + the head's backward, one pass over Z
+            # dZ[:, :n_deep] leaves the head already multiplied by relu'(last hidden layer): it IS dH[nmlp-1]
             ops.logit_head(self.Z, P["out_W"], P["out_b"], self.labels, self.dZ, G["out_W"], G["out_b"],
-                           p_out=self.p_raw, loss=self.loss)
+                           p_out=self.p_raw, loss=self.loss, relu_cols=self.n_deep)
         # MLP backward (relu masks from the saved activations)
         with ph("mlp_bwd"):
-            ops.act_bwd(self.dZ[:, :self.n_deep], acts[nmlp], 0, out=self.dH[nmlp - 1])
             for i in reversed(range(nmlp)):
                 # weight / bias gradients are only consumed by the dense Adam at the end of the step: they run
                 # on the side stream (after the key sort), off the dgrad -> InteractingLayer-backward chain

@@ -67,6 +67,7 @@ PROTOTYPES = {
     "rs_bce_sigmoid_fwd_bwd": (_i, [_p, _i, _p, _f, _p, _p, _i, _i, _p]),
     "rs_logit_head_workspace_bytes": (_sz, [_i, _i]),
     "rs_logit_head_fwd_bwd": (_i, [_p, _i64, _i, _p, _p, _p, _f, _p, _p, _p, _i64, _p, _p, _i, _i, _p, _sz, _p]),
+    "rs_logit_head_fwd_bwd_relu": (_i, [_p, _i64, _i, _p, _p, _p, _f, _p, _p, _p, _i64, _p, _p, _i, _i, _i, _p, _sz, _p]),
     "rs_transpose2d": (_i, [_p, _i64, _p, _i64, _i, _i, _i, _p]),
 }
 

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32)
 logit_head_kernel(const T* __restrict__ Z, int64_t ldz, const float* __restrict__ w,
                   const float* __restrict__ bias, const float* __restrict__ y, float a,
                   T* __restrict__ p_out, T* __restrict__ dZ, int64_t lddz, float* __restrict__ part,
-                  int B, int zw) {
+                  int B, int zw, int relu_cols) {
   extern __shared__ float head_smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float wv[NV][4], dw[NV][4];
@@ -34,18 +34,32 @@ logit_head_kernel(const T* __restrict__ Z, int64_t ldz, const float* __restrict_
   const float b0 = bias[0];
   const float invB = 1.f / (float)B;
   float db = 0.f, loss = 0.f;
-  for (int64_t r = (int64_t)blockIdx.x * HEAD_WARPS + wid; r < B; r += (int64_t)gridDim.x * HEAD_WARPS) {
-    float z[NV][4];
-    float dot = 0.f;
+  // rows are software-pipelined: the next row's loads are in flight while the current row is reduced
+  const int64_t rstep = (int64_t)gridDim.x * HEAD_WARPS;
+  int64_t r = (int64_t)blockIdx.x * HEAD_WARPS + wid;
+  float zn[NV][4];
+  auto load_row = [&](int64_t rr, float (&zz)[NV][4]) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c < zw) v = load4<T>(Z + r * ldz + c);
-      z[i][0] = v.x; z[i][1] = v.y; z[i][2] = v.z; z[i][3] = v.w;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) dot = fmaf(z[i][u], wv[i][u], dot);
+      if (c < zw && rr < B) v = load4<T>(Z + rr * ldz + c);
+      zz[i][0] = v.x; zz[i][1] = v.y; zz[i][2] = v.z; zz[i][3] = v.w;
     }
+  };
+  load_row(r, zn);
+  for (; r < B; r += rstep) {
+    float z[NV][4];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        z[i][u] = zn[i][u];
+        dot = fmaf(z[i][u], wv[i][u], dot);
+      }
+    }
+    load_row(r + rstep, zn);
     dot = warp_sum(dot);
     const float pr = 1.f / (1.f + expf(-(dot + b0)));
     const float prs = to_f<T>(from_f<T>(pr));        // the stored activation (bf16-rounded in bf16 mode)
@@ -61,8 +75,17 @@ logit_head_kernel(const T* __restrict__ Z, int64_t ldz, const float* __restrict_
       const int c = (i * 32 + lane) * 4;
 #pragma unroll
       for (int u = 0; u < 4; ++u) dw[i][u] = fmaf(dz, z[i][u], dw[i][u]);
-      if (c < zw)
-        store4<T>(dZ + r * lddz + c, make_float4(dz * wv[i][0], dz * wv[i][1], dz * wv[i][2], dz * wv[i][3]));
+      if (c < zw) {
+        float o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          o[u] = dz * wv[i][u];
+          // columns [0, relu_cols) of Z are the output of a Dense(relu): their gradient is handed on already
+          // masked by relu' (saves the separate activation-backward pass over dZ[:, :relu_cols])
+          if (c + u < relu_cols && !(z[i][u] > 0.f)) o[u] = 0.f;
+        }
+        store4<T>(dZ + r * lddz + c, make_float4(o[0], o[1], o[2], o[3]));
+      }
     }
   }
   // warp partials -> smem [HEAD_WARPS][zw + 2] -> CTA partial (fixed warp order)
@@ -117,10 +140,11 @@ size_t rs_logit_head_workspace_bytes(int B, int zw) {
   return (size_t)head_grid(B > 0 ? B : 1) * (size_t)(zw + 2) * sizeof(float);
 }
 
-int rs_logit_head_fwd_bwd(const void* Z, int64_t ldz, int dtype, const float* w, const float* bias,
-                          const float* y, float a, void* p_out, float* loss_out, void* dZ,
-                          int64_t lddz, float* dw, float* db, int B, int zw, void* ws,
-                          size_t ws_bytes, void* stream) {
+int rs_logit_head_fwd_bwd_relu(const void* Z, int64_t ldz, int dtype, const float* w, const float* bias,
+                               const float* y, float a, void* p_out, float* loss_out, void* dZ,
+                               int64_t lddz, float* dw, float* db, int B, int zw, int relu_cols, void* ws,
+                               size_t ws_bytes, void* stream) {
+  RS_REQUIRE(relu_cols >= 0 && relu_cols <= zw, "logit_head: relu_cols=%d", relu_cols);
   RS_REQUIRE(B > 0 && zw > 0 && zw % 4 == 0 && zw <= 2048, "logit_head: B=%d zw=%d (zw %% 4 == 0, <= 2048)", B, zw);
   RS_REQUIRE(ldz % 4 == 0 && lddz % 4 == 0, "logit_head: leading dims must be multiples of 4");
   RS_REQUIRE(dtype == RS_F32 || dtype == RS_BF16, "logit_head: bad dtype");
@@ -134,19 +158,28 @@ int rs_logit_head_fwd_bwd(const void* Z, int64_t ldz, int dtype, const float* w,
     auto kern = logit_head_kernel<NV, TT>;                                                          \
     RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
     kern<<<grid, HEAD_WARPS * 32, smem, st>>>((const TT*)Z, ldz, w, bias, y, a, (TT*)p_out, (TT*)dZ, \
-                                              lddz, (float*)ws, B, zw);                             \
+                                              lddz, (float*)ws, B, zw, relu_cols);                  \
   } while (0)
   if (dtype == RS_F32) {
-    if (nv <= 4) RS_HEAD_GO(4, float); else if (nv <= 8) RS_HEAD_GO(8, float); else RS_HEAD_GO(16, float);
+    if (nv <= 4) RS_HEAD_GO(4, float); else if (nv <= 6) RS_HEAD_GO(6, float); else if (nv <= 8) RS_HEAD_GO(8, float);
+    else RS_HEAD_GO(16, float);
   } else {
-    if (nv <= 4) RS_HEAD_GO(4, __nv_bfloat16); else if (nv <= 8) RS_HEAD_GO(8, __nv_bfloat16);
-    else RS_HEAD_GO(16, __nv_bfloat16);
+    if (nv <= 4) RS_HEAD_GO(4, __nv_bfloat16); else if (nv <= 6) RS_HEAD_GO(6, __nv_bfloat16);
+    else if (nv <= 8) RS_HEAD_GO(8, __nv_bfloat16); else RS_HEAD_GO(16, __nv_bfloat16);
   }
 #undef RS_HEAD_GO
   if (int e = check_launch("logit_head")) return e;
   logit_head_reduce_kernel<<<(unsigned)cdiv((zw + 2) * 32, 256), 256, 0, st>>>((const float*)ws, grid, zw, dw, db,
                                                                          loss_out, 1.f / (float)B);
   return check_launch("logit_head_reduce");
+}
+
+int rs_logit_head_fwd_bwd(const void* Z, int64_t ldz, int dtype, const float* w, const float* bias,
+                          const float* y, float a, void* p_out, float* loss_out, void* dZ,
+                          int64_t lddz, float* dw, float* db, int B, int zw, void* ws,
+                          size_t ws_bytes, void* stream) {
+  return rs_logit_head_fwd_bwd_relu(Z, ldz, dtype, w, bias, y, a, p_out, loss_out, dZ, lddz, dw, db, B, zw, 0, ws, ws_bytes,
+                                    stream);
 }
 
 }  // extern "C"

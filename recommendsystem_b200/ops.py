@@ -285,14 +285,15 @@ def transpose2d(src, out=None):
     return out
 
 
-def logit_head(Z, w, bias, y, dZ, dw, db, p_out=None, loss=None, a=1.0):
-    """Fused Dense(1, sigmoid) + clip + BCE + head backward (rs_logit_head_fwd_bwd)."""
+def logit_head(Z, w, bias, y, dZ, dw, db, p_out=None, loss=None, a=1.0, relu_cols=0):
+    """Fused Dense(1, sigmoid) + clip + BCE + head backward (rs_logit_head_fwd_bwd[_relu]); dZ[:, :relu_cols] comes
+    out multiplied by relu'(Z)."""
     B, zw = Z.shape
     p_out = torch.empty(B, 1, dtype=Z.dtype, device=Z.device) if p_out is None else p_out
     loss = torch.empty(1, dtype=torch.float32, device=Z.device) if loss is None else loss
     ws = WS.get("head", cabi.load().rs_logit_head_workspace_bytes(B, zw), Z.device)
-    call("rs_logit_head_fwd_bwd", _ptr(Z), Z.stride(0), _dt(Z), _ptr(w), _ptr(bias), _ptr(y), a, _ptr(p_out),
-         _ptr(loss), _ptr(dZ), dZ.stride(0), _ptr(dw), _ptr(db), B, zw, _ptr(ws), ws.numel(), _stream())
+    call("rs_logit_head_fwd_bwd_relu", _ptr(Z), Z.stride(0), _dt(Z), _ptr(w), _ptr(bias), _ptr(y), a, _ptr(p_out),
+         _ptr(loss), _ptr(dZ), dZ.stride(0), _ptr(dw), _ptr(db), B, zw, int(relu_cols), _ptr(ws), ws.numel(), _stream())
     return p_out, loss
 
 
