@@ -122,6 +122,13 @@ int rs_embed_gather_rows_ld(const float* table, int64_t table_ld, const int32_t*
 int rs_embed_gather_peer_fwd(const float* const* peer_tables, int64_t table_ld, int world, const int64_t* ids,
                              const int64_t* local_base, const int64_t* rows, int64_t n, int F, int d,
                              void* out, int out_dtype, void* stream);
+/* The backward half of the same exchange: row i of `src` (this rank's gradient rows, `row_bytes` each) is stored
+ * into peer_recv[owner] (HOST array of `world` DEVICE pointers to every rank's receive buffer, rs_ipc_import) at
+ * slot my_rank * cap + k, where index[i] = owner * cap + k is the lookup's slot in the send order produced by
+ * rs_route_ids_padded (index[i] < 0: skipped).  Replaces permute + all-to-all; the caller separates it from the
+ * owners' reads by a cross-rank barrier. */
+int rs_scatter_rows_peer(const void* src, void* const* peer_recv, int world, int my_rank,
+                         const int32_t* index, int64_t n, int cap, int row_bytes, void* stream);
 /* CUDA-IPC plumbing for the above: export the allocation containing `ptr` (64-byte handle + byte offset
  * of ptr inside it); import maps a peer's allocation (peer access enabled lazily) and returns
  * base + offset. */

@@ -636,11 +636,46 @@ __global__ void permute_rows_kernel(const T* __restrict__ src, T* __restrict__ o
   }
 }
 
+// Gradient push of the row-sharded path as peer STORES over NVLink: lookup i of this rank sits in slot
+// index[i] = owner * cap + k of its send order (rs_route_ids_padded); its gradient row goes straight into the
+// owner's receive buffer at slot (my_rank * cap + k) — the permute and the all-to-all of the NCCL path in one
+// kernel.  Slots that stay unwritten hold padding rows (row -1 in the owner's keys) and are never read.
+struct PeerBufs { void* p[RS_MAX_PEERS]; };
+
+__global__ void scatter_rows_peer_kernel(const uint2* __restrict__ src, PeerBufs dst, const int32_t* __restrict__ index,
+                                         int64_t n, int vec_per_row, int cap, int my_rank) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = t / vec_per_row;
+  const int c = (int)(t % vec_per_row);
+  if (i >= n) return;
+  const int32_t j = index[i];
+  if (j < 0) return;
+  const int owner = j / cap, k = j - owner * cap;
+  uint2* o = reinterpret_cast<uint2*>(dst.p[owner]);
+  o[((int64_t)my_rank * cap + k) * vec_per_row + c] = src[i * vec_per_row + c];
+}
+
 }  // namespace rs
 
 using namespace rs;
 
 extern "C" {
+
+int rs_scatter_rows_peer(const void* src, void* const* peer_recv, int world, int my_rank, const int32_t* index,
+                         int64_t n, int cap, int row_bytes, void* stream) {
+  RS_REQUIRE(world >= 1 && world <= RS_MAX_PEERS && my_rank >= 0 && my_rank < world, "scatter_rows_peer: world=%d rank=%d",
+             world, my_rank);
+  RS_REQUIRE(row_bytes > 0 && row_bytes % 8 == 0 && cap > 0, "scatter_rows_peer: row_bytes=%d cap=%d", row_bytes, cap);
+  if (n == 0) return 0;
+  PeerBufs dst;
+  for (int r = 0; r < RS_MAX_PEERS; ++r) dst.p[r] = r < world ? peer_recv[r] : nullptr;
+  const int vec = row_bytes / 8;
+  const int threads = 256;
+  const int64_t blocks = cdiv(n * vec, threads);
+  scatter_rows_peer_kernel<<<(unsigned)blocks, threads, 0, as_stream(stream)>>>((const uint2*)src, dst, index, n, vec, cap,
+                                                                             my_rank);
+  return check_launch("scatter_rows_peer");
+}
 
 int rs_embed_gather_fwd_ld(const float* table, int64_t table_ld, const int64_t* ids, const int64_t* row_base,
                            const int64_t* rows, int64_t n, int F, int d, void* out, int out_dtype,

@@ -114,26 +114,35 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
             self.side2 = torch.cuda.Stream(device=dev)
             self.route_done = torch.cuda.Event()
             self.barrier_buf = torch.zeros(1, device=dev)
+            self.barrier_buf2 = torch.zeros(1, device=dev)
 
-    def _map_peer_tables(self, group):
-        """Exchange CUDA-IPC handles of every rank's table shard and map them into this process."""
+    def _map_peers(self, tensor, group):
+        """Exchange CUDA-IPC handles of `tensor` (one per rank) and map every rank's copy into this process;
+        returns a host array of W device pointers (a kernel argument)."""
         handle = (ctypes.c_ubyte * 64)()
         off = ctypes.c_ulonglong(0)
-        cabi.call("rs_ipc_export", self.table.data_ptr(), ctypes.addressof(handle), ctypes.addressof(off))
-        mine = (bytes(handle), int(off.value))
+        cabi.call("rs_ipc_export", tensor.data_ptr(), ctypes.addressof(handle), ctypes.addressof(off))
         everyone = [None] * self.world
-        dist.all_gather_object(everyone, mine, group=group)
+        dist.all_gather_object(everyone, (bytes(handle), int(off.value)), group=group)
         ptrs = (ctypes.c_void_p * self.world)()
+        opened = getattr(self, "_ipc_opened", {})
         for r, (h, o) in enumerate(everyone):
             if r == self.rank:
-                ptrs[r] = self.table.data_ptr()
+                ptrs[r] = tensor.data_ptr()
                 continue
-            hb = (ctypes.c_ubyte * 64).from_buffer_copy(h)
-            out = ctypes.c_void_p(0)
-            cabi.call("rs_ipc_import", ctypes.addressof(hb), o, ctypes.addressof(out))
-            ptrs[r] = out.value
-        self.peer_ptrs = ptrs               # host array of W device pointers (kernel argument)
+            if (r, h) not in opened:                  # an allocation may be opened once per process
+                hb = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                base = ctypes.c_void_p(0)
+                cabi.call("rs_ipc_import", ctypes.addressof(hb), 0, ctypes.addressof(base))
+                opened[(r, h)] = base.value
+            ptrs[r] = opened[(r, h)] + o
+        self._ipc_opened = opened
         dist.barrier(group=group)
+        return ptrs
+
+    def _map_peer_tables(self, group):
+        self.peer_ptrs = self._map_peers(self.table, group)          # every rank's table shard
+        self.peer_grecv = self._map_peers(self.g_recv, group)         # every rank's gradient receive buffer
 
     def _alloc_tables(self, tables):
         cfg, d, W = self.cfg, self.cfg.embed_dim, self.world
@@ -203,11 +212,21 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
         d = c.embed_dim
         if self.peer_gather:
             main.wait_event(self.route_done)   # inverse permutation + sorted keys of this step
-        with ph("permute_grads"):
-            self.g_send.zero_()
-            ops.permute_rows(self.dX.view(-1, d), self.inverse, scatter=True, out=self.g_send)
-        with ph("a2a_grads"):
-            self.ex.all_to_all(self.g_recv, self.g_send)
+        if self.peer_gather:
+            # gradient rows go straight into the owners' receive buffers (peer stores over NVLink): the permute
+            # and the all-to-all in one kernel; a one-element all-reduce separates the stores from the owners' reads
+            with ph("scatter_grads_peer"):
+                row_bytes = d * self.dX.element_size()
+                cabi.call("rs_scatter_rows_peer", self.dX.data_ptr(), ctypes.addressof(self.peer_grecv), self.world,
+                          self.rank, self.inverse.data_ptr(), c.batch * c.num_fields, self.cap, row_bytes, st)
+            with ph("peer_barrier"):
+                dist.all_reduce(self.barrier_buf2, group=self.ex.group)
+        else:
+            with ph("permute_grads"):
+                self.g_send.zero_()
+                ops.permute_rows(self.dX.view(-1, d), self.inverse, scatter=True, out=self.g_send)
+            with ph("a2a_grads"):
+                self.ex.all_to_all(self.g_recv, self.g_send)
         if not self.peer_gather:
             main.wait_event(self.sort_done)    # sorted keys (the dense all-reduce / Adam stay on the side stream)
         with ph("embed_segsum_adam"):
