@@ -164,6 +164,7 @@ def algorithmic(phase, B, act_bytes, n_unique):
     t = {
         "embed_gather": (n * (8 + D * 4 + D * act_bytes + 8), 0),          # + 8 B sort key written
         "embed_gather_peer": (n * (8 + D * 4 + D * act_bytes), 0),          # rows read over NVLink (W-1)/W of them
+        "scatter_grads_peer": (n * (4 + 2 * D * act_bytes), 0),             # grads stored over NVLink (W-1)/W of them
         # x in, y out, + the L saved pre-LayerNorm rows (fp32) the tcgen05 forward writes / backward reads
         "interacting_fwd": (n * (D + U) * act_bytes + L * n * U * 4, inter_f),
         "interacting_bwd": (n * (U + 2 * D) * act_bytes + L * n * U * 4, 3 * inter_f),
