@@ -129,6 +129,12 @@ int rs_embed_gather_peer_fwd(const float* const* peer_tables, int64_t table_ld, 
  * owners' reads by a cross-rank barrier. */
 int rs_scatter_rows_peer(const void* src, void* const* peer_recv, int world, int my_rank,
                          const int32_t* index, int64_t n, int cap, int row_bytes, void* stream);
+/* Cross-rank barrier over peer memory for the two calls above (every rank launches it, in the same order, on its
+ * own GPU): peer_flags[r] (HOST array of `world` DEVICE pointers, rs_ipc_import) is rank r's flag array of
+ * RS_MAX_PEERS + 1 zero-initialised uint32; rank `rank` release-stores its next epoch into slot `rank` of every
+ * array and spins (acquire loads) until all `world` slots of its own array have reached it.  Everything the rank
+ * wrote before (peer stores included) is visible to a peer once that peer leaves the barrier. */
+int rs_peer_barrier(unsigned int* const* peer_flags, int world, int rank, void* stream);
 /* CUDA-IPC plumbing for the above: export the allocation containing `ptr` (64-byte handle + byte offset
  * of ptr inside it); import maps a peer's allocation (peer access enabled lazily) and returns
  * base + offset. */

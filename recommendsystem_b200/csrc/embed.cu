@@ -655,11 +655,42 @@ __global__ void scatter_rows_peer_kernel(const uint2* __restrict__ src, PeerBufs
   o[((int64_t)my_rank * cap + k) * vec_per_row + c] = src[i * vec_per_row + c];
 }
 
+// Cross-rank barrier over peer memory (one process per GPU, all ranks launch it in the same order): rank r
+// publishes its next epoch into slot r of every rank's flag array (system-scope release store over NVLink)
+// and spins until every slot of its own array has reached that epoch (acquire loads).  ~2 NVLink latencies
+// instead of a NCCL all-reduce launch; no host state, so it is a CUDA-graph node.  The epoch lives in device
+// memory next to the flags (slot `world`).
+struct PeerFlags { unsigned int* p[RS_MAX_PEERS]; };
+
+__global__ void peer_barrier_kernel(PeerFlags flags, int world, int rank) {
+  unsigned int* mine = flags.p[rank];
+  const unsigned int epoch = mine[RS_MAX_PEERS] + 1u;       // written only by this rank, read back next call
+  const int t = threadIdx.x;
+  if (t < world) {
+    __threadfence_system();                                 // everything this rank wrote before is visible first
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flags.p[t] + rank), "r"(epoch) : "memory");
+    unsigned int seen;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine + t) : "memory");
+    } while ((int)(seen - epoch) < 0);
+  }
+  __syncthreads();
+  if (t == 0) mine[RS_MAX_PEERS] = epoch;
+}
+
 }  // namespace rs
 
 using namespace rs;
 
 extern "C" {
+
+int rs_peer_barrier(unsigned int* const* peer_flags, int world, int rank, void* stream) {
+  RS_REQUIRE(world >= 1 && world <= RS_MAX_PEERS && rank >= 0 && rank < world, "peer_barrier: world=%d rank=%d", world, rank);
+  PeerFlags f;
+  for (int r = 0; r < RS_MAX_PEERS; ++r) f.p[r] = r < world ? peer_flags[r] : nullptr;
+  peer_barrier_kernel<<<1, 32, 0, as_stream(stream)>>>(f, world, rank);
+  return check_launch("peer_barrier");
+}
 
 int rs_scatter_rows_peer(const void* src, void* const* peer_recv, int world, int my_rank, const int32_t* index,
                          int64_t n, int cap, int row_bytes, void* stream) {

@@ -12,9 +12,10 @@ ids / rows / gradients exchanged by NCCL all-to-all over NVLink (one process per
 needs straight out of the owners' HBM over NVLink / NVSwitch (CUDA-IPC mappings of every rank's shard,
 rs_embed_gather_peer_fwd): no id all-to-all, owner gather, row all-to-all or un-permute on the critical
 path.  The routing + id all-to-all still run — on a side stream, hidden behind the dense forward — because
-the owners need the (row, position) keys for the backward's sorted-segment update; a one-element
-all-reduce after the sparse update is the cross-rank barrier that orders every owner's update before the
-next step's peer reads.
+the owners need the (row, position) keys for the backward's sorted-segment update.  The backward pushes the
+gradient rows into the owners' receive buffers with peer stores (rs_scatter_rows_peer).  Two flag barriers over
+peer memory (rs_peer_barrier) order things: stores before the owners' reads, and every owner's sparse update
+before the next step's peer reads.
 
 Buckets have a fixed capacity, so there is no host round trip for the counts and the whole
 step — collectives included — is one CUDA graph.  A bucket overflow (skewed ids) sets a device
@@ -113,8 +114,6 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
             self._map_peer_tables(group)
             self.side2 = torch.cuda.Stream(device=dev)
             self.route_done = torch.cuda.Event()
-            self.barrier_buf = torch.zeros(1, device=dev)
-            self.barrier_buf2 = torch.zeros(1, device=dev)
 
     def _map_peers(self, tensor, group):
         """Exchange CUDA-IPC handles of `tensor` (one per rank) and map every rank's copy into this process;
@@ -143,6 +142,14 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
     def _map_peer_tables(self, group):
         self.peer_ptrs = self._map_peers(self.table, group)          # every rank's table shard
         self.peer_grecv = self._map_peers(self.g_recv, group)         # every rank's gradient receive buffer
+        self.flags = torch.zeros(16, dtype=torch.int32, device=self.dev)   # RS_MAX_PEERS slots + the epoch
+        torch.cuda.synchronize(self.dev)
+        self.peer_flags = self._map_peers(self.flags, group)
+
+    def _barrier(self, ph, name):
+        """Cross-rank barrier on the current stream: a flag kernel over peer memory (rs_peer_barrier)."""
+        with ph(name):
+            cabi.call("rs_peer_barrier", ctypes.addressof(self.peer_flags), self.world, self.rank, ops._stream())
 
     def _alloc_tables(self, tables):
         cfg, d, W = self.cfg, self.cfg.embed_dim, self.world
@@ -219,8 +226,7 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
                 row_bytes = d * self.dX.element_size()
                 cabi.call("rs_scatter_rows_peer", self.dX.data_ptr(), ctypes.addressof(self.peer_grecv), self.world,
                           self.rank, self.inverse.data_ptr(), c.batch * c.num_fields, self.cap, row_bytes, st)
-            with ph("peer_barrier"):
-                dist.all_reduce(self.barrier_buf2, group=self.ex.group)
+            self._barrier(ph, "peer_barrier")
         else:
             with ph("permute_grads"):
                 self.g_send.zero_()
@@ -238,8 +244,7 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
             # runs beside the dense Adam
             self.side2.wait_stream(main)
             with torch.cuda.stream(self.side2):
-                with ph("peer_barrier"):
-                    dist.all_reduce(self.barrier_buf, group=self.ex.group)
+                self._barrier(ph, "peer_barrier_end")
             self._join_side2 = True
 
     def _dense_sync(self, ph):
