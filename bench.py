@@ -155,6 +155,17 @@ def workload_config(args, dtype):
 
 
 # ------------------------------------------------------------------------------ own arm
+# DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernels from the committed
+# `ncu --set full` capture of THIS workload (profiles/r1d_ncu_full_metrics.csv; batch 8192, bf16, 1 GPU).  ncu
+# replays kernels serialised and cold, so these are per-launch byte counts, not timings.
+NCU_TRAFFIC_BYTES = {
+    "interacting_bwd": 82.645e6 + 3.282e6,
+    "interacting_fwd": 10.267e6 + 15.252e6,
+    "embed_gather": 22.937e6 + 0.326e6,
+    "embed_segsum_adam": 73.986e6 + 23.438e6,
+}
+
+
 def algorithmic(phase, B, act_bytes, n_unique):
     """(bytes, flops) per launch of each phase — DESIGN.md §kernels; SURVEY.md §8d."""
     n = B * F
@@ -295,6 +306,9 @@ def run_own(args):
     else:
         roof = {"bound": "hbm", "achieved": top["GBps"], "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": (top["GBps"] or 0) / pk["hbm_gbs"], "traffic": None}
+    if world == 1 and args.dtype == "bf16" and BATCH == 8192:
+        roof["traffic"] = NCU_TRAFFIC_BYTES.get(top["phase"])
+        roof["traffic_source"] = "profiles/r1d_ncu_full_metrics.csv (bytes per launch)"
     roof.update({"kernel": top["phase"], "peak_source": pk["source"] + " (sustained: kernel timed inside the step)",
                  "share_of_step": top["share"]})
     gk = next(k for k in kernels if k["phase"] in ("embed_gather", "embed_gather_peer"))
