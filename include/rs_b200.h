@@ -268,7 +268,7 @@ int rs_permute_rows(const void* src, void* out, const int32_t* index, int64_t n,
  * Parameters are fp32.
  * compute_bf16 != 0 runs every contraction of the layer on tcgen05 tensor cores (tf32
  * projections / QK^T, bf16 P.V and gradient products, fp32 TMEM accumulators) for the
- * shapes built (D = U = 16, H = 2, 32 < F <= 40) and falls back to FFMA arithmetic for the
+ * shapes built (D = U = 16, H = 2, F <= 48) and falls back to FFMA arithmetic for the
  * others; 0 = fp32 FFMA everywhere (parity mode).
  */
 size_t rs_interacting_workspace_bytes(int B, int F, int D, int U);

@@ -301,10 +301,21 @@ static int launch_itc_fwd(const IFwdArgs& a) {
 
 // Returns RS_ERR_UNSUPPORTED (without setting an error) when the shape is not built for the
 // tensor-core path; the caller then uses the FFMA kernels.
+// Built for D = U = 16, 2 heads, bf16 activations and up to 48 fields: a tile holds floor(128 / FP) whole samples
+// with FP = F rounded up to 8 (F = 39 -> 3 samples, 26 -> 4, 16 -> 8, 48 -> 2).
 bool interacting_tc_supported(int F, int D, int U, int H, int dtype) {
-  return dtype == RS_BF16 && D == 16 && U == 16 && H == 2 && F > 32 && F <= 40;
+  return dtype == RS_BF16 && D == 16 && U == 16 && H == 2 && F >= 1 && F <= 48;
 }
 
-int interacting_tc_fwd(const IFwdArgs& a) { return launch_itc_fwd<5, __nv_bfloat16>(a); }
+int interacting_tc_fwd(const IFwdArgs& a) {
+  switch ((a.F + 7) / 8) {
+    case 1: return launch_itc_fwd<1, __nv_bfloat16>(a);
+    case 2: return launch_itc_fwd<2, __nv_bfloat16>(a);
+    case 3: return launch_itc_fwd<3, __nv_bfloat16>(a);
+    case 4: return launch_itc_fwd<4, __nv_bfloat16>(a);
+    case 5: return launch_itc_fwd<5, __nv_bfloat16>(a);
+    default: return launch_itc_fwd<6, __nv_bfloat16>(a);
+  }
+}
 
 }  // namespace rs

@@ -627,7 +627,16 @@ static int launch_itc_bwd(const IBwdArgs& a) {
   return check_launch("interacting_tc_bwd_reduce");
 }
 
-int interacting_tc_bwd(const IBwdArgs& a) { return launch_itc_bwd<5, __nv_bfloat16>(a); }
+int interacting_tc_bwd(const IBwdArgs& a) {
+  switch ((a.F + 7) / 8) {
+    case 1: return launch_itc_bwd<1, __nv_bfloat16>(a);
+    case 2: return launch_itc_bwd<2, __nv_bfloat16>(a);
+    case 3: return launch_itc_bwd<3, __nv_bfloat16>(a);
+    case 4: return launch_itc_bwd<4, __nv_bfloat16>(a);
+    case 5: return launch_itc_bwd<5, __nv_bfloat16>(a);
+    default: return launch_itc_bwd<6, __nv_bfloat16>(a);
+  }
+}
 
 #ifdef RS_ITB_PROFILE
 extern "C" int rs_debug_itb_exp(int mode) {

@@ -84,7 +84,11 @@ def test_interacting_unsupported_shape_raises(cuda_dev):
                             torch.ones(24, device=cuda_dev), torch.zeros(24, device=cuda_dev), 1e-3, 2, 1)
 
 
-@pytest.mark.parametrize("B,F,L", [(1, 39, 1), (3, 39, 1), (5, 39, 3), (1000, 39, 3), (64, 33, 2), (7, 40, 1)])
+TC_SHAPES = [(1, 39, 1), (3, 39, 1), (5, 39, 3), (1000, 39, 3), (64, 33, 2), (7, 40, 1),
+             (37, 26, 3), (100, 16, 2), (50, 13, 2), (21, 48, 2), (300, 5, 1), (9, 1, 2), (33, 24, 3)]
+
+
+@pytest.mark.parametrize("B,F,L", TC_SHAPES)
 @pytest.mark.parametrize("use_res", [True, False])
 def test_interacting_tc_fwd(cuda_dev, B, F, L, use_res):
     """tcgen05 forward (compute_bf16=1): bf16 projection operands, tf32 QK^T, bf16 P.V, fp32 accumulation
@@ -112,7 +116,7 @@ def test_interacting_tc_fwd(cuda_dev, B, F, L, use_res):
         assert_close(y1, ref1, REL_BF16, "LayerNorm(saved[0])")
 
 
-@pytest.mark.parametrize("B,F,L", [(1, 39, 1), (3, 39, 1), (5, 39, 3), (1000, 39, 3), (64, 33, 2), (7, 40, 1)])
+@pytest.mark.parametrize("B,F,L", TC_SHAPES)
 @pytest.mark.parametrize("use_res", [True, False])
 def test_interacting_tc_bwd(cuda_dev, B, F, L, use_res):
     """tcgen05 backward (compute_bf16=1) against the fp64 oracle gradient evaluated at the activations the
