@@ -149,7 +149,7 @@ def workload_config(args, dtype):
     return {"workload": "AutoInt(layer_num=3,unit_num=16,head_num=2)+DNN(256,128), 39 fields, 1M-row tables d=16, "
                         f"batch {BATCH}/GPU, fwd+bwd+sparse Adam+dense Adam (BASELINE configs[1])",
             "batch_per_gpu": BATCH, "global_batch": BATCH * args.gpus, "fields": F, "embed_dim": D,
-            "rows_per_field": ROWS, "act_dtype": dtype, "ids": "uniform, fresh batch every step",
+            "rows_per_field": ROWS, "act_dtype": dtype, "ids": ("uniform" if getattr(args, "ids", "uniform") == "uniform" else "Zipf(1.05) over permuted rows") + ", fresh batch every step",
             "l2": "tables+Adam state 7.5 GB per GPU >> 126 MB L2 (inputs larger than L2, no flush needed)",
             "parallelism": f"dp{args.gpus}" + ("+row-sharded tables (all-to-all)" if args.gpus > 1 else "")}
 
@@ -227,7 +227,15 @@ def run_own(args):
     K, W = args.steps, args.warmup
     g = torch.Generator(device=dev).manual_seed(SEED + rank)
     nb = K + W
-    ids_dev = torch.randint(0, ROWS, (nb, BATCH, F), device=dev, generator=g)
+    if args.ids == "zipf":
+        # secondary workload: Zipf(s = 1.05) popularity over a random permutation of each field's rows
+        # -> many duplicate rows per batch (long sorted-segment runs, L2-resident hot rows)
+        w = 1.0 / torch.arange(1, ROWS + 1, device=dev, dtype=torch.float64) ** 1.05
+        rank_of = torch.multinomial(w.float(), nb * BATCH * F, replacement=True, generator=g).view(nb, BATCH, F)
+        perm = torch.randperm(ROWS, device=dev, generator=g)
+        ids_dev = perm[rank_of]
+    else:
+        ids_dev = torch.randint(0, ROWS, (nb, BATCH, F), device=dev, generator=g)
     y_dev = (torch.rand(nb, BATCH, 1, device=dev, generator=g) < 0.25).float()
     act_bytes = 4 if args.dtype == "f32" else 2
 
@@ -352,6 +360,8 @@ def main():
     ap.add_argument("--dtype", default=os.environ.get("RS_BENCH_DTYPE", "bf16"), choices=["f32", "bf16"])
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"],
+                    help="id distribution of the synthetic batches (headline: uniform; zipf = skewed secondary workload)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

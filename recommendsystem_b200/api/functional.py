@@ -20,7 +20,9 @@ class InteractingFn(torch.autograd.Function):
     def forward(ctx, x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res, dropout_rate=0.0, dropout_seed=0):
         _require_cuda(x, Wqkvr)
         x = x.contiguous()
-        y, saved = ops.interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res,
+        # bf16 activations take the tcgen05 kernels where they are built (falls back to FFMA arithmetic otherwise)
+        ctx.tc = x.dtype == torch.bfloat16
+        y, saved = ops.interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res, compute_bf16=ctx.tc,
                                        dropout_rate=dropout_rate, dropout_seed=dropout_seed)
         ctx.save_for_backward(x, saved if saved is not None else x.new_empty(0), Wqkvr, bqkvr, gamma, beta)
         ctx.cfg = (ln_eps, H, L, use_res, dropout_rate, dropout_seed)
@@ -32,7 +34,7 @@ class InteractingFn(torch.autograd.Function):
         ln_eps, H, L, use_res, rate, seed = ctx.cfg
         dx, dW, db, dg, dbt = ops.interacting_bwd(x, saved if saved.numel() else None, Wqkvr, bqkvr, gamma, beta,
                                                   ln_eps, H, L, dy.contiguous().to(x.dtype), use_res,
-                                                  dropout_rate=rate, dropout_seed=seed)
+                                                  compute_bf16=ctx.tc, dropout_rate=rate, dropout_seed=seed)
         return dx, dW, db, dg, dbt, None, None, None, None, None, None
 
 

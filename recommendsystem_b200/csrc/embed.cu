@@ -336,19 +336,73 @@ embed_segsum_kernel(const uint64_t* __restrict__ keys, const GT* __restrict__ gr
         }
       }
     }
-    // runs longer than one: walk the rest of the run in order.
+    // runs longer than one: the head's group walks the rest of the run in order — inside this warp's 32-key
+    // window only (at most 31 steps).
+    const int64_t wend = base + 32 < n ? base + 32 : n;
 #pragma unroll
     for (int s = 0; s < G; ++s) {
       const int src = s * GROUPS + gj;
       const bool smore = __shfl_sync(0xffffffffu, (int)more, src) != 0;
       if (smore && col_ok) {
         int64_t q = base + src + 1;
-        while (q < n) {
+        while (q < wend) {
           const uint64_t kq = keys[q];
           if ((uint32_t)(kq >> 32) != srow[s]) break;
           const float4 g = load_grad<GT>(grad, (uint32_t)kq, d, gl, a.grad_scale);
           acc[s].x += g.x; acc[s].y += g.y; acc[s].z += g.z; acc[s].w += g.w;
           ++q;
+        }
+      }
+    }
+    // A run that leaves the window (skewed ids: a hot row can occur thousands of times in a batch) can only be
+    // the window's LAST run.  If its head is in this window, the whole warp continues it: 32 keys per trip, their
+    // gradient rows loaded by all lane groups at once, then added ONE ROW AT A TIME IN POSITION ORDER — the
+    // same left-to-right fp32 sum as the sequential walk (bit-identical), without its dependent-load chain.
+    {
+      const uint32_t row_last = __shfl_sync(0xffffffffu, row, 31);
+      const uint32_t next_last = __shfl_sync(0xffffffffu, next, 31);
+      const uint32_t same = __ballot_sync(0xffffffffu, row == row_last);
+      const int hi = __ffs(same) - 1;                                  // first key of the last run inside the window
+      const bool hi_is_head = __shfl_sync(0xffffffffu, (int)head, hi) != 0;
+      if (row_last != 0xffffffffu && base + 32 < n && next_last == row_last && hi_is_head) {   // warp-uniform
+        const int s_h = hi / GROUPS, g_h = hi % GROUPS;
+        float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int s = 0; s < G; ++s)
+          if (s == s_h) run = acc[s];
+        run.x = __shfl_sync(0xffffffffu, run.x, g_h * G + gl); run.y = __shfl_sync(0xffffffffu, run.y, g_h * G + gl);
+        run.z = __shfl_sync(0xffffffffu, run.z, g_h * G + gl); run.w = __shfl_sync(0xffffffffu, run.w, g_h * G + gl);
+        int64_t q = base + 32;
+        bool done = false;
+        while (!done) {
+          const uint64_t kq = (q + lane < n) ? keys[q + lane] : ~0ull;
+          const uint32_t mt = __ballot_sync(0xffffffffu, (uint32_t)(kq >> 32) == row_last);
+          const int cnt = mt == 0xffffffffu ? 32 : __ffs(~mt) - 1;    // sorted keys: the matches are a prefix
+          float4 v[G];
+#pragma unroll
+          for (int t = 0; t < G; ++t) {                                // group gj loads rows t*GROUPS + gj
+            const int pidx = t * GROUPS + gj;
+            const uint32_t pos = __shfl_sync(0xffffffffu, (uint32_t)kq, pidx);
+            v[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pidx < cnt && col_ok) v[t] = load_grad<GT>(grad, pos, d, gl, a.grad_scale);
+          }
+#pragma unroll
+          for (int t = 0; t < G; ++t) {
+#pragma unroll
+            for (int j = 0; j < GROUPS; ++j) {
+              if (t * GROUPS + j < cnt) {                             // warp-uniform
+                run.x += __shfl_sync(0xffffffffu, v[t].x, j * G + gl); run.y += __shfl_sync(0xffffffffu, v[t].y, j * G + gl);
+                run.z += __shfl_sync(0xffffffffu, v[t].z, j * G + gl); run.w += __shfl_sync(0xffffffffu, v[t].w, j * G + gl);
+              }
+            }
+          }
+          q += 32;
+          done = cnt < 32 || q >= n;
+        }
+        if (gj == g_h) {
+#pragma unroll
+          for (int s = 0; s < G; ++s)
+            if (s == s_h) acc[s] = run;
         }
       }
     }

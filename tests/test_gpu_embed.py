@@ -264,3 +264,38 @@ def test_embed_gather_peer_sharded_layout(cuda_dev, W, d, odt):
                                  torch.from_numpy(rows).to(cuda_dev), dt)
     assert torch.equal(got, ref)
     assert float(got[5, 2].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("d", [8, 16, 32])
+@pytest.mark.parametrize("hot", [[(7, 1000)], [(3, 33), (9, 64), (11, 500)], [(0, 4097), (1, 31), (2, 32), (5, 95)]])
+def test_segsum_long_runs_bit_exact(cuda_dev, d, hot):
+    """Skewed ids: rows that occur hundreds / thousands of times in a batch (runs spanning many 32-key warp
+    windows, at every alignment).  The warp-cooperative continuation must add the rows in the same
+    left-to-right order as the oracle: bit-exact segment sums, and the fused Adam update on top of them."""
+    from oracle import oracle_np as onp
+    from recommendsystem_b200 import ops
+    rng = np.random.default_rng(d + len(hot))
+    R = 64
+    rowidx = [rng.integers(12, R, size=700).astype(np.int32)]
+    for r, cnt in hot:
+        rowidx.append(np.full(cnt, r, np.int32))
+    rowidx = np.concatenate(rowidx)
+    rng.shuffle(rowidx)
+    n = len(rowidx)
+    grad = rng.standard_normal((n, d)).astype(np.float32)
+    ks = _sorted_keys(ops, _t(rowidx, cuda_dev), R)
+    seg_rows, seg_sum = ops.segsum(_t(grad, cuda_dev), ks)
+    heads = seg_rows.cpu().numpy() >= 0
+    uniq, sums = onp.segment_sum_sorted(rowidx, grad)
+    assert np.array_equal(seg_rows.cpu().numpy()[heads].astype(np.int64), uniq)
+    assert np.array_equal(seg_sum.cpu().numpy()[heads], sums)
+    # fused sparse Adam over the same keys
+    w = (rng.standard_normal((R, d)) * 0.1).astype(np.float32)
+    wt, mt, vt = _t(w, cuda_dev), torch.zeros(R, d, device=cuda_dev), torch.zeros(R, d, device=cuda_dev)
+    scal = torch.zeros(4, device=cuda_dev)
+    ops.adam_advance(scal, 0.9, 0.999)
+    ops.segsum_adam(wt, mt, vt, _t(grad, cuda_dev), ks, 1e-2, 0.9, 0.999, 1e-8, scal)
+    _, _, corr = onp.adam_scalars(1, 0.9, 0.999)
+    w2, m2, v2 = onp.sparse_adam(w.astype(np.float64), np.zeros((R, d)), np.zeros((R, d)), rowidx, grad, 1e-2, 0.9, 0.999,
+                                 1e-8, float(corr))
+    assert_close(wt.cpu().numpy(), w2, REL_F32, "sparse Adam after long runs")
