@@ -146,7 +146,10 @@ constexpr float DIN_PAD_SCORE = -4294967296.0f;  // float32(-2**32 + 1), staytim
 // Positions are walked 64 at a time (two per lane per step, any T); mode B keeps
 // a running (max, sum, weighted sum) so the softmax needs no second pass.
 template <int MODE, int H, int HD, typename T>
-__global__ void __launch_bounds__(DIN_WARPS * 32, 3)
+#ifndef RS_DIN_MINB
+#define RS_DIN_MINB 4
+#endif
+__global__ void __launch_bounds__(DIN_WARPS * 32, RS_DIN_MINB)
 din_fwd_kernel(const T* __restrict__ q, const T* __restrict__ keys, const T* __restrict__ values,
                int64_t kv_ld, const int32_t* __restrict__ seq_len, const uint8_t* __restrict__ mask,
                const float* __restrict__ W1, const float* __restrict__ b1,
@@ -218,10 +221,17 @@ din_fwd_kernel(const T* __restrict__ q, const T* __restrict__ keys, const T* __r
 }
 
 // ----------------------------------------------------------------- backward
-// Per-warp shared stash (Tpad = T rounded up to 64 rows): k rows, h1 -> dh1 rows,
-// and three per-position scalars (score -> softmax weight, dS, live flag).
+// Per-warp shared stash (Tpad = T rounded up to 64 rows): h1 -> dh1 rows and three
+// per-position scalars (score -> softmax weight, dS, live flag).  The k rows are not
+// stashed for the whole sequence: phase 2 re-reads the row of its position (L2-resident
+// since phase 1) into a 32-row chunk and the outer products of phase 3 are accumulated
+// chunk by chunk, in the same position order.  15.5 KB per warp for T = 100: three
+// CTAs per SM instead of two.
 template <int MODE, int H, int HD, typename T>
-__global__ void __launch_bounds__(DIN_WARPS * 32)
+#ifndef RS_DIN_BWD_MINB
+#define RS_DIN_BWD_MINB 3
+#endif
+__global__ void __launch_bounds__(DIN_WARPS * 32, RS_DIN_BWD_MINB)
 din_bwd_kernel(const T* __restrict__ q, const T* __restrict__ keys, const T* __restrict__ values,
                int64_t kv_ld, const int32_t* __restrict__ seq_len, const uint8_t* __restrict__ mask,
                const float* __restrict__ W1, const float* __restrict__ b1,
@@ -235,13 +245,13 @@ din_bwd_kernel(const T* __restrict__ q, const T* __restrict__ keys, const T* __r
   float* Ws = reinterpret_cast<float*>(din_smem4);
   float* warp_base = Ws + ((S::NP + 3) & ~3);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int per_warp = S::NW + HD + HD + H + Tpad * (S::KS + S::DS + 3);
+  const int per_warp = S::NW + HD + HD + H + 32 * S::KS + Tpad * (S::DS + 3);
   float* Weff = warp_base + wid * per_warp;
   float* cq = Weff + S::NW;
   float* gs = cq + HD;            // g[j] = sum_t dh1_t[j]
   float* dos = gs + HD;           // dout of the sample
-  float* Ks = dos + H;            // [Tpad][KS]
-  float* Ds = Ks + Tpad * S::KS;  // [Tpad][DS]  h1, then dh1
+  float* Kc = dos + H;            // [32][KS]    k rows of the current chunk (phase 2/3)
+  float* Ds = Kc + 32 * S::KS;    // [Tpad][DS]  h1, then dh1
   float* Sc = Ds + Tpad * S::DS;  // [Tpad] score, then softmax weight (B)
   float* Dp = Sc + Tpad;          // [Tpad] A: dout.v   B: dout.f, then dS
   float* Lv = Dp + Tpad;          // [Tpad] 1 if gradient reaches the score
@@ -286,11 +296,6 @@ din_bwd_kernel(const T* __restrict__ q, const T* __restrict__ keys, const T* __r
       din_load_row<H, T>(keys + (b * Tn + t1) * kv_ld, in1, k1);
       float h0[HD], h1[HD];
       din_hidden2<H, HD>(Weff, cq, k0, k1, h0, h1);
-#pragma unroll
-      for (int c = 0; c < H; c += 4) {
-        *reinterpret_cast<float4*>(Ks + t0 * S::KS + c) = make_float4(k0[c], k0[c + 1], k0[c + 2], k0[c + 3]);
-        *reinterpret_cast<float4*>(Ks + t1 * S::KS + c) = make_float4(k1[c], k1[c + 1], k1[c + 2], k1[c + 3]);
-      }
 #pragma unroll
       for (int j = 0; j < HD; j += 4) {
         *reinterpret_cast<float4*>(Ds + t0 * S::DS + j) = make_float4(h0[j], h0[j + 1], h0[j + 2], h0[j + 3]);
@@ -352,10 +357,17 @@ din_bwd_kernel(const T* __restrict__ q, const T* __restrict__ keys, const T* __r
         Dp[t] = p * (Dp[t] - dsum);
       }
     }
-    // ---- phase 2: per position dh1 and dk; rows of dkeys / dfacts
+    // ---- phase 2 + 3: per position dh1 and dk (rows of dkeys / dfacts); per 32-position
+    //      chunk G[c][j] += sum_t k_t[c] dh1_t[j] (lane slice), then g[j] and dq
+    float G[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) G[e] = 0.f;
 #pragma unroll 1
-    for (int t = lane; t < Tpad; t += 32) {
+    for (int tb = 0; tb < Tpad; tb += 32) {
+      const int t = tb + lane;
       const bool in = t < Tn;
+      float kr[H];
+      din_load_row<H, T>(keys + (b * Tn + t) * kv_ld, in, kr);
       const float ds = Lv[t] != 0.f ? Dp[t] : 0.f;
       const float pw = Sc[t];
       float dh[HD];
@@ -387,9 +399,23 @@ din_bwd_kernel(const T* __restrict__ q, const T* __restrict__ keys, const T* __r
         dk[c] = (MODE == RS_DIN_B) ? fmaf(pw, dov[c], acc) : acc;
       }
       if (in) din_store_row<H, T>(dkeys + (b * Tn + t) * dkv_ld, dk);
+#pragma unroll
+      for (int c = 0; c < H; c += 4)
+        *reinterpret_cast<float4*>(Kc + lane * S::KS + c) = make_float4(kr[c], kr[c + 1], kr[c + 2], kr[c + 3]);
+      __syncwarp();
+      const int nt = min(32, Tn - tb);
+#pragma unroll 4
+      for (int u = 0; u < nt; ++u) {
+        const float kc = Kc[u * S::KS + gc];
+#pragma unroll
+        for (int e = 0; e < EPL; e += 4) {
+          const float4 d4 = *reinterpret_cast<const float4*>(Ds + (tb + u) * S::DS + gj0 + e);
+          G[e] = fmaf(kc, d4.x, G[e]); G[e + 1] = fmaf(kc, d4.y, G[e + 1]);
+          G[e + 2] = fmaf(kc, d4.z, G[e + 2]); G[e + 3] = fmaf(kc, d4.w, G[e + 3]);
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
-    // ---- phase 3: G[c][j] = sum_t k_t[c] dh1_t[j] (lane slice), g[j], dq
     {
       const int j = lane % HD, half = lane / HD;      // HD == 16: two lanes per column
       float g = 0.f;
@@ -397,19 +423,6 @@ din_bwd_kernel(const T* __restrict__ q, const T* __restrict__ keys, const T* __r
 #pragma unroll
       for (int o = HD; o < 32; o <<= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
       if (lane < HD) { gs[lane] = g; ab1 += g; }
-    }
-    float G[EPL];
-#pragma unroll
-    for (int e = 0; e < EPL; ++e) G[e] = 0.f;
-#pragma unroll 4
-    for (int t = 0; t < Tn; ++t) {
-      const float kc = Ks[t * S::KS + gc];
-#pragma unroll
-      for (int e = 0; e < EPL; e += 4) {
-        const float4 d4 = *reinterpret_cast<const float4*>(Ds + t * S::DS + gj0 + e);
-        G[e] = fmaf(kc, d4.x, G[e]); G[e + 1] = fmaf(kc, d4.y, G[e + 1]);
-        G[e + 2] = fmaf(kc, d4.z, G[e + 2]); G[e + 3] = fmaf(kc, d4.w, G[e + 3]);
-      }
     }
     __syncwarp();
     const float qv = __shfl_sync(0xffffffffu, qc, gc);
@@ -490,15 +503,24 @@ template <int H, int HD>
 static size_t din_bwd_smem(int Tpad) {
   using S = DinShape<H, HD>;
   return (size_t)(((S::NP + 3) & ~3) +
-                  DIN_WARPS * (S::NW + HD + HD + H + Tpad * (S::KS + S::DS + 3))) * sizeof(float);
+                  DIN_WARPS * (S::NW + HD + HD + H + 32 * S::KS + Tpad * (S::DS + 3))) * sizeof(float);
 }
 
-static int din_grid(int B) {
+// Persistent grid: one warp per sample, at most `per_sm` CTAs per SM.  per_sm is the
+// number of CTAs that are resident at once (a larger grid runs a second, partly empty wave).
+constexpr int DIN_MAX_CTAS_PER_SM = 4;
+static int din_grid(int B, int per_sm = DIN_MAX_CTAS_PER_SM) {
   int64_t g = cdiv(B, DIN_WARPS);
-  const int64_t cap = (int64_t)sm_count() * 4;
+  const int64_t cap = (int64_t)sm_count() * per_sm;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
+}
+
+static int din_resident(const void* kern, size_t smem) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, DIN_WARPS * 32, smem) != cudaSuccess) occ = 1;
+  return occ < 1 ? 1 : (occ > DIN_MAX_CTAS_PER_SM ? DIN_MAX_CTAS_PER_SM : occ);
 }
 
 struct DinArgs {
@@ -512,7 +534,7 @@ static int din_launch_fwd(const DinArgs& a) {
   auto kern = din_fwd_kernel<MODE, H, HD, T>;
   const size_t smem = din_fwd_smem<H, HD>();
   RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<din_grid(a.B), DIN_WARPS * 32, smem, a.st>>>(
+  kern<<<din_grid(a.B, din_resident((const void*)kern, smem)), DIN_WARPS * 32, smem, a.st>>>(
       (const T*)a.q, (const T*)a.keys, (const T*)a.values, a.kv_ld, a.seq_len, a.mask, a.W1, a.b1, a.W2,
       a.b2, (T*)a.out, a.B, a.T);
   return check_launch("din_fwd");
@@ -529,7 +551,7 @@ static int din_launch_bwd(const DinArgs& a) {
     return RS_ERR_UNSUPPORTED;
   }
   RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = din_grid(a.B);
+  const int grid = din_grid(a.B, din_resident((const void*)kern, smem));
   if (a.ws_bytes < (size_t)grid * S::NP * sizeof(float)) {
     set_error("din_bwd: workspace %zu < %zu", a.ws_bytes, (size_t)grid * S::NP * sizeof(float));
     return RS_ERR_WORKSPACE;
