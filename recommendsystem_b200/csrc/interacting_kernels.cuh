@@ -617,10 +617,18 @@ static size_t bwd_smem_bytes() {
   return (size_t)(D * 4 * U + 4 * U + 2 * U + NT * (S::SA + S::SB + S::SX) + NT * 3 * H) * 4;
 }
 
-inline int interacting_bwd_grid(int B, int F, int NT) {
+// CTAs of `kern` that are resident on one SM at once, clamped to [1, cap]: the persistent
+// grids below are sized to exactly one full wave.
+static inline int resident_ctas(const void* kern, int threads, size_t smem, int cap) {
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess) occ = 1;
+  return occ < 1 ? 1 : (occ > cap ? cap : occ);
+}
+
+inline int interacting_bwd_grid(int B, int F, int NT, int per_sm = 2) {
   const int SPT = NT / F;
   const int ntiles = (B + SPT - 1) / SPT;
-  int g = sm_count() * 2;
+  int g = sm_count() * per_sm;
   if (g > ntiles) g = ntiles;
   if (g < 1) g = 1;
   return g;
@@ -633,7 +641,7 @@ static int launch_fwd(const IFwdArgs& a) {
   RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int SPT = NT / a.F;
   const int ntiles = (a.B + SPT - 1) / SPT;
-  int grid = sm_count() * 4;
+  int grid = sm_count() * resident_ctas((const void*)kern, NT, smem, 8);
   if (grid > ntiles) grid = ntiles;
   kern<<<grid, NT, smem, a.st>>>((const T*)a.x, a.x_ld, a.x_bs, a.W, a.b, a.gm, a.bt, a.eps, (T*)a.y, a.y_ld, a.y_bs,
                                  (float*)a.saved, a.B, a.F, a.L, a.use_res, drop_cfg(a.drop_rate, a.drop_seed));
@@ -645,7 +653,7 @@ static int launch_bwd(const IBwdArgs& a) {
   const size_t smem = bwd_smem_bytes<D, U, H, NT>();
   auto kern = interacting_bwd_kernel<D, U, H, NT, T>;
   RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int grid = interacting_bwd_grid(a.B, a.F, NT);
+  const int grid = interacting_bwd_grid(a.B, a.F, NT, resident_ctas((const void*)kern, NT, smem, 2));
   const int np = D * 4 * U + 6 * U;
   if (a.ws_bytes < (size_t)grid * np * sizeof(float)) {
     set_error("interacting_bwd: workspace %zu < %zu", a.ws_bytes, (size_t)grid * np * sizeof(float));
