@@ -13,6 +13,62 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def _checkpoint_checks(sh, kw, b, world, rank, dev, table, dense0):
+    """W-way save -> W-way load, W-way save -> 1-way load, 1-way save -> W-way load: all bit-exact."""
+    import tempfile
+    from recommendsystem_b200 import checkpoint as ck
+    from recommendsystem_b200.autoint import AutoIntConfig, AutoIntTrainer
+    from recommendsystem_b200.sharded import ShardedAutoIntTrainer
+    box = [tempfile.mkdtemp(prefix="rs_ckpt_") if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    root = box[0]
+    ok = True
+
+    def check(name, cond):
+        nonlocal ok
+        print(f"[rank {rank}] " + ("PASS " if cond else "FAIL ") + name, flush=True)
+        ok = ok and bool(cond)
+
+    def real_rows_equal(x, y):
+        # padding rows (fields whose row count is not a multiple of W) are not part of a checkpoint
+        a, c = x.cpu().numpy(), y.cpu().numpy()
+        same = True
+        for f in range(len(sh.rows_host)):
+            n = len(range(rank, int(sh.rows_host[f]), world))
+            lo = int(sh.local_base[f])
+            same = same and np.array_equal(a[lo:lo + n], c[lo:lo + n])
+        return same
+
+    ck.save_checkpoint(sh, os.path.join(root, "w"), step=3)
+    dist.barrier()
+    sh2 = ShardedAutoIntTrainer(AutoIntConfig(batch=b, **kw), dev)          # fresh random state
+    meta = ck.load_checkpoint(sh2, os.path.join(root, "w"))
+    check("ckpt W->W arena", meta["world"] == world and real_rows_equal(sh2.arena, sh.arena))
+    check("ckpt W->W dense", torch.equal(sh2.flat, sh.flat) and torch.equal(sh2.flat_m, sh.flat_m)
+          and torch.equal(sh2.flat_v, sh.flat_v) and torch.equal(sh2.adam_scalars, sh.adam_scalars))
+    if rank == 0:
+        one = AutoIntTrainer(AutoIntConfig(batch=b, **kw), dev)
+        ck.load_checkpoint(one, os.path.join(root, "w"))
+        ck.save_checkpoint(one, os.path.join(root, "one"))
+        # row g of field f must be row g // W of field f in shard g % W
+        mine = sh.arena.cpu().numpy()
+        full = one.arena.cpu().numpy()
+        same = True
+        for f in range(len(one.rows_host)):
+            src = full[int(one.base_host[f]) + rank: int(one.base_host[f] + one.rows_host[f]): world]
+            same = same and np.array_equal(mine[int(sh.local_base[f]): int(sh.local_base[f]) + len(src)], src)
+        check("ckpt W->1 arena (rank 0's rows)", same)
+    dist.barrier()
+    sh2.arena.zero_()
+    ck.load_checkpoint(sh2, os.path.join(root, "one"))
+    check("ckpt 1->W arena", real_rows_equal(sh2.arena, sh.arena))
+    dist.barrier()
+    if rank == 0:
+        import shutil
+        shutil.rmtree(root, ignore_errors=True)
+    return ok
+
+
 def main():
     from util import rel_err
     from recommendsystem_b200.autoint import AutoIntConfig, AutoIntTrainer
@@ -86,8 +142,9 @@ def main():
                 got = s[int(sh.local_base[f]): int(sh.local_base[f]) + len(src)]
                 worst = max(worst, float(np.max(np.abs(got - src))) / float(np.max(np.abs(full))))
         check("table shards after steps", worst <= 1e-5, f"rel {worst:.2e}")
+    ok = _checkpoint_checks(sh, kw, b, world, rank, dev, table, dense0) and ok
     flag = torch.tensor([1 if ok else 0], device=dev)
-    dist.broadcast(flag, src=0)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     code = 0 if int(flag.item()) == 1 else 1
     torch.cuda.synchronize()
     sys.stdout.flush()

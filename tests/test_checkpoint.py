@@ -1,0 +1,80 @@
+"""Checkpoint layout / resharding logic on CPU (no GPU, no CUDA library calls)."""
+import json
+
+import numpy as np
+import pytest
+
+from recommendsystem_b200 import checkpoint as ck
+
+
+def _global_tables(rows, d, seed=3):
+    rng = np.random.default_rng(seed)
+    return [rng.standard_normal((int(r), 3, d)).astype(np.float32) for r in rows]
+
+
+def _write_world(tmp_path, tabs, rows, d, W):
+    """Write the shards a W-way job would: shard s holds global rows s, s+W, ... of every field."""
+    local_rows, local_base = ck.shard_rows(rows, W)
+    for s in range(W):
+        arena = np.zeros((int(local_rows.sum()), 3, d), np.float32)
+        for f, t in enumerate(tabs):
+            part = t[s::W]
+            arena[local_base[f]: local_base[f] + part.shape[0]] = part
+        n = ck.write_shard(ck.shard_path(tmp_path, s, W), iter([arena[:5], arena[5:]]))
+        assert n == arena.shape[0]
+    meta = {"format": ck.FORMAT, "world": W, "embed_dim": d, "rows_per_field": [int(r) for r in rows]}
+    (tmp_path / "meta.json").write_text(json.dumps(meta))
+    return meta
+
+
+@pytest.mark.parametrize("old_w,new_w", [(1, 1), (1, 2), (2, 1), (2, 3), (3, 2), (4, 8), (8, 2)])
+def test_reshard_any_world(tmp_path, old_w, new_w):
+    rows, d = [17, 1, 64, 9, 2], 4          # ragged, includes fields with fewer rows than ranks
+    tabs = _global_tables(rows, d)
+    meta = _write_world(tmp_path, tabs, rows, d, old_w)
+    assert ck.read_meta(tmp_path)["world"] == old_w
+    new_rows, new_base = ck.shard_rows(rows, new_w)
+    for r in range(new_w):
+        arena = np.full((int(new_rows.sum()), 3, d), np.nan, np.float32)
+        for dst, rec in ck.load_shard_rows(tmp_path, meta, new_w, r, chunk_rows=7):
+            assert np.isnan(arena[dst]).all()             # every destination row written once
+            arena[dst] = rec
+        for f, t in enumerate(tabs):
+            want = t[r::new_w]
+            got = arena[new_base[f]: new_base[f] + want.shape[0]]
+            np.testing.assert_array_equal(got, want)      # bit-exact
+
+
+def test_shard_rows_matches_sharded_layout():
+    from recommendsystem_b200.sharded import shard_layout
+    rows = [1000, 7, 33]
+    for W in (1, 2, 3, 8):
+        a, b = ck.shard_rows(rows, W)
+        c, e = shard_layout(rows, W)
+        np.testing.assert_array_equal(a, c)
+        np.testing.assert_array_equal(b, e)
+
+
+def test_bad_format_raises(tmp_path):
+    (tmp_path / "meta.json").write_text(json.dumps({"format": "something else"}))
+    with pytest.raises(ValueError):
+        ck.read_meta(tmp_path)
+
+
+def test_load_keras_state_names():
+    import torch
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.din_nn_0 = torch.nn.ParameterDict({"kernel": torch.nn.Parameter(torch.zeros(3, 2))})
+            self.kernel0 = torch.nn.Parameter(torch.zeros(2, 2))
+
+    m = M()
+    w = {"din_nn_0/kernel:0": np.arange(6, dtype=np.float32).reshape(3, 2), "kernel0:0": np.eye(2, dtype=np.float32)}
+    assert sorted(ck.load_keras_state(m, w)) == ["din_nn_0_kernel", "kernel0"]
+    assert m.din_nn_0["kernel"][2, 1].item() == 5.0
+    with pytest.raises(KeyError):
+        ck.load_keras_state(m, {"nope/kernel:0": np.zeros((1,))})
+    with pytest.raises(ValueError):
+        ck.load_keras_state(m, {"kernel0:0": np.zeros((3, 3), np.float32)})
