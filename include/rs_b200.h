@@ -417,6 +417,35 @@ int rs_logit_head_fwd_bwd_relu(const void* Z, int64_t ldz, int dtype, const floa
 int rs_transpose2d(const void* src, int64_t lds, void* dst, int64_t ldd, int M, int N,
                    int dtype, void* stream);
 
+/* ---- input labels and metrics: the steps either side of the train step ------------------
+ * rs_staytime_labels replaces the label half of `parse_input_func` (staytime/parse.py:30-68):
+ *   wt        = min(watch_ms / 1000, cap_s)                                  (:41-43, cap 160)
+ *   label[b,j]= exp((bins[j] - wt)^2 / (-2 sigma^2)) / (sqrt(2 pi) sigma) * (right-left)/(nbins-1)
+ *               for j < nbins, label[b,nbins] = wt                           (:45-64)
+ *   short/long= watch_ms > short_ms / long_ms  (int64 0/1)                   (:30-39, 7000 / 18000)
+ *   weight    = landing[b] ? landing_weight : 1                              (:66, 5.0; the regex on
+ *               `extra_info` is host string work, its result comes in as a byte per sample)
+ * staytime_label is [B, nbins+1] fp32, dense; short_label, long_label,
+ * sample_weight and landing may be NULL.  fp32 arithmetic in the reference's operation order. */
+int rs_staytime_labels(const int64_t* watch_ms, const uint8_t* landing, const float* bins, int nbins,
+                       int B, float* staytime_label, int64_t* short_label, int64_t* long_label,
+                       float* sample_weight, int64_t short_ms, int64_t long_ms, float cap_s, float sigma,
+                       float left, float right, float landing_weight, void* stream);
+
+/* Streaming binary metrics of `compile(metrics=[BinaryAccuracy(), AUC(), tn.metric.CTR(), tn.metric.COPC()])`
+ * (rough_rank/model.py:215-219, staytime/model.py:78-82).  `state` is rs_binary_metrics_state_bytes(T)
+ * of zero-initialised device memory that accumulates over calls: exact integer confusion histograms
+ * for the T ascending thresholds (Keras: pred > threshold, label cast to bool), sample and correct
+ * counts, and ordered (deterministic) double sums of labels and predictions.
+ * rs_binary_metrics_result writes 6 doubles: AUC (ROC, 'interpolation' summation as keras AUC.result()),
+ * accuracy at acc_threshold, CTR = sum(label)/n, COPC = sum(label)/sum(pred), n, mean prediction. */
+size_t rs_binary_metrics_state_bytes(int num_thresholds);
+size_t rs_binary_metrics_workspace_bytes(int64_t n);
+int rs_binary_metrics_update(const void* pred, int pred_dtype, const float* label, int64_t n,
+                             const float* thresholds, int num_thresholds, float acc_threshold,
+                             void* state, void* ws, size_t ws_bytes, void* stream);
+int rs_binary_metrics_result(const void* state, int num_thresholds, double* out6, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

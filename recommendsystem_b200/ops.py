@@ -333,3 +333,50 @@ def bce_sigmoid_fwd_bwd(p_raw, y, a=1.0, want_grad=True):
     dz = torch.empty_like(p_raw) if want_grad else None
     call("rs_bce_sigmoid_fwd_bwd", _ptr(p_raw), _dt(p_raw), _ptr(y), a, _ptr(loss), _ptr(dz), B, k, _stream())
     return loss, dz
+
+
+# ------------------------------------------------------- labels and metrics
+def staytime_labels(watch_ms, bins, landing=None, short_ms=7000, long_ms=18000, cap_s=160.0, sigma=4.0,
+                    left=-19.0, right=180.5, landing_weight=5.0, want_weight=True):
+    """rs_staytime_labels (staytime/parse.py:30-68): int64 watch durations [B] (ms) ->
+    (staytime_label [B, nbins+1] fp32, short_label [B] int64, long_label [B] int64, sample_weight [B,1] | None)."""
+    _need(watch_ms.dtype == torch.int64 and watch_ms.dim() == 1, "staytime_labels: watch_ms must be int64 [B]")
+    _need(bins.dtype == torch.float32 and bins.dim() == 1 and bins.is_contiguous(), "staytime_labels: bins fp32 [nbins]")
+    if landing is not None:
+        _need(landing.dtype in (torch.uint8, torch.bool) and landing.shape == watch_ms.shape,
+              "staytime_labels: landing must be uint8/bool [B]")
+        landing = landing.view(torch.uint8) if landing.dtype == torch.bool else landing
+    B, nb = watch_ms.numel(), bins.numel()
+    dev = watch_ms.device
+    label = torch.empty(B, nb + 1, dtype=torch.float32, device=dev)
+    short = torch.empty(B, dtype=torch.int64, device=dev)
+    long_ = torch.empty(B, dtype=torch.int64, device=dev)
+    weight = torch.empty(B, 1, dtype=torch.float32, device=dev) if want_weight else None
+    call("rs_staytime_labels", _ptr(watch_ms.contiguous()), _ptr(landing), _ptr(bins), nb, B, _ptr(label), _ptr(short),
+         _ptr(long_), _ptr(weight), int(short_ms), int(long_ms), float(cap_s), float(sigma), float(left), float(right),
+         float(landing_weight), _stream())
+    return label, short, long_, weight
+
+
+def binary_metrics_state(num_thresholds, device):
+    n = cabi.load().rs_binary_metrics_state_bytes(int(num_thresholds))
+    return torch.zeros(n // 8, dtype=torch.int64, device=device)
+
+
+def binary_metrics_update(state, pred, label, thresholds, acc_threshold=0.5):
+    """Accumulate one batch into `state` (rs_binary_metrics_update).  pred fp32 / bf16, label fp32, same numel."""
+    _need(pred.numel() == label.numel(), "binary_metrics: pred and label sizes differ")
+    _need(label.dtype == torch.float32, "binary_metrics: label must be float32")
+    pred, label = pred.contiguous(), label.contiguous()
+    n, T = pred.numel(), thresholds.numel()
+    nbytes = cabi.load().rs_binary_metrics_workspace_bytes(n)
+    ws = WS.get("binary_metrics", nbytes, pred.device)
+    call("rs_binary_metrics_update", _ptr(pred), _dt(pred), _ptr(label), n, _ptr(thresholds), T, float(acc_threshold),
+         _ptr(state), _ptr(ws), ws.numel(), _stream())
+
+
+def binary_metrics_result(state, num_thresholds, out=None):
+    """-> float64[6] on the device: AUC, accuracy, CTR, COPC, n, mean prediction (rs_binary_metrics_result)."""
+    out = torch.empty(6, dtype=torch.float64, device=state.device) if out is None else out
+    call("rs_binary_metrics_result", _ptr(state), int(num_thresholds), _ptr(out), _stream())
+    return out

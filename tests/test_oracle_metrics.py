@@ -1,0 +1,52 @@
+"""Oracle for labels / metrics (CPU): internal consistency and pins against independent definitions."""
+import numpy as np
+import pytest
+
+from oracle import oracle_metrics as om
+
+
+def test_staytime_label_shape_and_mass():
+    watch = np.array([0, 500, 7000, 7001, 18000, 18001, 60_000, 159_999, 160_000, 400_000], np.int64)
+    lab, sh, lo, w = om.staytime_labels(watch, dtype=np.float64)
+    assert lab.shape == (10, 401) and sh.tolist() == [0, 0, 0, 1, 1, 1, 1, 1, 1, 1]
+    assert lo.tolist() == [0, 0, 0, 0, 0, 1, 1, 1, 1, 1]
+    assert lab[-1, -1] == 160.0 and lab[1, -1] == 0.5
+    # a Gaussian of sigma 4 sampled every 0.5 s times the bin width: sums to ~1 away from the edges
+    assert abs(lab[6, :400].sum() - 1.0) < 1e-3
+    assert np.argmax(lab[6, :400]) == om.BIN_LIST.index(60.0)
+    lab32 = om.staytime_labels(watch, dtype=np.float32)[0]
+    np.testing.assert_allclose(lab32, lab, rtol=2e-5, atol=1e-30)
+    w5 = om.staytime_labels(watch, np.arange(10) % 2)[3]
+    assert w5.reshape(-1).tolist() == [1, 5] * 5
+
+
+def test_keras_thresholds():
+    t = om.keras_thresholds()
+    assert t.shape == (200,) and t[0] < 0 and t[-1] > 1 and np.all(np.diff(t) > 0)
+    assert t[1] == np.float32(1 / 199)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_keras_auc_tracks_exact_auc(seed):
+    rng = np.random.default_rng(seed)
+    y = (rng.random(5000) < 0.3).astype(np.float32)
+    p = np.clip(0.3 + 0.25 * (y - 0.3) + 0.2 * rng.standard_normal(5000), 0, 1).astype(np.float32)
+    a, e = om.keras_auc(y, p), om.exact_roc_auc(y, p)
+    assert abs(a - e) < 2e-3                       # 200-threshold trapezoid vs the pairwise statistic
+    assert om.keras_auc(y, y) == pytest.approx(1.0, abs=1e-12)
+    assert om.keras_auc(y, 1 - y) == pytest.approx(0.0, abs=1e-12)
+    assert om.keras_auc(y, np.full_like(y, 0.5)) == pytest.approx(0.5, abs=1e-12)
+
+
+def test_degenerate_labels_use_div_no_nan():
+    p = np.linspace(0, 1, 50, dtype=np.float32)
+    assert om.keras_auc(np.zeros(50), p) == 0.0
+    assert om.keras_auc(np.ones(50), p) == 0.0
+
+
+def test_simple_metrics():
+    y = np.array([1, 0, 1, 0], np.float32)
+    p = np.array([0.9, 0.6, 0.5, 0.1], np.float32)
+    assert om.binary_accuracy(y, p) == 0.5           # 0.5 is not > 0.5
+    assert om.ctr(y) == 0.5
+    assert om.copc(y, p) == pytest.approx(2 / 2.1, rel=1e-6)
