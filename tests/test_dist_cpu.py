@@ -108,3 +108,65 @@ def test_route_padded_oracle_overflow_flag():
     ids = np.zeros((50, 1), np.int64)          # every lookup goes to owner 0
     send, inv, cnt, ovf = onp.route_ids_padded(ids, 1, [100], [0], 2, 16)
     assert ovf == 1 and (inv >= 0).sum() == 16 and cnt.tolist() == [50, 0]
+
+
+def _metric_state_np(y, p, T=200):
+    """The accumulator rs_binary_metrics_update builds, restated with the oracle (int64 words + 2 double sums)."""
+    from oracle import oracle_metrics as om
+    thr = om.keras_thresholds(T)
+    k = (np.asarray(p, np.float32)[:, None] > thr[None, :]).sum(1)
+    pos = np.asarray(y) > 0.5
+    st = np.zeros(2 * T + 6, np.int64)
+    st[:T + 1] = np.bincount(k[pos], minlength=T + 1)
+    st[T + 1:2 * T + 2] = np.bincount(k[~pos], minlength=T + 1)
+    st[2 * T + 2] = len(y)
+    st[2 * T + 3] = int(((np.asarray(p, np.float32) > 0.5) == pos).sum())
+    st[2 * T + 4:] = np.array([np.sum(y, dtype=np.float64), np.sum(np.asarray(p, np.float64))]).view(np.int64)
+    return st
+
+
+def _metrics_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle_metrics as om
+        from recommendsystem_b200.api.metrics import merge_metric_states
+        rng = np.random.default_rng(77)
+        y = (rng.random(4000) < 0.3).astype(np.float32)
+        p = rng.random(4000).astype(np.float32)
+        lo, hi = rank * 2000, (rank + 1) * 2000
+        st = torch.from_numpy(_metric_state_np(y[lo:hi], p[lo:hi]))
+        merge_metric_states(st, 200)
+        full = _metric_state_np(y, p)
+        T = 200
+        assert np.array_equal(st.numpy()[:2 * T + 4], full[:2 * T + 4]), "integer words"
+        s, f = st.numpy()[2 * T + 4:].view(np.float64), full[2 * T + 4:].view(np.float64)
+        assert np.allclose(s, f, rtol=1e-14), "double sums"
+        # the merged histogram gives the AUC of the union
+        ph, nh = st.numpy()[:T + 1], st.numpy()[T + 1:2 * T + 2]
+        tp = np.cumsum(ph[::-1])[::-1][1:].astype(np.float64)
+        fp = np.cumsum(nh[::-1])[::-1][1:].astype(np.float64)
+        auc = om.keras_auc_from_counts(tp, fp, nh.sum() - fp, ph.sum() - tp)
+        assert abs(auc - om.keras_auc(y, p)) < 1e-12
+        q.put((rank, "ok"))
+    except Exception:
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_metric_states_merge_world2_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_metrics_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=150) for _ in range(world)]
+    for p in procs:
+        p.join(30)
+    for rank, msg in res:
+        assert msg == "ok", f"rank {rank}:\n{msg}"

@@ -81,6 +81,10 @@ def test_binary_metrics_vs_oracle(cuda_dev, n):
     np.testing.assert_array_equal(np.cumsum(pos_h[::-1])[::-1][1:], tp.astype(np.int64))
     np.testing.assert_array_equal(np.cumsum(neg_h[::-1])[::-1][1:], fp.astype(np.int64))
     assert st[2 * T + 2] == n
+    from test_dist_cpu import _metric_state_np          # the accumulator layout the gloo merge test restates
+    want = _metric_state_np(y, p)
+    np.testing.assert_array_equal(st[:2 * T + 4], want[:2 * T + 4])
+    np.testing.assert_allclose(st[2 * T + 4:].view(np.float64), want[2 * T + 4:].view(np.float64), rtol=1e-13)
     r, o = m.result(), _oracle_all(y, p)
     assert r["count"] == n
     for key in ("auc", "binary_accuracy", "ctr", "copc"):
