@@ -347,7 +347,10 @@ int rs_din_bwd(int mode, const void* q, const void* keys, const void* values,
  * (`DNN.call` rough_rank/layer.py:100-109; MultiLayerDense autoint:40-41,49-50;
  *  expert/gate Dense staytime/VideoDnn.py:135-147, multidnn.py:62-63,83-85.)
  * transA: A is stored [K,M] (ld lda); transB: B is stored [N,K] (ld ldb).
- * dtype_ab RS_F32  -> fp32 FFMA kernel (parity mode), any transA/transB.
+ * dtype_ab RS_F32  -> any transA/transB.  Problems with 16-byte aligned bases / leading dims (ld % 4 == 0),
+ *   fp32 C and M*N*K >= 2^21 run on the tensor cores as 3xTF32 (hi/lo split inside the kernel, three
+ *   tcgen05.mma.kind::tf32 products, ~2^-20 relative error per product: inside the 1e-5 fp32 bar);
+ *   everything else, or everything after rs_set_fp32_gemm_mode(1), runs the fp32 FFMA kernel.
  * dtype_ab RS_BF16 -> tcgen05 tensor-core kernel (TMA-fed, fp32 accumulation in
  *   TMEM).  It consumes K-major operands only: transA = 0 and transB = 1 (weights
  *   are kept as bf16 [out,in] shadows; activations feeding a weight gradient are
@@ -357,6 +360,7 @@ int rs_din_bwd(int mode, const void* q, const void* keys, const void* values,
  * dtype_c is the dtype of C / aux.  ws >= rs_gemm_workspace_bytes() (may be
  * NULL for RS_F32). */
 size_t rs_gemm_workspace_bytes(void);
+int rs_set_fp32_gemm_mode(int mode);   /* 0 = 3xTF32 tensor cores when eligible (default), 1 = FFMA only; returns the previous mode */
 int rs_gemm(const void* A, int64_t lda, int transA,
             const void* B, int64_t ldb, int transB,
             void* C, int64_t ldc, const float* bias,

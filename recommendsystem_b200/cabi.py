@@ -71,6 +71,7 @@ PROTOTYPES = {
     "rs_logit_head_fwd_bwd": (_i, [_p, _i64, _i, _p, _p, _p, _f, _p, _p, _p, _i64, _p, _p, _i, _i, _p, _sz, _p]),
     "rs_logit_head_fwd_bwd_relu": (_i, [_p, _i64, _i, _p, _p, _p, _f, _p, _p, _p, _i64, _p, _p, _i, _i, _i, _p, _sz, _p]),
     "rs_transpose2d": (_i, [_p, _i64, _p, _i64, _i, _i, _i, _p]),
+    "rs_set_fp32_gemm_mode": (_i, [_i]),
     "rs_staytime_labels": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i64, _i64, _f, _f, _f, _f, _f, _p]),
     "rs_binary_metrics_state_bytes": (_sz, [_i]),
     "rs_binary_metrics_workspace_bytes": (_sz, [_i64]),

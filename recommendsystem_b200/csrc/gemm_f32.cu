@@ -11,6 +11,12 @@ int gemm_bf16_tc(const void* A, int64_t lda, int transA, const void* B, int64_t 
                  int epilogue, int M, int N, int K, int dtype_c, void* ws, size_t ws_bytes,
                  cudaStream_t st);
 size_t gemm_tc_workspace_bytes();
+bool gemm_tf32x3_usable(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int dtype_c,
+                        int epilogue, size_t ws_bytes);
+int gemm_tf32x3(const void* A, int64_t lda, int transA, const void* B, int64_t ldb, int transB, void* C,
+                int64_t ldc, const float* bias, const void* aux, int64_t ldaux, int epilogue, int M, int N,
+                int K, void* ws, size_t ws_bytes, cudaStream_t st);
+std::atomic<int> g_fp32_gemm_mode{0};      // 0: 3xTF32 tensor cores when the problem qualifies, 1: FFMA only
 int splitk_reduce(const float* partial, int splits, void* C, int64_t ldc, int M, int N, int accumulate,
                   int dtype_c, cudaStream_t st);
 
@@ -108,6 +114,10 @@ sgemm_kernel(const float* __restrict__ A, int64_t lda, int transA, const float* 
 using namespace rs;
 
 extern "C" size_t rs_gemm_workspace_bytes(void) { return gemm_tc_workspace_bytes(); }
+extern "C" int rs_set_fp32_gemm_mode(int mode) {
+  RS_REQUIRE(mode == 0 || mode == 1, "rs_set_fp32_gemm_mode: mode %d", mode);
+  return g_fp32_gemm_mode.exchange(mode);
+}
 
 extern "C" int rs_gemm(const void* A, int64_t lda, int transA, const void* B, int64_t ldb,
                        int transB, void* C, int64_t ldc, const float* bias, const void* aux,
@@ -124,6 +134,9 @@ extern "C" int rs_gemm(const void* A, int64_t lda, int transA, const void* B, in
     return gemm_bf16_tc(A, lda, transA, B, ldb, transB, C, ldc, bias, aux, ldaux, epilogue, M, N, K,
                         dtype_c, ws, ws_bytes, st);
   RS_REQUIRE(dtype_ab == RS_F32, "gemm: bad operand dtype %d", dtype_ab);
+  if (g_fp32_gemm_mode.load(std::memory_order_relaxed) == 0 && gemm_tf32x3_usable(A, lda, B, ldb, M, N, K, dtype_c, epilogue,
+                                                                                 ws != nullptr ? ws_bytes : 0))
+    return gemm_tf32x3(A, lda, transA, B, ldb, transB, C, ldc, bias, aux, ldaux, epilogue, M, N, K, ws, ws_bytes, st);
   // deep-K, small-output problems (weight gradients over the batch): split K across CTAs
   const int tiles = (int)(cdiv(N, TN) * cdiv(M, TM));
   int splits = 1;

@@ -427,6 +427,313 @@ int gemm_bf16_tc(const void* A, int64_t lda, int transA, const void* B, int64_t 
   return 0;
 }
 
+// =================================================================================================
+// fp32 operands on the tensor cores: 3xTF32.  x = hi + lo with hi = x with the low 13 mantissa bits
+// cleared (exactly a tf32 number) and lo = x - hi (exact in fp32, 13 significant bits of which the tensor
+// core keeps 11): a.b ~= hi.hi + hi.lo + lo.hi, relative error ~2^-20 per product, i.e. fp32-grade
+// results (the 1e-5 parity bar) at tensor-core rate instead of the FFMA kernel.
+//
+//   warp 0      TMA producer: raw fp32 tiles (32 floats = one 128-byte SWIZZLE_128B row per K slab)
+//   warps 2..5  splitters: hi overwrites the raw tile in place, lo goes to a twin tile at the same
+//               offsets (an elementwise pass is layout-agnostic, so the swizzle is untouched);
+//               fence.proxy.async, then arrive on the stage's `split` barrier.  Afterwards: epilogue.
+//   warp 1      MMA issuer: waits for `split`, issues 3 x 4 tcgen05.mma.kind::tf32 (K = 8) per stage.
+// Operands may each be K-major (stored [rows, K]) or MN-major (stored [K, rows]): Dense forward
+// x[M,K] . W[K,N] (Keras [in,out] weights as they lie), dgrad dy . W^T, wgrad x^T . dy - no transposes.
+constexpr int T3_BK = 32;          // fp32 elements per stage along K
+
+// MN-major tf32 operands exist in one shared-memory layout only: SWIZZLE_128B_BASE32B (descriptor layout
+// type 1; TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 32-byte chunks of a 128-byte row (32 floats along M|N)
+// XOR-ed with the K row index mod 4; atom = 4 K rows x 128 B.  LBO = bytes between 32-float atoms along
+// M|N, SBO = bytes between 4-row K groups.
+__device__ __forceinline__ uint64_t make_sw128b32_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+
+template <int BN, int STAGES>
+struct T3Smem {
+  static constexpr int A_BYTES = TC_BM * T3_BK * 4;            // 16 KB
+  static constexpr int B_BYTES = BN * T3_BK * 4;
+  static constexpr int RAW_BYTES = A_BYTES + B_BYTES;          // [A raw->hi | B raw->hi]
+  static constexpr int STAGE_BYTES = 2 * RAW_BYTES;            // ... [A lo | B lo]
+  static constexpr int STG_PITCH = BN + 4;
+  static constexpr int STG_BYTES = TC_BM * STG_PITCH * 4;
+  static constexpr int MAIN_BYTES = STAGES * STAGE_BYTES > STG_BYTES ? STAGES * STAGE_BYTES : STG_BYTES;
+  static constexpr int TOTAL = MAIN_BYTES + 1024 + 256;
+};
+
+template <int BN, int STAGES, bool AMN, bool BMN, typename CT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   CT* __restrict__ C, int64_t ldc, const float* __restrict__ bias,
+                   const CT* __restrict__ aux, int64_t ldaux, int epi, int M, int N, int K,
+                   int kb_per_split, float* __restrict__ partial, int vec_ok) {
+  using S = T3Smem<BN, STAGES>;
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::MAIN_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* split_bar = empty_bar + STAGES;
+  uint64_t* acc_bar = split_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int kb_total = (K + T3_BK - 1) / T3_BK;
+  const int kb0 = blockIdx.z * kb_per_split;
+  const int kb1 = min(kb_total, kb0 + kb_per_split);
+  const int nkb = kb1 - kb0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&split_bar[s], 128);
+    }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_expect_tx(&full_bar[s], S::RAW_BYTES);
+        uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+        const int k0 = (kb0 + i) * T3_BK;
+        if constexpr (!AMN) {
+          tma_load_2d(a_dst, &tmA, &full_bar[s], k0, m0);                 // box 32 K x 128 rows
+        } else {
+#pragma unroll
+          for (int at = 0; at < TC_BM / 32; ++at)                          // box 32 M x 32 K rows = 4 KB atom column
+            tma_load_2d(a_dst + at * 4096, &tmA, &full_bar[s], m0 + at * 32, k0);
+        }
+        if constexpr (!BMN) {
+          tma_load_2d(a_dst + S::A_BYTES, &tmB, &full_bar[s], k0, n0);
+        } else {
+#pragma unroll
+          for (int at = 0; at < BN / 32; ++at)
+            tma_load_2d(a_dst + S::A_BYTES + at * 4096, &tmB, &full_bar[s], n0 + at * 32, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(2, TC_BM, BN, AMN ? 1 : 0, BMN ? 1 : 0);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+        mbar_wait(&split_bar[s], ph);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + s * S::STAGE_BYTES);
+        // K-major: +32 B per K = 8 step inside the swizzle row; MN-major: LBO 4096 between 32-float
+        // atoms (one TMA box each), SBO 512 between 4-row K groups, a K = 8 step is two groups = +1024 B
+        const uint64_t a_hi = AMN ? make_sw128b32_desc(base, 4096, 512) : make_sw128_kmajor_desc(base);
+        const uint64_t b_hi = BMN ? make_sw128b32_desc(base + S::A_BYTES, 4096, 512) : make_sw128_kmajor_desc(base + S::A_BYTES);
+        const uint64_t a_lo = AMN ? make_sw128b32_desc(base + S::RAW_BYTES, 4096, 512) : make_sw128_kmajor_desc(base + S::RAW_BYTES);
+        const uint64_t b_lo = BMN ? make_sw128b32_desc(base + S::RAW_BYTES + S::A_BYTES, 4096, 512)
+                                  : make_sw128_kmajor_desc(base + S::RAW_BYTES + S::A_BYTES);
+        constexpr uint64_t ka = AMN ? 64 : 2, kb = BMN ? 64 : 2;
+        // The tensor core truncates when it adds a product into the fp32 accumulator: the error grows with
+        // the number of accumulation steps times the accumulator's ulp.  The two correction products are
+        // 2^-11 smaller, so they get their own accumulator (columns [BN, 2BN)): the main one then sees K/8
+        // steps instead of 3K/8 (measured at K = 4096: 1.9e-5 -> 6e-6 of max|C|); the epilogue adds the two.
+#pragma unroll
+        for (int k = 0; k < T3_BK / 8; ++k)
+          tc_mma_tf32(tmem_base + BN, a_lo + ka * k, b_hi + kb * k, idesc, (i | k) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < T3_BK / 8; ++k) tc_mma_tf32(tmem_base + BN, a_hi + ka * k, b_lo + kb * k, idesc, 1u);
+#pragma unroll
+        for (int k = 0; k < T3_BK / 8; ++k)
+          tc_mma_tf32(tmem_base, a_hi + ka * k, b_hi + kb * k, idesc, (i | k) ? 1u : 0u);
+        tc_commit(&empty_bar[s]);
+      }
+      tc_commit(acc_bar);
+    }
+  } else {
+    // ---- splitters, then epilogue (warps 2..5)
+    const int t = threadIdx.x - 64;
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % STAGES;
+      const uint32_t ph = (uint32_t)(i / STAGES) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      uint8_t* raw = smem + s * S::STAGE_BYTES;
+#pragma unroll 4
+      for (int o = t * 16; o < S::RAW_BYTES; o += 128 * 16) {
+        const uint4 x = *reinterpret_cast<const uint4*>(raw + o);
+        uint4 h, l;
+        h.x = x.x & 0xFFFFE000u; h.y = x.y & 0xFFFFE000u; h.z = x.z & 0xFFFFE000u; h.w = x.w & 0xFFFFE000u;
+        l.x = __float_as_uint(__uint_as_float(x.x) - __uint_as_float(h.x));
+        l.y = __float_as_uint(__uint_as_float(x.y) - __uint_as_float(h.y));
+        l.z = __float_as_uint(__uint_as_float(x.z) - __uint_as_float(h.z));
+        l.w = __float_as_uint(__uint_as_float(x.w) - __uint_as_float(h.w));
+        *reinterpret_cast<uint4*>(raw + o) = h;
+        *reinterpret_cast<uint4*>(raw + S::RAW_BYTES + o) = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&split_bar[s])) : "memory");
+    }
+    const int lg = warp & 3;
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    constexpr int PITCH = S::STG_PITCH;
+    float* stg = reinterpret_cast<float*>(smem) + (size_t)lg * 32 * PITCH;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= N) break;
+      uint32_t r[32], q[32];
+      tc_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, r);
+      tc_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(BN + c0), q);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(stg + lane * PITCH + c0 + j) =
+            make_float4(__uint_as_float(r[j]) + __uint_as_float(q[j]), __uint_as_float(r[j + 1]) + __uint_as_float(q[j + 1]),
+                        __uint_as_float(r[j + 2]) + __uint_as_float(q[j + 2]), __uint_as_float(r[j + 3]) + __uint_as_float(q[j + 3]));
+    }
+    __syncwarp();
+    const int rows_here = min(32, M - (m0 + lg * 32));
+    if (rows_here > 0) {
+      float* part_rows = partial ? partial + ((int64_t)blockIdx.z * M + m0 + lg * 32) * N + n0 : nullptr;
+      CT* c_rows = C + (int64_t)(m0 + lg * 32) * ldc + n0;
+      const CT* a_rows = aux ? aux + (int64_t)(m0 + lg * 32) * ldaux + n0 : nullptr;
+      const int ncols = N - n0;
+#define RS_EPI_GO(E) epilogue_rows<BN, E, CT>(stg, rows_here, lane, ncols, N, c_rows, ldc, a_rows, ldaux, bias ? bias + n0 : nullptr, vec_ok)
+      if (part_rows) epilogue_partial<BN>(stg, rows_here, lane, ncols, N, part_rows);
+      else switch (epi) {
+        case RS_EPI_BIAS: RS_EPI_GO(RS_EPI_BIAS); break;
+        case RS_EPI_BIAS_RELU: RS_EPI_GO(RS_EPI_BIAS_RELU); break;
+        case RS_EPI_BIAS_SIGMOID: RS_EPI_GO(RS_EPI_BIAS_SIGMOID); break;
+        case RS_EPI_MUL_RELU_MASK: RS_EPI_GO(RS_EPI_MUL_RELU_MASK); break;
+        case RS_EPI_MUL_DSIGMOID: RS_EPI_GO(RS_EPI_MUL_DSIGMOID); break;
+        case RS_EPI_ACCUM: RS_EPI_GO(RS_EPI_ACCUM); break;
+        default: RS_EPI_GO(RS_EPI_NONE);
+      }
+#undef RS_EPI_GO
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN));
+  }
+}
+
+// 2-D fp32 row-major [rows, cols] with leading dim ld (elements); box = box_cols x box_rows.
+static int make_map_f32(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols,
+                        int box_rows, bool mn_major) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) { set_error("gemm_tf32x3: cuTensorMapEncodeTiled unavailable"); return RS_ERR_UNSUPPORTED; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("gemm_tf32x3: cuTensorMapEncodeTiled failed (%d)", (int)r); return RS_ERR_INVALID; }
+  return 0;
+}
+
+template <int BN, int STAGES, bool AMN, bool BMN, typename CT>
+static int launch_t3(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, int64_t ldc, const float* bias,
+                     const void* aux, int64_t ldaux, int epi, int M, int N, int K, int splits, int kbps,
+                     float* partial, int vec_ok, cudaStream_t st) {
+  auto kern = gemm_tf32x3_kernel<BN, STAGES, AMN, BMN, CT>;
+  const int smem = T3Smem<BN, STAGES>::TOTAL;
+  RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid((unsigned)cdiv(N, BN), (unsigned)cdiv(M, TC_BM), (unsigned)splits);
+  kern<<<grid, TC_THREADS, smem, st>>>(tmA, tmB, (CT*)C, ldc, bias, (const CT*)aux, ldaux, epi, M, N, K, kbps,
+                                       partial, vec_ok);
+  return check_launch("gemm_tf32x3");
+}
+
+// Can this fp32 problem run on the tensor cores?  (16-byte TMA strides and bases; big enough to matter.)
+bool gemm_tf32x3_usable(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int dtype_c,
+                        int epilogue, size_t ws_bytes) {
+  if (dtype_c != RS_F32) return false;
+  // one accumulation chain stays <= 4096 deep (truncating accumulator, see the kernel): longer K needs
+  // split-K, i.e. a plain / accumulate epilogue and room for the partial tiles
+  if (K > 4096) {
+    if (!(epilogue == RS_EPI_NONE || epilogue == RS_EPI_ACCUM)) return false;
+    const size_t max_splits = ws_bytes / ((size_t)M * N * sizeof(float));
+    if (max_splits < 1 || cdiv(K, (int64_t)max_splits) > 4096) return false;
+  }
+  if (lda % 4 || ldb % 4 || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) return false;
+  if (N < 8 || K < 32 || M < 64) return false;
+  return (int64_t)M * N * K >= ((int64_t)1 << 21);
+}
+
+int gemm_tf32x3(const void* A, int64_t lda, int transA, const void* B, int64_t ldb, int transB, void* C,
+                int64_t ldc, const float* bias, const void* aux, int64_t ldaux, int epilogue, int M, int N,
+                int K, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const bool amn = transA != 0;          // A stored [K, M]
+  const bool bmn = transB == 0;          // B stored [K, N]
+  const int sms = sm_count();
+  int BN = 128;
+  if (N <= 32) BN = 32;
+  else if (N <= 64) BN = 64;
+  else if ((int64_t)cdiv(M, TC_BM) * cdiv(N, 128) < sms && N % 128 != 0 && N % 128 <= 64) BN = 64;
+  else if ((int64_t)cdiv(M, TC_BM) * cdiv(N, 128) * 2 <= sms) BN = 64;
+  const int tiles = (int)(cdiv(M, TC_BM) * cdiv(N, BN));
+  const int kb_total = (int)cdiv(K, T3_BK);
+  int splits = 1;
+  const bool can_split = (epilogue == RS_EPI_NONE || epilogue == RS_EPI_ACCUM) && ws != nullptr;
+  if (can_split && tiles * 2 <= sms && kb_total >= 16) {
+    splits = sms / tiles;
+    if (splits > kb_total / 4) splits = kb_total / 4;
+  }
+  if (can_split && cdiv(kb_total, splits) > 2048 / T3_BK) splits = (int)cdiv(kb_total, 2048 / T3_BK);   // chain <= 2048
+  if (can_split && (size_t)splits * M * N * sizeof(float) > ws_bytes)
+    splits = (int)(ws_bytes / ((size_t)M * N * sizeof(float)));
+  if (splits < 1) splits = 1;
+  if (cdiv(kb_total, splits) > 4096 / T3_BK) {
+    set_error("gemm(fp32, 3xTF32): K=%d needs split-K workspace (%zu bytes given)", K, ws_bytes);
+    return RS_ERR_WORKSPACE;
+  }
+  int kbps = (int)cdiv(kb_total, splits);
+  splits = (int)cdiv(kb_total, kbps);
+  float* partial = splits > 1 ? (float*)ws : nullptr;
+  CUtensorMap tmA, tmB;
+  if (!amn) { if (int e = make_map_f32(&tmA, A, M, K, lda, T3_BK, TC_BM, false)) return e; }
+  else      { if (int e = make_map_f32(&tmA, A, K, M, lda, 32, T3_BK, true)) return e; }
+  if (!bmn) { if (int e = make_map_f32(&tmB, B, N, K, ldb, T3_BK, BN, false)) return e; }
+  else      { if (int e = make_map_f32(&tmB, B, K, N, ldb, 32, T3_BK, true)) return e; }
+  int vec_ok = ((uintptr_t)C % 16 == 0) && ((ldc * 4) % 16 == 0);
+  if (aux) vec_ok = vec_ok && ((uintptr_t)aux % 16 == 0) && ((ldaux * 4) % 16 == 0);
+  int rc;
+#define RS_T3_GO2(BNV, ST, AM, BM) \
+  rc = launch_t3<BNV, ST, AM, BM, float>(tmA, tmB, C, ldc, bias, aux, ldaux, epilogue, M, N, K, splits, kbps, partial, vec_ok, st)
+#define RS_T3_GO(BNV, ST)                                   \
+  if (amn && bmn) { RS_T3_GO2(BNV, ST, true, true); }       \
+  else if (amn) { RS_T3_GO2(BNV, ST, true, false); }        \
+  else if (bmn) { RS_T3_GO2(BNV, ST, false, true); }        \
+  else { RS_T3_GO2(BNV, ST, false, false); }
+  if (BN == 32) { RS_T3_GO(32, 4) }
+  else if (BN == 64) { RS_T3_GO(64, 4) }
+  else { RS_T3_GO(128, 3) }
+#undef RS_T3_GO
+#undef RS_T3_GO2
+  if (rc) return rc;
+  if (splits > 1) return splitk_reduce(partial, splits, C, ldc, M, N, epilogue == RS_EPI_ACCUM, RS_F32, st);
+  return 0;
+}
+
 #ifdef RS_GEMM_PROFILE
 extern "C" int rs_debug_gemm_profile(long long* out16) {
   cudaDeviceSynchronize();

@@ -216,3 +216,54 @@ def test_gemm_f32_splitk_wgrad(cuda_dev, M, N, K):
     ref = X.double().cpu().numpy().T @ dY.double().cpu().numpy()
     assert_close(dW.cpu().numpy(), ref, REL_F32, "f32 wgrad split-K")
     assert torch.equal(dW, dW2)
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 200, 100), (2048, 256, 1712), (128, 32, 4096), (300, 72, 260), (4096, 8, 64)])
+@pytest.mark.parametrize("tA,tB", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("epi", [0, 2, 6])
+def test_gemm_f32_tf32x3(cuda_dev, M, N, K, tA, tB, epi):
+    """fp32 operands on the tensor cores (3xTF32, hi/lo split in the kernel): every storage order of A and B,
+    K / M / N tails, fused epilogues, split-K; fp32-grade accuracy and the FFMA kernel as a cross-check."""
+    from recommendsystem_b200 import cabi, ops
+    rng = np.random.default_rng(M + N + K + epi)
+    A = rng.standard_normal((K, M) if tA else (M, K)).astype(np.float32)
+    B = (rng.standard_normal((N, K) if tB else (K, N)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    cold = rng.standard_normal((M, N)).astype(np.float32)
+    acc = (A.T if tA else A).astype(np.float64) @ (B.T if tB else B).astype(np.float64)
+    ref = _ref_epi(acc, epi, bias.astype(np.float64), None, cold.astype(np.float64))
+    lib = cabi.load()
+    n0 = lib.rs_launch_count()
+    C = _t(cold, cuda_dev)
+    ops.gemm(_t(A, cuda_dev), _t(B, cuda_dev), C, bias=_t(bias, cuda_dev), epilogue=epi, transA=tA, transB=tB)
+    launches_tc = lib.rs_launch_count() - n0
+    prev = lib.rs_set_fp32_gemm_mode(1)
+    try:
+        C2 = _t(cold, cuda_dev)
+        ops.gemm(_t(A, cuda_dev), _t(B, cuda_dev), C2, bias=_t(bias, cuda_dev), epilogue=epi, transA=tA, transB=tB)
+    finally:
+        lib.rs_set_fp32_gemm_mode(prev)
+    assert prev == 0 and launches_tc >= 1
+    assert_close(C.cpu().numpy(), ref, REL_F32, "gemm 3xTF32")
+    assert_close(C2.cpu().numpy(), ref, REL_F32, "gemm FFMA")
+    # element-wise too: a dropped lo term would show up as ~1e-3 errors on individual outputs
+    scale = np.abs(ref).max()
+    assert np.abs(C.cpu().numpy() - ref).max() <= 2e-5 * scale
+
+
+def test_gemm_f32_tf32x3_is_deterministic_and_handles_extremes(cuda_dev):
+    from recommendsystem_b200 import ops
+    rng = np.random.default_rng(4)
+    A = rng.standard_normal((1024, 512)).astype(np.float32)
+    A[0, :8] = [0.0, -0.0, 1e-38, -1e-38, 3e38, 0.0, 1.0, 2.0 ** -126]        # zeros, near-denormal, near-max
+    B = np.zeros((512, 64), np.float32)
+    B[:8, 0] = 1.0
+    B[8:, 1:] = rng.standard_normal((504, 63)).astype(np.float32) / 16
+    At, Bt = _t(A, cuda_dev), _t(B, cuda_dev)
+    C1, C2 = ops.gemm(At, Bt), ops.gemm(At, Bt)
+    assert torch.equal(C1, C2)
+    ref = A.astype(np.float64) @ B.astype(np.float64)
+    got = C1.cpu().numpy()
+    assert np.isfinite(got).all()
+    np.testing.assert_allclose(got[1:], ref[1:], rtol=0, atol=2e-5 * np.abs(ref).max())
+    assert got[0, 0] == pytest.approx(ref[0, 0], rel=1e-6)
