@@ -137,7 +137,7 @@ class AUTOINT:
         leaves = [embs[s].detach().requires_grad_(True) for s in self.slots]
         pred = self.sub_model(leaves)
         if self.opt is None:
-            self.opt = torch.optim.Adam(self.sub_model.parameters(), lr=1e-5, betas=(0.9, 0.999), eps=1e-8)
+            self.opt = torch.optim.Adam(self.sub_model.parameters(), lr=1e-5, betas=(0.9, 0.999), eps=1e-8, capturable=True)
         loss = cross_entropy(labels, pred).mean()
         self.opt.zero_grad(set_to_none=True)
         loss.backward()

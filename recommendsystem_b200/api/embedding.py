@@ -96,6 +96,7 @@ class EmbeddingFeatures:
             raise TypeError("sparse_opt must be api.embedding.Adam or AdaGrad")
         self.row_bits = ops.row_bits(total)
         self._last = None
+        self._geom_cache = {}
 
     def __call__(self, inputs: Dict[str, torch.Tensor]):
         out, plan = {}, []
@@ -106,8 +107,7 @@ class EmbeddingFeatures:
         if len(single) > 1:
             ids = torch.stack([inputs[self.cols[ci].categorical_column.key].reshape(-1) for ci in single], dim=1)
             ids = ids.to(self.dev, torch.int64).contiguous()
-            base = torch.as_tensor(self.base[single], device=self.dev)
-            rows = torch.as_tensor(self.rows[single], device=self.dev)
+            base, rows = self._geom(tuple(single))
             emb, keys, _ = ops.embed_gather(self.table, ids, base, rows, torch.float32, want_keys=True)
             for j, ci in enumerate(single):
                 out[self.cols[ci].key] = emb[:, j, :].to(self.out_dtype)
@@ -118,8 +118,7 @@ class EmbeddingFeatures:
             if ci in single:
                 continue
             ids = inputs[c.categorical_column.key].to(self.dev, torch.int64)
-            base = torch.tensor([int(self.base[ci])], device=self.dev)
-            rows = torch.tensor([int(self.rows[ci])], device=self.dev)
+            base, rows = self._geom((ci,))
             if c.combiner is None:                               # sequence column -> ([B,T,d], mask)
                 T = c.seq_max_len or ids.shape[1]
                 seq = ids[:, :T].contiguous()
@@ -143,6 +142,17 @@ class EmbeddingFeatures:
                     plan.append((c.key, keys, None, (bag, cnt)))
         self._last = plan
         return out
+
+    def _geom(self, cols):
+        """(row_base, rows) device tensors of a column group, created once (no host->device copy per call:
+        the step stays CUDA-graph capturable)."""
+        g = self._geom_cache.get(cols)
+        if g is None:
+            idx = list(cols)
+            g = (torch.as_tensor(np.asarray(self.base)[idx], device=self.dev),
+                 torch.as_tensor(np.asarray(self.rows)[idx], device=self.dev))
+            self._geom_cache[cols] = g
+        return g
 
     def backward(self, grads: Dict[str, torch.Tensor]):
         """Push d(loss)/d(output) of every column: segment-sum per touched row + optimizer update."""

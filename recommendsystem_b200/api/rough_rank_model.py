@@ -185,7 +185,7 @@ class DssmNet:
         leaves = {k: v.detach().requires_grad_(True) for k, v in e.items()}
         out = self.sub_model(leaves, inputs[C.DENSE_MASK_ID].to(self.emb.dev))
         if self.opt is None:
-            self.opt = torch.optim.Adam(self.sub_model.parameters(), lr=0.0001, betas=(0.9, 0.999), eps=1e-8)
+            self.opt = torch.optim.Adam(self.sub_model.parameters(), lr=0.0001, betas=(0.9, 0.999), eps=1e-8, capturable=True)
         loss = (binary_crossentropy(labels["student"], out["student"]) +
                 binary_crossentropy(labels["teacher"], out["teacher"]) + y_pred_loss(None, out["distill"]))
         self.opt.zero_grad(set_to_none=True)

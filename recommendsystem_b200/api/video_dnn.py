@@ -209,7 +209,7 @@ class MtlNet:
         ls = {s: (v[0].detach().requires_grad_(True), v[1]) for s, v in seqs.items()}
         out, _ = self.sub_model(le, ls)
         if self.opt is None:
-            self.opt = torch.optim.Adam(self.sub_model.parameters(), lr=0.0005, betas=(0.9, 0.999), eps=1e-8)
+            self.opt = torch.optim.Adam(self.sub_model.parameters(), lr=0.0005, betas=(0.9, 0.999), eps=1e-8, capturable=True)
         loss = sum(LOSS_WEIGHTS[k] * LOSSES[k](labels[k], out[k]).mean() for k in TASK_KEYS)
         self.opt.zero_grad(set_to_none=True)
         loss.backward()

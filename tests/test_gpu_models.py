@@ -133,3 +133,55 @@ def test_mtl_net_and_dssm_train_steps(cuda_dev):
     assert out["student"].shape == (B, 1) and out["distill"].shape == (B,)
     dlosses = [float(dnet.train_step(din, dl)[0]) for _ in range(6)]
     assert all(np.isfinite(dlosses)) and dlosses[-1] < dlosses[0], dlosses
+
+
+def test_graphed_train_step_matches_eager(cuda_dev):
+    """api.graph.GraphedTrainStep: the whole DSSM / VideoDnn train step (gather, forward, backward, dense Adam,
+    sparse push) captured in ONE CUDA graph replays to the same losses and parameters as eager launches."""
+    from recommendsystem_b200.api.graph import GraphedTrainStep
+    from recommendsystem_b200.api.rough_rank_model import DSSM, config as RC
+    from recommendsystem_b200.api.staytime_config import Config as C
+    from recommendsystem_b200.api.video_dnn import TASK_KEYS, mtl_net
+    B, T = 48, 50
+    g = torch.Generator().manual_seed(3)
+    din = {f: torch.randint(0, 10 ** 9, (B,), generator=g).to(cuda_dev) for f in RC.USER_FEATURE_IDS + RC.ITEM_FEATURE_IDS}
+    din[RC.DENSE_MASK_ID] = (torch.rand(B, 1, generator=g) < 0.5).float().to(cuda_dev)
+    dl = {"student": (torch.rand(B, 1, generator=g) < 0.3).float().to(cuda_dev),
+          "teacher": (torch.rand(B, 1, generator=g) < 0.3).float().to(cuda_dev)}
+    vin = {s: torch.randint(0, 10 ** 9, (B,), generator=g).to(cuda_dev) for s in C.SLOTS}
+    for s in C.SEQ_SLOTS:
+        ids = torch.randint(0, 10 ** 9, (B, T), generator=g)
+        lens = torch.randint(0, T + 1, (B,), generator=g)
+        ids[torch.arange(T)[None, :] >= lens[:, None]] = -1
+        vin[s] = ids.to(cuda_dev)
+    y0 = torch.softmax(torch.randn(B, 400, generator=g), -1)
+    vl = {TASK_KEYS[0]: torch.cat([y0, torch.zeros(B, 1)], 1).to(cuda_dev),
+          TASK_KEYS[1]: (torch.rand(B, 1, generator=g) < 0.3).float().to(cuda_dev),
+          TASK_KEYS[2]: (torch.rand(B, 1, generator=g) < 0.3).float().to(cuda_dev)}
+
+    def build(kind):
+        if kind == "dssm":
+            net, inp, lab = DSSM(bucket_size=1000, device=str(cuda_dev))["net"], din, dl
+        else:
+            net, inp, lab = mtl_net(C.SLOTS, C.SEQ_SLOTS, T, dnn_hidden_units=(64, 32), bucket_size=1000,
+                                    device=str(cuda_dev))["net"], vin, vl
+        torch.manual_seed(11)           # layers build (draw their weights) lazily at the first forward, like Keras
+        net.predict(inp)
+        return net, inp, lab
+
+    for kind in ("dssm", "video_dnn"):
+        a, inp, lab = build(kind)
+        b, _, _ = build(kind)
+        pa, pb = list(a.sub_model.parameters()), list(b.sub_model.parameters())
+        assert len(pa) > 10 and all(torch.equal(x, y) for x, y in zip(pa, pb)), "same seed must give the same initial weights"
+        eager = [float(a.train_step(inp, lab)[0]) for _ in range(6)]
+        gs = GraphedTrainStep(b, inp, lab, warmup=3)               # 3 real steps, then the capture
+        graphed = [float(gs(inp, lab)[0]) for _ in range(3)]
+        assert graphed == eager[3:], (kind, eager, graphed)        # bit for bit: deterministic kernels
+        for x, y in zip(pa, pb):
+            assert torch.equal(x, y), kind
+        assert torch.equal(a.emb.table, b.emb.table), kind
+        # new data through the static buffers
+        lab2 = {k: 1.0 - v if v.shape[-1] == 1 else v for k, v in lab.items()}
+        l2 = float(gs(inp, lab2)[0])
+        assert np.isfinite(l2) and l2 != graphed[-1]

@@ -15,7 +15,17 @@ dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
 
 
-def run(name, step, B, warm=3, reps=8):
+def run(name, step, B, warm=3, reps=8, net=None, inputs=None, labels=None):
+    if net is not None:
+        _run(name + " [eager]", step, B, warm, reps)
+        from recommendsystem_b200.api.graph import GraphedTrainStep
+        gs = GraphedTrainStep(net, inputs, labels)
+        _run(name + " [CUDA graph]", lambda: gs(inputs, labels), B, warm, reps * 4)
+    else:
+        _run(name, step, B, warm, reps)
+
+
+def _run(name, step, B, warm=3, reps=8):
     for _ in range(warm):
         step()
     torch.cuda.synchronize()
@@ -49,7 +59,7 @@ def video_dnn(B=16384, T=50):
     labels = {TASK_KEYS[0]: torch.cat([y0, torch.zeros(B, 1)], 1).to(dev),
               TASK_KEYS[1]: (torch.rand(B, 1, generator=g) < 0.3).float().to(dev),
               TASK_KEYS[2]: (torch.rand(B, 1, generator=g) < 0.3).float().to(dev)}
-    run("VideoDnn mtl_net (cfg5: 91 slots x 32, 3 seq slots T=50)", lambda: net.train_step(inputs, labels), B)
+    run("VideoDnn mtl_net (cfg5: 91 slots x 32, 3 seq slots T=50)", lambda: net.train_step(inputs, labels), B, net=net, inputs=inputs, labels=labels)
 
 
 def dssm(B=16384):
@@ -59,7 +69,7 @@ def dssm(B=16384):
     din[RC.DENSE_MASK_ID] = (torch.rand(B, 1, generator=g) < 0.5).float().to(dev)
     dl = {"student": (torch.rand(B, 1, generator=g) < 0.3).float().to(dev),
           "teacher": (torch.rand(B, 1, generator=g) < 0.3).float().to(dev)}
-    run("DSSM rough_rank (52 features x 16)", lambda: net.train_step(din, dl), B)
+    run("DSSM rough_rank (52 features x 16)", lambda: net.train_step(din, dl), B, net=net, inputs=din, labels=dl)
 
 
 def rank_ctr(B=4096):
@@ -71,7 +81,7 @@ def rank_ctr(B=4096):
     net = Model(cfg, bucket_size=265000, device=str(dev)).run()["net"]
     inputs = {s: torch.randint(0, 10 ** 9, (B,), generator=g).to(dev) for s in net.layout.sparse_slots}
     labels = {t: (torch.rand(B, 1, generator=g) < 0.3).float().to(dev) for t in TASK_NAMES}
-    run("rank/ctr production model (176 slots x 96, InteractingLayer F=175)", lambda: net.train_step(inputs, labels), B)
+    run("rank/ctr production model (176 slots x 96, InteractingLayer F=175)", lambda: net.train_step(inputs, labels), B, net=net, inputs=inputs, labels=labels)
 
 
 if __name__ == "__main__":

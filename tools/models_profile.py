@@ -15,7 +15,7 @@ def capture(name, step, B, **kw):
     steps[name] = step
 
 
-mb.run = capture
+mb.run = capture  # (name, step, B, **kw)
 which = sys.argv[1] if len(sys.argv) > 1 else "video_dnn"
 getattr(mb, which)()
 (name, step), = steps.items()
