@@ -348,7 +348,7 @@ int rs_din_bwd(int mode, const void* q, const void* keys, const void* values,
  *  expert/gate Dense staytime/VideoDnn.py:135-147, multidnn.py:62-63,83-85.)
  * transA: A is stored [K,M] (ld lda); transB: B is stored [N,K] (ld ldb).
  * dtype_ab RS_F32  -> any transA/transB.  Problems with 16-byte aligned bases / leading dims (ld % 4 == 0),
- *   fp32 C and M*N*K >= 2^21 run on the tensor cores as 3xTF32 (hi/lo split inside the kernel, three
+ *   fp32 C, M, N, K >= 8 and M*N*K >= 2^20 run on the tensor cores as 3xTF32 (hi/lo split inside the kernel, three
  *   tcgen05.mma.kind::tf32 products, ~2^-20 relative error per product: inside the 1e-5 fp32 bar);
  *   everything else, or everything after rs_set_fp32_gemm_mode(1), runs the fp32 FFMA kernel.
  * dtype_ab RS_BF16 -> tcgen05 tensor-core kernel (TMA-fed, fp32 accumulation in

@@ -675,8 +675,8 @@ bool gemm_tf32x3_usable(const void* A, int64_t lda, const void* B, int64_t ldb, 
     if (max_splits < 1 || cdiv(K, (int64_t)max_splits) > 4096) return false;
   }
   if (lda % 4 || ldb % 4 || ((uintptr_t)A & 15) || ((uintptr_t)B & 15)) return false;
-  if (N < 8 || K < 32 || M < 64) return false;
-  return (int64_t)M * N * K >= ((int64_t)1 << 21);
+  if (N < 8 || K < 8 || M < 8) return false;
+  return (int64_t)M * N * K >= ((int64_t)1 << 20);
 }
 
 int gemm_tf32x3(const void* A, int64_t lda, int transA, const void* B, int64_t ldb, int transB, void* C,

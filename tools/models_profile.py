@@ -11,8 +11,13 @@ from torch.profiler import ProfilerActivity, profile
 steps = {}
 
 
-def capture(name, step, B, **kw):
-    steps[name] = step
+def capture(name, step, B, net=None, inputs=None, labels=None, **kw):
+    if net is not None and len(sys.argv) > 2 and sys.argv[2] == "graph":
+        from recommendsystem_b200.api.graph import GraphedTrainStep
+        gs = GraphedTrainStep(net, inputs, labels)
+        steps[name + " [CUDA graph]"] = lambda: gs(inputs, labels)
+    else:
+        steps[name] = step
 
 
 mb.run = capture  # (name, step, B, **kw)
@@ -27,4 +32,4 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
         step()
     torch.cuda.synchronize()
 print(name)
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=22, max_name_column_width=90))
