@@ -94,32 +94,31 @@ binary_metrics_kernel(const PT* __restrict__ pred, const float* __restrict__ lab
   __syncthreads();
   double sl = 0.0, sp = 0.0;
   unsigned int correct = 0;
+  const float t_first = thr[0];
+  const float t_scale = (T > 1 && thr[T - 1] > thr[0]) ? (float)(T - 1) / (thr[T - 1] - thr[0]) : 0.f;
   // four independent elements per thread and iteration (strided by the grid so that every load
-  // instruction of a warp stays coalesced): the 8-step threshold searches overlap
+  // instruction of a warp stays coalesced)
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
     float p[4], y[4];
-    int lo[4], hi[4];
+    int lo[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int64_t i = i0 + u * stride;
       const bool in = i < n;
       p[u] = in ? metric_val<PT>(pred, i) : 0.f;
       y[u] = in ? label[i] : 0.f;
-      lo[u] = 0; hi[u] = T;
     }
-    // k = #{t : p > thr[t]} for ascending thresholds (Keras compares pred > threshold per threshold)
-    bool more = true;
-    while (more) {
-      more = false;
+    // k = #{t : p > thr[t]} for ascending thresholds (Keras compares pred > threshold per threshold):
+    // start from the bucket an evenly spaced grid would give (Keras' thresholds are one) and walk to the
+    // exact answer - usually 0 or 1 steps; correct for any ascending thresholds
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (lo[u] < hi[u]) {
-          const int mid = (lo[u] + hi[u]) >> 1;
-          if (p[u] > thr[mid]) lo[u] = mid + 1; else hi[u] = mid;
-          more = more || lo[u] < hi[u];
-        }
-      }
+    for (int u = 0; u < 4; ++u) {
+      const float g = fminf(fmaxf((p[u] - t_first) * t_scale, 0.f), (float)T);     // NaN -> 0
+      int k = (int)g;
+      while (k < T && p[u] > thr[k]) ++k;
+      while (k > 0 && !(p[u] > thr[k - 1])) --k;
+      lo[u] = k;
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
