@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 2
+#define RS_ABI_VERSION 3   /* 3: + rs_staytime_labels, rs_binary_metrics_*, rs_set_fp32_gemm_mode */
 
 enum rs_dtype { RS_F32 = 0, RS_BF16 = 1 };
 

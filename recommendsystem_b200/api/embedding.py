@@ -85,11 +85,18 @@ class EmbeddingFeatures:
         total = int(rows.sum())
         gen = torch.Generator(device=self.dev).manual_seed(seed)
         scale = getattr(sparse_opt, "initial_scale", 0.1) if isinstance(sparse_opt, AdaGrad) else 0.1
-        self.table = torch.empty(total, self.d, device=self.dev).normal_(0.0, float(scale), generator=gen)
         if isinstance(sparse_opt, Adam):
-            self.m, self.v = torch.zeros_like(self.table), torch.zeros_like(self.table)
+            # one [w | m | v] record per row: the sparse update touches ONE contiguous 12d-byte
+            # block per row instead of three far-apart ones (random DRAM / TLB accesses, not bytes, bound it)
+            self.arena = torch.zeros(total, 3, self.d, device=self.dev)
+            self.table, self.m, self.v = self.arena[:, 0, :], self.arena[:, 1, :], self.arena[:, 2, :]
+            chunk = 1 << 22
+            for r0 in range(0, total, chunk):
+                r1 = min(total, r0 + chunk)
+                self.table[r0:r1] = torch.empty(r1 - r0, self.d, device=self.dev).normal_(0.0, float(scale), generator=gen)
             self.scalars = torch.zeros(4, device=self.dev)
         elif isinstance(sparse_opt, AdaGrad):
+            self.table = torch.empty(total, self.d, device=self.dev).normal_(0.0, float(scale), generator=gen)
             shape = (total, self.d) if sparse_opt.per_element else (total,)
             self.g2sum = torch.full(shape, float(sparse_opt.initial_g2sum), device=self.dev)
         else:
