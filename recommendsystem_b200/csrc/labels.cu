@@ -49,7 +49,10 @@ staytime_label_kernel(StayArgs a) {
         // parse.py:53-63  label = exp(|bin - wt|^2 / (-2 sigma^2)) / (sqrt(2 pi) sigma) * width
         const float dist = s_bins[j] - wt;
         const float sq = dist * dist;
-        v = div_const(expf(div_const(sq, a.neg_two_sigma2, a.rcp_n2s2)), a.div_num, a.rcp_div) * a.width;
+        // exp(x) < 2^-150 rounds to +0 in fp32 whatever follows: skip the tail of the Gaussian (about half of
+        // the 400 bins of a row; a warp's 32 consecutive bins take the branch together)
+        const float xarg = div_const(sq, a.neg_two_sigma2, a.rcp_n2s2);
+        v = xarg < -106.f ? 0.f : div_const(expf(xarg), a.div_num, a.rcp_div) * a.width;
       }
       out[j] = v;
     }
