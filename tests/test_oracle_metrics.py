@@ -50,3 +50,27 @@ def test_simple_metrics():
     assert om.binary_accuracy(y, p) == 0.5           # 0.5 is not > 0.5
     assert om.ctr(y) == 0.5
     assert om.copc(y, p) == pytest.approx(2 / 2.1, rel=1e-6)
+
+
+def test_product_thresholds_and_regex_match_the_oracle():
+    """Host logic of the product side (no GPU): the AUC thresholds it uploads are the oracle's, bit for bit, and the
+    landing-page match follows RE2 full-match semantics ('.' does not cross a newline, parse.py:66)."""
+    from recommendsystem_b200.api.metrics import keras_auc_thresholds
+    from recommendsystem_b200.api.staytime_parse import landing_mask
+    for T in (2, 3, 50, 200, 1000):
+        np.testing.assert_array_equal(keras_auc_thresholds(T), om.keras_thresholds(T))
+    with pytest.raises(ValueError):
+        keras_auc_thresholds(1)
+    got = landing_mask(["video_homepage_landing", "x video_homepage_landing y", b"video_homepage_landing",
+                        "video_homepage_landin", "", "a\nvideo_homepage_landing", "label"])
+    assert got.tolist() == [1, 1, 1, 0, 0, 0, 0]
+
+
+def test_no_cpu_fallback_for_labels_and_metrics():
+    import torch
+    from recommendsystem_b200.api.metrics import BinaryMetrics
+    from recommendsystem_b200.api.staytime_parse import staytime_labels
+    with pytest.raises(RuntimeError):
+        BinaryMetrics(device="cpu")
+    with pytest.raises(RuntimeError):
+        staytime_labels(torch.zeros(4, dtype=torch.int64))
