@@ -74,3 +74,15 @@ def test_no_cpu_fallback_for_labels_and_metrics():
         BinaryMetrics(device="cpu")
     with pytest.raises(RuntimeError):
         staytime_labels(torch.zeros(4, dtype=torch.int64))
+
+
+def test_staytime_label_is_a_sampled_normal_pdf():
+    """Independent statement of parse.py:53-63: label[b, j] = N(bin_j; wt_b, sigma = 4) * bin width (scipy)."""
+    from scipy.stats import norm
+    watch = np.array([0, 12_345, 60_000, 159_000, 999_999], np.int64)
+    lab = om.staytime_labels(watch, dtype=np.float64)[0]
+    wt = np.minimum(watch / 1000.0, 160.0)
+    width = (180.5 + 19) / 399
+    want = norm.pdf(np.asarray(om.BIN_LIST)[None, :], loc=wt[:, None], scale=4.0) * width
+    np.testing.assert_allclose(lab[:, :400], want, rtol=1e-12, atol=1e-300)
+    np.testing.assert_array_equal(lab[:, 400], wt)
