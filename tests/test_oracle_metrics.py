@@ -86,3 +86,16 @@ def test_staytime_label_is_a_sampled_normal_pdf():
     want = norm.pdf(np.asarray(om.BIN_LIST)[None, :], loc=wt[:, None], scale=4.0) * width
     np.testing.assert_allclose(lab[:, :400], want, rtol=1e-12, atol=1e-300)
     np.testing.assert_array_equal(lab[:, 400], wt)
+
+
+def test_auc_against_sklearn():
+    """Second, independent pin: scikit-learn's ROC AUC equals the rank-statistic restatement exactly and the
+    Keras 200-threshold AUC to within its discretisation error."""
+    from sklearn.metrics import roc_auc_score
+    rng = np.random.default_rng(9)
+    for n, pos in ((2000, 0.5), (20000, 0.05)):
+        y = (rng.random(n) < pos).astype(np.float32)
+        p = np.clip(0.4 * y + 0.3 + 0.25 * rng.standard_normal(n), 0, 1).astype(np.float32)
+        sk = roc_auc_score(y, p)
+        assert om.exact_roc_auc(y, p) == pytest.approx(sk, abs=1e-12)
+        assert abs(om.keras_auc(y, p) - sk) < 3e-3
