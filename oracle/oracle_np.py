@@ -528,3 +528,22 @@ def autoint_fwd_bwd(X, P, y, H, L, ln_eps, use_res=True):
     return dict(p=np.clip(p_raw, 1e-6, 1.0), p_raw=p_raw, loss=loss, dX=dX, A=A,
                 grads=dict(Wqkvr=dW, bqkvr=db, gamma=dgamma, beta=dbeta, mlp_W=g_mlpW, mlp_b=g_mlpb,
                            out_W=g_outW, out_b=g_outb))
+
+
+# ---------------------------------------------------------------- numerics model of the 3xTF32 GEMM
+def tf32_truncate(x):
+    """fp32 -> the tf32 value the tensor core sees when it ignores the low 13 mantissa bits."""
+    return (np.asarray(x, np.float32).view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def gemm_tf32x3_model(A, B):
+    """What csrc/gemm_tc.cu::gemm_tf32x3_kernel computes, with exact (fp64) accumulation: x = hi + lo,
+    hi = tf32_truncate(x), lo = x - hi (exact in fp32; the tensor core keeps its top 11 bits), and
+    C = hi.hi + hi.lo + lo.hi.  The dropped lo.lo term and the truncation of lo bound the relative error of
+    every product by ~2^-20; the GPU adds the accumulator's own rounding on top (tests/test_gpu_gemm.py)."""
+    A = np.asarray(A, np.float32)
+    B = np.asarray(B, np.float32)
+    ah, bh = tf32_truncate(A), tf32_truncate(B)
+    al, bl = tf32_truncate(A - ah), tf32_truncate(B - bh)
+    f = lambda a: a.astype(np.float64)
+    return f(ah) @ f(bh) + f(ah) @ f(bl) + f(al) @ f(bh)
