@@ -325,6 +325,34 @@ def run_own(args):
              "gather_frac_of_8TBps": gk["GBps"] / 8000.0, "scatter_adam_GBps": sk["GBps"],
              "scatter_adam_frac_of_measured_hbm": sk["GBps"] / pk["hbm_gbs"], "unique_rows": n_unique,
              "gather_kernel": gk["phase"]}
+    if world == 1:
+        # The per-phase times above come from an eager pass with one CUDA-event pair per phase: for a 13 us kernel
+        # the pair itself adds several us.  Time the same gather launch (this batch's ids, the trainer's table)
+        # ten times inside one CUDA graph as well.
+        try:
+            from recommendsystem_b200 import ops as _ops
+
+            def _gather():
+                return _ops.embed_gather(tr.table, tr.ids, tr.base_t, tr.rows_t, out_dtype=tr.act_dtype, want_keys=True)
+            for _ in range(3):
+                _gather()
+            torch.cuda.synchronize()
+            gs_, gr_ = torch.cuda.Stream(), torch.cuda.CUDAGraph()
+            with torch.cuda.stream(gs_):
+                with torch.cuda.graph(gr_, stream=gs_):
+                    for _ in range(10):
+                        _gather()
+            ts_ = []
+            for _ in range(7):
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record(); gr_.replay(); b_.record(); torch.cuda.synchronize()
+                ts_.append(a_.elapsed_time(b_) / 10)
+            t_g = sorted(ts_)[len(ts_) // 2]
+            by_g, _ = algorithmic("embed_gather", BATCH, act_bytes, n_unique)
+            embed.update({"gather_ms_in_graph": t_g, "gather_GBps_in_graph": by_g / t_g / 1e6,
+                          "gather_frac_of_measured_hbm_in_graph": by_g / t_g / 1e6 / pk["hbm_gbs"]})
+        except Exception as e:                       # a reporting extra: never fail the bench line over it
+            embed["gather_in_graph_error"] = repr(e)[:200]
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
