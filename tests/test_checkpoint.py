@@ -78,3 +78,34 @@ def test_load_keras_state_names():
         ck.load_keras_state(m, {"nope/kernel:0": np.zeros((1,))})
     with pytest.raises(ValueError):
         ck.load_keras_state(m, {"kernel0:0": np.zeros((3, 3), np.float32)})
+
+
+def test_reshard_plan_partitions_every_row_exactly_once():
+    """Property (hypothesis): for any ragged table set and any W -> W', the plans of the W' new ranks together
+    read every saved row exactly once and write every destination row exactly once."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(rows=st.lists(st.integers(1, 200), min_size=1, max_size=6), old_w=st.integers(1, 9), new_w=st.integers(1, 9),
+           chunk=st.integers(1, 64))
+    def prop(rows, old_w, new_w, chunk):
+        _, old_base = ck.shard_rows(rows, old_w)
+        new_rows, new_base = ck.shard_rows(rows, new_w)
+        seen_src = set()
+        for r in range(new_w):
+            seen_dst = set()
+            for s, src, dst in ck.reshard_plan(rows, old_w, new_w, r, chunk_rows=chunk):
+                assert len(src) == len(dst) > 0
+                for a, b in zip(src.tolist(), dst.tolist()):
+                    assert (s, a) not in seen_src and b not in seen_dst
+                    seen_src.add((s, a)); seen_dst.add(b)
+                    # the pair addresses the same global row of the same field
+                    f = int(np.searchsorted(old_base, a, side="right") - 1)
+                    g_old = (a - old_base[f]) * old_w + s
+                    f2 = int(np.searchsorted(new_base, b, side="right") - 1)
+                    g_new = (b - new_base[f2]) * new_w + r
+                    assert f == f2 and g_old == g_new < rows[f]
+            assert len(seen_dst) == sum(len(range(r, R, new_w)) for R in rows)
+        assert len(seen_src) == sum(rows)
+
+    prop()
