@@ -41,7 +41,7 @@ __device__ __forceinline__ void epilogue_rows(const float* stg, int rows_here, i
   const int col = lane * CPL;
   if (col >= ncols) return;
   const bool lane_full = col + CPL <= ncols;
-  const bool vec = vec_ok && lane_full && CPL == 4;
+  const bool vec = vec_ok && lane_full && (CPL % 4) == 0;
   float bv[CPL];
 #pragma unroll
   for (int e = 0; e < CPL; ++e) bv[e] = (NEED_BIAS && col + e < ncols) ? bias[col + e] : 0.f;
@@ -56,9 +56,13 @@ __device__ __forceinline__ void epilogue_rows(const float* stg, int rows_here, i
       if (NEED_AUX || EPI == RS_EPI_ACCUM) {
         const CT* src = (NEED_AUX ? a_rows + (int64_t)rr * ldaux : c_rows + (int64_t)rr * ldc) + col;
         if (vec) {
-          const float4 a4 = load4<CT>(src);
-          av[u][0] = a4.x;
-          if constexpr (CPL == 4) { av[u][1] = a4.y; av[u][2] = a4.z; av[u][3] = a4.w; }
+          if constexpr (CPL % 4 == 0) {
+#pragma unroll
+            for (int q = 0; q < CPL; q += 4) {
+              const float4 a4 = load4<CT>(src + q);
+              av[u][q] = a4.x; av[u][q + 1] = a4.y; av[u][q + 2] = a4.z; av[u][q + 3] = a4.w;
+            }
+          }
         } else {
 #pragma unroll
           for (int e = 0; e < CPL; ++e)
@@ -83,7 +87,10 @@ __device__ __forceinline__ void epilogue_rows(const float* stg, int rows_here, i
       }
       CT* crow = c_rows + (int64_t)(r0 + u) * ldc + col;
       if (vec) {
-        if constexpr (CPL == 4) store4<CT>(crow, make_float4(v[0], v[1], v[2], v[3]));
+        if constexpr (CPL % 4 == 0) {
+#pragma unroll
+          for (int q = 0; q < CPL; q += 4) store4<CT>(crow + q, make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]));
+        }
       } else {
 #pragma unroll
         for (int e = 0; e < CPL; ++e)
@@ -106,8 +113,11 @@ __device__ __forceinline__ void epilogue_partial(const float* stg, int rows_here
     float* dst = dst_rows + (int64_t)rr * N + col;
     const float* src = stg + rr * PITCH + col;
     if (vec) {
-      if constexpr (CPL == 4) *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src);
-      else if constexpr (CPL == 2) *reinterpret_cast<float2*>(dst) = make_float2(src[0], src[1]);
+      if constexpr (CPL % 4 == 0) {
+#pragma unroll
+        for (int q = 0; q < CPL; q += 4)
+          *reinterpret_cast<float4*>(dst + q) = *reinterpret_cast<const float4*>(src + q);
+      } else if constexpr (CPL == 2) *reinterpret_cast<float2*>(dst) = make_float2(src[0], src[1]);
       else dst[0] = src[0];
     } else {
 #pragma unroll
@@ -690,6 +700,9 @@ int gemm_tf32x3(const void* A, int64_t lda, int transA, const void* B, int64_t l
   else if (N <= 64) BN = 64;
   else if ((int64_t)cdiv(M, TC_BM) * cdiv(N, 128) < sms && N % 128 != 0 && N % 128 <= 64) BN = 64;
   else if ((int64_t)cdiv(M, TC_BM) * cdiv(N, 128) * 2 <= sms) BN = 64;
+  // wide tiles when 128-wide ones would need more than one round of CTAs: the A tile is split (and
+  // streamed by the MMAs) once per 256 output columns instead of once per 128
+  else if (N % 256 == 0 && (int64_t)cdiv(M, TC_BM) * (N / 128) > sms) BN = 256;
   const int tiles = (int)(cdiv(M, TC_BM) * cdiv(N, BN));
   const int kb_total = (int)cdiv(K, T3_BK);
   int splits = 1;
@@ -726,6 +739,7 @@ int gemm_tf32x3(const void* A, int64_t lda, int transA, const void* B, int64_t l
   else { RS_T3_GO2(BNV, ST, false, false); }
   if (BN == 32) { RS_T3_GO(32, 4) }
   else if (BN == 64) { RS_T3_GO(64, 4) }
+  else if (BN == 256) { RS_T3_GO(256, 2) }
   else { RS_T3_GO(128, 3) }
 #undef RS_T3_GO
 #undef RS_T3_GO2

@@ -219,7 +219,7 @@ def test_gemm_f32_splitk_wgrad(cuda_dev, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(512, 200, 100), (2048, 256, 1712), (128, 32, 4096), (300, 72, 260), (4096, 8, 64),
-                                   (16384, 8, 16), (16, 8, 16384), (8200, 12, 16)])
+                                   (16384, 8, 16), (16, 8, 16384), (8200, 12, 16), (16384, 256, 96), (9500, 512, 72)])
 @pytest.mark.parametrize("tA,tB", [(False, False), (True, False), (False, True), (True, True)])
 @pytest.mark.parametrize("epi", [0, 2, 6])
 def test_gemm_f32_tf32x3(cuda_dev, M, N, K, tA, tB, epi):
