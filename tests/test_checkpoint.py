@@ -109,3 +109,50 @@ def test_reshard_plan_partitions_every_row_exactly_once():
         assert len(seen_src) == sum(rows)
 
     prop()
+
+
+def test_keras_import_export_host_logic():
+    """Name mapping of import_keras_autoint / export_keras_autoint on a stub trainer (CPU tensors): packing of the four
+    projections into Wqkvr, `use_res=False`, the ':0' suffix and prefix handling, error cases."""
+    import types
+
+    import torch
+    d = U = 4
+    spec = {"Wqkvr": (d, 4 * U), "bqkvr": (4 * U,), "gamma": (U,), "beta": (U,), "mlp_W0": (3 * d, 8), "mlp_b0": (8,),
+            "out_W": (8 + 3 * U, 1), "out_b": (1,)}
+
+    def stub(use_res=True):
+        cfg = types.SimpleNamespace(use_res=use_res, unit_num=U, embed_dim=d, mlp_hidden=(8,))
+        return types.SimpleNamespace(cfg=cfg, P={k: torch.zeros(s) for k, s in spec.items()})
+
+    rng = np.random.default_rng(0)
+    w = {}
+    for nm in ("query", "key", "value", "res"):
+        w[f"model/{nm}_dense/kernel:0"] = rng.standard_normal((d, U)).astype(np.float32)
+        w[f"model/{nm}_dense/bias:0"] = rng.standard_normal(U).astype(np.float32)
+    w["model/layer_normalization/gamma:0"] = rng.standard_normal(U).astype(np.float32)
+    w["model/layer_normalization/beta:0"] = rng.standard_normal(U).astype(np.float32)
+    w["model/dense_0/kernel"] = rng.standard_normal((3 * d, 8)).astype(np.float32)       # MultiLayerDense default names, no ':0'
+    w["model/dense_0/bias"] = rng.standard_normal(8).astype(np.float32)
+    w["model/logits/kernel:0"] = rng.standard_normal((8 + 3 * U, 1)).astype(np.float32)
+    w["model/logits/bias:0"] = rng.standard_normal(1).astype(np.float32)
+    tr = stub()
+    rep = ck.import_keras_autoint(tr, w, prefix="model/")
+    assert rep["mlp_W0"] == "dense_0/kernel" and rep["gamma"] == "layer_normalization/gamma"
+    for i, nm in enumerate(("query", "key", "value", "res")):
+        np.testing.assert_array_equal(tr.P["Wqkvr"][:, i * U:(i + 1) * U].numpy(), w[f"model/{nm}_dense/kernel:0"])
+        np.testing.assert_array_equal(tr.P["bqkvr"][i * U:(i + 1) * U].numpy(), w[f"model/{nm}_dense/bias:0"])
+    back = ck.export_keras_autoint(tr)
+    np.testing.assert_array_equal(back["res_dense/kernel:0"], w["model/res_dense/kernel:0"])
+    np.testing.assert_array_equal(back["mlp_0/kernel:0"], w["model/dense_0/kernel"])
+
+    # use_res=False: no res_dense weights expected, the packed block stays zero and is not exported
+    w2 = {k: v for k, v in w.items() if "res_dense" not in k}
+    tr2 = stub(use_res=False)
+    ck.import_keras_autoint(tr2, w2, prefix="model/")
+    assert float(tr2.P["Wqkvr"][:, 3 * U:].abs().sum()) == 0.0
+    assert "res_dense/kernel:0" not in ck.export_keras_autoint(tr2)
+    with pytest.raises(KeyError):
+        ck.import_keras_autoint(stub(use_res=False), w, prefix="model/")        # stray res_dense weights
+    with pytest.raises(KeyError):
+        ck.import_keras_autoint(stub(), w2, prefix="model/")                     # res_dense missing
