@@ -59,3 +59,39 @@ def test_no_cpu_fallback_for_host_tensors():
     from recommendsystem_b200 import ops
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.transpose2d(torch.zeros(4, 4))
+
+
+def test_product_never_imports_the_oracle_or_the_reference():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may use it, and
+    nothing that runs on the GPU box may read /root/reference.  Enforced on the sources (AST import scan)."""
+    import ast
+    import pathlib
+    root = pathlib.Path(__file__).resolve().parent.parent
+    offenders = []
+    for path in sorted((root / "recommendsystem_b200").rglob("*.py")):
+        tree = ast.parse(path.read_text())
+        for node in ast.walk(tree):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            if any(n == "oracle" or n.startswith("oracle.") for n in names):
+                offenders.append(f"{path.relative_to(root)}:{node.lineno}")
+        if "/root/reference" in path.read_text():
+            offenders.append(f"{path.relative_to(root)}: mentions /root/reference")
+    assert not offenders, offenders
+    # bench.py and __graft_entry__.py may import the oracle, but only inside the functions that are the CPU legs
+    for fname, allowed in (("bench.py", {"cpu_autoint_samples_per_s", "run_reference"}), ("__graft_entry__.py", {"smoke", "build"})):
+        tree = ast.parse((root / fname).read_text())
+        for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)]:
+            for node in ast.walk(fn):
+                mods = [a.name for a in node.names] if isinstance(node, ast.Import) else (
+                    [node.module or ""] if isinstance(node, ast.ImportFrom) else [])
+                if any(m == "oracle" or m.startswith("oracle.") for m in mods):
+                    assert fn.name in allowed, f"{fname}:{node.lineno} imports oracle inside {fn.name}()"
+        top = [n for n in tree.body if isinstance(n, (ast.Import, ast.ImportFrom))]
+        for node in top:
+            mods = [a.name for a in node.names] if isinstance(node, ast.Import) else [node.module or ""]
+            assert not any(m == "oracle" or m.startswith("oracle.") for m in mods), f"{fname}: top-level oracle import"
+        assert "/root/reference" not in (root / fname).read_text(), fname
