@@ -148,7 +148,7 @@ class AutoIntTrainer:
         self.X = e(B, F, d)
         self.keys = torch.empty(B * F, dtype=torch.int64, device=self.dev)
         self.keys_sorted = torch.empty_like(self.keys)
-        self.saved = e(cfg.layer_num, B * F, U, dtype=torch.float32)     # rs_interacting_saved_bytes
+        self.saved = ops.interacting_saved(B, F, U, cfg.layer_num, self.dev)
         self.H = [e(B, w) for w in cfg.mlp_hidden[:-1]]
         self.Z = e(B, self.zw)
         self.p_raw = e(B, 1)

@@ -27,7 +27,8 @@ size_t rs_interacting_workspace_bytes(int B, int F, int D, int U) {
 }
 
 size_t rs_interacting_saved_bytes(int B, int F, int U, int L) {
-  return (size_t)L * (size_t)B * (size_t)F * (size_t)U * sizeof(float);
+  // [L, B*F, U] activations, then [L, B*F, 4] per-head softmax statistics of the tensor-core kernels
+  return (size_t)L * (size_t)B * (size_t)F * (size_t)(U + 4) * sizeof(float);
 }
 
 int rs_interacting_fwd_dropout(const void* x, int64_t x_ld, int64_t x_bs, int dtype, const float* Wqkvr,

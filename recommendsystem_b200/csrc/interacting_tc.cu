@@ -26,29 +26,35 @@
 namespace rs {
 
 
-template <int D, int U, int H, int NCHF, typename T>
+// samples per 128-row tile: whole samples of FP = 8 NCHF padded fields, at most 4 (the expanded Q operand has
+// 8 SPT columns per head and the P.V product N = 8 SPT <= 32)
+template <int NCHF> struct ItcGeom {
+  static constexpr int FP = NCHF * 8;
+  static constexpr int SPT = (128 / FP) < 4 ? (128 / FP) : 4;
+  static constexpr int NCHK = SPT * 2;                 // 16-byte chunks per row of the expanded K operand (tf32)
+  static constexpr int KP = (FP + 15) / 16 * 16;       // key dimension padded to the bf16 K step
+  static constexpr int KX_BYTES = NCHF * NCHK * 128;   // [FP keys][8 SPT] tf32
+  static constexpr int VX_BYTES = (KP / 8) * 512;      // [KP keys][32 = (sample, e)] bf16, MN-major
+};
+
+template <int NCHF, typename T>
 __global__ void __launch_bounds__(128, 2)
 interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, const float* __restrict__ W,
                           const float* __restrict__ bias, const float* __restrict__ gamma,
                           const float* __restrict__ beta, float eps, T* __restrict__ y, int64_t y_ld,
                           int64_t y_bs, float* __restrict__ saved, int B, int F, int L, int use_res) {
-  static_assert(D == 16 && U == 16 && H == 2, "tensor-core path is built for D = U = 16, 2 heads");
-  constexpr int DH = U / H;          // 8 -> one tf32 K step
-  constexpr int N4 = 4 * U;          // 64
-  constexpr int FP = NCHF * 8;       // padded fields per sample (key-window width)
-  constexpr int SPT = 128 / FP;      // samples per tile
-  // ---- shared memory carve-up (1024-byte aligned base for the swizzled P tiles)
-  constexpr int P_BYTES = 128 * 256;             // [128 rows][128 keys] bf16
-  constexpr int OFF_P = 0;                       // H buffers
-  constexpr int OFF_X = OFF_P + H * P_BYTES;     // [128][x_hi(16) | x_lo(16)] tf32, 8 chunks/row  16 KB
-  constexpr int OFF_V = OFF_X + 16384;           // [128 keys][16] bf16            4 KB
-  constexpr int OFF_Q = OFF_V + 4096;            // H x [128][8] tf32, 2 chunks/row
-  constexpr int OFF_K = OFF_Q + H * 4096;
-  constexpr int OFF_W = OFF_K + H * 4096;        // W_hi | W_lo, each [64 n][16 k] tf32   8 KB
-  constexpr int OFF_F = OFF_W + 8192;            // bias[64] gamma[16] beta[16] fp32
+  constexpr int D = 16, U = 16, H = 2, DH = 8, N4 = 64;
+  using G = ItcGeom<NCHF>;
+  constexpr int FP = G::FP, SPT = G::SPT, NCHK = G::NCHK, KP = G::KP;
+  constexpr int FMIN = NCHF == 2 ? 0 : FP - 8;           // F > FMIN is guaranteed (NCHF = 2 also serves F <= 8)
+  // ---- shared memory: only B operands live here (every A operand is TMEM-resident)
+  constexpr int OFF_KX = 0;                              // H x [FP keys][8 SPT] tf32, K-major: row j = [k_0j | k_1j | ..]
+  constexpr int OFF_VX = OFF_KX + H * G::KX_BYTES;       // H x [KP keys][32] bf16, MN-major: chunk s of row j = v_sj
+  constexpr int OFF_W = OFF_VX + H * G::VX_BYTES;        // W_hi | W_lo, each [64 n][16 k] tf32
+  constexpr int OFF_F = OFF_W + 8192;                    // bias[64] gamma[16] beta[16] fp32
   constexpr int OFF_BAR = OFF_F + (N4 + 2 * U) * 4;
   extern __shared__ uint8_t itc_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(itc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(itc_smem_raw) + 127) & ~(uintptr_t)127);
   float* bs = reinterpret_cast<float*>(smem + OFF_F);
   float* gs = bs + N4;
   float* be = gs + U;
@@ -56,43 +62,53 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  // ---- one-time setup: barrier, TMEM, weights (bf16 W^T in UMMA layout), zeroed P buffers
   if (tid == 0) {
-    mbar_init(bar, 2);
+    mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = tid; i < H * P_BYTES / 16; i += 128) reinterpret_cast<uint4*>(smem + OFF_P)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < OFF_W / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < N4 + 2 * U; i += 128) bs[i] = i < N4 ? bias[i] : (i < N4 + U ? gamma[i - N4] : beta[i - N4 - U]);
-  stage_w_3xtf32(smem + OFF_W, W, tid, 128);     // B operands of the projection
+  stage_w_3xtf32(smem + OFF_W, W, tid, 128);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;        // this warp's TMEM lanes
-  constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_Z = 128, TM_O0 = 0, TM_O1 = 128;
-
-  // descriptors that never change
+  const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's TMEM lanes (thread = lane = tile row)
+  // TMEM columns: Z (64; later O_h at h*32) | S_h at 64 + h*FP (P_h, packed bf16, over its first KP/2 columns) |
+  // expanded Q_h at 160 + h*32 | [x_hi | x_lo] at 224
+  constexpr uint32_t C_Z = 0, C_S = 64, C_QX = 160, C_X = 224;
+  {
+    uint32_t z16[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z16[i] = 0u;
+#pragma unroll
+    for (int c = 0; c < 64; c += 16) tc_st_32x16(tl + C_QX + c, z16);   // a lane only ever rewrites its own samples' columns
+    tc_wait_st();
+  }
   const uint32_t sbase = smem_u32(smem);
+  const uint32_t b16 = sbase >> 4;
   constexpr uint32_t ID_Z = make_idesc(2, 128, N4, 0, 0);               // tf32, N = 64
-  constexpr uint32_t ID_S = make_idesc(2, 128, 128, 0, 0);              // tf32, N = 128
-  constexpr uint32_t ID_O = make_idesc(1, 128, U, 0, 1);                // bf16, B = V MN-major, N = 16
+  constexpr uint32_t ID_S = make_idesc(2, 128, FP, 0, 0);               // tf32, N = FP, K = 8 per sample
+  constexpr uint32_t ID_O = make_idesc(1, 128, 32, 0, 1);               // bf16, B = V MN-major, N = 32
 
   const int s_loc = tid / FP, f_loc = tid - s_loc * FP;
-  const int issuer = tid == 0 ? 0 : (tid == 32 ? 1 : -1);   // one MMA issuer per head; both commit every phase
+  const bool in_tile = s_loc < SPT;
   const int ntiles = (B + SPT - 1) / SPT;
   const float scale_log2 = ITC_LOG2E / sqrtf((float)DH);
   uint32_t phase = 0;
   // samples whose rows intersect this warp's 32 lanes (warp-uniform loop bounds)
-  const int ws_lo = (warp * 32) / FP, ws_hi = min((warp * 32 + 31) / FP, SPT - 1);
+  const int ws_lo = min((warp * 32) / FP, SPT - 1), ws_hi = min((warp * 32 + 31) / FP, SPT - 1);
+  const int64_t total_rows = (int64_t)B * F;
+  float* lse_base = saved ? saved + (int64_t)L * total_rows * U : nullptr;
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t smp = (int64_t)tile * SPT + s_loc;
-    const bool active = s_loc < SPT && f_loc < F && smp < B;
+    const bool active = in_tile && f_loc < F && smp < B;
     float xr[D];
     if (active) {
 #pragma unroll
@@ -106,162 +122,186 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
     }
     float yv[U];
     for (int it = 0; it < L; ++it) {
-      // ---- 1. X tile (3xTF32 split of the fp32 row) -> Z = X W, fp32-grade
+      // ---- 1. [x_hi | x_lo] -> TMEM ; Z = X W (3xTF32: fp32-grade pre-activations)
+      {
+        uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        stage_x4_3xtf32(smem + OFF_X, tid, c, xr[c * 4], xr[c * 4 + 1], xr[c * 4 + 2], xr[c * 4 + 3]);
-      fence_async_smem();
+        for (int c = 0; c < D; ++c) {
+          const float h_ = tf32_hi(xr[c]);
+          hi[c] = __float_as_uint(h_);
+          lo[c] = __float_as_uint(xr[c] - h_);
+        }
+        tc_st_32x16(tl + C_X, hi);
+        tc_st_32x16(tl + C_X + 16, lo);
+        tc_wait_st();
+      }
       tc_fence_before();
       __syncthreads();
-      if (issuer >= 0) {
+      if (tid == 0) {
         tc_fence_after();
-        if (issuer == 0) issue_proj_3xtf32(tmem + TM_Z, sbase + OFF_X, sbase + OFF_W, ID_Z);
+        issue_proj_3xtf32_ts(tmem + C_Z, tmem + C_X, sbase + OFF_W, ID_Z);
         tc_commit(bar);
       }
       mbar_wait(bar, phase); phase ^= 1u;
       tc_fence_after();
-      float q[U], r[U];
+      float r[U];
       {
         uint32_t z[32];
-        tc_ld_32x32(tmem + lane_base + TM_Z, z);                       // q | k pre-activations
+        tc_ld_32x32(tl + C_Z, z);                                      // q | k pre-activations
+        float q[U], kk[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) q[u] = fmaxf(__uint_as_float(z[u]) + bs[u], 0.f);
-        float kk[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) kk[u] = fmaxf(__uint_as_float(z[U + u]) + bs[U + u], 0.f);
+        for (int u = 0; u < U; ++u) {
+          q[u] = active ? fmaxf(__uint_as_float(z[u]) + bs[u], 0.f) : 0.f;
+          kk[u] = active ? fmaxf(__uint_as_float(z[U + u]) + bs[U + u], 0.f) : 0.f;
+        }
 #pragma unroll
         for (int h = 0; h < H; ++h) {
+          for (int s = ws_lo; s <= ws_hi; ++s) {                       // warp-uniform: 1 or 2 trips
+            uint32_t v8[8];
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {                                // tf32 = fp32 bits, 4 per chunk
-            *reinterpret_cast<float4*>(smem + OFF_Q + h * 4096 + nosw_off<2>(tid, c)) =
-                make_float4(q[h * DH + c * 4], q[h * DH + c * 4 + 1], q[h * DH + c * 4 + 2], q[h * DH + c * 4 + 3]);
-            *reinterpret_cast<float4*>(smem + OFF_K + h * 4096 + nosw_off<2>(tid, c)) =
-                make_float4(kk[h * DH + c * 4], kk[h * DH + c * 4 + 1], kk[h * DH + c * 4 + 2], kk[h * DH + c * 4 + 3]);
+            for (int e = 0; e < DH; ++e) v8[e] = s == s_loc ? __float_as_uint(q[h * DH + e]) : 0u;
+            tc_st_32x8(tl + C_QX + h * 32 + s * 8, v8);
+          }
+          if (in_tile) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+              *reinterpret_cast<float4*>(smem + OFF_KX + h * G::KX_BYTES + nosw_off<NCHK>(f_loc, s_loc * 2 + c)) =
+                  make_float4(kk[h * DH + c * 4], kk[h * DH + c * 4 + 1], kk[h * DH + c * 4 + 2], kk[h * DH + c * 4 + 3]);
           }
         }
-      }
-      uint32_t zvr[32];                                                // v | r pre-activations: read now (S_1 aliases
-      tc_ld_32x32(tmem + lane_base + TM_Z + 32, zvr);                  // these columns), used under the S MMA
-      // ---- 2. S_h = Q_h K_h^T (both heads), Z columns are dead now
-      fence_async_smem();
-      tc_fence_before();
-      __syncthreads();
-      if (issuer >= 0) {
-        tc_fence_after();
-        const int h = issuer;
-        tc_mma_tf32(tmem + (h == 0 ? TM_S0 : TM_S1), make_nosw_desc(sbase + OFF_Q + h * 4096, 128, 256),
-                    make_nosw_desc(sbase + OFF_K + h * 4096, 128, 256), ID_S, 0u);
-        tc_commit(bar);
-      }
-      {
+        uint32_t zvr[32];
+        tc_ld_32x32(tl + C_Z + 32, zvr);                               // v | r pre-activations
         float vv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          vv[u] = fmaxf(__uint_as_float(zvr[u]) + bs[2 * U + u], 0.f);
+          vv[u] = active ? fmaxf(__uint_as_float(zvr[u]) + bs[2 * U + u], 0.f) : 0.f;
           r[u] = fmaxf(__uint_as_float(zvr[U + u]) + bs[3 * U + u], 0.f);
         }
+        if (in_tile) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {                                  // V: MN-major B, row = key (read by P.V, phase 3)
-          uint4 v;
-          v.x = pack_bf16x2(vv[c * 8 + 0], vv[c * 8 + 1]); v.y = pack_bf16x2(vv[c * 8 + 2], vv[c * 8 + 3]);
-          v.z = pack_bf16x2(vv[c * 8 + 4], vv[c * 8 + 5]); v.w = pack_bf16x2(vv[c * 8 + 6], vv[c * 8 + 7]);
-          *reinterpret_cast<uint4*>(smem + OFF_V + nosw_off<2>(tid, c)) = v;
+          for (int h = 0; h < H; ++h) {
+            uint4 v;
+            v.x = pack_bf16x2(vv[h * DH + 0], vv[h * DH + 1]); v.y = pack_bf16x2(vv[h * DH + 2], vv[h * DH + 3]);
+            v.z = pack_bf16x2(vv[h * DH + 4], vv[h * DH + 5]); v.w = pack_bf16x2(vv[h * DH + 6], vv[h * DH + 7]);
+            *reinterpret_cast<uint4*>(smem + OFF_VX + h * G::VX_BYTES + nosw_off<4>(f_loc, s_loc)) = v;
+          }
         }
+      }
+      // ---- 2. S_h[row, j] = q_row . k_(own sample, j): the Q operand is expanded along K by sample (zeros in the
+      //         other samples' slots), so all 128 rows read THEIR keys from the same FP columns
+      fence_async_smem();
+      tc_wait_st();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+#pragma unroll
+          for (int ks = 0; ks < SPT; ++ks)
+            tc_mma_tf32_ts(tmem + C_S + h * FP, tmem + C_QX + h * 32 + ks * 8,
+                           mk_desc(b16, OFF_KX + h * G::KX_BYTES + ks * 256, 128, NCHK * 128), ID_S, ks ? 1u : 0u);
+        tc_commit(bar);
       }
       mbar_wait(bar, phase); phase ^= 1u;
       tc_fence_after();
-      float linv[H];
+      float linv[H], lse2[H];
 #pragma unroll
       for (int h = 0; h < H; ++h) {
         float p[FP];
-#pragma unroll
-        for (int j = 0; j < FP; ++j) p[j] = -INFINITY;
-        for (int s = ws_lo; s <= ws_hi; ++s) {                          // warp-uniform; 1 or 2 trips
-          const uint32_t col = (h == 0 ? TM_S0 : TM_S1) + (uint32_t)(s * FP);
-          const bool mine = s == s_loc;
+        {
+          uint32_t t[FP];
 #pragma unroll
           for (int c0 = 0; c0 < FP; c0 += 8) {
             uint32_t t8[8];
-            tc_ld_32x8(tmem + lane_base + col + c0, t8);
-            tc_wait_ld();
+            tc_ld_32x8(tl + C_S + h * FP + c0, t8);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (mine && c0 + j < F) p[c0 + j] = __uint_as_float(t8[j]);
+            for (int j = 0; j < 8; ++j) t[c0 + j] = t8[j];
           }
-        }
-        float m4[4] = {p[0], p[1], p[2], p[3]};
+          tc_wait_ld();
 #pragma unroll
-        for (int j = 4; j < FP; ++j) m4[j & 3] = fmaxf(m4[j & 3], p[j]);
-        float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        if (!active) m = 0.f;
+          for (int j = 0; j < FP; ++j) p[j] = (j < FMIN || j < F) ? __uint_as_float(t[j]) : -INFINITY;
+        }
+        float m3[2] = {p[0], p[1]};
+#pragma unroll
+        for (int j = 2; j + 1 < FP; j += 2) m3[(j >> 1) & 1] = fmax3(m3[(j >> 1) & 1], p[j], p[j + 1]);
+        const float m = fmaxf(m3[0], m3[1]);
         const float mb = m * scale_log2;
-        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+        const float2 c2 = make_float2(scale_log2, scale_log2), nmb2 = make_float2(-mb, -mb);
+        float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < FP; j += 2) {
-          // -inf -> 0 for padded keys; round to the bf16 value the MMA will see, so that the
-          // normaliser l is the sum of exactly the weights used (a true convex combination).
-          // (same expression as the backward's recomputation: interacting_tc_bwd.cu)
-          p[j] = ex2_approx(fmaf(p[j], scale_log2, -mb));
-          p[j + 1] = ex2_approx(fmaf(p[j + 1], scale_log2, -mb));
-          bf16_round2(p[j], p[j + 1]);
-          l4[j & 3] += p[j];
-          l4[(j + 1) & 3] += p[j + 1];
+        for (int j = 0; j < FP; j += 4) {
+          float2 t0 = ffma2(make_float2(p[j], p[j + 1]), c2, nmb2);
+          float2 t1 = ffma2(make_float2(p[j + 2], p[j + 3]), c2, nmb2);
+          t0.x = ex2_approx(t0.x); t0.y = ex2_approx(t0.y);
+          t1.x = ex2_approx(t1.x); t1.y = ex2_approx(t1.y);
+          l2a = fadd2(l2a, t0);
+          l2b = fadd2(l2b, t1);
+          p[j] = t0.x; p[j + 1] = t0.y; p[j + 2] = t1.x; p[j + 3] = t1.y;
         }
-        const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        const float l = (l2a.x + l2a.y) + (l2b.x + l2b.y);
         linv[h] = active ? 1.f / l : 0.f;
-        // P row: chunks [s_loc*NCHF, +NCHF) of the 16 chunks, SWIZZLE_128B (chunk ^= row & 7)
-        if (s_loc < SPT) {
+        lse2[h] = mb + lg2_approx(l);
+        // unnormalised bf16 P row -> TMEM (A operand of P.V), zero beyond the FP keys and for idle rows
 #pragma unroll
-          for (int c = 0; c < NCHF; ++c) {
-            const int ch = s_loc * NCHF + c;                           // 0..15
-            uint4 v;
-            v.x = pack_bf16x2(p[c * 8 + 0], p[c * 8 + 1]); v.y = pack_bf16x2(p[c * 8 + 2], p[c * 8 + 3]);
-            v.z = pack_bf16x2(p[c * 8 + 4], p[c * 8 + 5]); v.w = pack_bf16x2(p[c * 8 + 6], p[c * 8 + 7]);
-            if (!active) v = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(smem + OFF_P + h * P_BYTES + (ch >> 3) * 16384 + tid * 128 +
-                                      (((ch & 7) ^ (tid & 7)) << 4)) = v;
+        for (int c0 = 0; c0 < KP / 2; c0 += 8) {
+          uint32_t v8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int j = (c0 + e) * 2;
+            v8[e] = (j < FP && active) ? pack_bf16x2(p[j < FP ? j : 0], p[j + 1 < FP ? j + 1 : 0]) : 0u;
           }
+          tc_st_32x8(tl + C_S + h * FP + c0, v8);
         }
       }
-      // ---- 3. O_h = P_h V  (K = 128 keys = 8 steps of 16), S columns are dead now
-      fence_async_smem();
+      // ---- 3. O_h[row, (s, e)] = sum_j P[row, j] v_(s, j)[e]; a row keeps the 8 columns of its own sample
+      tc_wait_st();
       tc_fence_before();
       __syncthreads();
-      if (issuer >= 0) {
+      if (tid == 0) {
         tc_fence_after();
-        const int h = issuer;
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t pa = sbase + OFF_P + h * P_BYTES + (ks >> 2) * 16384 + (ks & 3) * 32;
-          // V advances 16 keys = 2 K-groups of 256 B per step
-          tc_mma_bf16(tmem + (h == 0 ? TM_O0 : TM_O1), make_sw128_kmajor_desc(pa),
-                      make_nosw_desc(sbase + OFF_V + ks * 512, 256, 128), ID_O, ks ? 1u : 0u);
-        }
+        for (int h = 0; h < H; ++h)
+#pragma unroll
+          for (int ks = 0; ks < KP / 16; ++ks)
+            tc_mma_bf16_ts(tmem + C_Z + h * 32, tmem + C_S + h * FP + ks * 8,
+                           mk_desc(b16, OFF_VX + h * G::VX_BYTES + ks * 1024, 512, 128), ID_O, ks ? 1u : 0u);
         tc_commit(bar);
+      }
+      if (active && saved) {
+        float* lp = lse_base + ((int64_t)it * total_rows + smp * F + f_loc) * H;
+        *reinterpret_cast<float2*>(lp) = make_float2(lse2[0], lse2[1]);
       }
       mbar_wait(bar, phase); phase ^= 1u;
       tc_fence_after();
       {
         float o[U];
 #pragma unroll
-        for (int h = 0; h < H; ++h) {
-          uint32_t t16[16];
-          tc_ld_32x16(tmem + lane_base + (h == 0 ? TM_O0 : TM_O1), t16);
+        for (int u = 0; u < U; ++u) o[u] = 0.f;
+        for (int s = ws_lo; s <= ws_hi; ++s) {
+          uint32_t t0[8], t1[8];
+          tc_ld_32x8(tl + C_Z + s * 8, t0);
+          tc_ld_32x8(tl + C_Z + 32 + s * 8, t1);
           tc_wait_ld();
+          if (s == s_loc) {
 #pragma unroll
-          for (int e = 0; e < DH; ++e) o[h * DH + e] = __uint_as_float(t16[h * DH + e]) * linv[h];
+            for (int e = 0; e < DH; ++e) { o[e] = __uint_as_float(t0[e]); o[DH + e] = __uint_as_float(t1[e]); }
+          }
         }
         // residual, ReLU, LayerNorm (InteractingLayer.py:57-60)
         float a[U], mean, rstd;
 #pragma unroll
-        for (int u = 0; u < U; ++u) a[u] = fmaxf(use_res ? o[u] + r[u] : o[u], 0.f);
+        for (int u = 0; u < U; ++u) {
+          const float on = o[u] * linv[u / DH];
+          a[u] = fmaxf(use_res ? on + r[u] : on, 0.f);
+        }
         ln_row_stats<U>(a, eps, mean, rstd);
 #pragma unroll
         for (int u = 0; u < U; ++u) yv[u] = ln_apply(a[u], mean, rstd, gs[u], be[u]);
         // saved for the backward: the pre-LayerNorm activations of EVERY iteration (the backward
         // re-derives each iteration's input as LayerNorm(a) and differentiates ReLU/LayerNorm at a)
         if (active && saved) {
-          float* sp = saved + ((int64_t)it * B * F + smp * F + f_loc) * U;
+          float* sp = saved + ((int64_t)it * total_rows + smp * F + f_loc) * U;
 #pragma unroll
           for (int u = 0; u < U; u += 4) *reinterpret_cast<float4*>(sp + u) = make_float4(a[u], a[u + 1], a[u + 2], a[u + 3]);
         }
@@ -287,11 +327,11 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
 
 template <int NCHF, typename T>
 static int launch_itc_fwd(const IFwdArgs& a) {
-  auto kern = interacting_tc_fwd_kernel<16, 16, 2, NCHF, T>;
-  constexpr int smem = 2 * 128 * 256 + 16384 + 4096 + 2 * 4096 + 2 * 4096 + 8192 + 96 * 4 + 64 + 1024;
+  auto kern = interacting_tc_fwd_kernel<NCHF, T>;
+  using G = ItcGeom<NCHF>;
+  constexpr int smem = 2 * G::KX_BYTES + 2 * G::VX_BYTES + 8192 + 96 * 4 + 64 + 128;
   RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  constexpr int SPT = 128 / (NCHF * 8);
-  const int ntiles = (a.B + SPT - 1) / SPT;
+  const int ntiles = (a.B + G::SPT - 1) / G::SPT;
   int grid = sm_count() * 2;
   if (grid > ntiles) grid = ntiles;
   kern<<<grid, 128, smem, a.st>>>((const T*)a.x, a.x_ld, a.x_bs, a.W, a.b, a.gm, a.bt, a.eps, (T*)a.y, a.y_ld,
@@ -309,7 +349,7 @@ bool interacting_tc_supported(int F, int D, int U, int H, int dtype) {
 
 int interacting_tc_fwd(const IFwdArgs& a) {
   switch ((a.F + 7) / 8) {
-    case 1: return launch_itc_fwd<1, __nv_bfloat16>(a);
+    case 1:                                                            // N = 8 is not an M = 128 shape
     case 2: return launch_itc_fwd<2, __nv_bfloat16>(a);
     case 3: return launch_itc_fwd<3, __nv_bfloat16>(a);
     case 4: return launch_itc_fwd<4, __nv_bfloat16>(a);

@@ -190,13 +190,22 @@ def permute_rows(src, index, scatter=False, out=None):
 # ------------------------------------------------------------- interacting
 
 
+def interacting_saved(B, F, U, L, device):
+    """rs_interacting_saved_bytes(B, F, U, L) bytes; returned as the [L, B*F, U] view of the activations (the
+    per-head softmax statistics of the tensor-core kernels follow them in the same storage)."""
+    n = L * B * F
+    buf = torch.empty(n * (U + 4), dtype=torch.float32, device=device)
+    assert buf.numel() * 4 == cabi.load().rs_interacting_saved_bytes(B, F, U, L)
+    return buf[:n * U].view(L, B * F, U)
+
+
 def interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res=True, save=True, compute_bf16=False,
                     dropout_rate=0.0, dropout_seed=0):
     B, F, D = x.shape
     U = Wqkvr.shape[1] // 4
     _need(x.is_contiguous(), "x must be contiguous")
     y = torch.empty(B, F, U, dtype=x.dtype, device=x.device)
-    saved = torch.empty(L, B * F, U, dtype=torch.float32, device=x.device) if save else None   # rs_interacting_saved_bytes
+    saved = interacting_saved(B, F, U, L, x.device) if save else None
     call("rs_interacting_fwd_dropout", _ptr(x), D, 0, _dt(x), _ptr(Wqkvr), _ptr(bqkvr), _ptr(gamma), _ptr(beta),
          ln_eps, _ptr(y), U, 0, _ptr(saved), B, F, D, U, H, L, int(use_res), int(compute_bf16),
          float(dropout_rate), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _stream())
