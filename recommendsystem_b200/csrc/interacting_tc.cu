@@ -37,8 +37,13 @@ template <int NCHF> struct ItcGeom {
   static constexpr int VX_BYTES = (KP / 8) * 512;      // [KP keys][32 = (sample, e)] bf16, MN-major
 };
 
+// tile-private TMEM columns (per warpgroup): Z [0,64) -> expanded Q_h over [0,32), [32,64) once the thread has its
+// Z row in registers (a lane's columns are private to its thread) -> O_h at h*32 ; S_h at 64 + h*FP with P_h
+// (packed bf16) over its first KP/2 columns and [x_hi | x_lo] over [64,96) before S is issued ; [1 1 0..] at 160
+constexpr uint32_t ITC_TILE_COLS = 168;
+
 template <int NCHF, typename T>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(384, 1)
 interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, const float* __restrict__ W,
                           const float* __restrict__ bias, const float* __restrict__ gamma,
                           const float* __restrict__ beta, float eps, T* __restrict__ y, int64_t y_ld,
@@ -48,81 +53,97 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
   constexpr int FP = G::FP, SPT = G::SPT, NCHK = G::NCHK, KP = G::KP;
   constexpr int FMIN = NCHF == 2 ? 0 : FP - 8;           // F > FMIN is guaranteed (NCHF = 2 also serves F <= 8)
   // ---- shared memory: only B operands live here (every A operand is TMEM-resident)
+  constexpr int WG_BYTES = H * G::KX_BYTES + H * G::VX_BYTES;
   constexpr int OFF_KX = 0;                              // H x [FP keys][8 SPT] tf32, K-major: row j = [k_0j | k_1j | ..]
-  constexpr int OFF_VX = OFF_KX + H * G::KX_BYTES;       // H x [KP keys][32] bf16, MN-major: chunk s of row j = v_sj
-  constexpr int OFF_W = OFF_VX + H * G::VX_BYTES;        // W_hi | W_lo, each [64 n][16 k] tf32
-  constexpr int OFF_F = OFF_W + 8192;                    // bias[64] gamma[16] beta[16] fp32
-  constexpr int OFF_BAR = OFF_F + (N4 + 2 * U) * 4;
-  extern __shared__ uint8_t itc_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(itc_smem_raw) + 127) & ~(uintptr_t)127);
-  float* bs = reinterpret_cast<float*>(smem + OFF_F);
-  float* gs = bs + N4;
-  float* be = gs + U;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  constexpr int OFF_VX = H * G::KX_BYTES;                // H x [KP keys][32] bf16, MN-major: chunk s of row j = v_sj
+  constexpr int OFF_W = 3 * WG_BYTES;                    // W_hi | W_lo, each [64 n][16 k] tf32
+  constexpr int OFF_BT = OFF_W + 8192;                   // [64 n][8 k] tf32: k = 0 b_hi, k = 1 b_lo (bias through the MMA)
+  constexpr int OFF_F = OFF_BT + 2048;                   // gamma[16] beta[16] fp32
+  constexpr int OFF_BAR = OFF_F + 2 * U * 4;
+  extern __shared__ __align__(128) uint8_t itc_smem[];
+  uint8_t* smem = itc_smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  if (tid == 0) {
-    mbar_init(bar, 1);
+  const uint32_t warp = uniform_u32(threadIdx.x >> 5);   // uniform register
+  const uint32_t wg = warp >> 2, wq = warp & 3;          // warpgroup = tile slot, warp within it = TMEM subpartition
+  const int row = threadIdx.x & 127;                     // tile row = TMEM lane
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) mbar_init(bars + i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = tid; i < OFF_W / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < N4 + 2 * U; i += 128) bs[i] = i < N4 ? bias[i] : (i < N4 + U ? gamma[i - N4] : beta[i - N4 - U]);
-  stage_w_3xtf32(smem + OFF_W, W, tid, 128);
+  for (int i = threadIdx.x; i < OFF_W / 16; i += 384) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x < 2 * U) reinterpret_cast<float*>(smem + OFF_F)[threadIdx.x] =
+      threadIdx.x < U ? gamma[threadIdx.x] : beta[threadIdx.x - U];
+  stage_w_3xtf32(smem + OFF_W, W, threadIdx.x, 384);
+  for (int i = threadIdx.x; i < N4 * 2; i += 384) {
+    const int n = i >> 1, c = i & 1;
+    const float bv = bias[n], bh = tf32_hi(bv);
+    *reinterpret_cast<float4*>(smem + OFF_BT + nosw_off<2>(n, c)) = c ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(bh, bv - bh, 0.f, 0.f);
+  }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's TMEM lanes (thread = lane = tile row)
-  // TMEM columns: Z (64; later O_h at h*32) | S_h at 64 + h*FP (P_h, packed bf16, over its first KP/2 columns) |
-  // expanded Q_h at 160 + h*32 | [x_hi | x_lo] at 224
-  constexpr uint32_t C_Z = 0, C_S = 64, C_QX = 160, C_X = 224;
+  const uint32_t tmem = uniform_u32(*tmem_slot) + wg * ITC_TILE_COLS;   // this tile's columns
+  const uint32_t tl = tmem + ((wq * 32u) << 16);                        // this warp's lanes of them
+  constexpr uint32_t C_Z = 0, C_S = 64, C_X = 64, C_ONE = 160;
+  const int s_loc = row / FP, f_loc = row - s_loc * FP;
+  const bool in_tile = s_loc < SPT;
   {
-    uint32_t z16[16];
+    uint32_t one8[8];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) z16[i] = 0u;
-#pragma unroll
-    for (int c = 0; c < 64; c += 16) tc_st_32x16(tl + C_QX + c, z16);   // a lane only ever rewrites its own samples' columns
+    for (int i = 0; i < 8; ++i) one8[i] = i < 2 ? 0x3F800000u : 0u;
+    tc_st_32x8(tl + C_ONE, one8);
     tc_wait_st();
   }
+  uint8_t* wsm = smem + wg * WG_BYTES;
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t b16 = sbase >> 4;
+  const uint32_t wb16 = (sbase + wg * WG_BYTES) >> 4;
+  uint64_t* bar = bars + wg;
+  const float4* gb4 = reinterpret_cast<const float4*>(smem + OFF_F);
   constexpr uint32_t ID_Z = make_idesc(2, 128, N4, 0, 0);               // tf32, N = 64
   constexpr uint32_t ID_S = make_idesc(2, 128, FP, 0, 0);               // tf32, N = FP, K = 8 per sample
   constexpr uint32_t ID_O = make_idesc(1, 128, 32, 0, 1);               // bf16, B = V MN-major, N = 32
 
-  const int s_loc = tid / FP, f_loc = tid - s_loc * FP;
-  const bool in_tile = s_loc < SPT;
   const int ntiles = (B + SPT - 1) / SPT;
   const float scale_log2 = ITC_LOG2E / sqrtf((float)DH);
   uint32_t phase = 0;
-  // samples whose rows intersect this warp's 32 lanes (warp-uniform loop bounds)
-  const int ws_lo = min((warp * 32) / FP, SPT - 1), ws_hi = min((warp * 32 + 31) / FP, SPT - 1);
+  // samples whose rows intersect this warp's 32 lanes (uniform)
+  const uint32_t ws_lo = min((wq * 32u) / FP, (uint32_t)(SPT - 1)), ws_hi = min((wq * 32u + 31u) / FP, (uint32_t)(SPT - 1));
   const int64_t total_rows = (int64_t)B * F;
   float* lse_base = saved ? saved + (int64_t)L * total_rows * U : nullptr;
+  const int tstride = (int)gridDim.x * 3;
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int64_t smp = (int64_t)tile * SPT + s_loc;
-    const bool active = in_tile && f_loc < F && smp < B;
-    float xr[D];
-    if (active) {
+  auto load_x = [&](int tile_, float (&dst)[D]) {
+    const int64_t smp_ = (int64_t)tile_ * SPT + s_loc;
+    if (in_tile && f_loc < F && smp_ < B) {
 #pragma unroll
       for (int c = 0; c < D; c += 4) {
-        const float4 t4 = load4<T>(x + smp * x_bs + (int64_t)f_loc * x_ld + c);
-        xr[c] = t4.x; xr[c + 1] = t4.y; xr[c + 2] = t4.z; xr[c + 3] = t4.w;
+        const float4 t4 = load4<T>(x + smp_ * x_bs + (int64_t)f_loc * x_ld + c);
+        dst[c] = t4.x; dst[c + 1] = t4.y; dst[c + 2] = t4.z; dst[c + 3] = t4.w;
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < D; ++c) xr[c] = 0.f;
+      for (int c = 0; c < D; ++c) dst[c] = 0.f;
     }
-    float yv[U];
+  };
+  auto wg_sync = [&]() { named_bar_sync(1 + wg, 128); };
+
+  int tile = (int)blockIdx.x * 3 + (int)wg;
+  float xr[D];
+  if (tile < ntiles) load_x(tile, xr);
+  for (; tile < ntiles; tile += tstride) {
+    const int64_t smp = (int64_t)tile * SPT + s_loc;
+    const bool active = in_tile && f_loc < F && smp < B;
+    float yv[U], xn[D];
     for (int it = 0; it < L; ++it) {
-      // ---- 1. [x_hi | x_lo] -> TMEM ; Z = X W (3xTF32: fp32-grade pre-activations)
+      // ---- 1. [x_hi | x_lo] -> TMEM ; Z = [X | 1] [W ; b] (3xTF32: fp32-grade pre-activations, bias included)
       {
         uint32_t hi[16], lo[16];
 #pragma unroll
@@ -136,71 +157,69 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
         tc_wait_st();
       }
       tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
+      wg_sync();
+      if (wq == 0 && elect_one()) {
         tc_fence_after();
         issue_proj_3xtf32_ts(tmem + C_Z, tmem + C_X, sbase + OFF_W, ID_Z);
+        tc_mma_tf32_ts(tmem + C_Z, tmem + C_ONE, make_nosw_desc(sbase + OFF_BT, 128, 256), ID_Z, 1u);
         tc_commit(bar);
       }
+      if (it + 1 == L && tile + tstride < ntiles) load_x(tile + tstride, xn);      // next tile's rows: a whole step of cover
       mbar_wait(bar, phase); phase ^= 1u;
       tc_fence_after();
       float r[U];
       {
-        uint32_t z[32];
-        tc_ld_32x32(tl + C_Z, z);                                      // q | k pre-activations
-        float q[U], kk[U];
+        uint32_t z[32], zvr[32];
+        tc_ld_32x32(tl + C_Z, z);                                      // q | k
+        tc_ld_32x32(tl + C_Z + 32, zvr);                               // v | r   (all of Z in registers: its columns are reused)
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          q[u] = active ? fmaxf(__uint_as_float(z[u]) + bs[u], 0.f) : 0.f;
-          kk[u] = active ? fmaxf(__uint_as_float(z[U + u]) + bs[U + u], 0.f) : 0.f;
-        }
+        for (int u = 0; u < 2 * U; ++u) z[u] = __float_as_uint(fmaxf(__uint_as_float(z[u]), 0.f));
 #pragma unroll
         for (int h = 0; h < H; ++h) {
-          for (int s = ws_lo; s <= ws_hi; ++s) {                       // warp-uniform: 1 or 2 trips
+          // every sample slot is rewritten (zeros outside the row's own sample): the columns held Z a moment ago
+#pragma unroll
+          for (int s = 0; s < SPT; ++s) {
             uint32_t v8[8];
 #pragma unroll
-            for (int e = 0; e < DH; ++e) v8[e] = s == s_loc ? __float_as_uint(q[h * DH + e]) : 0u;
-            tc_st_32x8(tl + C_QX + h * 32 + s * 8, v8);
+            for (int e = 0; e < DH; ++e) v8[e] = s == s_loc ? z[h * DH + e] : 0u;
+            tc_st_32x8(tl + C_Z + h * 32 + s * 8, v8);
           }
           if (in_tile) {
 #pragma unroll
             for (int c = 0; c < 2; ++c)
-              *reinterpret_cast<float4*>(smem + OFF_KX + h * G::KX_BYTES + nosw_off<NCHK>(f_loc, s_loc * 2 + c)) =
-                  make_float4(kk[h * DH + c * 4], kk[h * DH + c * 4 + 1], kk[h * DH + c * 4 + 2], kk[h * DH + c * 4 + 3]);
+              *reinterpret_cast<uint4*>(wsm + OFF_KX + h * G::KX_BYTES + nosw_off<NCHK>(f_loc, s_loc * 2 + c)) =
+                  make_uint4(z[U + h * DH + c * 4], z[U + h * DH + c * 4 + 1], z[U + h * DH + c * 4 + 2], z[U + h * DH + c * 4 + 3]);
           }
-        }
-        uint32_t zvr[32];
-        tc_ld_32x32(tl + C_Z + 32, zvr);                               // v | r pre-activations
-        float vv[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          vv[u] = active ? fmaxf(__uint_as_float(zvr[u]) + bs[2 * U + u], 0.f) : 0.f;
-          r[u] = fmaxf(__uint_as_float(zvr[U + u]) + bs[3 * U + u], 0.f);
         }
         if (in_tile) {
 #pragma unroll
           for (int h = 0; h < H; ++h) {
+            float vv[DH];
+#pragma unroll
+            for (int e = 0; e < DH; ++e) vv[e] = fmaxf(__uint_as_float(zvr[h * DH + e]), 0.f);
             uint4 v;
-            v.x = pack_bf16x2(vv[h * DH + 0], vv[h * DH + 1]); v.y = pack_bf16x2(vv[h * DH + 2], vv[h * DH + 3]);
-            v.z = pack_bf16x2(vv[h * DH + 4], vv[h * DH + 5]); v.w = pack_bf16x2(vv[h * DH + 6], vv[h * DH + 7]);
-            *reinterpret_cast<uint4*>(smem + OFF_VX + h * G::VX_BYTES + nosw_off<4>(f_loc, s_loc)) = v;
+            v.x = pack_bf16x2(vv[0], vv[1]); v.y = pack_bf16x2(vv[2], vv[3]);
+            v.z = pack_bf16x2(vv[4], vv[5]); v.w = pack_bf16x2(vv[6], vv[7]);
+            *reinterpret_cast<uint4*>(wsm + OFF_VX + h * G::VX_BYTES + nosw_off<4>(f_loc, s_loc)) = v;
           }
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u) r[u] = fmaxf(__uint_as_float(zvr[U + u]), 0.f);
       }
       // ---- 2. S_h[row, j] = q_row . k_(own sample, j): the Q operand is expanded along K by sample (zeros in the
       //         other samples' slots), so all 128 rows read THEIR keys from the same FP columns
       fence_async_smem();
       tc_wait_st();
       tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
+      wg_sync();
+      if (wq == 0 && elect_one()) {
         tc_fence_after();
 #pragma unroll
         for (int h = 0; h < H; ++h)
 #pragma unroll
           for (int ks = 0; ks < SPT; ++ks)
-            tc_mma_tf32_ts(tmem + C_S + h * FP, tmem + C_QX + h * 32 + ks * 8,
-                           mk_desc(b16, OFF_KX + h * G::KX_BYTES + ks * 256, 128, NCHK * 128), ID_S, ks ? 1u : 0u);
+            tc_mma_tf32_ts(tmem + C_S + h * FP, tmem + C_Z + h * 32 + ks * 8,
+                           mk_desc(wb16, OFF_KX + h * G::KX_BYTES + ks * 256, 128, NCHK * 128), ID_S, ks ? 1u : 0u);
         tc_commit(bar);
       }
       mbar_wait(bar, phase); phase ^= 1u;
@@ -222,34 +241,34 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
 #pragma unroll
           for (int j = 0; j < FP; ++j) p[j] = (j < FMIN || j < F) ? __uint_as_float(t[j]) : -INFINITY;
         }
-        float m3[2] = {p[0], p[1]};
+        float m4[4] = {p[0], p[1], p[2], p[3]};
 #pragma unroll
-        for (int j = 2; j + 1 < FP; j += 2) m3[(j >> 1) & 1] = fmax3(m3[(j >> 1) & 1], p[j], p[j + 1]);
-        const float m = fmaxf(m3[0], m3[1]);
+        for (int j = 4; j + 1 < FP; j += 2) m4[(j >> 1) & 3] = fmax3(m4[(j >> 1) & 3], p[j], p[j + 1]);
+        const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         const float mb = m * scale_log2;
         const float2 c2 = make_float2(scale_log2, scale_log2), nmb2 = make_float2(-mb, -mb);
-        float2 l2a = make_float2(0.f, 0.f), l2b = make_float2(0.f, 0.f);
+        float2 l2[4];
 #pragma unroll
-        for (int j = 0; j < FP; j += 4) {
+        for (int i = 0; i < 4; ++i) l2[i] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < FP; j += 2) {
           float2 t0 = ffma2(make_float2(p[j], p[j + 1]), c2, nmb2);
-          float2 t1 = ffma2(make_float2(p[j + 2], p[j + 3]), c2, nmb2);
           t0.x = ex2_approx(t0.x); t0.y = ex2_approx(t0.y);
-          t1.x = ex2_approx(t1.x); t1.y = ex2_approx(t1.y);
-          l2a = fadd2(l2a, t0);
-          l2b = fadd2(l2b, t1);
-          p[j] = t0.x; p[j + 1] = t0.y; p[j + 2] = t1.x; p[j + 3] = t1.y;
+          l2[(j >> 1) & 3] = fadd2(l2[(j >> 1) & 3], t0);
+          p[j] = t0.x; p[j + 1] = t0.y;
         }
-        const float l = (l2a.x + l2a.y) + (l2b.x + l2b.y);
-        linv[h] = active ? 1.f / l : 0.f;
+        const float2 lt = fadd2(fadd2(l2[0], l2[1]), fadd2(l2[2], l2[3]));
+        const float l = lt.x + lt.y;
+        linv[h] = 1.f / l;
         lse2[h] = mb + lg2_approx(l);
-        // unnormalised bf16 P row -> TMEM (A operand of P.V), zero beyond the FP keys and for idle rows
+        // unnormalised bf16 P row -> TMEM (A operand of P.V), zero beyond the FP keys
 #pragma unroll
         for (int c0 = 0; c0 < KP / 2; c0 += 8) {
           uint32_t v8[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int j = (c0 + e) * 2;
-            v8[e] = (j < FP && active) ? pack_bf16x2(p[j < FP ? j : 0], p[j + 1 < FP ? j + 1 : 0]) : 0u;
+            v8[e] = j < FP ? pack_bf16x2(p[j < FP ? j : 0], p[j + 1 < FP ? j + 1 : 0]) : 0u;
           }
           tc_st_32x8(tl + C_S + h * FP + c0, v8);
         }
@@ -257,15 +276,15 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       // ---- 3. O_h[row, (s, e)] = sum_j P[row, j] v_(s, j)[e]; a row keeps the 8 columns of its own sample
       tc_wait_st();
       tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
+      wg_sync();
+      if (wq == 0 && elect_one()) {
         tc_fence_after();
 #pragma unroll
         for (int h = 0; h < H; ++h)
 #pragma unroll
           for (int ks = 0; ks < KP / 16; ++ks)
             tc_mma_bf16_ts(tmem + C_Z + h * 32, tmem + C_S + h * FP + ks * 8,
-                           mk_desc(b16, OFF_VX + h * G::VX_BYTES + ks * 1024, 512, 128), ID_O, ks ? 1u : 0u);
+                           mk_desc(wb16, OFF_VX + h * G::VX_BYTES + ks * 1024, 512, 128), ID_O, ks ? 1u : 0u);
         tc_commit(bar);
       }
       if (active && saved) {
@@ -278,12 +297,12 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
         float o[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) o[u] = 0.f;
-        for (int s = ws_lo; s <= ws_hi; ++s) {
+        for (uint32_t s = ws_lo; s <= ws_hi; ++s) {
           uint32_t t0[8], t1[8];
           tc_ld_32x8(tl + C_Z + s * 8, t0);
           tc_ld_32x8(tl + C_Z + 32 + s * 8, t1);
           tc_wait_ld();
-          if (s == s_loc) {
+          if ((int)s == s_loc) {
 #pragma unroll
             for (int e = 0; e < DH; ++e) { o[e] = __uint_as_float(t0[e]); o[DH + e] = __uint_as_float(t1[e]); }
           }
@@ -291,13 +310,16 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
         // residual, ReLU, LayerNorm (InteractingLayer.py:57-60)
         float a[U], mean, rstd;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const float on = o[u] * linv[u / DH];
-          a[u] = fmaxf(use_res ? on + r[u] : on, 0.f);
-        }
+        for (int u = 0; u < U; ++u) a[u] = fmaxf(use_res ? fmaf(o[u], linv[u / DH], r[u]) : o[u] * linv[u / DH], 0.f);
         ln_row_stats<U>(a, eps, mean, rstd);
 #pragma unroll
-        for (int u = 0; u < U; ++u) yv[u] = ln_apply(a[u], mean, rstd, gs[u], be[u]);
+        for (int u4 = 0; u4 < U / 4; ++u4) {
+          const float4 g4 = gb4[u4], b4 = gb4[U / 4 + u4];
+          yv[u4 * 4 + 0] = ln_apply(a[u4 * 4 + 0], mean, rstd, g4.x, b4.x);
+          yv[u4 * 4 + 1] = ln_apply(a[u4 * 4 + 1], mean, rstd, g4.y, b4.y);
+          yv[u4 * 4 + 2] = ln_apply(a[u4 * 4 + 2], mean, rstd, g4.z, b4.z);
+          yv[u4 * 4 + 3] = ln_apply(a[u4 * 4 + 3], mean, rstd, g4.w, b4.w);
+        }
         // saved for the backward: the pre-LayerNorm activations of EVERY iteration (the backward
         // re-derives each iteration's input as LayerNorm(a) and differentiates ReLU/LayerNorm at a)
         if (active && saved) {
@@ -316,12 +338,14 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       for (int u = 0; u < U; u += 4)
         store4<T>(y + smp * y_bs + (int64_t)f_loc * y_ld + u, make_float4(yv[u], yv[u + 1], yv[u + 2], yv[u + 3]));
     }
+#pragma unroll
+    for (int c = 0; c < D; ++c) xr[c] = xn[c];
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
   }
 }
 
@@ -329,12 +353,12 @@ template <int NCHF, typename T>
 static int launch_itc_fwd(const IFwdArgs& a) {
   auto kern = interacting_tc_fwd_kernel<NCHF, T>;
   using G = ItcGeom<NCHF>;
-  constexpr int smem = 2 * G::KX_BYTES + 2 * G::VX_BYTES + 8192 + 96 * 4 + 64 + 128;
+  constexpr int smem = 3 * (2 * G::KX_BYTES + 2 * G::VX_BYTES) + 8192 + 2048 + 128 + 64;
   RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int ntiles = (a.B + G::SPT - 1) / G::SPT;
-  int grid = sm_count() * 2;
-  if (grid > ntiles) grid = ntiles;
-  kern<<<grid, 128, smem, a.st>>>((const T*)a.x, a.x_ld, a.x_bs, a.W, a.b, a.gm, a.bt, a.eps, (T*)a.y, a.y_ld,
+  int grid = sm_count();
+  if (grid * 3 > ntiles) grid = (ntiles + 2) / 3;
+  kern<<<grid, 384, smem, a.st>>>((const T*)a.x, a.x_ld, a.x_bs, a.W, a.b, a.gm, a.bt, a.eps, (T*)a.y, a.y_ld,
                                   a.y_bs, (float*)a.saved, a.B, a.F, a.L, a.use_res);
   return check_launch("interacting_tc_fwd");
 }

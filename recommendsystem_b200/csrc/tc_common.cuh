@@ -134,23 +134,38 @@ __device__ __forceinline__ uint32_t nosw_off(int row, int c) {
   return (uint32_t)((row >> 3) * (NCH * 128) + c * 128 + (row & 7) * 16);
 }
 
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c);
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b);
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b);
+
 // LayerNorm of one register row (InteractingLayer.py:60).  ONE definition, explicit fma/mul, shared by
 // the tcgen05 forward and backward so that the backward's recomputed iteration input is bit-identical
 // to what the forward fed to its next iteration.
 template <int U>
 __device__ __forceinline__ void ln_row_stats(const float (&a)[U], float eps, float& mean, float& rstd) {
-  float m = 0.f;
+  static_assert(U == 16 || U == 8, "pairwise tree written for 8 / 16 columns");
+  // fixed pairwise trees (depth 4) instead of 16-deep dependent chains: at 2-3 warps per scheduler the chain
+  // latency was exposed; the order is still fixed, so forward and backward agree bit for bit
+  float2 t[U / 2];
 #pragma unroll
-  for (int u = 0; u < U; ++u) m = __fadd_rn(m, a[u]);
-  m = __fmul_rn(m, 1.f / U);
-  float var = 0.f;
+  for (int i = 0; i < U / 2; ++i) t[i] = make_float2(a[2 * i], a[2 * i + 1]);
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const float d = __fsub_rn(a[u], m);
-    var = __fmaf_rn(d, d, var);
+  for (int w = U / 4; w >= 1; w >>= 1)
+#pragma unroll
+    for (int i = 0; i < w; ++i) t[i] = fadd2(t[i], t[i + w]);
+  const float m = __fmul_rn(__fadd_rn(t[0].x, t[0].y), 1.f / U);
+  const float2 nm = make_float2(-m, -m);
+#pragma unroll
+  for (int i = 0; i < U / 2; ++i) {
+    const float2 d = fadd2(make_float2(a[2 * i], a[2 * i + 1]), nm);
+    t[i] = fmul2(d, d);
   }
+#pragma unroll
+  for (int w = U / 4; w >= 1; w >>= 1)
+#pragma unroll
+    for (int i = 0; i < w; ++i) t[i] = fadd2(t[i], t[i + w]);
   mean = m;
-  rstd = rsqrtf(__fmaf_rn(var, 1.f / U, eps));
+  rstd = rsqrtf(__fmaf_rn(__fadd_rn(t[0].x, t[0].y), 1.f / U, eps));
 }
 __device__ __forceinline__ float ln_apply(float a, float mean, float rstd, float gamma, float beta) {
   return __fmaf_rn(__fmul_rn(__fsub_rn(a, mean), rstd), gamma, beta);
@@ -281,6 +296,18 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
+}
+// warp index as a UNIFORM value (CREDUX -> uniform register): TMEM addresses, descriptors and warp-level loop
+// bounds derived from it stay in the uniform datapath (tcgen05.ld/st/mma take uniform-register addresses; a
+// threadIdx-derived base cost one R2UR per TMEM instruction)
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ float lg2_approx(float x) {
   float y;
