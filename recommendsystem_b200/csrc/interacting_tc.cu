@@ -26,17 +26,6 @@
 namespace rs {
 
 
-// samples per 128-row tile: whole samples of FP = 8 NCHF padded fields, at most 4 (the expanded Q operand has
-// 8 SPT columns per head and the P.V product N = 8 SPT <= 32)
-template <int NCHF> struct ItcGeom {
-  static constexpr int FP = NCHF * 8;
-  static constexpr int SPT = (128 / FP) < 4 ? (128 / FP) : 4;
-  static constexpr int NCHK = SPT * 2;                 // 16-byte chunks per row of the expanded K operand (tf32)
-  static constexpr int KP = (FP + 15) / 16 * 16;       // key dimension padded to the bf16 K step
-  static constexpr int KX_BYTES = NCHF * NCHK * 128;   // [FP keys][8 SPT] tf32
-  static constexpr int VX_BYTES = (KP / 8) * 512;      // [KP keys][32 = (sample, e)] bf16, MN-major
-};
-
 // tile-private TMEM columns (per warpgroup): Z [0,64) -> expanded Q_h over [0,32), [32,64) once the thread has its
 // Z row in registers (a lane's columns are private to its thread) -> O_h at h*32 ; S_h at 64 + h*FP with P_h
 // (packed bf16) over its first KP/2 columns and [x_hi | x_lo] over [64,96) before S is issued ; [1 1 0..] at 160
@@ -81,11 +70,7 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
   if (threadIdx.x < 2 * U) reinterpret_cast<float*>(smem + OFF_F)[threadIdx.x] =
       threadIdx.x < U ? gamma[threadIdx.x] : beta[threadIdx.x - U];
   stage_w_3xtf32(smem + OFF_W, W, threadIdx.x, 384);
-  for (int i = threadIdx.x; i < N4 * 2; i += 384) {
-    const int n = i >> 1, c = i & 1;
-    const float bv = bias[n], bh = tf32_hi(bv);
-    *reinterpret_cast<float4*>(smem + OFF_BT + nosw_off<2>(n, c)) = c ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(bh, bv - bh, 0.f, 0.f);
-  }
+  stage_bias_tile(smem + OFF_BT, bias, threadIdx.x, 384);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();

@@ -1,59 +1,35 @@
 // interacting_tc_bwd.cu — K4 backward on the 5th-gen tensor cores (bf16 mode): the gradient of
 // InteractingLayer.call (InteractingLayer.py:37-61) with every contraction issued as tcgen05.mma.
 //
-// One CTA of 256 threads per SM owns a tile of SPT whole samples (sample s = tile rows
-// [s*FP, s*FP+F), FP = F rounded up to 8; F = 39 -> 3 samples per 128-row tile).  Two warpgroups
-// share the 128 TMEM lanes: thread (wg, row) IS tile row `row`; warpgroup h does the per-head work
-// of head h (softmax row, dS row, its 8 columns of q/k/v and their gradients) and both do the
-// cheap row-wise LayerNorm/ReLU algebra redundantly, so no value ever crosses threads except
-// through an MMA operand.  Flash-style: the forward saved only the pre-LayerNorm activations a of
-// each iteration (64 B per row); iteration inputs are re-derived as LayerNorm(a), the attention is
-// recomputed with the forward's own arithmetic, and P.V is never needed again (the softmax
-// backward takes delta = sum_j P_ij dP_ij).  Per iteration (last to first, weights shared):
+// CTA = 128 threads = one 128-row tile of SPT whole samples (sample s = tile rows [s*FP, s*FP+F), FP = F rounded
+// up to 8; F = 39 -> 3 samples); thread t IS tile row t and TMEM lane t; two CTAs share an SM (256 TMEM columns,
+// ~97 KB of shared memory each).  Flash-style: the forward saved the pre-LayerNorm activations a of every
+// iteration (64 B per row) and the per-head softmax statistics lse (8 B per row); iteration inputs are re-derived
+// as LayerNorm(a) and P = exp2(S c - lse) is recomputed already normalised (no max / sum pass).  Per (tile,
+// iteration), last iteration first, weights shared:
 //
-//   1. Z = X Wqkvr                    3xTF32        -> q k v r (ReLU), masks; LayerNorm/ReLU backward
-//                                                      at the stored a -> dT (= dO, dR)
-//   2. S_h = Q_h K_h^T                tf32, K = 8   -> P = softmax row (bf16 tile in smem)
-//   3. dP_h = dO_h V_h^T              tf32, K = 8
-//      dV_h = P_h^T dO_h              bf16, A = the P tile read MN-major (transposed)
-//                                      -> dS = P (dP - delta) / sqrt(dh)  overwrites P in place
-//   4. dQ_h = dS_h K_h ; dK_h = dS_h^T Q_h          bf16 (dS tile read K-major and MN-major)
-//   5. dX = dZ Wqkvr^T                bf16, K = 64  -> gradient of the previous iteration's output
-//      [dW^T | db ; dgamma ; dbeta] += [dZ | g*xhat | g]^T [X | 1]      bf16, K = 128 rows,
-//      accumulated in TMEM for the CTA's whole lifetime (fixed order => deterministic)
+//   Z = [X | 1] [W ; b]         3xTF32, A = [x_hi | x_lo | 1 1 0..] in TMEM        -> q k v (ReLU), r mask;
+//                                                                                     LayerNorm/ReLU backward -> dT
+//   per head h (the two heads are pipelined: the MMAs of one run under the thread work of the other):
+//   S_h  = Qx_h Kx_h^T          tf32, A in TMEM.  Qx is the row's q placed in the K slot of its own sample
+//   dP_h = dOx_h Vx_h^T         (zeros elsewhere), Kx row j = [k_(0,j) | k_(1,j) | ..]: every row finds ITS sample's
+//                               FP keys in the same FP accumulator columns (no 128-wide block-diagonal product)
+//        -> P, dS = P (dP - sum_j P dP) as compact [128][FP] bf16 tiles in shared memory
+//   dQ_h = dS_h K_h             bf16, A = the dS tile K-major, B = [key][(sample, e)]: a row keeps its sample's 8 columns
+//   dV_h = P_h^T dO_h           bf16, M = 64 per sample: A = the compact tile read MN-major (transposed) over the
+//   dK_h = dS_h^T Q_h           sample's rows, B = dO / Q rows of that sample; dV lands in TMEM lanes 0-15 of each
+//                               subpartition, dK in lanes 16-31 (interleaved half-subpartitions): one tcgen05.ld
+//                               hands 32 lanes their (key, head) gradient rows, which they mask and store to dZ
+//   dX = dZ W^T ; [dW^T | db ; dgamma ; dbeta] += [dZ | g*xhat | g]^T [X | 1] (accumulated in TMEM for the CTA's
+//   lifetime, fixed order => deterministic) ; Z of the NEXT step rides in the same phase.
 //
-// Every shared-memory operand tile is the no-swizzle canonical layout [row/8][chunk][row%8][16 B]
-// written by the thread that owns the row; the same bytes serve as K-major and MN-major operand.
-// Rows outside a sample (padding fields, the 8 spare rows, samples past B) carry g = 0 and P = 0,
-// which makes every gradient they could contribute exactly zero.
+// Every shared-memory operand tile is the no-swizzle canonical layout [row/8][chunk][row%8][16 B] written by the
+// thread that owns the row; the same bytes serve as K-major and MN-major operand.  Rows outside a sample carry
+// g = 0 and lse = +inf (P = 0), which makes every gradient they could contribute exactly zero.
 #include "tc_common.cuh"
 #include "interacting_args.cuh"
 
 namespace rs {
-
-// own-sample window (FP columns) of a [128 x 128] TMEM accumulator; a warp whose 32 lanes span
-// two samples loads both windows (tcgen05.ld is warp-wide) and each lane keeps its own.
-template <int FP>
-__device__ __forceinline__ void ld_window(uint32_t taddr, int ws_lo, int ws_hi, int s_loc, int F, float fill,
-                                          float (&out)[FP]) {
-#pragma unroll
-  for (int j = 0; j < FP; ++j) out[j] = fill;
-  for (int s = ws_lo; s <= ws_hi; ++s) {
-    uint32_t t[FP];
-#pragma unroll
-    for (int c0 = 0; c0 < FP; c0 += 8) {
-      uint32_t t8[8];
-      tc_ld_32x8(taddr + (uint32_t)(s * FP + c0), t8);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) t[c0 + j] = t8[j];
-    }
-    tc_wait_ld();
-    const bool mine = s == s_loc;
-#pragma unroll
-    for (int j = 0; j < FP; ++j)
-      if (mine && j < F) out[j] = __uint_as_float(t[j]);
-  }
-}
 
 __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
   uint4 u;
@@ -61,139 +37,119 @@ __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
   u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
   return u;
 }
+// 0xFFFF in each half whose bf16 value is > 0
+__device__ __forceinline__ uint32_t bf16x2_pos_mask(uint32_t v) {
+  const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&v), z);
+}
 
-// element e of this thread's head inside a 16-wide register row (compile-time indices + select:
-// a runtime index would push the array to local memory)
-#ifdef RS_ITB_PROFILE
-// what-if timing experiments (WRONG results, profile builds only; tools/itb_whatif.py): bit 0 = no MMA issue,
-// bit 1 = no fence.proxy.async, bit 2 = no exponentials in the softmax, bit 3 = no P / dS tile stores;
-// bit 8 = clock64 phase hooks on (tools/itb_profile.py)
-__device__ int itb_exp_mode = 0;
-#define EXP(bit) (itb_exp_mode & (1 << (bit)))
-__device__ unsigned long long itb_prof[32];
-#define PROF(i)                                         \
-  if (blockIdx.x == 0 && tid == 0 && EXP(8)) {          \
-    const long long t_now = clock64();                  \
-    itb_prof[i] += (unsigned long long)(t_now - t_last); \
-    t_last = t_now;                                     \
-  }
-#define PROFW(i)                                                                     \
-  if (blockIdx.x == 0 && (tid == 0 || tid == 32) && EXP(8)) {                         \
-    const long long t_now = clock64();                                               \
-    itb_prof[(tid == 0 ? 16 : 24) + (i)] += (unsigned long long)(t_now - t_w);        \
-    t_w = t_now;                                                                     \
-  }
-#else
-#define PROF(i)
-#define PROFW(i)
-#define EXP(bit) 0
-#endif
+struct uint4x2_t { uint4 a, b; };
 
-#define HSEL(a, e) (wg ? (a)[8 + (e)] : (a)[(e)])
-#define HSELF(a, e) __uint_as_float(HSEL(a, e))
+template <int NCHF> struct ItbSmem {
+  using G = ItcGeom<NCHF>;
+  static constexpr int PC_BYTES = 16 * NCHF * 128 + 1024;    // [128][FP] bf16 + zeroed pad (operand over-reads)
+  static constexpr int XR = G::SPT * G::KP;                  // rows of the sample-expanded [row][16] bf16 operands
+  static constexpr int X16_BYTES = (XR / 8) * 256;
+  static constexpr int OFF_PC = 0;                           // P   (A of dV, transposed)
+  static constexpr int OFF_DS = PC_BYTES;                    // dS  (A of dQ K-major, of dK transposed)
+  static constexpr int OFF_KX = 2 * PC_BYTES;                // H x [FP keys][8 SPT] tf32           (B of S)
+  static constexpr int OFF_VX = OFF_KX + 2 * G::KX_BYTES;    // H x same, v / sqrt(dh)             (B of dP)
+  static constexpr int OFF_K16 = OFF_VX + 2 * G::KX_BYTES;   // H x [KP keys][32] bf16 MN-major     (B of dQ)
+  static constexpr int OFF_Q16 = OFF_K16 + 2 * G::VX_BYTES;  // [SPT x KP rows][16] bf16            (B of dK)
+  static constexpr int OFF_DO16 = OFF_Q16 + X16_BYTES;       // same                                (B of dV)
+  static constexpr int OFF_DZ = OFF_DO16 + X16_BYTES;        // [128][96] bf16: dq dk dv dr | g*xhat | g, 12 chunks/row
+  static constexpr int OFF_XB = OFF_DZ + 16 * 12 * 128 + 512;   // [128][32] bf16: x | 1 0.. | 0      (B of dW)
+  static constexpr int OFF_W32 = OFF_XB + 8192;              // W_hi | W_lo, each [64 n][16 k] tf32  (B of Z)
+  static constexpr int OFF_BT = OFF_W32 + 8192;              // bias tile                           (B of Z)
+  static constexpr int OFF_WT = OFF_BT + 2048;               // [16 n = d][64 k] bf16               (B of dX)
+  static constexpr int OFF_F = OFF_WT + 2048;                // gamma[16] beta[16]
+  static constexpr int OFF_BAR = OFF_F + 128;
+  static constexpr int TOTAL = OFF_BAR + 64;
+};
 
 template <int NCHF, typename T>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(128, 2)
 interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, const float* __restrict__ saved,
                           const float* __restrict__ W, const float* __restrict__ bias,
                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                           const T* __restrict__ dy, int64_t dy_ld, int64_t dy_bs, T* __restrict__ dx, int64_t dx_ld,
                           int64_t dx_bs, float* __restrict__ part, int B, int F, int L, int use_res) {
   constexpr int D = 16, U = 16, H = 2, DH = 8, N4 = 64;
-  constexpr int FP = NCHF * 8;
-  constexpr int SPT = 128 / FP;
-  // ---- shared memory map
-  constexpr int OFF_P = 0;                         // H x [128][128] bf16, 16 chunks/row: P then dS
-  constexpr int OFF_DZ = OFF_P + H * 32768;        // [128][128] bf16: dq|dk|dv|dr | g*xhat | g | 0
-  constexpr int OFF_XB = OFF_DZ + 32768;           // [128][32] bf16: x | 1 0..0 | 0      (B of dW)
-  constexpr int OFF_X = OFF_XB + 16384;            // [128][x_hi | x_lo] tf32, 8 chunks/row (A of Z)
-  constexpr int OFF_Q32 = OFF_X + 16384;           // H x [128][8] tf32
-  constexpr int OFF_K32 = OFF_Q32 + H * 4096;
-  constexpr int OFF_V32 = OFF_K32 + H * 4096;
-  constexpr int OFF_DO32 = OFF_V32 + H * 4096;
-  constexpr int OFF_Q16 = OFF_DO32 + H * 4096;     // [128][16] bf16, MN-major B operands
-  constexpr int OFF_K16 = OFF_Q16 + 4096;
-  constexpr int OFF_DO16 = OFF_K16 + 4096;
-  constexpr int OFF_W32 = OFF_DO16 + 4096;         // W_hi | W_lo, each [64 n][16 k] tf32  (B of Z)
-  constexpr int OFF_WT = OFF_W32 + 8192;           // [16 n = d][64 k] bf16                (B of dX)
-  constexpr int OFF_F = OFF_WT + 2048;             // bias[64] gamma[16] beta[16]
-  constexpr int OFF_BAR = OFF_F + (N4 + 2 * U) * 4;
-  extern __shared__ uint8_t itb_smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(itb_smem_raw) + 1023) & ~(uintptr_t)1023);
-  float* bs = reinterpret_cast<float*>(smem + OFF_F);
-  float* gs = bs + N4;
-  float* be = gs + U;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  using G = ItcGeom<NCHF>;
+  using SM = ItbSmem<NCHF>;
+  constexpr int FP = G::FP, SPT = G::SPT, NCHK = G::NCHK, KP = G::KP;
+  constexpr int FMIN = NCHF == 2 ? 0 : FP - 8;
+  extern __shared__ __align__(128) uint8_t itb_smem[];
+  uint8_t* smem = itb_smem;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const float4* gb4 = reinterpret_cast<const float4*>(smem + SM::OFF_F);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int wg = tid >> 7;                  // warpgroup = head this thread works for
-  const int row = tid & 127;                // tile row = TMEM lane
-  if (tid == 0) {
-    mbar_init(bar, 4);
+  const int row = threadIdx.x;                               // tile row = TMEM lane
+  const uint32_t wq = uniform_u32(threadIdx.x >> 5);         // warp = TMEM subpartition (uniform register)
+  const int lane = threadIdx.x & 31;
+  if (row == 0) {
+    mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
+  if (wq == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  // zero P/dS, dZ and XB; then the constant ones column of XB (chunk 2, element 0)
-  for (int i = tid; i < (OFF_X - OFF_P) / 16; i += 256) reinterpret_cast<uint4*>(smem + OFF_P)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < N4 + 2 * U; i += 256) bs[i] = i < N4 ? bias[i] : (i < N4 + U ? gamma[i - N4] : beta[i - N4 - U]);
-  stage_w_3xtf32(smem + OFF_W32, W, tid, 256);     // B of Z
-  for (int i = tid; i < D * 8; i += 256) {         // B of dX: row n = d, chunk c = 8 consecutive n4 (bf16)
-    const int d = i >> 3, c = i & 7;
+  // zero every operand tile (static zeros: pads, rows of other samples, the spare rows); constants
+  for (int i = row; i < SM::OFF_W32 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (row < 2 * U) reinterpret_cast<float*>(smem + SM::OFF_F)[row] = row < U ? gamma[row] : beta[row - U];
+  stage_w_3xtf32(smem + SM::OFF_W32, W, row, 128);
+  stage_bias_tile(smem + SM::OFF_BT, bias, row, 128);
+  {                                                          // B of dX: row n = d, chunk c = 8 consecutive n4 (bf16)
+    const int d = row >> 3, c = row & 7;
     float w8[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) w8[e] = W[d * N4 + c * 8 + e];
-    *reinterpret_cast<uint4*>(smem + OFF_WT + nosw_off<8>(d, c)) = pack8_bf16(w8);
+    *reinterpret_cast<uint4*>(smem + SM::OFF_WT + nosw_off<8>(d, c)) = pack8_bf16(w8);
   }
   __syncthreads();
-  if (tid < 128) *reinterpret_cast<uint4*>(smem + OFF_XB + nosw_off<4>(tid, 2)) = make_uint4(0x00003F80u, 0, 0, 0);
+  *reinterpret_cast<uint4*>(smem + SM::OFF_XB + nosw_off<4>(row, 2)) = make_uint4(0x00003F80u, 0, 0, 0);   // ones column
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);     // this warp's TMEM lanes
-  constexpr uint32_t TM_S = 0;        // S_h / dP_h at h*128
-  constexpr uint32_t TM_Z = 256;      // 64
-  constexpr uint32_t TM_DV = 352;     // +h*16
-  constexpr uint32_t TM_DQ = 384;
-  constexpr uint32_t TM_DK = 416;
-  constexpr uint32_t TM_DX = 448;     // 16
-  constexpr uint32_t TM_DW = 464;     // 32, persistent
-
+  const uint32_t tmem = uniform_u32(*tmem_slot);
+  const uint32_t tl = tmem + ((wq * 32u) << 16);
+  // TMEM columns: A = Z (64), later the dQ / dV|dK accumulators ; expanded q / dO of the current head ;
+  // S_h | dP_h, later [x_hi | x_lo | 1 1 0..] (40) and dX (16) ; dW (persistent)
+  constexpr uint32_t C_A = 0, C_QX = 64, C_DOX = 96, C_S = 128, C_DP = 176, C_X = 128, C_DX = 168, C_DW = 224;
+  {
+    uint32_t z16[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z16[i] = 0u;
+#pragma unroll
+    for (int c = 0; c < 64; c += 16) tc_st_32x16(tl + C_QX + c, z16);   // a lane only ever rewrites its own sample's slot
+    tc_wait_st();
+  }
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t b16 = sbase >> 4;                              // descriptor start-address unit
+  const uint32_t b16 = sbase >> 4;
   constexpr uint32_t ID_Z = make_idesc(2, 128, N4, 0, 0);       // tf32
-  constexpr uint32_t ID_S = make_idesc(2, 128, 128, 0, 0);      // tf32 (S and dP)
-  constexpr uint32_t ID_AK = make_idesc(1, 128, 16, 0, 1);      // bf16, A K-major, B MN-major (dQ)
-  constexpr uint32_t ID_AT = make_idesc(1, 128, 16, 1, 1);      // bf16, A MN-major (transposed), B MN-major (dV, dK)
+  constexpr uint32_t ID_S = make_idesc(2, 128, FP, 0, 0);       // tf32 (S and dP), K = 8 per sample
+  constexpr uint32_t ID_DQ = make_idesc(1, 128, 32, 0, 1);      // bf16, A K-major, B MN-major
+  constexpr uint32_t ID_T = make_idesc(1, 64, 8, 1, 1);         // bf16, M = 64, A MN-major (transposed), B MN-major
   constexpr uint32_t ID_DX = make_idesc(1, 128, 16, 0, 0);      // bf16, both K-major
   constexpr uint32_t ID_DW = make_idesc(1, 128, 32, 1, 1);      // bf16, A = dZ^T, B = [X|1]
 
   const int s_loc = row / FP, f_loc = row - s_loc * FP;
+  const bool row_ok = s_loc < SPT && f_loc < F;
   const int ntiles = (B + SPT - 1) / SPT;
   const float scale = 1.f / sqrtf((float)DH);
   const float scale_log2 = ITC_LOG2E * scale;
-  const int wq = warp & 3;
-  const int ws_lo = (wq * 32) / FP, ws_hi = min((wq * 32 + 31) / FP, SPT - 1);
+  const uint32_t ws_lo = min((wq * 32u) / FP, (uint32_t)(SPT - 1)), ws_hi = min((wq * 32u + 31u) / FP, (uint32_t)(SPT - 1));
   const int64_t total_rows = (int64_t)B * F;
-  const bool row_ok = s_loc < SPT && f_loc < F;
-  const int hb = wg * DH;              // first column of this thread's head
-  // Four MMA issuers (lane 0 of warps 0, 1, 4, 5): independent accumulator chains are issued
-  // concurrently; every issuer commits to the one mbarrier each phase (count 4).
-  const int issuer = tid == 0 ? 0 : (tid == 32 ? 1 : (tid == 128 ? 2 : (tid == 160 ? 3 : -1)));
-#ifdef RS_ITB_PROFILE
-  long long t_last = clock64();
-  long long t_w = clock64();
-#endif
+  const float* lse_base = saved + (int64_t)L * total_rows * U;
+  // dV / dK writer role: lanes 0-15 of warp w own dV of key 16 w + lane, lanes 16-31 dK of the same key
+  const int jw = (int)wq * 16 + (lane & 15);
+  const bool is_dk = lane >= 16;
   uint32_t phase = 0;
   uint32_t dw_acc = 0;                 // 0 until the first dW MMA of this CTA
 
-  // x-source row of step (tile, it): the bf16 layer input (it == 0) or the stored activations of
-  // iteration it-1 (LayerNorm is applied when the row is staged)
   auto load_xsrc = [&](int tile_, int it_, float (&dst)[U]) {
     const int64_t smp_ = (int64_t)tile_ * SPT + s_loc;
     if (row_ok && smp_ < B) {
@@ -216,7 +172,12 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       for (int c = 0; c < U; ++c) dst[c] = 0.f;
     }
   };
-  // first-step-of-a-tile rows: stored activations of the last iteration and the incoming gradient
+  auto load_lse = [&](int tile_, int it_) -> float2 {
+    const int64_t smp_ = (int64_t)tile_ * SPT + s_loc;
+    if (row_ok && smp_ < B)
+      return *reinterpret_cast<const float2*>(lse_base + ((int64_t)it_ * total_rows + smp_ * F + f_loc) * H);
+    return make_float2(INFINITY, INFINITY);                  // P = exp2(S c - inf) = 0 for rows outside a sample
+  };
   auto load_tile_head = [&](int tile_, float (&a_)[U], float (&g_)[U]) {
     const int64_t smp_ = (int64_t)tile_ * SPT + s_loc;
     if (row_ok && smp_ < B) {
@@ -233,44 +194,67 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       for (int c = 0; c < U; ++c) { a_[c] = 0.f; g_[c] = 0.f; }
     }
   };
-  // stage this warpgroup's half of the step input: X tile (3xTF32 split); returns the half row
-  auto stage_x = [&](const float (&src)[U], int it_, bool act_, float (&xh)[8]) {
+  // step input row -> [x_hi | x_lo | 1 1 0..] in TMEM (A of Z); returns the row as packed bf16 (B of dW)
+  auto stage_x = [&](const float (&src)[U], int it_, bool act_) -> uint4x2_t {
+    float xh[U];
     if (act_ && it_ > 0) {
       float mean, rstd;
       ln_row_stats<U>(src, eps, mean, rstd);      // bit-identical to the forward's LayerNorm
 #pragma unroll
-      for (int e = 0; e < 8; ++e) xh[e] = ln_apply(HSEL(src, e), mean, rstd, gs[hb + e], be[hb + e]);
+      for (int u4 = 0; u4 < U / 4; ++u4) {
+        const float4 g4 = gb4[u4], b4 = gb4[U / 4 + u4];
+        xh[u4 * 4 + 0] = ln_apply(src[u4 * 4 + 0], mean, rstd, g4.x, b4.x);
+        xh[u4 * 4 + 1] = ln_apply(src[u4 * 4 + 1], mean, rstd, g4.y, b4.y);
+        xh[u4 * 4 + 2] = ln_apply(src[u4 * 4 + 2], mean, rstd, g4.z, b4.z);
+        xh[u4 * 4 + 3] = ln_apply(src[u4 * 4 + 3], mean, rstd, g4.w, b4.w);
+      }
     } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) xh[e] = act_ ? HSEL(src, e) : 0.f;
+      for (int u = 0; u < U; ++u) xh[u] = act_ ? src[u] : 0.f;
+    }
+    uint32_t hi[16], lo[16], one8[8];
+#pragma unroll
+    for (int c = 0; c < U; ++c) {
+      const float h_ = tf32_hi(xh[c]);
+      hi[c] = __float_as_uint(h_);
+      lo[c] = __float_as_uint(xh[c] - h_);
     }
 #pragma unroll
-    for (int c = 0; c < 2; ++c)
-      stage_x4_3xtf32(smem + OFF_X, row, wg * 2 + c, xh[c * 4], xh[c * 4 + 1], xh[c * 4 + 2], xh[c * 4 + 3]);
+    for (int i = 0; i < 8; ++i) one8[i] = i < 2 ? 0x3F800000u : 0u;
+    tc_st_32x16(tl + C_X, hi);
+    tc_st_32x16(tl + C_X + 16, lo);
+    tc_st_32x8(tl + C_X + 32, one8);
+    uint4x2_t r;
+    r.a = pack8_bf16(xh);
+    r.b = pack8_bf16(xh + 8);
+    return r;
   };
 
-  // ---- prologue: first step's rows, X tile, Z MMA
+  // ---- prologue: first step's rows, X operand, Z MMA
   int tile = blockIdx.x, it = L - 1;
   const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int nsteps = my_tiles * L;
   bool active = row_ok && (int64_t)tile * SPT + s_loc < B;
   float a[U], g[U], xs[U];
+  float2 lse = load_lse(tile, it);
   load_tile_head(tile, a, g);
   load_xsrc(tile, it, xs);
   {
-    float xh[8];
-    stage_x(xs, it, active, xh);
-    *reinterpret_cast<uint4*>(smem + OFF_XB + nosw_off<4>(row, wg)) = pack8_bf16(xh);
+    const uint4x2_t xb = stage_x(xs, it, active);
+    *reinterpret_cast<uint4*>(smem + SM::OFF_XB + nosw_off<4>(row, 0)) = xb.a;
+    *reinterpret_cast<uint4*>(smem + SM::OFF_XB + nosw_off<4>(row, 1)) = xb.b;
   }
   fence_async_smem();
+  tc_wait_st();
   tc_fence_before();
   __syncthreads();
-  if (issuer >= 0) {
+  if (wq == 0 && elect_one()) {
     tc_fence_after();
-    if (issuer == 0) issue_proj_3xtf32(tmem + TM_Z, sbase + OFF_X, sbase + OFF_W32, ID_Z);
+    issue_proj_3xtf32_ts(tmem + C_A, tmem + C_X, sbase + SM::OFF_W32, ID_Z);
+    tc_mma_tf32_ts(tmem + C_A, tmem + C_X + 32, make_nosw_desc(sbase + SM::OFF_BT, 128, 256), ID_Z, 1u);
     tc_commit(bar);
   }
-  mbar_wait(bar, phase); phase ^= 1u;
+  mbar_wait(bar, phase); phase ^= 1u;              // Z of the first step
   tc_fence_after();
 
   for (int step = 0; step < nsteps; ++step) {
@@ -280,281 +264,301 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
     const int nit = new_tile ? L - 1 : it - 1;
     const bool nactive = !last && row_ok && (int64_t)ntile * SPT + s_loc < B;
     const int64_t smp = (int64_t)tile * SPT + s_loc;
-    // ================= E1a. Z -> q k (the operands of S) ; v, r pre-activations stay in registers
-    uint32_t qmask = 0, kmask = 0, vmask = 0;
-    uint32_t zv[8], zr[16];
+    // ================= T1. Z -> q k v (ReLU) for both heads, r mask; LayerNorm / ReLU backward at the stored a
+    uint32_t q16[8];                               // this row's q, packed bf16 (ReLU' mask of dq later)
+    float q1[DH], dO1[DH];                         // head 1's TMEM operands, staged once head 0's products are done
     {
-      uint32_t zq[8], zk[8];
-      tc_ld_32x8(tl + TM_Z + hb, zq);
-      tc_ld_32x8(tl + TM_Z + U + hb, zk);
-      tc_ld_32x8(tl + TM_Z + 2 * U + hb, zv);
-      tc_ld_32x16(tl + TM_Z + 3 * U, zr);
-      tc_wait_ld();
-      float q[DH], kk[DH];
+      uint32_t z[32], zvr[32];
+      tc_ld_32x32(tl + C_A, z);                    // q | k
+      tc_ld_32x32(tl + C_A + 32, zvr);             // v | r
+      float qk[32], vv[U];
 #pragma unroll
-      for (int e = 0; e < DH; ++e) {
-        q[e] = fmaxf(__uint_as_float(zq[e]) + bs[hb + e], 0.f);
-        kk[e] = fmaxf(__uint_as_float(zk[e]) + bs[U + hb + e], 0.f);
-        qmask |= (q[e] > 0.f ? 1u : 0u) << e;
-        kmask |= (kk[e] > 0.f ? 1u : 0u) << e;
-      }
+      for (int u = 0; u < 32; ++u) qk[u] = fmaxf(__uint_as_float(z[u]), 0.f);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        *reinterpret_cast<float4*>(smem + OFF_Q32 + wg * 4096 + nosw_off<2>(row, c)) =
-            make_float4(q[c * 4], q[c * 4 + 1], q[c * 4 + 2], q[c * 4 + 3]);
-        *reinterpret_cast<float4*>(smem + OFF_K32 + wg * 4096 + nosw_off<2>(row, c)) =
-            make_float4(kk[c * 4], kk[c * 4 + 1], kk[c * 4 + 2], kk[c * 4 + 3]);
-      }
-      *reinterpret_cast<uint4*>(smem + OFF_Q16 + nosw_off<2>(row, wg)) = pack8_bf16(q);
-      *reinterpret_cast<uint4*>(smem + OFF_K16 + nosw_off<2>(row, wg)) = pack8_bf16(kk);
-    }
-    // ================= 2. S_h = Q_h K_h^T
-    if (!EXP(1)) fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    PROF(0)
-    if (issuer >= 0) {
-      tc_fence_after();
-      if (!EXP(0)) {
-      if ((issuer & 1) == 0) {
-        const int h = issuer >> 1;
-        tc_mma_tf32(tmem + TM_S + h * 128, mk_desc(b16, OFF_Q32 + h * 4096, 128, 256),
-                    mk_desc(b16, OFF_K32 + h * 4096, 128, 256), ID_S, 0u);
-      }
-      }
-      tc_commit(bar);
-    }
-    PROF(1)
-    // ================= E1b (under the S MMA). v ; LayerNorm / ReLU backward at the stored a
-    {
-      float vv[DH];
-      uint32_t rmask = 0;
-#pragma unroll
-      for (int e = 0; e < DH; ++e) {
-        vv[e] = fmaxf(__uint_as_float(zv[e]) + bs[2 * U + hb + e], 0.f);
-        vmask |= (vv[e] > 0.f ? 1u : 0u) << e;
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) rmask |= (__uint_as_float(zr[u]) + bs[3 * U + u] > 0.f ? 1u : 0u) << u;
-#pragma unroll
-      for (int c = 0; c < 2; ++c)
-        *reinterpret_cast<float4*>(smem + OFF_V32 + wg * 4096 + nosw_off<2>(row, c)) =
-            make_float4(vv[c * 4], vv[c * 4 + 1], vv[c * 4 + 2], vv[c * 4 + 3]);
-      // ---- LayerNorm + ReLU backward at the stored activations a (InteractingLayer.py:59-60)
+      for (int u = 0; u < U; ++u) vv[u] = fmaxf(__uint_as_float(zvr[u]), 0.f) * scale;   // 1/sqrt(dh) rides on V: dP arrives scaled
+      // ---- LayerNorm + ReLU backward (InteractingLayer.py:59-60)
       float mean, rstd;
       ln_row_stats<U>(a, eps, mean, rstd);
-      float xhat[U], s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+      float xhat[U], gg[U];
+      float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+      const float2 nm = make_float2(-mean, -mean), rs2 = make_float2(rstd, rstd);
 #pragma unroll
-      for (int u = 0; u < U; u += 2) {
-        xhat[u] = (a[u] - mean) * rstd;
-        xhat[u + 1] = (a[u + 1] - mean) * rstd;
-        const float g0 = g[u] * gs[u], g1 = g[u + 1] * gs[u + 1];
-        s1a += g0; s1b += g1;
-        s2a = fmaf(g0, xhat[u], s2a); s2b = fmaf(g1, xhat[u + 1], s2b);
+      for (int u4 = 0; u4 < U / 4; ++u4) {
+        const float4 g4 = gb4[u4];
+        const float gm[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+        for (int e = 0; e < 4; e += 2) {
+          const int u = u4 * 4 + e;
+          const float2 xh2 = fmul2(fadd2(make_float2(a[u], a[u + 1]), nm), rs2);
+          const float2 gg2 = fmul2(make_float2(g[u], g[u + 1]), make_float2(gm[e], gm[e + 1]));
+          xhat[u] = xh2.x; xhat[u + 1] = xh2.y;
+          gg[u] = gg2.x; gg[u + 1] = gg2.y;
+          s1 = fadd2(s1, gg2);
+          s2 = ffma2(gg2, xh2, s2);
+        }
       }
-      const float s1 = (s1a + s1b) * (1.f / U), s2 = (s2a + s2b) * (1.f / U);
-      // this head's 8 columns of dT = dO = dR
-      float dTh[8], t8[8];
+      const float m1 = (s1.x + s1.y) * (1.f / U), m2 = (s2.x + s2.y) * (1.f / U);
+      float dT[U];
 #pragma unroll
-      for (int e = 0; e < DH; ++e) {
-        const float ae = HSEL(a, e), xe = HSEL(xhat, e);
-        const float dA = (HSEL(g, e) * gs[hb + e] - s1 - xe * s2) * rstd;
-        dTh[e] = (active && ae > 0.f) ? dA : 0.f;
+      for (int u = 0; u < U; ++u) {
+        const float dA = (gg[u] - m1 - xhat[u] * m2) * rstd;
+        dT[u] = a[u] > 0.f ? dA : 0.f;             // rows outside a sample have g = 0 -> dA = 0
       }
-      // operands: dO_h (tf32 A of dP; bf16 B of dV), and the dR, g*xhat, g columns of dZ
+      // ---- operands.  shared memory: B of S / dP (tf32), of dQ / dK / dV (bf16); dr, g*xhat, g columns of dZ
+      if (s_loc < SPT) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c)
-        *reinterpret_cast<float4*>(smem + OFF_DO32 + wg * 4096 + nosw_off<2>(row, c)) =
-            make_float4(dTh[c * 4], dTh[c * 4 + 1], dTh[c * 4 + 2], dTh[c * 4 + 3]);
-      *reinterpret_cast<uint4*>(smem + OFF_DO16 + nosw_off<2>(row, wg)) = pack8_bf16(dTh);
-      const uint32_t rm = rmask >> hb;
+        for (int h = 0; h < H; ++h) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) t8[e] = (use_res && ((rm >> e) & 1u)) ? dTh[e] : 0.f;
-      *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, 6 + wg)) = pack8_bf16(t8);
+          for (int c = 0; c < 2; ++c) {
+            *reinterpret_cast<float4*>(smem + SM::OFF_KX + h * G::KX_BYTES + nosw_off<NCHK>(f_loc, s_loc * 2 + c)) =
+                make_float4(qk[U + h * DH + c * 4], qk[U + h * DH + c * 4 + 1], qk[U + h * DH + c * 4 + 2], qk[U + h * DH + c * 4 + 3]);
+            *reinterpret_cast<float4*>(smem + SM::OFF_VX + h * G::KX_BYTES + nosw_off<NCHK>(f_loc, s_loc * 2 + c)) =
+                make_float4(vv[h * DH + c * 4], vv[h * DH + c * 4 + 1], vv[h * DH + c * 4 + 2], vv[h * DH + c * 4 + 3]);
+          }
+          *reinterpret_cast<uint4*>(smem + SM::OFF_K16 + h * G::VX_BYTES + nosw_off<4>(f_loc, s_loc)) = pack8_bf16(qk + U + h * DH);
+          const uint4 qp = pack8_bf16(qk + h * DH);
+          q16[h * 4 + 0] = qp.x; q16[h * 4 + 1] = qp.y; q16[h * 4 + 2] = qp.z; q16[h * 4 + 3] = qp.w;
+          *reinterpret_cast<uint4*>(smem + SM::OFF_Q16 + nosw_off<2>(s_loc * KP + f_loc, h)) = qp;
+          *reinterpret_cast<uint4*>(smem + SM::OFF_DO16 + nosw_off<2>(s_loc * KP + f_loc, h)) = pack8_bf16(dT + h * DH);
+        }
+      } else {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) t8[e] = HSEL(g, e) * HSEL(xhat, e);
-      *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, 8 + wg)) = pack8_bf16(t8);
+        for (int i = 0; i < 8; ++i) q16[i] = 0u;
+      }
+      {
+        float t8[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) t8[e] = HSEL(g, e);
-      *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, 10 + wg)) = pack8_bf16(t8);
+        for (int h = 0; h < H; ++h) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            t8[e] = (use_res && __uint_as_float(zvr[U + h * DH + e]) > 0.f) ? dT[h * DH + e] : 0.f;
+          *reinterpret_cast<uint4*>(smem + SM::OFF_DZ + nosw_off<12>(row, 6 + h)) = pack8_bf16(t8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) t8[e] = g[h * DH + e] * xhat[h * DH + e];
+          *reinterpret_cast<uint4*>(smem + SM::OFF_DZ + nosw_off<12>(row, 8 + h)) = pack8_bf16(t8);
+          *reinterpret_cast<uint4*>(smem + SM::OFF_DZ + nosw_off<12>(row, 10 + h)) = pack8_bf16(g + h * DH);
+        }
+      }
+      // TMEM: head 0's expanded q / dO (own sample's slot; the other slots stay zero)
+      for (uint32_t s = ws_lo; s <= ws_hi; ++s) {
+        uint32_t v8[8], w8[8];
+#pragma unroll
+        for (int e = 0; e < DH; ++e) {
+          v8[e] = (int)s == s_loc ? __float_as_uint(qk[e]) : 0u;
+          w8[e] = (int)s == s_loc ? __float_as_uint(dT[e]) : 0u;
+        }
+        tc_st_32x8(tl + C_QX + s * 8, v8);
+        tc_st_32x8(tl + C_DOX + s * 8, w8);
+      }
+#pragma unroll
+      for (int e = 0; e < DH; ++e) { q1[e] = qk[DH + e]; dO1[e] = dT[DH + e]; }
+    }
+    fence_async_smem();
+    tc_wait_st();
+    tc_fence_before();
+    __syncthreads();
+    if (wq == 0 && elect_one()) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < SPT; ++ks) {
+        tc_mma_tf32_ts(tmem + C_S, tmem + C_QX + ks * 8, mk_desc(b16, SM::OFF_KX + ks * 256, 128, NCHK * 128), ID_S, ks ? 1u : 0u);
+        tc_mma_tf32_ts(tmem + C_DP, tmem + C_DOX + ks * 8, mk_desc(b16, SM::OFF_VX + ks * 256, 128, NCHK * 128), ID_S, ks ? 1u : 0u);
+      }
+      tc_commit(bar);
     }
     // ---- prefetch the next step's rows: a whole step of latency cover
     float xs_n[U], a_n[U], g_n[U];
-    if (!last) load_xsrc(ntile, nit, xs_n);
+    float2 lse_n = make_float2(INFINITY, INFINITY);
+    if (!last) { load_xsrc(ntile, nit, xs_n); lse_n = load_lse(ntile, nit); }
     if (!last && new_tile) load_tile_head(ntile, a_n, g_n);
-    mbar_wait(bar, phase); phase ^= 1u;
-    PROF(2)
+
+    // ================= per head: T2 (P, dS) ; the transposed / plain gradient products ; T3 (dq dk dv -> dZ)
+    auto softmax_bwd = [&](int h) {
+      float s[FP], dp[FP];
+      {
+        uint32_t t[FP], u[FP];
+#pragma unroll
+        for (int c0 = 0; c0 < FP; c0 += 8) {
+          uint32_t t8[8], u8[8];
+          tc_ld_32x8(tl + C_S + c0, t8);
+          tc_ld_32x8(tl + C_DP + c0, u8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { t[c0 + j] = t8[j]; u[c0 + j] = u8[j]; }
+        }
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < FP; ++j) { s[j] = __uint_as_float(t[j]); dp[j] = __uint_as_float(u[j]); }
+      }
+      const float nl = -(h == 0 ? lse.x : lse.y);
+      const float2 c2 = make_float2(scale_log2, scale_log2), nl2 = make_float2(nl, nl);
+      float2 d2[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d2[i] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < FP; j += 2) {
+        float2 e2 = ffma2(make_float2(s[j], s[j + 1]), c2, nl2);
+        e2.x = ex2_approx(e2.x); e2.y = ex2_approx(e2.y);
+        if (j >= FMIN) { e2.x = j < F ? e2.x : 0.f; e2.y = j + 1 < F ? e2.y : 0.f; }   // padded keys
+        s[j] = e2.x; s[j + 1] = e2.y;                                   // P, normalised
+        d2[(j >> 1) & 3] = ffma2(e2, make_float2(dp[j], dp[j + 1]), d2[(j >> 1) & 3]);
+      }
+      const float2 dt = fadd2(fadd2(d2[0], d2[1]), fadd2(d2[2], d2[3]));
+      const float nd = -(dt.x + dt.y);                                   // -sum_j P dP  (dP already carries 1/sqrt(dh))
+      const float2 nd2 = make_float2(nd, nd);
+#pragma unroll
+      for (int j = 0; j < FP; j += 2) {
+        const float2 ds2 = fmul2(make_float2(s[j], s[j + 1]), fadd2(make_float2(dp[j], dp[j + 1]), nd2));
+        dp[j] = ds2.x; dp[j + 1] = ds2.y;                               // dS
+      }
+#pragma unroll
+      for (int c = 0; c < NCHF; ++c) {
+        *reinterpret_cast<uint4*>(smem + SM::OFF_PC + nosw_off<NCHF>(row, c)) = pack8_bf16(s + c * 8);
+        *reinterpret_cast<uint4*>(smem + SM::OFF_DS + nosw_off<NCHF>(row, c)) = pack8_bf16(dp + c * 8);
+      }
+    };
+    auto issue_grads = [&](int h) {                 // dQ_h ; dV_h, dK_h per sample
+#pragma unroll
+      for (int ks = 0; ks < KP / 16; ++ks)
+        tc_mma_bf16(tmem + C_A, mk_desc(b16, SM::OFF_DS + ks * 256, 128, NCHF * 128),
+                    mk_desc(b16, SM::OFF_K16 + h * G::VX_BYTES + ks * 1024, 512, 128), ID_DQ, ks ? 1u : 0u);
+#pragma unroll
+      for (int s = 0; s < SPT; ++s)
+#pragma unroll
+        for (int ks = 0; ks < KP / 16; ++ks) {
+          const uint32_t arow = (uint32_t)((s * NCHF + 2 * ks) * (NCHF * 128));
+          const uint32_t brow = (uint32_t)((s * (KP / 8) + 2 * ks) * 256 + h * 128);
+          tc_mma_bf16(tmem + C_A + 32 + s * 8, mk_desc(b16, SM::OFF_PC + arow, NCHF * 128, 128),
+                      mk_desc(b16, SM::OFF_DO16 + brow, 256, 128), ID_T, ks ? 1u : 0u);
+          tc_mma_bf16(tmem + C_A + 32 + s * 8 + (16u << 16), mk_desc(b16, SM::OFF_DS + arow, NCHF * 128, 128),
+                      mk_desc(b16, SM::OFF_Q16 + brow, 256, 128), ID_T, ks ? 1u : 0u);
+        }
+    };
+    auto grads_to_dz = [&](int h) {
+      // own row: dq (the 8 columns of the row's sample), ReLU' from the packed q
+      {
+        uint32_t dq[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dq[e] = 0u;
+        for (uint32_t s = ws_lo; s <= ws_hi; ++s) {
+          uint32_t t8[8];
+          tc_ld_32x8(tl + C_A + s * 8, t8);
+          tc_wait_ld();
+          if ((int)s == s_loc) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dq[e] = t8[e];
+          }
+        }
+        uint4 v;
+        v.x = pack_bf16x2(__uint_as_float(dq[0]), __uint_as_float(dq[1])) & bf16x2_pos_mask(q16[h * 4 + 0]);
+        v.y = pack_bf16x2(__uint_as_float(dq[2]), __uint_as_float(dq[3])) & bf16x2_pos_mask(q16[h * 4 + 1]);
+        v.z = pack_bf16x2(__uint_as_float(dq[4]), __uint_as_float(dq[5])) & bf16x2_pos_mask(q16[h * 4 + 2]);
+        v.w = pack_bf16x2(__uint_as_float(dq[6]), __uint_as_float(dq[7])) & bf16x2_pos_mask(q16[h * 4 + 3]);
+        *reinterpret_cast<uint4*>(smem + SM::OFF_DZ + nosw_off<12>(row, h)) = v;
+      }
+      // dV (lanes 0-15) / dK (lanes 16-31) of key jw for every sample; ReLU' from the staged v / k rows
+      if (wq * 16 < FP) {                             // uniform
+        const uint8_t* msrc = smem + (is_dk ? SM::OFF_KX : SM::OFF_VX) + h * G::KX_BYTES;
+        const int jr = jw < FP ? jw : 0;
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) {
+          uint32_t t8[8];
+          tc_ld_32x8(tl + C_A + 32 + s * 8, t8);
+          const uint4 m0 = *reinterpret_cast<const uint4*>(msrc + nosw_off<NCHK>(jr, 2 * s));
+          const uint4 m1 = *reinterpret_cast<const uint4*>(msrc + nosw_off<NCHK>(jr, 2 * s + 1));
+          tc_wait_ld();
+          const uint32_t mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};   // relu outputs: > 0 <=> bits != 0
+          float t[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) t[e] = mm[e] ? __uint_as_float(t8[e]) : 0.f;
+          if (jw < FP)
+            *reinterpret_cast<uint4*>(smem + SM::OFF_DZ + nosw_off<12>(s * FP + jw, (is_dk ? 2 : 4) + h)) = pack8_bf16(t);
+        }
+      }
+    };
+
+    mbar_wait(bar, phase); phase ^= 1u;             // S_0, dP_0
     tc_fence_after();
-    float p[FP];                     // normalised attention row of this head
-    {
-#ifdef RS_ITB_PROFILE
-      t_w = clock64();
-#endif
-      ld_window<FP>(tl + TM_S + wg * 128, ws_lo, ws_hi, s_loc, F, -INFINITY, p);
-      PROFW(0)
-      float m4[4] = {p[0], p[1], p[2], p[3]};
+    softmax_bwd(0);
+    for (uint32_t s = ws_lo; s <= ws_hi; ++s) {     // head 1's expanded q / dO (head 0's products are complete)
+      uint32_t v8[8], w8[8];
 #pragma unroll
-      for (int j = 4; j < FP; ++j) m4[j & 3] = fmaxf(m4[j & 3], p[j]);
-      float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-      if (!active) m = 0.f;
-      const float mb = m * scale_log2;
-      float l4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int j = 0; j < FP; j += 2) {                                // the forward's P, bit for bit
-        p[j] = EXP(2) ? fmaf(p[j], scale_log2, -mb) : ex2_approx(fmaf(p[j], scale_log2, -mb));
-        p[j + 1] = EXP(2) ? fmaf(p[j + 1], scale_log2, -mb) : ex2_approx(fmaf(p[j + 1], scale_log2, -mb));
-        bf16_round2(p[j], p[j + 1]);
-        l4[j & 3] += p[j];
-        l4[(j + 1) & 3] += p[j + 1];
+      for (int e = 0; e < DH; ++e) {
+        v8[e] = (int)s == s_loc ? __float_as_uint(q1[e]) : 0u;
+        w8[e] = (int)s == s_loc ? __float_as_uint(dO1[e]) : 0u;
       }
-      const float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
-      const float linv = active ? 1.f / l : 0.f;
-#pragma unroll
-      for (int j = 0; j < FP; ++j) p[j] = active ? p[j] * linv : 0.f;
-      PROFW(1)
-      if (s_loc < SPT && !EXP(3)) {
-#pragma unroll
-        for (int c = 0; c < NCHF; ++c)
-          *reinterpret_cast<uint4*>(smem + OFF_P + wg * 32768 + nosw_off<16>(row, s_loc * NCHF + c)) = pack8_bf16(p + c * 8);
-      }
+      tc_st_32x8(tl + C_QX + s * 8, v8);
+      tc_st_32x8(tl + C_DOX + s * 8, w8);
     }
-    // ================= 3. dP_h = dO_h V_h^T ; dV_h = P_h^T dO_h
-    PROFW(2)
-    if (!EXP(1)) fence_async_smem();
-    PROFW(3)
+    fence_async_smem();
+    tc_wait_st();
     tc_fence_before();
     __syncthreads();
-    PROFW(4)
-    PROF(3)
-    if (issuer >= 0) {
+    if (wq == 0 && elect_one()) {
       tc_fence_after();
-      if (!EXP(0)) {
-      const int h = issuer >> 1;
-      if ((issuer & 1) == 0) {
-        tc_mma_tf32(tmem + TM_S + h * 128, mk_desc(b16, OFF_DO32 + h * 4096, 128, 256),
-                    mk_desc(b16, OFF_V32 + h * 4096, 128, 256), ID_S, 0u);
-      } else {
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)   // K = tile rows, 16 per step = 2 row groups of the P tile
-          tc_mma_bf16(tmem + TM_DV + h * 16, mk_desc(b16, OFF_P + h * 32768 + ks * 4096, 2048, 128),
-                      mk_desc(b16, OFF_DO16 + ks * 512, 256, 128), ID_AT, ks ? 1u : 0u);
+      for (int ks = 0; ks < SPT; ++ks) {            // S_1, dP_1 first: the threads need them next
+        tc_mma_tf32_ts(tmem + C_S, tmem + C_QX + ks * 8, mk_desc(b16, SM::OFF_KX + G::KX_BYTES + ks * 256, 128, NCHK * 128), ID_S, ks ? 1u : 0u);
+        tc_mma_tf32_ts(tmem + C_DP, tmem + C_DOX + ks * 8, mk_desc(b16, SM::OFF_VX + G::KX_BYTES + ks * 256, 128, NCHK * 128), ID_S, ks ? 1u : 0u);
       }
-      }
+      issue_grads(0);
       tc_commit(bar);
     }
-    PROF(4)
-    mbar_wait(bar, phase); phase ^= 1u;
-    PROF(5)
+    mbar_wait(bar, phase); phase ^= 1u;             // S_1, dP_1 and head 0's gradient products (P / dS tiles free again)
     tc_fence_after();
-    {
-      float dp[FP];
-      ld_window<FP>(tl + TM_S + wg * 128, ws_lo, ws_hi, s_loc, F, 0.f, dp);
-      // delta = sum_j P_ij dP_ij from the very P and dP used (not dO.o): the softmax Jacobian then
-      // annihilates any common-mode error of dP exactly (sum_j dS_ij = 0)
-      float d4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int j = 0; j < FP; ++j) d4[j & 3] = fmaf(p[j], dp[j], d4[j & 3]);
-      const float delta = (d4[0] + d4[1]) + (d4[2] + d4[3]);
-#pragma unroll
-      for (int j = 0; j < FP; ++j) dp[j] = p[j] * scale * (dp[j] - delta);     // dS (1/sqrt(dh) folded in)
-      if (s_loc < SPT && !EXP(3)) {
-#pragma unroll
-        for (int cc = 0; cc < NCHF; ++cc)
-          *reinterpret_cast<uint4*>(smem + OFF_P + wg * 32768 + nosw_off<16>(row, s_loc * NCHF + cc)) = pack8_bf16(dp + cc * 8);
-      }
-      uint32_t dv[16];
-      tc_ld_32x16(tl + TM_DV + wg * 16, dv);
-      tc_wait_ld();
-      float t8[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) t8[e] = ((vmask >> e) & 1u) ? HSELF(dv, e) : 0.f;
-      *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, 4 + wg)) = pack8_bf16(t8);
-    }
-    // ================= 4. dQ_h = dS_h K_h ; dK_h = dS_h^T Q_h
-    if (!EXP(1)) fence_async_smem();
+    grads_to_dz(0);
+    softmax_bwd(1);
+    fence_async_smem();
     tc_fence_before();
     __syncthreads();
-    PROF(6)
-    if (issuer >= 0) {
+    if (wq == 0 && elect_one()) {
       tc_fence_after();
-      if (!EXP(0)) {
-      const int h = issuer >> 1;
-      if ((issuer & 1) == 0) {
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          tc_mma_bf16(tmem + TM_DQ + h * 16, mk_desc(b16, OFF_P + h * 32768 + ks * 256, 128, 2048),
-                      mk_desc(b16, OFF_K16 + ks * 512, 256, 128), ID_AK, ks ? 1u : 0u);
-      } else {
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          tc_mma_bf16(tmem + TM_DK + h * 16, mk_desc(b16, OFF_P + h * 32768 + ks * 4096, 2048, 128),
-                      mk_desc(b16, OFF_Q16 + ks * 512, 256, 128), ID_AT, ks ? 1u : 0u);
-      }
-      }
+      issue_grads(1);
       tc_commit(bar);
     }
-    PROF(7)
-    // under the dQ / dK MMAs: the NEXT step's X tile (its Z MMA rides in the same phase as this
-    // step's dX / dW)
-    float xh_n[8];
-    if (!last) stage_x(xs_n, nit, nactive, xh_n);
+    // under head 1's gradient products: the NEXT step's X operand (S / dP columns are dead now)
+    uint4x2_t xb_n;
+    if (!last) xb_n = stage_x(xs_n, nit, nactive);
     mbar_wait(bar, phase); phase ^= 1u;
-    PROF(8)
     tc_fence_after();
-    {
-      uint32_t dq[16], dk[16];
-      tc_ld_32x16(tl + TM_DQ + wg * 16, dq);
-      tc_ld_32x16(tl + TM_DK + wg * 16, dk);
-      tc_wait_ld();
-      float t8[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) t8[e] = ((qmask >> e) & 1u) ? HSELF(dq, e) : 0.f;
-      *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, wg)) = pack8_bf16(t8);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) t8[e] = ((kmask >> e) & 1u) ? HSELF(dk, e) : 0.f;
-      *reinterpret_cast<uint4*>(smem + OFF_DZ + nosw_off<16>(row, 2 + wg)) = pack8_bf16(t8);
-    }
-    // ================= 5. dX = dZ W^T ; [dW^T | db ; dgamma ; dbeta] += [dZ | g*xhat | g]^T [X | 1] ; Z(next)
-    if (!EXP(1)) fence_async_smem();
+    grads_to_dz(1);
+    // ================= dX = dZ W^T ; [dW^T | db ; dgamma ; dbeta] += [dZ | g*xhat | g]^T [X | 1] ; Z(next)
+    fence_async_smem();
+    tc_wait_st();
     tc_fence_before();
     __syncthreads();
-    PROF(9)
-    if (issuer >= 0) {
+    if (wq == 0 && elect_one()) {
       tc_fence_after();
-      if (!EXP(0)) {
-      if (issuer == 0) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          tc_mma_bf16(tmem + TM_DX, mk_desc(b16, OFF_DZ + ks * 256, 128, 2048),
-                      mk_desc(b16, OFF_WT + ks * 256, 128, 1024), ID_DX, ks ? 1u : 0u);
-      } else if (issuer == 1) {
+      for (int ks = 0; ks < 4; ++ks)
+        tc_mma_bf16(tmem + C_DX, mk_desc(b16, SM::OFF_DZ + ks * 256, 128, 1536),
+                    mk_desc(b16, SM::OFF_WT + ks * 256, 128, 1024), ID_DX, ks ? 1u : 0u);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          tc_mma_bf16(tmem + TM_DW, mk_desc(b16, OFF_DZ + ks * 4096, 2048, 128),
-                      mk_desc(b16, OFF_XB + ks * 1024, 512, 128), ID_DW, ks ? 1u : dw_acc);
-      } else if (issuer == 2 && !last) {
-        issue_proj_3xtf32(tmem + TM_Z, sbase + OFF_X, sbase + OFF_W32, ID_Z);
-      }
+      for (int ks = 0; ks < 8; ++ks)
+        tc_mma_bf16(tmem + C_DW, mk_desc(b16, SM::OFF_DZ + ks * 3072, 1536, 128),
+                    mk_desc(b16, SM::OFF_XB + ks * 1024, 512, 128), ID_DW, ks ? 1u : dw_acc);
+      if (!last) {
+        issue_proj_3xtf32_ts(tmem + C_A, tmem + C_X, sbase + SM::OFF_W32, ID_Z);
+        tc_mma_tf32_ts(tmem + C_A, tmem + C_X + 32, make_nosw_desc(sbase + SM::OFF_BT, 128, 256), ID_Z, 1u);
       }
       tc_commit(bar);
     }
     dw_acc = 1u;
-    PROF(10)
     mbar_wait(bar, phase); phase ^= 1u;
-    PROF(11)
     tc_fence_after();
     {
       uint32_t dxr[16];
-      tc_ld_32x16(tl + TM_DX, dxr);
+      tc_ld_32x16(tl + C_DX, dxr);
       tc_wait_ld();
       if (it > 0) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) g[u] = active ? __uint_as_float(dxr[u]) : 0.f;   // stays fp32 between iterations
+        for (int u = 0; u < U; ++u) g[u] = __uint_as_float(dxr[u]);      // stays fp32 between iterations
       } else {
         if (active) {
-          T* dp = dx + smp * dx_bs + (int64_t)f_loc * dx_ld + hb;
-          store4<T>(dp, make_float4(HSELF(dxr, 0), HSELF(dxr, 1), HSELF(dxr, 2), HSELF(dxr, 3)));
-          store4<T>(dp + 4, make_float4(HSELF(dxr, 4), HSELF(dxr, 5), HSELF(dxr, 6), HSELF(dxr, 7)));
+          T* dp_ = dx + smp * dx_bs + (int64_t)f_loc * dx_ld;
+#pragma unroll
+          for (int u = 0; u < U; u += 4)
+            store4<T>(dp_ + u, make_float4(__uint_as_float(dxr[u]), __uint_as_float(dxr[u + 1]), __uint_as_float(dxr[u + 2]),
+                                           __uint_as_float(dxr[u + 3])));
         }
         if (!last) {
 #pragma unroll
@@ -563,20 +567,22 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       }
       if (!last) {
         // dW of this step has consumed XB: the next step's bf16 x row may land now
-        *reinterpret_cast<uint4*>(smem + OFF_XB + nosw_off<4>(row, wg)) = pack8_bf16(xh_n);
+        *reinterpret_cast<uint4*>(smem + SM::OFF_XB + nosw_off<4>(row, 0)) = xb_n.a;
+        *reinterpret_cast<uint4*>(smem + SM::OFF_XB + nosw_off<4>(row, 1)) = xb_n.b;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           a[u] = new_tile ? a_n[u] : xs[u];      // same tile: a of iteration it-1 = this step's x-source
           xs[u] = xs_n[u];
         }
+        lse = lse_n;
       }
     }
     tile = ntile; it = nit; active = nactive;
   }
   // ---- per-CTA partials in the layout of the FFMA kernel: dW[D][4U] | db[4U] | dgamma[U] | dbeta[U]
-  if (wg == 0) {
+  {
     uint32_t acc[32];
-    tc_ld_32x32(tl + TM_DW, acc);
+    tc_ld_32x32(tl + C_DW, acc);
     float* mine = part + (int64_t)blockIdx.x * (D * N4 + 6 * U);
     if (row < N4) {
 #pragma unroll
@@ -586,9 +592,9 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (wq == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(256));
   }
 }
 
@@ -604,11 +610,11 @@ static __global__ void itb_reduce_partials_kernel(const float* __restrict__ part
 template <int NCHF, typename T>
 static int launch_itc_bwd(const IBwdArgs& a) {
   auto kern = interacting_tc_bwd_kernel<NCHF, T>;
-  constexpr int smem = 2 * 32768 + 32768 + 16384 + 16384 + 4 * 2 * 4096 + 3 * 4096 + 8192 + 2048 + (64 + 32) * 4 + 64 + 1024;
+  constexpr int smem = ItbSmem<NCHF>::TOTAL;
   RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  constexpr int SPT = 128 / (NCHF * 8);
-  const int ntiles = (a.B + SPT - 1) / SPT;
-  int grid = sm_count();
+  using G = ItcGeom<NCHF>;
+  const int ntiles = (a.B + G::SPT - 1) / G::SPT;
+  int grid = sm_count() * 2;
   if (grid > ntiles) grid = ntiles;
   const int np = 16 * 64 + 6 * 16;
   if (a.saved == nullptr) {
@@ -619,7 +625,7 @@ static int launch_itc_bwd(const IBwdArgs& a) {
     set_error("interacting_tc_bwd: workspace %zu < %zu", a.ws_bytes, (size_t)grid * np * sizeof(float));
     return RS_ERR_WORKSPACE;
   }
-  kern<<<grid, 256, smem, a.st>>>((const T*)a.x, a.x_ld, a.x_bs, (const float*)a.saved, a.W, a.b, a.gm, a.bt, a.eps,
+  kern<<<grid, 128, smem, a.st>>>((const T*)a.x, a.x_ld, a.x_bs, (const float*)a.saved, a.W, a.b, a.gm, a.bt, a.eps,
                                   (const T*)a.dy, a.dy_ld, a.dy_bs, (T*)a.dx, a.dx_ld, a.dx_bs, (float*)a.ws, a.B, a.F,
                                   a.L, a.use_res);
   if (int e = check_launch("interacting_tc_bwd")) return e;
@@ -629,7 +635,7 @@ static int launch_itc_bwd(const IBwdArgs& a) {
 
 int interacting_tc_bwd(const IBwdArgs& a) {
   switch ((a.F + 7) / 8) {
-    case 1: return launch_itc_bwd<1, __nv_bfloat16>(a);
+    case 1:
     case 2: return launch_itc_bwd<2, __nv_bfloat16>(a);
     case 3: return launch_itc_bwd<3, __nv_bfloat16>(a);
     case 4: return launch_itc_bwd<4, __nv_bfloat16>(a);
@@ -637,22 +643,5 @@ int interacting_tc_bwd(const IBwdArgs& a) {
     default: return launch_itc_bwd<6, __nv_bfloat16>(a);
   }
 }
-
-#ifdef RS_ITB_PROFILE
-extern "C" int rs_debug_itb_exp(int mode) {
-  cudaDeviceSynchronize();
-  cudaMemcpyToSymbol(itb_exp_mode, &mode, sizeof(int));
-  return 0;
-}
-extern "C" int rs_debug_itb_profile(unsigned long long* out32, int reset) {
-  cudaDeviceSynchronize();
-  if (out32) cudaMemcpyFromSymbol(out32, itb_prof, sizeof(unsigned long long) * 32);
-  if (reset) {
-    unsigned long long z[32] = {0};
-    cudaMemcpyToSymbol(itb_prof, z, sizeof(z));
-  }
-  return 0;
-}
-#endif
 
 }  // namespace rs

@@ -325,4 +325,26 @@ __device__ __forceinline__ void issue_proj_3xtf32_ts(uint32_t tmem_z, uint32_t t
   }
 }
 
+// samples per 128-row tile: whole samples of FP = 8 NCHF padded fields, at most 4 (the expanded Q operand has
+// 8 SPT columns per head and the P.V product N = 8 SPT <= 32)
+template <int NCHF> struct ItcGeom {
+  static constexpr int FP = NCHF * 8;
+  static constexpr int SPT = (128 / FP) < 4 ? (128 / FP) : 4;
+  static constexpr int NCHK = SPT * 2;                 // 16-byte chunks per row of the expanded K operand (tf32)
+  static constexpr int KP = (FP + 15) / 16 * 16;       // key dimension padded to the bf16 K step
+  static constexpr int KX_BYTES = NCHF * NCHK * 128;   // [FP keys][8 SPT] tf32
+  static constexpr int VX_BYTES = (KP / 8) * 512;      // [KP keys][32 = (sample, e)] bf16, MN-major
+};
+
+// bias through the MMA: B tile [64 n][8 k] tf32 with k = 0 -> b_hi[n], k = 1 -> b_lo[n]; the A operand carries
+// the constant columns [1 1 0 0 0 0 0 0] next to [x_hi | x_lo]
+__device__ __forceinline__ void stage_bias_tile(uint8_t* bt_smem, const float* __restrict__ bias, int tid, int nthreads) {
+  for (int i = tid; i < 64 * 2; i += nthreads) {
+    const int n = i >> 1, c = i & 1;
+    const float bv = bias[n], bh = tf32_hi(bv);
+    *reinterpret_cast<float4*>(bt_smem + nosw_off<2>(n, c)) =
+        c ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(bh, bv - bh, 0.f, 0.f);
+  }
+}
+
 }  // namespace rs
