@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 3   /* 3: + rs_staytime_labels, rs_binary_metrics_*, rs_set_fp32_gemm_mode */
+#define RS_ABI_VERSION 4   /* 4: + rs_interacting_path; saved buffer grows by the per-head softmax statistics */
 
 enum rs_dtype { RS_F32 = 0, RS_BF16 = 1 };
 
@@ -255,7 +255,9 @@ int rs_permute_rows(const void* src, void* out, const int32_t* index, int64_t n,
  * element (b,f,c) lives at ptr[b*bs + f*ld + c] (ld = field stride, bs = sample
  * stride in elements; bs = 0 means F*ld), so the layer can read / write the
  * Flatten()ed [B, F*U] columns of a wider concat buffer in place (autoint:36,45).
- * `saved` (training): rs_interacting_saved_bytes(B,F,U,L) bytes = fp32 [L, B*F, U],
+ * `saved` (training): rs_interacting_saved_bytes(B,F,U,L) bytes = fp32 [L, B*F, U] (then
+ * fp32 [L, B*F, 4], tensor-core kernels only: the per-head softmax statistics
+ * lse = max_j(s c) + log2 sum_j exp2(s c - max) of every row, first H of the 4 slots),
  * written by the forward and handed unchanged to the backward of the SAME
  * compute_bf16 mode; its content is private to that pair (kept in fp32 whatever
  * `dtype` is, so a bf16 run rounds only at the layer's input and output):
@@ -268,9 +270,16 @@ int rs_permute_rows(const void* src, void* out, const int32_t* index, int64_t n,
  * Parameters are fp32.
  * compute_bf16 != 0 runs every contraction of the layer on tcgen05 tensor cores (tf32
  * projections / QK^T, bf16 P.V and gradient products, fp32 TMEM accumulators) for the
- * shapes built (D = U = 16, H = 2, F <= 48) and falls back to FFMA arithmetic for the
- * others; 0 = fp32 FFMA everywhere (parity mode).
+ * shapes built (D = U = 16, H = 2, F <= 48, bf16 activations, no dropout) and uses the
+ * FFMA kernels for the others; 0 = fp32 FFMA everywhere (parity mode).
+ * rs_interacting_path tells which kernels a call with these arguments runs:
+ * RS_PATH_TCGEN05, RS_PATH_FFMA, or RS_PATH_NONE (shape not built: the call would fail
+ * with RS_ERR_UNSUPPORTED) — tests assert the path instead of inferring it.
  */
+#define RS_PATH_NONE 0
+#define RS_PATH_FFMA 1
+#define RS_PATH_TCGEN05 2
+int rs_interacting_path(int F, int D, int U, int H, int dtype, int compute_bf16, float dropout_rate);
 size_t rs_interacting_workspace_bytes(int B, int F, int D, int U);
 size_t rs_interacting_saved_bytes(int B, int F, int U, int L);
 int rs_interacting_fwd(const void* x, int64_t x_ld, int64_t x_bs, int dtype,

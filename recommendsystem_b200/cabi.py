@@ -14,6 +14,7 @@ RS_F32, RS_BF16 = 0, 1
 (EPI_NONE, EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_SIGMOID, EPI_MUL_RELU_MASK, EPI_MUL_DSIGMOID,
  EPI_ACCUM) = range(7)
 DIN_A, DIN_B = 0, 1
+PATH_NONE, PATH_FFMA, PATH_TCGEN05 = 0, 1, 2
 
 _p, _i, _i64, _f, _sz, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t, C.c_uint64
 
@@ -47,6 +48,7 @@ PROTOTYPES = {
     "rs_permute_rows": (_i, [_p, _p, _p, _i64, _i, _i, _i, _p]),
     "rs_interacting_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "rs_interacting_saved_bytes": (_sz, [_i, _i, _i, _i]),
+    "rs_interacting_path": (_i, [_i, _i, _i, _i, _i, _i, _f]),
     "rs_interacting_fwd": (_i, [_p, _i64, _i64, _i, _p, _p, _p, _p, _f, _p, _i64, _i64, _p,
                                 _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "rs_interacting_fwd_dropout": (_i, [_p, _i64, _i64, _i, _p, _p, _p, _p, _f, _p, _i64, _i64, _p,

@@ -31,6 +31,15 @@ size_t rs_interacting_saved_bytes(int B, int F, int U, int L) {
   return (size_t)L * (size_t)B * (size_t)F * (size_t)(U + 4) * sizeof(float);
 }
 
+int rs_interacting_path(int F, int D, int U, int H, int dtype, int compute_bf16, float dropout_rate) {
+  if (compute_bf16 && dropout_rate == 0.f && interacting_tc_supported(F, D, U, H, dtype)) return RS_PATH_TCGEN05;
+#define RS_CASE(DD, UU, HH) \
+  if (D == DD && U == UU && H == HH) return RS_PATH_FFMA;
+  RS_INTERACT_SHAPES(RS_CASE)
+#undef RS_CASE
+  return RS_PATH_NONE;
+}
+
 int rs_interacting_fwd_dropout(const void* x, int64_t x_ld, int64_t x_bs, int dtype, const float* Wqkvr,
                                const float* bqkvr, const float* ln_gamma, const float* ln_beta,
                                float ln_eps, void* y, int64_t y_ld, int64_t y_bs, void* saved, int B, int F, int D, int U,
@@ -51,7 +60,7 @@ int rs_interacting_fwd_dropout(const void* x, int64_t x_ld, int64_t x_bs, int dt
   a.drop_rate = dropout_rate;
   a.drop_seed = dropout_seed;
   // attention dropout is built into the FFMA kernels only: the tensor-core path is taken without it
-  if (compute_bf16 && dropout_rate == 0.f && interacting_tc_supported(F, D, U, H, dtype)) return interacting_tc_fwd(a);
+  if (rs_interacting_path(F, D, U, H, dtype, compute_bf16, dropout_rate) == RS_PATH_TCGEN05) return interacting_tc_fwd(a);
 #define RS_CASE(DD, UU, HH) \
   if (D == DD && U == UU && H == HH) return interacting_fwd_##DD##_##UU##_##HH(a);
   RS_INTERACT_SHAPES(RS_CASE)
@@ -91,7 +100,7 @@ int rs_interacting_bwd_dropout(const void* x, int64_t x_ld, int64_t x_bs, const 
              B, F, L, use_res, dtype, ws, ws_bytes, as_stream(stream)};
   a.drop_rate = dropout_rate;
   a.drop_seed = dropout_seed;
-  if (compute_bf16 && dropout_rate == 0.f && interacting_tc_supported(F, D, U, H, dtype)) return interacting_tc_bwd(a);
+  if (rs_interacting_path(F, D, U, H, dtype, compute_bf16, dropout_rate) == RS_PATH_TCGEN05) return interacting_tc_bwd(a);
 #define RS_CASE(DD, UU, HH) \
   if (D == DD && U == UU && H == HH) return interacting_bwd_##DD##_##UU##_##HH(a);
   RS_INTERACT_SHAPES(RS_CASE)

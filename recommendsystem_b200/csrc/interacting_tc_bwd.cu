@@ -150,26 +150,28 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
   uint32_t phase = 0;
   uint32_t dw_acc = 0;                 // 0 until the first dW MMA of this CTA
 
-  auto load_xsrc = [&](int tile_, int it_, float (&dst)[U]) {
+  // Rows are prefetched RAW (bf16 pairs stay packed, fp32 stays bits) and converted where they are used: a
+  // conversion at the load would make the warp wait for the load right there instead of a step later.
+  static_assert(sizeof(T) == 2, "bf16 activations");
+  auto load_xsrc = [&](int tile_, int it_, uint32_t (&dst)[U]) {
     const int64_t smp_ = (int64_t)tile_ * SPT + s_loc;
+#pragma unroll
+    for (int c = 0; c < U; ++c) dst[c] = 0u;
     if (row_ok && smp_ < B) {
       if (it_ == 0) {
 #pragma unroll
         for (int c = 0; c < U; c += 4) {
-          const float4 t4 = load4<T>(x + smp_ * x_bs + (int64_t)f_loc * x_ld + c);
-          dst[c] = t4.x; dst[c + 1] = t4.y; dst[c + 2] = t4.z; dst[c + 3] = t4.w;
+          const uint2 t2 = ldg_nc_u2(reinterpret_cast<const uint2*>(x + smp_ * x_bs + (int64_t)f_loc * x_ld + c));
+          dst[c / 2] = t2.x; dst[c / 2 + 1] = t2.y;
         }
       } else {
         const float* sp = saved + ((int64_t)(it_ - 1) * total_rows + smp_ * F + f_loc) * U;
 #pragma unroll
         for (int c = 0; c < U; c += 4) {
-          const float4 t4 = ldg_nc_f4(reinterpret_cast<const float4*>(sp + c));
+          const uint4 t4 = ldg_nc_u4(reinterpret_cast<const uint4*>(sp + c));
           dst[c] = t4.x; dst[c + 1] = t4.y; dst[c + 2] = t4.z; dst[c + 3] = t4.w;
         }
       }
-    } else {
-#pragma unroll
-      for (int c = 0; c < U; ++c) dst[c] = 0.f;
     }
   };
   auto load_lse = [&](int tile_, int it_) -> float2 {
@@ -178,7 +180,7 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       return *reinterpret_cast<const float2*>(lse_base + ((int64_t)it_ * total_rows + smp_ * F + f_loc) * H);
     return make_float2(INFINITY, INFINITY);                  // P = exp2(S c - inf) = 0 for rows outside a sample
   };
-  auto load_tile_head = [&](int tile_, float (&a_)[U], float (&g_)[U]) {
+  auto load_tile_head = [&](int tile_, float (&a_)[U], uint32_t (&g_)[U / 2]) {
     const int64_t smp_ = (int64_t)tile_ * SPT + s_loc;
     if (row_ok && smp_ < B) {
       const float* sp = saved + ((int64_t)(L - 1) * total_rows + smp_ * F + f_loc) * U;
@@ -186,18 +188,23 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       for (int c = 0; c < U; c += 4) {
         const float4 t4 = ldg_nc_f4(reinterpret_cast<const float4*>(sp + c));
         a_[c] = t4.x; a_[c + 1] = t4.y; a_[c + 2] = t4.z; a_[c + 3] = t4.w;
-        const float4 d4 = load4<T>(dy + smp_ * dy_bs + (int64_t)f_loc * dy_ld + c);
-        g_[c] = d4.x; g_[c + 1] = d4.y; g_[c + 2] = d4.z; g_[c + 3] = d4.w;
+        const uint2 d2 = ldg_nc_u2(reinterpret_cast<const uint2*>(dy + smp_ * dy_bs + (int64_t)f_loc * dy_ld + c));
+        g_[c / 2] = d2.x; g_[c / 2 + 1] = d2.y;
       }
     } else {
 #pragma unroll
-      for (int c = 0; c < U; ++c) { a_[c] = 0.f; g_[c] = 0.f; }
+      for (int c = 0; c < U; ++c) a_[c] = 0.f;
+#pragma unroll
+      for (int c = 0; c < U / 2; ++c) g_[c] = 0u;
     }
   };
   // step input row -> [x_hi | x_lo | 1 1 0..] in TMEM (A of Z); returns the row as packed bf16 (B of dW)
-  auto stage_x = [&](const float (&src)[U], int it_, bool act_) -> uint4x2_t {
+  auto stage_x = [&](const uint32_t (&raw)[U], int it_, bool act_) -> uint4x2_t {
     float xh[U];
     if (act_ && it_ > 0) {
+      float src[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) src[u] = __uint_as_float(raw[u]);
       float mean, rstd;
       ln_row_stats<U>(src, eps, mean, rstd);      // bit-identical to the forward's LayerNorm
 #pragma unroll
@@ -210,7 +217,10 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       }
     } else {
 #pragma unroll
-      for (int u = 0; u < U; ++u) xh[u] = act_ ? src[u] : 0.f;
+      for (int u = 0; u < U; u += 2) {                      // the bf16 layer input (zeros for rows outside a sample)
+        const float2 f2 = unpack_bf16x2(raw[u / 2]);
+        xh[u] = f2.x; xh[u + 1] = f2.y;
+      }
     }
     uint32_t hi[16], lo[16], one8[8];
 #pragma unroll
@@ -235,9 +245,18 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
   const int my_tiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int nsteps = my_tiles * L;
   bool active = row_ok && (int64_t)tile * SPT + s_loc < B;
-  float a[U], g[U], xs[U];
+  float a[U], g[U];
+  uint32_t xs[U];
   float2 lse = load_lse(tile, it);
-  load_tile_head(tile, a, g);
+  {
+    uint32_t g_raw[U / 2];
+    load_tile_head(tile, a, g_raw);
+#pragma unroll
+    for (int u = 0; u < U; u += 2) {
+      const float2 f2 = unpack_bf16x2(g_raw[u / 2]);
+      g[u] = f2.x; g[u + 1] = f2.y;
+    }
+  }
   load_xsrc(tile, it, xs);
   {
     const uint4x2_t xb = stage_x(xs, it, active);
@@ -367,7 +386,8 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       tc_commit(bar);
     }
     // ---- prefetch the next step's rows: a whole step of latency cover
-    float xs_n[U], a_n[U], g_n[U];
+    uint32_t xs_n[U], g_n[U / 2];
+    float a_n[U];
     float2 lse_n = make_float2(INFINITY, INFINITY);
     if (!last) { load_xsrc(ntile, nit, xs_n); lse_n = load_lse(ntile, nit); }
     if (!last && new_tile) load_tile_head(ntile, a_n, g_n);
@@ -562,7 +582,10 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
         }
         if (!last) {
 #pragma unroll
-          for (int u = 0; u < U; ++u) g[u] = g_n[u];
+          for (int u = 0; u < U; u += 2) {
+            const float2 f2 = unpack_bf16x2(g_n[u / 2]);
+            g[u] = f2.x; g[u + 1] = f2.y;
+          }
         }
       }
       if (!last) {
@@ -571,7 +594,7 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
         *reinterpret_cast<uint4*>(smem + SM::OFF_XB + nosw_off<4>(row, 1)) = xb_n.b;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          a[u] = new_tile ? a_n[u] : xs[u];      // same tile: a of iteration it-1 = this step's x-source
+          a[u] = new_tile ? a_n[u] : __uint_as_float(xs[u]);      // same tile: a of iteration it-1 = this step's x-source
           xs[u] = xs_n[u];
         }
         lse = lse_n;

@@ -190,6 +190,12 @@ def permute_rows(src, index, scatter=False, out=None):
 # ------------------------------------------------------------- interacting
 
 
+def interacting_path(F, D, U, H, dtype, compute_bf16, dropout_rate=0.0):
+    """Which kernels rs_interacting_fwd/_bwd run for these arguments: cabi.PATH_TCGEN05 / PATH_FFMA / PATH_NONE."""
+    dt = cabi.RS_BF16 if dtype == torch.bfloat16 else cabi.RS_F32
+    return int(cabi.load().rs_interacting_path(F, D, U, H, dt, int(compute_bf16), float(dropout_rate)))
+
+
 def interacting_saved(B, F, U, L, device):
     """rs_interacting_saved_bytes(B, F, U, L) bytes; returned as the [L, B*F, U] view of the activations (the
     per-head softmax statistics of the tensor-core kernels follow them in the same storage)."""

@@ -169,3 +169,56 @@ def test_autoint_step_bf16(cuda_dev):
     # bf16 weight shadows track the fp32 masters after the step
     assert torch.equal(tr.P16["mlp_W0"], tr.P["mlp_W0"].to(torch.bfloat16))
     assert torch.equal(tr.WT16["mlp_W0"], tr.P["mlp_W0"].to(torch.bfloat16).t())
+
+
+def test_autoint_step_bf16_bench_size(cuda_dev):
+    """One bf16 train step at the benchmarked batch (B = 8192, F = 39, L = 3, DNN 256-128): loss and logits against the
+    fp64 oracle on the same tables / weights (1e-2), the embedding gather bit-exact."""
+    from oracle import oracle_np as onp
+    from recommendsystem_b200.autoint import AutoIntConfig, AutoIntTrainer
+    rng = np.random.default_rng(11)
+    B, F, d, H, L, hidden = 8192, 39, 16, 2, 3, (256, 128)
+    cfg = AutoIntConfig(num_fields=F, rows_per_field=5000, embed_dim=d, unit_num=d, head_num=H, layer_num=L,
+                        mlp_hidden=hidden, batch=B, dtype="bf16", lr_dense=1e-3, lr_sparse=1e-2)
+    tr = AutoIntTrainer(cfg, cuda_dev)
+    P0 = tr.dense_state()
+    table0 = tr.table.cpu().numpy().copy()
+    ids = rng.integers(0, 2 ** 40, size=(B, F)).astype(np.int64)
+    y = (rng.random((B, 1)) < 0.25).astype(np.float32)
+    loss = tr.step(torch.from_numpy(ids).to(cuda_dev), torch.from_numpy(y).to(cuda_dev))
+    torch.cuda.synchronize()
+    X, rows = onp.embed_gather(table0, ids, tr.rows_host, tr.base_host)
+    Xb = tr.X.float().cpu().numpy()
+    assert np.array_equal(Xb, torch.from_numpy(X).to(torch.bfloat16).float().numpy())
+    res = onp.autoint_fwd_bwd(f64(Xb), _oracle_params(P0), f64(y), H, L, cfg.ln_eps)
+    assert abs(float(loss) - res["loss"]) <= REL_BF16 * abs(res["loss"]), (float(loss), res["loss"])
+    assert_close(tr.p_raw.float().cpu().numpy(), res["p_raw"], REL_BF16, "bf16 logits B=8192")
+    # end-to-end gradient of the embedding rows: direction and size (see test_interacting_tc_bwd_end_to_end)
+    a, r = f64(tr.dX.float().cpu().numpy()).ravel(), f64(res["dX"]).ravel()
+    cos = float(a @ r / (np.linalg.norm(a) * np.linalg.norm(r)))
+    print("dX cosine vs fp64 oracle", cos, "norm ratio", float(np.linalg.norm(a) / np.linalg.norm(r)))
+    assert cos >= 0.99
+
+
+def test_autoint_bf16_tracks_fp32_training(cuda_dev):
+    """200 train steps from the same initial state on the same batches: the bf16 / tcgen05 trainer against the
+    fp32 parity-mode trainer.  Mean loss over the last 20 steps within 1 % — the end-to-end statement that the
+    bf16 gradients train the model the way the fp32 ones do."""
+    from recommendsystem_b200.autoint import AutoIntConfig, AutoIntTrainer
+    B, F = 512, 39
+    mk = lambda dt: AutoIntConfig(num_fields=F, rows_per_field=300, embed_dim=16, unit_num=16, head_num=2, layer_num=3,
+                                  mlp_hidden=(128, 64), batch=B, dtype=dt, lr_dense=2e-3, lr_sparse=2e-2, seed=123)
+    a, b = AutoIntTrainer(mk("f32"), cuda_dev), AutoIntTrainer(mk("bf16"), cuda_dev)
+    assert torch.equal(a.table, b.table) and torch.equal(a.flat, b.flat)
+    g = torch.Generator(device=cuda_dev).manual_seed(77)
+    # a learnable synthetic target: the label depends on two of the id fields
+    la, lb = [], []
+    for i in range(200):
+        ids = torch.randint(0, 300, (B, F), device=cuda_dev, generator=g)
+        y = (((ids[:, 0] + 2 * ids[:, 5]) % 7) < 2).float().unsqueeze(1)
+        la.append(float(a.step(ids, y)))
+        lb.append(float(b.step(ids, y)))
+    fa, fb = sum(la[-20:]) / 20, sum(lb[-20:]) / 20
+    print(f"fp32 loss {la[0]:.4f} -> {fa:.4f}; bf16 loss {lb[0]:.4f} -> {fb:.4f}")
+    assert fa < 0.97 * la[0], "the fp32 run did not learn: the comparison would be vacuous"
+    assert abs(fb - fa) <= 0.01 * fa, (fa, fb)
