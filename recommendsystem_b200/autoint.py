@@ -378,13 +378,43 @@ class AutoIntTrainer:
         else:
             self._launch_step()
 
+    # ---- capture: the warm-up launch must not train ---------------------------------------------------
+    def _touched_rows(self) -> torch.Tensor:
+        """Arena rows the step on the CURRENT static id buffer updates (sorted unique int64)."""
+        rows = self.base_t[None, :] + torch.remainder(self.ids, self.rows_t[None, :])
+        return torch.unique(rows[self.ids >= 0])
+
+    def _snapshot(self):
+        """Everything one optimizer step changes: the [w|m|v] records of the touched rows, the dense parameters
+        with their moments and bf16 shadows, the Adam step scalars."""
+        rows = self._touched_rows()
+        snap = {"rows": rows, "arena": self.arena[rows].clone(), "flat": self.flat.clone(),
+                "flat_m": self.flat_m.clone(), "flat_v": self.flat_v.clone(), "flat_bf16": self.flat_bf16.clone(),
+                "scalars": self.adam_scalars.clone()}
+        if self.bf16:
+            snap["WT16"] = {k: v.clone() for k, v in self.WT16.items()}
+        return snap
+
+    def _restore(self, snap):
+        self.arena[snap["rows"]] = snap["arena"]
+        self.flat.copy_(snap["flat"]); self.flat_m.copy_(snap["flat_m"]); self.flat_v.copy_(snap["flat_v"])
+        self.flat_bf16.copy_(snap["flat_bf16"]); self.adam_scalars.copy_(snap["scalars"])
+        for k, v in snap.get("WT16", {}).items():
+            self.WT16[k].copy_(v)
+
     def capture(self):
-        """Capture the step into a CUDA graph (after a warm-up launch on a side stream)."""
+        """Capture the step into a CUDA graph.  The warm-up launch (one real step on whatever the static id / label
+        buffers hold) is undone afterwards — tables, optimizer state, dense parameters and the Adam step counter
+        are restored bit for bit — so capture() may be called after load_checkpoint / import_keras_autoint
+        without changing the loaded weights, and exact resume holds."""
+        snap = self._snapshot()
         s = torch.cuda.Stream(device=self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
             self._launch_step()
         torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self._restore(snap)
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):

@@ -128,6 +128,11 @@ def save_checkpoint(trainer, directory, step: int | None = None) -> Path:
 
     write_shard(shard_path(directory, r, W), chunks())
     if r == 0:
+        # a reused directory may hold table shards of an earlier save at another world size: remove them so
+        # that the directory only ever describes ONE checkpoint (meta.json names the world size that counts)
+        for stale in directory.glob("tables.rank*of*.bin"):
+            if not stale.name.endswith(f"of{W}.bin"):
+                stale.unlink()
         dense = {}
         for name, shape, off in trainer.spec:
             k = int(np.prod(shape))
@@ -186,6 +191,11 @@ def load_checkpoint(trainer, directory, tables: bool = True, dense: bool = True)
             trainer.adam_scalars.copy_(torch.from_numpy(z["adam_scalars"]))
         _refresh_dense_shadows(trainer)
     torch.cuda.synchronize(trainer.dev)
+    if W > 1:
+        # the next step's peer gather reads the OTHER ranks' shards at its very start: nobody may run ahead of a
+        # rank that is still copying its shard in
+        import torch.distributed as dist
+        dist.barrier(group=getattr(getattr(trainer, "ex", None), "group", None))
     return meta
 
 

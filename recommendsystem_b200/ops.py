@@ -40,17 +40,24 @@ def _need(cond, msg):
 
 
 class _Workspace:
-    """Per-device grow-only scratch buffers keyed by purpose (stable addresses once
-    warmed up, so CUDA-graph capture sees fixed pointers)."""
+    """Scratch buffers keyed by (purpose, device, STREAM).  Two rules make them safe under captured multi-stream
+    steps: (1) a buffer is never freed — when a larger request replaces it the old tensor is retired, not
+    released, because an already captured CUDA graph may still hold its address; (2) every stream has its own
+    buffer per purpose, so kernels that the step runs concurrently on the main and the side stream (split-K
+    partials of a weight-gradient GEMM beside a dgrad GEMM) never share scratch."""
 
     def __init__(self):
         self.bufs = {}
+        self.retired = []
 
     def get(self, key, nbytes, device):
-        k = (key, device)
+        dev = torch.device(device)
+        k = (key, dev, torch.cuda.current_stream(dev).cuda_stream)
         b = self.bufs.get(k)
         if b is None or b.numel() < nbytes:
-            b = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            if b is not None:
+                self.retired.append(b)
+            b = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=dev)
             self.bufs[k] = b
         return b
 

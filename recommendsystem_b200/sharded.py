@@ -85,14 +85,15 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
 
     def __init__(self, cfg: AutoIntConfig, device, group=None, global_tables: torch.Tensor | None = None,
                  dense_init: dict | None = None, capacity_factor: float | None = None,
-                 peer_gather: bool | None = None):
+                 peer_gather: bool | None = None, capacity: int | None = None):
         self.ex = Exchange(group)
         self.world, self.rank = self.ex.world, self.ex.rank
         self._global_tables = global_tables
         self._capacity_factor = capacity_factor
         super().__init__(cfg, device, tables=None, dense_init=dense_init)
         W, n, d = self.world, cfg.batch * cfg.num_fields, cfg.embed_dim
-        self.cap = bucket_capacity(n, W, capacity_factor)
+        # `capacity` pins the slots per (source, owner) bucket exactly (tests: buckets filled to the brim, forced overflow)
+        self.cap = int(capacity) if capacity is not None else bucket_capacity(n, W, capacity_factor)
         T = self.act_dtype
         dev = self.dev
         self.send_rows = torch.empty(W * self.cap, dtype=torch.int32, device=dev)
@@ -251,13 +252,57 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
         with ph("allreduce_dense"):
             self.ex.all_reduce_mean(self.flat_g)
 
+    def _touched_rows(self) -> torch.Tensor:
+        """LOCAL arena rows the step on the current static id buffers of ALL ranks updates on this rank."""
+        everyone = [torch.empty_like(self.ids) for _ in range(self.world)]
+        dist.all_gather(everyone, self.ids, group=self.ex.group)
+        ids = torch.cat(everyone, 0)
+        g = torch.remainder(ids, self.rows_t[None, :])
+        mine = (torch.remainder(g, self.world) == self.rank) & (ids >= 0)
+        local = self.lbase_t[None, :] + torch.div(g, self.world, rounding_mode="floor")
+        return torch.unique(local[mine])
+
     def capture(self):
-        """Capture the sharded step (collectives included).  The warm-up launches run on whatever
-        the static id buffer holds (zeros unless the caller filled it), which may legitimately
-        overflow the buckets; the flag is cleared afterwards so it reports real steps only."""
+        """Capture the sharded step (collectives included).  The warm-up launch runs on whatever the static id
+        buffer holds (zeros unless the caller filled it), which may legitimately overflow the buckets; the flag is
+        cleared afterwards so it reports real steps only.  As in the single-GPU trainer the warm-up's optimizer
+        step is undone (every rank restores the rows it owns); a barrier keeps any rank from gathering rows of a
+        peer that is still restoring."""
         g = super().capture()
         self.overflow.zero_()
+        torch.cuda.synchronize(self.dev)
+        dist.barrier(group=self.ex.group)
         return g
+
+    @torch.no_grad()
+    def predict(self, ids: torch.Tensor) -> torch.Tensor:
+        """Forward only on this rank's batch (clip(sigmoid) probabilities): the gather goes through the sharded
+        path (_embed_forward: peer reads, or route + all-to-alls), never through the local shard with global row
+        numbers.  Collective: every rank must call it."""
+        c = self.cfg
+        F, d, U, B = c.num_fields, c.embed_dim, c.unit_num, c.batch
+        assert ids.shape == (B, F)
+        self.ids.copy_(ids)
+        T = ops._DT[self.act_dtype]
+        st = ops._stream()
+        P = self.P
+
+        class _NoTimer:
+            def __enter__(self): return self
+            def __exit__(self, *a): return False
+        self._embed_forward(lambda name: _NoTimer(), st, T)
+        main = torch.cuda.current_stream(self.dev)
+        if self.peer_gather:
+            main.wait_stream(self.side2)           # the owners' key work of _embed_forward is not needed here
+        cabi.call("rs_interacting_fwd", self.X.data_ptr(), d, 0, T, P["Wqkvr"].data_ptr(), P["bqkvr"].data_ptr(),
+                  P["gamma"].data_ptr(), P["beta"].data_ptr(), c.ln_eps, self.Z[:, self.n_deep:].data_ptr(), U,
+                  self.zw, None, B, F, d, U, c.head_num, c.layer_num, int(c.use_res), 0, st)
+        acts = [self.X.view(B, F * d)] + self.H + [self.Z[:, :self.n_deep]]
+        for i in range(len(c.mlp_hidden)):
+            self._dense_fwd(acts[i], f"mlp_W{i}", f"mlp_b{i}", acts[i + 1])
+        ops.logit_head(self.Z, P["out_W"], P["out_b"], self.labels, self.dZ, self.G["out_W"], self.G["out_b"],
+                       p_out=self.p_raw, loss=self.loss)
+        return self.p_raw.float().clamp(1e-6, 1.0)
 
     def check_overflow(self):
         """Raise if any routing bucket ever exceeded its capacity (ids too skewed for `capacity_factor`)."""
