@@ -95,7 +95,7 @@ def main():
     capacity = None
     if capmode != "auto":
         g = np.where(ids_all >= 0, ids_all % np.asarray(rows, np.int64)[None, :], -1)
-        owner = np.where(g >= 0, g % world, -1)
+        owner = np.where(g >= 0, g % world, 0)         # a padding id keeps a slot in its rank's owner-0 bucket
         worst = max(int(np.sum(owner[r * b:(r + 1) * b] == o)) for r in range(world) for o in range(world))
         capacity = worst if capmode == "tight" else worst - 1
     sh = ShardedAutoIntTrainer(AutoIntConfig(batch=b, **kw), dev, global_tables=torch.from_numpy(table), capacity=capacity)
@@ -111,9 +111,11 @@ def main():
         sh.labels.copy_(torch.from_numpy(y_all[lo:hi]))
         sh.capture()
     losses = []
-    for _ in range(steps):
+    for i in range(steps):
         l = sh.step(torch.from_numpy(ids_all[lo:hi]).to(dev), torch.from_numpy(y_all[lo:hi]).to(dev))
         losses.append(l.clone())
+        if i == 0:
+            table1, flat1 = sh.table.contiguous().clone(), sh.flat.clone()
     if capmode == "overflow":
         raised = False
         try:
@@ -136,6 +138,8 @@ def main():
     mine = sh.table.contiguous()                      # the shard is a strided view of the [w | m | v] arena
     shards = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
     dist.gather(mine, shards, dst=0)
+    shards1 = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+    dist.gather(table1, shards1, dst=0)
     # the sharded predict() goes through the sharded gather (collective)
     p_sh = sh.predict(torch.from_numpy(ids_all[lo:hi]).to(dev)).cpu().numpy().copy()
     ok = True
@@ -143,17 +147,38 @@ def main():
         # the SAME-dtype single-GPU trainer on the global batch
         ref = AutoIntTrainer(AutoIntConfig(batch=world * b, **kw), dev, tables=torch.from_numpy(table),
                              dense_init=dense0)
-        ref_losses = []
-        for _ in range(steps):
-            ref_losses.append(float(ref.step(torch.from_numpy(ids_all).to(dev), torch.from_numpy(y_all).to(dev))))
-        X_ref = ref.X.float().cpu().numpy()[lo:hi]
         def check(name, cond, info=""):
             nonlocal ok
             print(("PASS " if cond else "FAIL ") + name, info, flush=True)
             ok = ok and cond
+
+        def shard_err(shard_list, full):
+            worst = 0.0
+            for r in range(world):
+                s_ = shard_list[r].cpu().numpy()
+                for f in range(F):
+                    src = full[int(ref.base_host[f]) + r: int(ref.base_host[f] + ref.rows_host[f]): world]
+                    got = s_[int(sh.local_base[f]): int(sh.local_base[f]) + len(src)]
+                    worst = max(worst, float(np.max(np.abs(got - src))) / float(np.max(np.abs(full))))
+            return worst
+        ref_losses = []
+        for i in range(steps):
+            ref_losses.append(float(ref.step(torch.from_numpy(ids_all).to(dev), torch.from_numpy(y_all).to(dev))))
+            if i == 0:
+                # ONE step from identical state: every per-sample value is computed by the same kernels on the same
+                # numbers in both runs (only fp32 summation orders differ) -> 1e-5 in any dtype
+                e = shard_err(shards1, ref.table.cpu().numpy())
+                check("table shards after ONE step", e <= 1e-5, f"rel {e:.2e}")
+                e = rel_err(flat1.cpu().numpy(), ref.flat.cpu().numpy())
+                check("dense params after ONE step", e <= 1e-5, f"rel {e:.2e}")
+        X_ref = ref.X.float().cpu().numpy()[lo:hi]
         # (tables moved between steps, so compare the same step's values: both sides gathered
         #  step-3 inputs from tables updated twice; equality here needs the updates to agree too)
-        tol = 1e-5 if dtype == "f32" else 2e-3     # bf16: per-rank vs global-batch rounding of bf16 activations
+        # later steps in bf16: the 1e-7 differences of the all-reduced dense weights flip bf16 roundings / ReLU masks of
+        # a few activations, and Adam's normalised update turns a flipped small gradient component into an O(lr)
+        # difference of that table element: the bound after 3 steps is a fraction of 3 * lr_sparse, not 1e-5
+        tol = 1e-5 if dtype == "f32" else 2e-3
+        tol_tab = 1e-5 if dtype == "f32" else 3 * 1e-2 / float(np.max(np.abs(table)))
         e = rel_err(X_sh, X_ref)
         check("gathered X (after 2 updates)", e <= (1e-5 if dtype == "f32" else 8e-3), f"rel {e:.2e}")
         for i in range(steps):
@@ -161,15 +186,8 @@ def main():
             check(f"loss step {i}", e <= tol, f"{float(lt[i]):.6f} vs {ref_losses[i]:.6f}")
         e = rel_err(sh.flat.cpu().numpy(), ref.flat.cpu().numpy())
         check("dense params after steps", e <= tol, f"rel {e:.2e}")
-        full = ref.table.cpu().numpy()
-        worst = 0.0
-        for r in range(world):
-            s = shards[r].cpu().numpy()
-            for f in range(F):
-                src = full[int(ref.base_host[f]) + r: int(ref.base_host[f] + ref.rows_host[f]): world]
-                got = s[int(sh.local_base[f]): int(sh.local_base[f]) + len(src)]
-                worst = max(worst, float(np.max(np.abs(got - src))) / float(np.max(np.abs(full))))
-        check("table shards after steps", worst <= tol, f"rel {worst:.2e}")
+        worst = shard_err(shards, ref.table.cpu().numpy())
+        check("table shards after steps", worst <= tol_tab, f"rel {worst:.2e} (bound {tol_tab:.1e})")
         p_ref = ref.predict(torch.from_numpy(ids_all).to(dev)).cpu().numpy()[lo:hi]
         e = rel_err(p_sh, p_ref)
         check("sharded predict() == single-GPU predict()", e <= (1e-5 if dtype == "f32" else 1e-2), f"rel {e:.2e}")
