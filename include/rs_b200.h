@@ -293,6 +293,9 @@ int rs_interacting_fwd(const void* x, int64_t x_ld, int64_t x_bs, int dtype,
  * inverted-dropout mask before P.V.  The mask is a pure function of (dropout_seed, iteration, sample, head,
  * query, key) — a splitmix64 hash of the element's linear index, kept iff its top 24 bits >= rate * 2^24 — so
  * the backward regenerates it; pass the SAME rate and seed to both, and a fresh seed every step.
+ * dropout_step (device pointer, may be NULL): the mask seed becomes dropout_seed + 0x9E3779B97F4A7C15 * (*dropout_step),
+ * read by the kernel at launch — a step whose scalar arguments are frozen in a CUDA graph still gets a fresh
+ * mask on every replay when the caller bumps the counter inside the graph.
  * dropout_rate == 0 is exactly rs_interacting_fwd / _bwd.  Built into the FFMA kernels (any shape). */
 int rs_interacting_fwd_dropout(const void* x, int64_t x_ld, int64_t x_bs, int dtype,
                                const float* Wqkvr, const float* bqkvr,
@@ -300,7 +303,7 @@ int rs_interacting_fwd_dropout(const void* x, int64_t x_ld, int64_t x_bs, int dt
                                void* y, int64_t y_ld, int64_t y_bs, void* saved,
                                int B, int F, int D, int U, int H, int L, int use_res,
                                int compute_bf16, float dropout_rate, unsigned long long dropout_seed,
-                               void* stream);
+                               const unsigned long long* dropout_step, void* stream);
 int rs_interacting_bwd_dropout(const void* x, int64_t x_ld, int64_t x_bs, const void* saved, int dtype,
                                const float* Wqkvr, const float* bqkvr,
                                const float* ln_gamma, const float* ln_beta, float ln_eps,
@@ -308,6 +311,7 @@ int rs_interacting_bwd_dropout(const void* x, int64_t x_ld, int64_t x_bs, const 
                                void* dx, int64_t dx_ld, int64_t dx_bs, float* dparams,
                                int B, int F, int D, int U, int H, int L, int use_res,
                                int compute_bf16, float dropout_rate, unsigned long long dropout_seed,
+                               const unsigned long long* dropout_step,
                                void* ws, size_t ws_bytes, void* stream);
 /* dx [B,F,D] (ld dx_ld), dparams: fp32 [D*4U + 4U + U + U] = dW | db | dgamma |
  * dbeta, OVERWRITTEN.  ws >= rs_interacting_workspace_bytes. */
@@ -429,6 +433,22 @@ int rs_logit_head_fwd_bwd_relu(const void* Z, int64_t ldz, int dtype, const floa
  * present activations K-major to the tensor-core weight-gradient GEMMs. */
 int rs_transpose2d(const void* src, int64_t lds, void* dst, int64_t ldd, int M, int N,
                    int dtype, void* stream);
+
+/* ---- DCN-v1 cross network ------------------------------------------------------------------
+ * CrossNet.call (rough_rank/layer.py:256-264) and DeepCrossLayer.call (staytime/layer.py:66-72):
+ *   x_{l+1} = x0 * (x_l . w_l) + b_l + x_l ,  l = 0..L-1 ,  x_0 = x0 ;  out = x_L.
+ * x, out, dout, dx are [B, dim] with leading dims (elements); W, b are fp32 [L, dim] (the
+ * reference's [dim,1] kernels / [dim] or [dim,1] biases laid side by side); dW, db fp32 [L, dim],
+ * OVERWRITTEN.  One pass over the rows forward, two backward (HBM bound: dim * (in + out) bytes per
+ * sample forward); weight gradients are reduced over fixed batch chunks in a fixed order
+ * (deterministic).  dim % 4 == 0, L <= 8.  ws >= rs_cross_workspace_bytes(B, dim, L). */
+size_t rs_cross_workspace_bytes(int B, int dim, int L);
+int rs_cross_fwd(const void* x, int64_t x_ld, int dtype, const float* W, const float* b,
+                 void* out, int64_t out_ld, int B, int dim, int L,
+                 void* ws, size_t ws_bytes, void* stream);
+int rs_cross_bwd(const void* x, int64_t x_ld, const void* dout, int64_t dout_ld, int dtype,
+                 const float* W, const float* b, void* dx, int64_t dx_ld, float* dW, float* db,
+                 int B, int dim, int L, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- input labels and metrics: the steps either side of the train step ------------------
  * rs_staytime_labels replaces the label half of `parse_input_func` (staytime/parse.py:30-68):

@@ -282,18 +282,47 @@ def rank_ctr_layout(model_config):
     return max_embed, structure, b, gate
 
 
-def _interacting(xp, x, P, name, H, L, eps=1e-3):
-    """InteractingLayer.call (InteractingLayer.py:37-61) with the layer's own Dense / LayerNorm parameters."""
+def _interacting(xp, x, P, name, H, L, eps=1e-3, dropout=None):
+    """InteractingLayer.call (InteractingLayer.py:37-61) with the layer's own Dense / LayerNorm parameters.
+    dropout = (rate, seed): training-mode attention dropout (:53-54) with the kernels' counter-based mask."""
     g = lambda k: P["%s.%s" % (name, k)]
     if xp is NP:
         from . import oracle_np as onp
         W = np.concatenate([g("query_dense_kernel"), g("key_dense_kernel"), g("value_dense_kernel"), g("res_dense_kernel")], 1)
         b = np.concatenate([g("query_dense_bias"), g("key_dense_bias"), g("value_dense_bias"), g("res_dense_bias")])
-        return onp.interacting_fwd(x, W, b, g("layer_norm_gamma"), g("layer_norm_beta"), eps, H, L, True)
+        return onp.interacting_fwd(x, W, b, g("layer_norm_gamma"), g("layer_norm_beta"), eps, H, L, True, dropout=dropout)
     from . import oracle_torch as ot
     return ot.interacting_layer(x, g("query_dense_kernel"), g("query_dense_bias"), g("key_dense_kernel"), g("key_dense_bias"),
                                 g("value_dense_kernel"), g("value_dense_bias"), g("res_dense_kernel"), g("res_dense_bias"),
-                                g("layer_norm_gamma"), g("layer_norm_beta"), eps, H, L, True)
+                                g("layer_norm_gamma"), g("layer_norm_beta"), eps, H, L, True, dropout=dropout)
+
+
+# rank/multi_head/multidnn.py:207 MultiLabelInfo.label_list — the order of the 7 outputs
+AUTOINT_LABELS = ["like_pred", "click_comment_pred", "comment_pred", "click_sharing_pred", "follow_pred",
+                  "click_avatar_pred", "unlike_pred"]
+
+
+def autoint_multihead_fwd(xp, embs, P, deep_hidden_units=(32, 16), dropout=None, eps=1e-3):
+    """create_autoint_sub_model (rank/multi_head/multidnn.py:14-212).  embs: list of [B, 8] slot embeddings in
+    `linear_features` order; P keyed by the Keras layer names (interacting_layer.*, dnn_{i}, expert_{i}_fc1,
+    gate_{i}_fc2, <label>_pred); returns [B, 7] in MultiLabelInfo.label_list order (:206-209).
+    dropout = (rate 0.2, seed) in training (:54), None at inference.  The `dense_weight_*` inputs (:30-31) are
+    declared by the reference but feed nothing (the sub-model is built on emb_inputs only, :211)."""
+    all_inputs = xp.stack([e for e in embs], 1)                                     # :25-27,50  [B, F, 8]
+    autoint = _interacting(xp, all_inputs, P, "interacting_layer", 2, 1, eps, dropout)   # :54  (1 iteration, 8 units, 2 heads)
+    B = all_inputs.shape[0]
+    autoint = autoint.reshape(B, -1)                                                # :56 Flatten
+    deep = all_inputs.reshape(B, -1)                                                # :60 Flatten
+    for i in range(len(deep_hidden_units)):
+        deep = _dense(xp, deep, P, "dnn_%d" % i, "relu")                            # :62-63 (regularizers add no forward term)
+    result = xp.cat([deep, autoint], 1)                                             # :72
+    experts = xp.stack([_dense(xp, result, P, "expert_%d_fc1" % i, "relu") for i in range(7)], 1)   # :80-92: 8 built, [0:7] used
+    preds = []
+    for i, label in enumerate(AUTOINT_LABELS):
+        gate = _dense(xp, result, P, "gate_%d_fc2" % i, "softmax")                  # :97-99
+        mixed = xp.sum(experts * xp.expand(gate, -1), 1)                            # :104-108
+        preds.append(_dense(xp, mixed, P, label, "sigmoid"))                        # :118-205
+    return xp.cat(preds, 1)
 
 
 def rank_ctr_fwd(xp, emb, P, structure, bias, gate):

@@ -24,13 +24,13 @@ def layer_norm(x, gamma, beta, eps):
 
 
 def interacting_layer(x, Wq, bq, Wk, bk, Wv, bv, Wr, br, gamma, beta, ln_eps, head_num, layer_num,
-                      use_res=True):
+                      use_res=True, dropout=None):
     """InteractingLayer.call, InteractingLayer.py:37-61, written with the same
     split/concat ops as the reference."""
     if x.dim() != 3:
         raise ValueError("The rank of input of InteractingLayer must be 3, but now is %d" % x.dim())
     output = x
-    for _ in range(layer_num):                                            # :41
+    for it in range(layer_num):                                           # :41
         query = torch.relu(output @ Wq + bq)                              # :42
         key = torch.relu(output @ Wk + bk)                                # :43
         value = torch.relu(output @ Wv + bv)                              # :44
@@ -42,6 +42,11 @@ def interacting_layer(x, Wq, bq, Wk, bk, Wv, bv, Wr, br, gamma, beta, ln_eps, he
         weight = torch.matmul(query, key.transpose(1, 2))                 # :50
         weight = weight / (key.shape[-1] ** 0.5)                          # :51
         weight = torch.softmax(weight, dim=-1)                            # :52
+        if dropout is not None:                                           # :53-54 (training); dropout = (rate, seed):
+            from . import oracle_np as onp                                # the kernels' counter-based mask, [H,B,F,F]
+            B_, F_ = x.shape[0], x.shape[1]
+            sc = onp.dropout_scale(dropout[1], it, B_, head_num, F_, dropout[0]).reshape(head_num * B_, F_, F_)
+            weight = weight * torch.from_numpy(sc).to(weight.dtype)
         output = torch.matmul(weight, value)                              # :55
         output = torch.cat(torch.chunk(output, head_num, dim=0), dim=2)   # :56
         if use_res:

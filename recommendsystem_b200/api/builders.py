@@ -1,7 +1,8 @@
 """Model builders of the reference's CTR path, wired from the drop-in layers.
 
     AutoInt(model_config).run()                     autoint:11-60 (+ rank/ctr/base_model.py output_layer)
-    AUTOINT(linear_slots, bucket_size, ...)         rank/multi_head/multidnn.py:14-259 (AutoInt + DNN +
+    AUTOINT(linear_features, dense_features, training, dnn_hidden_units) -> ModelResult
+                                                    rank/multi_head/multidnn.py:14-259 (AutoInt + DNN +
                                                     7-expert / 7-gate MMoE, 7 sigmoid heads)
     cross_entropy                                   rank/multi_head/model.py:18-22, rank/ctr/base_model.py:7-12
 
@@ -18,6 +19,7 @@ from torch import nn
 
 from ..autoint import AutoIntConfig, AutoIntTrainer
 from .embedding import Adam, EmbeddingFeatures, category_column, embedding_column
+from .optim import DenseAdam
 from .functional import dense
 from .interacting_layer import InteractingLayer
 
@@ -81,66 +83,137 @@ class _KerasDense(nn.Module):
         return dense(x, self.kernel, self.bias, self.activation)
 
 
+# rank/multi_head/multidnn.py:206-209 MultiLabelInfo.label_list: the names (and order) of the 7 outputs
+AUTOINT_LABELS = ["like_pred", "click_comment_pred", "comment_pred", "click_sharing_pred", "follow_pred",
+                  "click_avatar_pred", "unlike_pred"]
+
+
 class AutoIntSubModel(nn.Module):
-    """create_autoint_sub_model (rank/multi_head/multidnn.py:14-212): InteractingLayer(1, 8, 2 heads) ||
-    Dense stack -> concat -> 7 (of 8 built) experts Dense(32, relu) -> 7 softmax gates -> 7 sigmoid heads."""
+    """create_autoint_sub_model (rank/multi_head/multidnn.py:14-212): InteractingLayer(1, 8, 2 heads, dropout 0.2) ||
+    Dense stack dnn_{i} -> concat -> experts expert_{i}_fc1 Dense(32, relu) (8 built, the first 7 used, :80-92) ->
+    7 softmax gates gate_{i}_fc2 -> 7 sigmoid heads named like the labels.  Sub-modules carry the reference's Keras
+    layer names, so `state_dict()` keys are `<keras name>.kernel / .bias` and `interacting_layer.*`."""
 
     NUM_LABELS = 7
 
     def __init__(self, deep_hidden_units: Sequence[int] = (32, 16), expert_num=7, expert_units=32):
         super().__init__()
         # multidnn.py:54: attention dropout 0.2 in training (fused into the kernel, counter-based mask)
-        self.interact = InteractingLayer(layer_num=1, unit_num=8, head_num=2, use_dropout=True, dropout_rate=0.2,
-                                         use_res=True)
-        self.deep = nn.ModuleList([_KerasDense(u, "relu") for u in deep_hidden_units])
-        self.experts = nn.ModuleList([_KerasDense(expert_units, "relu", 0.001) for _ in range(expert_num + 1)])
-        self.gates = nn.ModuleList([_KerasDense(expert_num, "softmax", 0.001) for _ in range(self.NUM_LABELS)])
-        self.heads = nn.ModuleList([_KerasDense(1, "sigmoid") for _ in range(self.NUM_LABELS)])
-        self.expert_num = expert_num
+        self.interacting_layer = InteractingLayer(layer_num=1, unit_num=8, head_num=2, use_dropout=True,
+                                                  dropout_rate=0.2, use_res=True)
+        for i, u in enumerate(deep_hidden_units):
+            self.add_module("dnn_%d" % i, _KerasDense(u, "relu"))
+        for i in range(expert_num + 1):
+            self.add_module("expert_%d_fc1" % i, _KerasDense(expert_units, "relu", 0.001))
+        for i in range(self.NUM_LABELS):
+            self.add_module("gate_%d_fc2" % i, _KerasDense(expert_num, "softmax", 0.001))
+        for label in AUTOINT_LABELS:
+            self.add_module(label, _KerasDense(1, "sigmoid"))
+        self.n_deep, self.expert_num = len(deep_hidden_units), expert_num
 
     def forward(self, embs: Sequence[torch.Tensor]):
         all_inputs = torch.stack(list(embs), dim=1)                       # :25-27,50  [B,F,8]
-        autoint = self.interact(all_inputs).flatten(1)                    # :54-56
+        autoint = self.interacting_layer(all_inputs).flatten(1)           # :54-56
         deep = all_inputs.flatten(1)                                      # :60
-        for layer in self.deep:
-            deep = layer(deep)                                            # :62-63
+        for i in range(self.n_deep):
+            deep = getattr(self, "dnn_%d" % i)(deep)                      # :62-63
         result = torch.cat([deep, autoint], dim=1)                        # :72
-        experts = torch.stack([e(result) for e in self.experts][: self.expert_num], dim=1)   # :80-92
+        # every expert is evaluated as the reference builds it; only [0:7] feed the gates (:92)
+        experts = [getattr(self, "expert_%d_fc1" % i)(result) for i in range(self.expert_num + 1)]
+        experts = torch.stack(experts[: self.expert_num], dim=1)
         preds = []
-        for g, h in zip(self.gates, self.heads):
-            gate = g(result).unsqueeze(-1)                                # :97-104
-            preds.append(h((experts * gate).sum(dim=1)))                  # :106-116, heads :118-206
-        return torch.cat(preds, dim=1)                                    # [B,7]
+        for i, label in enumerate(AUTOINT_LABELS):
+            gate = getattr(self, "gate_%d_fc2" % i)(result).unsqueeze(-1)             # :97-104
+            preds.append(getattr(self, label)((experts * gate).sum(dim=1)))           # :106-116, heads :118-206
+        return torch.cat(preds, dim=1)                                    # [B,7] in label_list order
 
 
-class AUTOINT:
-    """AUTOINT(linear_features, ...) — rank/multi_head/multidnn.py:214-259: 8-d embeddings (combiner mean,
-    sparse Adam lr 5e-5) feeding AutoIntSubModel.  `linear_features` is a list of slot names;
-    `bucket_size` replaces the missing src.* Config.  train_step() runs forward, summed BCE over the 7
-    labels, backward, dense Adam (lr 1e-5, rank/multi_head/model.py:53) and the sparse push."""
+class ModelResult:
+    """src.pipeline.model_result.ModelResult (not vendored by the reference; rank/multi_head/multidnn.py:247-250
+    fills `model`, `sub_model`, `model_predict`)."""
+    model = None
+    sub_model = None
+    model_predict = None
 
-    def __init__(self, linear_features: Sequence[str], bucket_size=100_000, dnn_hidden_units=(32, 16),
-                 device="cuda:0", seed=0):
-        cols = [embedding_column(category_column(s, bucket_size), dimension=8, combiner="mean") for s in linear_features]
-        self.slots = list(linear_features)
-        self.emb = EmbeddingFeatures(cols, Adam(5e-5, 0.9, 0.999, 1e-8), "linear", device=device, seed=seed)
-        self.sub_model = AutoIntSubModel(dnn_hidden_units).to(device)
+
+class _AutoIntFullModel:
+    """`full_model` of AUTOINT: sparse ids -> EmbeddingFeatures -> sub_model.  Callable like a Keras model
+    (`model(inputs)` -> [B,7] predictions); train_step() runs forward, the summed 7-label BCE
+    (rank/multi_head/model.py:18-22), backward, the dense Adam (lr 1e-5, :52-53: rs_dense_adam) and the sparse push."""
+
+    def __init__(self, slots, emb, sub_model, training, group=None):
+        self.slots, self.emb, self.sub_model, self.training = slots, emb, sub_model, bool(training)
         self.opt = None
+        self.group = group
+        self.sub_model.train(self.training)
+
+    def __call__(self, inputs: Dict[str, torch.Tensor]):
+        return self.predict(inputs)
 
     def predict(self, inputs: Dict[str, torch.Tensor]):
-        with torch.no_grad():
-            embs = self.emb(inputs)
-            return self.sub_model([embs[s] for s in self.slots])
+        was = self.sub_model.training
+        self.sub_model.eval()
+        try:
+            with torch.no_grad():
+                embs = self.emb(inputs)
+                return self.sub_model([embs[s] for s in self.slots])
+        finally:
+            self.sub_model.train(was)
 
-    def train_step(self, inputs: Dict[str, torch.Tensor], labels: torch.Tensor):
+    def train_step(self, inputs: Dict[str, torch.Tensor], labels):
+        if isinstance(labels, dict):
+            labels = torch.cat([labels[k].reshape(-1, 1) for k in AUTOINT_LABELS], dim=1)
         embs = self.emb(inputs)
         leaves = [embs[s].detach().requires_grad_(True) for s in self.slots]
         pred = self.sub_model(leaves)
         if self.opt is None:
-            self.opt = torch.optim.Adam(self.sub_model.parameters(), lr=1e-5, betas=(0.9, 0.999), eps=1e-8, capturable=True)
+            self.opt = DenseAdam(self.sub_model.parameters(), lr=1e-5, beta1=0.9, beta2=0.999, eps=1e-8, group=self.group)
         loss = cross_entropy(labels, pred).mean()
-        self.opt.zero_grad(set_to_none=True)
+        self.opt.zero_grad()
         loss.backward()
         self.opt.step()
         self.emb.backward({s: l.grad for s, l in zip(self.slots, leaves)})
         return loss.detach(), pred.detach()
+
+    # the InteractingLayer's device-side dropout counter is part of what a step changes (api.graph warm-up undo)
+    def extra_state_snapshot(self):
+        il = self.sub_model.interacting_layer
+        return (il._dropout_calls, None if il._drop_step is None else il._drop_step.clone())
+
+    def extra_state_restore(self, st):
+        il = self.sub_model.interacting_layer
+        il._dropout_calls = st[0]
+        if il._drop_step is not None:
+            if st[1] is None:
+                il._drop_step.zero_()
+            else:
+                il._drop_step.copy_(st[1])
+
+
+def create_autoint_sub_model(slot_zip_user_embs, dense_inputs_map, deep_hidden_units, training, device="cuda:0"):
+    """rank/multi_head/multidnn.py:14.  `slot_zip_user_embs` (slot, embedding) pairs fix the input order; the
+    `dense_inputs_map` inputs are declared by the reference but feed nothing (:30-31 vs :211)."""
+    del slot_zip_user_embs, dense_inputs_map
+    return AutoIntSubModel(deep_hidden_units).to(device).train(bool(training))
+
+
+def AUTOINT(linear_features, dense_features, training, dnn_hidden_units=(32, 16), *, bucket_size=100_000,
+            device="cuda:0", seed=0, embedding_cls=None, group=None):
+    """AUTOINT(linear_features, dense_features, training, dnn_hidden_units=(32,16)) -> ModelResult{model, sub_model,
+    model_predict} — rank/multi_head/multidnn.py:214-259.  8-d embeddings (combiner mean, tn.core.Adam lr 5e-5,
+    :222,235) of the sorted, de-duplicated slots (:215-218) feed create_autoint_sub_model in `linear_features` order
+    (:239).  Keyword-only extras stand in for the missing `src.*` Config: bucket_size (rows per slot table), device,
+    seed; embedding_cls / group select the row-sharded multi-GPU embedding (api.sharded_embedding)."""
+    features = sorted(set(linear_features))                                   # :215-218
+    cols = [embedding_column(category_column(s, bucket_size), dimension=8, combiner="mean") for s in features]
+    E = embedding_cls or EmbeddingFeatures
+    kw = {"group": group} if embedding_cls is not None else {}
+    emb = E(cols, Adam(5e-5, 0.9, 0.999, 1e-8), "linear", device=device, seed=seed, **kw)
+    sub_model = create_autoint_sub_model([(s, None) for s in linear_features], {k: None for k in dense_features},
+                                         dnn_hidden_units, training, device=device)
+    full = _AutoIntFullModel(list(linear_features), emb, sub_model, training, group=group)
+    ret = ModelResult()
+    ret.model = full                                                           # :247
+    ret.sub_model = sub_model                                                  # :248
+    ret.model_predict = full.predict                                           # :249
+    return ret

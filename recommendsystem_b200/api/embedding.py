@@ -150,6 +150,36 @@ class EmbeddingFeatures:
         self._last = plan
         return out
 
+    # ---- state one train step changes (GraphedTrainStep undoes its warm-up steps with these) -----------
+    def touched_rows(self, inputs: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """Sorted unique arena rows a step on `inputs` reads and updates."""
+        rows = []
+        for ci, c in enumerate(self.cols):
+            ids = inputs[c.categorical_column.key]
+            if isinstance(ids, (tuple, list)):                   # CSR bag: (values, offsets)
+                ids = ids[0]
+            ids = ids.to(self.dev, torch.int64).reshape(-1)
+            if c.combiner is None and c.seq_max_len:
+                ids = inputs[c.categorical_column.key].to(self.dev, torch.int64)[:, :c.seq_max_len].reshape(-1)
+            ids = ids[ids >= 0]
+            rows.append(int(self.base[ci]) + torch.remainder(ids, int(self.rows[ci])))
+        return torch.unique(torch.cat(rows)) if rows else torch.empty(0, dtype=torch.int64, device=self.dev)
+
+    def snapshot(self, inputs):
+        rows = self.touched_rows(inputs)
+        if isinstance(self.opt, Adam):
+            return {"rows": rows, "arena": self.arena[rows].clone(), "scalars": self.scalars.clone()}
+        return {"rows": rows, "table": self.table[rows].clone(), "g2sum": self.g2sum[rows].clone()}
+
+    def restore(self, snap):
+        rows = snap["rows"]
+        if isinstance(self.opt, Adam):
+            self.arena[rows] = snap["arena"]
+            self.scalars.copy_(snap["scalars"])
+        else:
+            self.table[rows] = snap["table"]
+            self.g2sum[rows] = snap["g2sum"]
+
     def _geom(self, cols):
         """(row_base, rows) device tensors of a column group, created once (no host->device copy per call:
         the step stays CUDA-graph capturable)."""

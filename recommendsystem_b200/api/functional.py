@@ -17,15 +17,17 @@ class InteractingFn(torch.autograd.Function):
     """InteractingLayer.call (InteractingLayer.py:37-61) fused forward / backward."""
 
     @staticmethod
-    def forward(ctx, x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res, dropout_rate=0.0, dropout_seed=0):
+    def forward(ctx, x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res, dropout_rate=0.0, dropout_seed=0,
+                dropout_step=None):
         _require_cuda(x, Wqkvr)
         x = x.contiguous()
         # bf16 activations take the tcgen05 kernels where they are built (falls back to FFMA arithmetic otherwise)
         ctx.tc = x.dtype == torch.bfloat16
         y, saved = ops.interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res, compute_bf16=ctx.tc,
-                                       dropout_rate=dropout_rate, dropout_seed=dropout_seed)
+                                       dropout_rate=dropout_rate, dropout_seed=dropout_seed, dropout_step=dropout_step)
         ctx.save_for_backward(x, saved if saved is not None else x.new_empty(0), Wqkvr, bqkvr, gamma, beta)
         ctx.cfg = (ln_eps, H, L, use_res, dropout_rate, dropout_seed)
+        ctx.dropout_step = dropout_step          # device counter: the backward of THIS step reads the same value
         return y
 
     @staticmethod
@@ -34,8 +36,31 @@ class InteractingFn(torch.autograd.Function):
         ln_eps, H, L, use_res, rate, seed = ctx.cfg
         dx, dW, db, dg, dbt = ops.interacting_bwd(x, saved if saved.numel() else None, Wqkvr, bqkvr, gamma, beta,
                                                   ln_eps, H, L, dy.contiguous().to(x.dtype), use_res,
-                                                  compute_bf16=ctx.tc, dropout_rate=rate, dropout_seed=seed)
-        return dx, dW, db, dg, dbt, None, None, None, None, None, None
+                                                  compute_bf16=ctx.tc, dropout_rate=rate, dropout_seed=seed,
+                                                  dropout_step=ctx.dropout_step)
+        return dx, dW, db, dg, dbt, None, None, None, None, None, None, None
+
+
+class CrossFn(torch.autograd.Function):
+    """DCN-v1 cross network (CrossNet.call rough_rank/layer.py:256-264; DeepCrossLayer.call staytime/layer.py:66-72):
+    W, b are the L per-layer kernels / biases stacked as fp32 [L, dim]."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        _require_cuda(x, W, b)
+        if x.stride(-1) != 1:
+            x = x.contiguous()
+        W, b = W.contiguous(), b.contiguous()
+        ctx.save_for_backward(x, W, b)
+        return ops.cross_fwd(x, W, b)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, W, b = ctx.saved_tensors
+        if dout.stride(-1) != 1 or dout.dtype != x.dtype:
+            dout = dout.contiguous().to(x.dtype)
+        dx, dW, db = ops.cross_bwd(x, dout, W, b)
+        return dx, dW, db
 
 
 class DinFn(torch.autograd.Function):

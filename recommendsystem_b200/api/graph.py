@@ -9,6 +9,10 @@ sort + sorted-segment sparse update - is captured ONCE and replayed:
     step = GraphedTrainStep(net, example_inputs, example_labels)      # warm-up + capture
     loss, outputs = step(inputs, labels)                               # copy into the static buffers, replay
 
+The warm-up steps (they allocate workspaces and create the optimizer state) are UNDONE before the capture: the
+embedding rows they touched, the dense parameters and both optimizers' state are restored bit for bit, so capturing
+after loading a checkpoint does not change the loaded weights and the first replay is the first train step.
+
 `net` is any object with `train_step(inputs: dict, labels: dict) -> (loss, outputs: dict)` (api.video_dnn.MtlNet,
 api.rough_rank_model.DssmNet, api.rank_ctr.RankCtrNet, ...).  Shapes and dtypes are fixed by the example batch;
 a different batch size needs its own GraphedTrainStep.  Inputs may live on the host (pinned or not): the copy
@@ -36,6 +40,7 @@ class GraphedTrainStep:
             raise RuntimeError("GraphedTrainStep needs a CUDA device")
         self.net, self.dev = net, dev
         self.inputs, self.labels = _static(inputs, dev), _static(labels, dev)
+        snap = self._snapshot(net, self.inputs)
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -43,10 +48,43 @@ class GraphedTrainStep:
                 net.train_step(self.inputs, self.labels)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        self._restore(net, snap)
+        torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss, self.outputs = net.train_step(self.inputs, self.labels)
-        self.warmup_steps = max(1, warmup)           # real optimizer steps taken on the example batch
+        self.warmup_steps = 0                        # the warm-up steps were undone: replay 1 is train step 1
+
+    @staticmethod
+    def _snapshot(net, inputs):
+        """Everything the warm-up steps change.  Lazily built layers are built first (a forward has no side effects)
+        so that there are initial weights to return to."""
+        if not hasattr(net, "emb") or not hasattr(net.emb, "snapshot"):
+            return None
+        with torch.no_grad():
+            net.predict(inputs)
+        snap = {"emb": net.emb.snapshot(inputs), "params": [p.detach().clone() for p in net.sub_model.parameters()]}
+        opt = getattr(net, "opt", None)
+        snap["opt"] = opt.snapshot() if opt is not None and hasattr(opt, "snapshot") else None
+        if hasattr(net, "extra_state_snapshot"):
+            snap["extra"] = net.extra_state_snapshot()
+        return snap
+
+    @staticmethod
+    def _restore(net, snap):
+        if snap is None:
+            return
+        net.emb.restore(snap["emb"])
+        opt = getattr(net, "opt", None)
+        if snap["opt"] is not None:
+            opt.restore(snap["opt"])
+        elif opt is not None and hasattr(opt, "flat_m"):          # created by the warm-up: back to a fresh state
+            opt.flat_m.zero_(); opt.flat_v.zero_(); opt.scalars.zero_()
+        with torch.no_grad():
+            for p, v in zip(net.sub_model.parameters(), snap["params"]):
+                p.copy_(v)
+        if "extra" in snap:
+            net.extra_state_restore(snap["extra"])
 
     def __call__(self, inputs: Dict, labels: Dict):
         for k, v in inputs.items():

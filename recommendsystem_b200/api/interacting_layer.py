@@ -33,6 +33,7 @@ class InteractingLayer(nn.Module):
         self.ln_eps = float(ln_eps)
         self.dropout_seed = int(kwargs.get("dropout_seed", 0x5DEECE66D))     # masks = f(seed, call counter)
         self._dropout_calls = 0
+        self._drop_step = None               # device-side call counter (int64[1]), created at the first training call
         self.last_dropout_seed = None
         if self.unit_num % self.head_num != 0:
             raise ValueError("head_num must divide unit_num (tf.split, InteractingLayer.py:47)")
@@ -69,17 +70,23 @@ class InteractingLayer(nn.Module):
             raise ValueError('The rank of input of InteractingLayer must be 3, but now is %d' % inputs.dim())
         if not self.built:
             self.build(inputs.shape, device=inputs.device)
-        rate, seed = 0.0, 0
+        rate, seed, step = 0.0, 0, None
         if self.use_dropout and self.training:
-            # tf.keras Dropout on the attention weights (InteractingLayer.py:53-54): a fresh counter-based mask
-            # per call, reproducible from (dropout_seed, call counter)
+            # tf.keras Dropout on the attention weights (InteractingLayer.py:53-54): a fresh counter-based mask per
+            # call.  The call counter lives on the DEVICE and is bumped in-stream: a CUDA graph of the step (api.graph)
+            # advances it on every replay, so replays draw fresh masks (a host-side counter would be frozen into the
+            # graph).  Effective seed of call k (1-based) = dropout_seed + 0x9E3779B97F4A7C15 * k.
             rate = float(self.dropout_rate)
-            seed = (self.dropout_seed + 0x9E3779B97F4A7C15 * self._dropout_calls) & 0xFFFFFFFFFFFFFFFF
-            self._dropout_calls += 1
-            self.last_dropout_seed = seed
+            seed = self.dropout_seed & 0xFFFFFFFFFFFFFFFF
+            if self._drop_step is None or self._drop_step.device != inputs.device:
+                self._drop_step = torch.zeros(1, dtype=torch.int64, device=inputs.device)
+            self._drop_step.add_(1)
+            step = self._drop_step
+            self._dropout_calls += 1            # host mirror (valid while the layer runs eagerly)
+            self.last_dropout_seed = (seed + 0x9E3779B97F4A7C15 * self._dropout_calls) & 0xFFFFFFFFFFFFFFFF
         W, b = self.packed()
         return InteractingFn.apply(inputs, W, b, self.layer_norm_gamma, self.layer_norm_beta, self.ln_eps,
-                                   self.head_num, self.layer_num, self.use_res, rate, seed)
+                                   self.head_num, self.layer_num, self.use_res, rate, seed, step)
 
     def get_config(self):
         return dict(layer_num=self.layer_num, unit_num=self.unit_num, head_num=self.head_num,

@@ -9,7 +9,7 @@ import math
 import torch
 from torch import nn
 
-from .functional import dense
+from .functional import CrossFn, dense
 
 
 def _glorot_normal(fan_in, fan_out, device, gen=None):
@@ -160,12 +160,10 @@ class CrossNet(nn.Module):
     def forward(self, inputs):
         if not self.built:
             self.build(inputs.shape[-1], inputs.device)
-        x0 = inputs.unsqueeze(2)
-        xl = x0
-        for i in range(self.layer_num):
-            xw = torch.tensordot(xl, self.kernels[i], dims=([1], [0]))      # [B,1,1]
-            xl = torch.matmul(x0, xw) + self.bias[i] + xl
-        return xl.squeeze(2)
+        # x_{l+1} = x0 (x_l . kernel_l) + bias_l + x_l for all layers in ONE fused row kernel (csrc/cross.cu)
+        W = torch.stack([k.reshape(-1) for k in self.kernels])
+        b = torch.stack([v.reshape(-1) for v in self.bias])
+        return CrossFn.apply(inputs, W, b)
 
     def get_config(self):
         return {"layer_num": self.layer_num, "l2_reg": self.l2_reg, "seed": self.seed}

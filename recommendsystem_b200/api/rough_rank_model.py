@@ -15,6 +15,7 @@ import torch
 from torch import nn
 
 from .builders import _KerasDense
+from .optim import DenseAdam
 from .embedding import Adam, EmbeddingFeatures, category_column, embedding_column
 from .rough_rank_layer import DNN, PLE, CrossNet, KDLoss
 
@@ -185,10 +186,10 @@ class DssmNet:
         leaves = {k: v.detach().requires_grad_(True) for k, v in e.items()}
         out = self.sub_model(leaves, inputs[C.DENSE_MASK_ID].to(self.emb.dev))
         if self.opt is None:
-            self.opt = torch.optim.Adam(self.sub_model.parameters(), lr=0.0001, betas=(0.9, 0.999), eps=1e-8, capturable=True)
+            self.opt = DenseAdam(self.sub_model.parameters(), lr=0.0001, beta1=0.9, beta2=0.999, eps=1e-8, group=getattr(self, 'group', None))
         loss = (binary_crossentropy(labels["student"], out["student"]) +
                 binary_crossentropy(labels["teacher"], out["teacher"]) + y_pred_loss(None, out["distill"]))
-        self.opt.zero_grad(set_to_none=True)
+        self.opt.zero_grad()
         loss.backward()
         self.opt.step()
         self.emb.backward({k: v.grad for k, v in leaves.items()})

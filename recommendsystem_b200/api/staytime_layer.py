@@ -6,7 +6,7 @@ from torch import nn
 
 from .. import cabi
 from .din import _glorot
-from .functional import DinFn
+from .functional import CrossFn, DinFn
 
 
 class DIN(nn.Module):
@@ -38,7 +38,7 @@ class DIN(nn.Module):
 
 class DeepCrossLayer(nn.Module):
     """staytime/layer.py:44-80 — DCN cross layers: cross <- inputs * (cross @ w_i) + b_i + cross.
-    Memory-bound mat-vec glue (not on the kernel hot path): composed from torch CUDA ops."""
+    HBM-bound: rs_cross_fwd / rs_cross_bwd read each row once forward, twice backward."""
 
     def __init__(self, num_layer=3, **kwargs):
         super().__init__()
@@ -53,10 +53,10 @@ class DeepCrossLayer(nn.Module):
     def forward(self, inputs):
         if not self.built:
             self.build(inputs.shape[-1], inputs.device)
-        cross = inputs
-        for i in range(self.num_layer):
-            cross = inputs * torch.matmul(cross, self.W[i]) + self.b[i] + cross      # :66-72
-        return cross
+        # cross <- inputs * (cross @ w_i) + b_i + cross (:66-72) for all layers in ONE fused row kernel (csrc/cross.cu)
+        W = torch.stack([w.reshape(-1) for w in self.W])
+        b = torch.stack([v.reshape(-1) for v in self.b])
+        return CrossFn.apply(inputs, W, b)
 
 
 class FMLayer(nn.Module):

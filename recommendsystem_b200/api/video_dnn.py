@@ -18,6 +18,7 @@ import torch
 from torch import nn
 
 from .builders import _KerasDense
+from .optim import DenseAdam
 from .embedding import AdaGrad, EmbeddingFeatures, category_column, embedding_column
 from .staytime_config import Config as C
 from .staytime_layer import DIN, DeepCrossLayer
@@ -209,9 +210,9 @@ class MtlNet:
         ls = {s: (v[0].detach().requires_grad_(True), v[1]) for s, v in seqs.items()}
         out, _ = self.sub_model(le, ls)
         if self.opt is None:
-            self.opt = torch.optim.Adam(self.sub_model.parameters(), lr=0.0005, betas=(0.9, 0.999), eps=1e-8, capturable=True)
+            self.opt = DenseAdam(self.sub_model.parameters(), lr=0.0005, beta1=0.9, beta2=0.999, eps=1e-8, group=getattr(self, 'group', None))
         loss = sum(LOSS_WEIGHTS[k] * LOSSES[k](labels[k], out[k]).mean() for k in TASK_KEYS)
-        self.opt.zero_grad(set_to_none=True)
+        self.opt.zero_grad()
         loss.backward()
         self.opt.step()
         grads = {"emb_col_%s" % s: v.grad for s, v in le.items()}

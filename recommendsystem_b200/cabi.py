@@ -52,9 +52,9 @@ PROTOTYPES = {
     "rs_interacting_fwd": (_i, [_p, _i64, _i64, _i, _p, _p, _p, _p, _f, _p, _i64, _i64, _p,
                                 _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "rs_interacting_fwd_dropout": (_i, [_p, _i64, _i64, _i, _p, _p, _p, _p, _f, _p, _i64, _i64, _p,
-                                        _i, _i, _i, _i, _i, _i, _i, _i, _f, _u64, _p]),
+                                        _i, _i, _i, _i, _i, _i, _i, _i, _f, _u64, _p, _p]),
     "rs_interacting_bwd_dropout": (_i, [_p, _i64, _i64, _p, _i, _p, _p, _p, _p, _f, _p, _i64, _i64, _p, _i64, _i64, _p,
-                                        _i, _i, _i, _i, _i, _i, _i, _i, _f, _u64, _p, _sz, _p]),
+                                        _i, _i, _i, _i, _i, _i, _i, _i, _f, _u64, _p, _p, _sz, _p]),
     "rs_interacting_bwd": (_i, [_p, _i64, _i64, _p, _i, _p, _p, _p, _p, _f, _p, _i64, _i64, _p, _i64, _i64, _p,
                                 _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
     "rs_din_fwd": (_i, [_i, _p, _p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
@@ -72,6 +72,9 @@ PROTOTYPES = {
     "rs_logit_head_workspace_bytes": (_sz, [_i, _i]),
     "rs_logit_head_fwd_bwd": (_i, [_p, _i64, _i, _p, _p, _p, _f, _p, _p, _p, _i64, _p, _p, _i, _i, _p, _sz, _p]),
     "rs_logit_head_fwd_bwd_relu": (_i, [_p, _i64, _i, _p, _p, _p, _f, _p, _p, _p, _i64, _p, _p, _i, _i, _i, _p, _sz, _p]),
+    "rs_cross_workspace_bytes": (_sz, [_i, _i, _i]),
+    "rs_cross_fwd": (_i, [_p, _i64, _i, _p, _p, _p, _i64, _i, _i, _i, _p, _sz, _p]),
+    "rs_cross_bwd": (_i, [_p, _i64, _p, _i64, _i, _p, _p, _p, _i64, _p, _p, _i, _i, _i, _p, _sz, _p]),
     "rs_transpose2d": (_i, [_p, _i64, _p, _i64, _i, _i, _i, _p]),
     "rs_set_fp32_gemm_mode": (_i, [_i]),
     "rs_staytime_labels": (_i, [_p, _p, _p, _i, _i, _p, _p, _p, _p, _i64, _i64, _f, _f, _f, _f, _f, _p]),

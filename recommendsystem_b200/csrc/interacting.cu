@@ -44,7 +44,7 @@ int rs_interacting_fwd_dropout(const void* x, int64_t x_ld, int64_t x_bs, int dt
                                const float* bqkvr, const float* ln_gamma, const float* ln_beta,
                                float ln_eps, void* y, int64_t y_ld, int64_t y_bs, void* saved, int B, int F, int D, int U,
                                int H, int L, int use_res, int compute_bf16, float dropout_rate,
-                               unsigned long long dropout_seed, void* stream) {
+                               unsigned long long dropout_seed, const unsigned long long* dropout_step, void* stream) {
   RS_REQUIRE(dropout_rate >= 0.f && dropout_rate < 1.f, "interacting_fwd: dropout_rate %g not in [0, 1)", dropout_rate);
   RS_REQUIRE(B > 0 && F > 0 && L >= 1, "interacting_fwd: B=%d F=%d L=%d", B, F, L);
   RS_REQUIRE(H > 0 && U % H == 0, "interacting_fwd: head_num %d must divide unit_num %d", H, U);
@@ -59,6 +59,7 @@ int rs_interacting_fwd_dropout(const void* x, int64_t x_ld, int64_t x_bs, int dt
              dtype, as_stream(stream)};
   a.drop_rate = dropout_rate;
   a.drop_seed = dropout_seed;
+  a.drop_step = dropout_step;
   // attention dropout is built into the FFMA kernels only: the tensor-core path is taken without it
   if (rs_interacting_path(F, D, U, H, dtype, compute_bf16, dropout_rate) == RS_PATH_TCGEN05) return interacting_tc_fwd(a);
 #define RS_CASE(DD, UU, HH) \
@@ -74,7 +75,7 @@ int rs_interacting_fwd(const void* x, int64_t x_ld, int64_t x_bs, int dtype, con
                        float ln_eps, void* y, int64_t y_ld, int64_t y_bs, void* saved, int B, int F, int D, int U,
                        int H, int L, int use_res, int compute_bf16, void* stream) {
   return rs_interacting_fwd_dropout(x, x_ld, x_bs, dtype, Wqkvr, bqkvr, ln_gamma, ln_beta, ln_eps, y, y_ld, y_bs, saved,
-                                    B, F, D, U, H, L, use_res, compute_bf16, 0.f, 0ULL, stream);
+                                    B, F, D, U, H, L, use_res, compute_bf16, 0.f, 0ULL, nullptr, stream);
 }
 
 int rs_interacting_bwd_dropout(const void* x, int64_t x_ld, int64_t x_bs, const void* saved, int dtype,
@@ -82,7 +83,8 @@ int rs_interacting_bwd_dropout(const void* x, int64_t x_ld, int64_t x_bs, const 
                                const float* ln_beta, float ln_eps, const void* dy, int64_t dy_ld,
                                int64_t dy_bs, void* dx, int64_t dx_ld, int64_t dx_bs, float* dparams, int B, int F, int D,
                                int U, int H, int L, int use_res, int compute_bf16, float dropout_rate,
-                               unsigned long long dropout_seed, void* ws, size_t ws_bytes, void* stream) {
+                               unsigned long long dropout_seed, const unsigned long long* dropout_step, void* ws,
+                               size_t ws_bytes, void* stream) {
   RS_REQUIRE(dropout_rate >= 0.f && dropout_rate < 1.f, "interacting_bwd: dropout_rate %g not in [0, 1)", dropout_rate);
   RS_REQUIRE(B > 0 && F > 0 && L >= 1, "interacting_bwd: B=%d F=%d L=%d", B, F, L);
   RS_REQUIRE(H > 0 && U % H == 0, "interacting_bwd: head_num %d must divide unit_num %d", H, U);
@@ -100,6 +102,7 @@ int rs_interacting_bwd_dropout(const void* x, int64_t x_ld, int64_t x_bs, const 
              B, F, L, use_res, dtype, ws, ws_bytes, as_stream(stream)};
   a.drop_rate = dropout_rate;
   a.drop_seed = dropout_seed;
+  a.drop_step = dropout_step;
   if (rs_interacting_path(F, D, U, H, dtype, compute_bf16, dropout_rate) == RS_PATH_TCGEN05) return interacting_tc_bwd(a);
 #define RS_CASE(DD, UU, HH) \
   if (D == DD && U == UU && H == HH) return interacting_bwd_##DD##_##UU##_##HH(a);
@@ -115,7 +118,7 @@ int rs_interacting_bwd(const void* x, int64_t x_ld, int64_t x_bs, const void* sa
                        int64_t dy_bs, void* dx, int64_t dx_ld, int64_t dx_bs, float* dparams, int B, int F, int D, int U, int H, int L,
                        int use_res, int compute_bf16, void* ws, size_t ws_bytes, void* stream) {
   return rs_interacting_bwd_dropout(x, x_ld, x_bs, saved, dtype, Wqkvr, bqkvr, ln_gamma, ln_beta, ln_eps, dy, dy_ld, dy_bs,
-                                    dx, dx_ld, dx_bs, dparams, B, F, D, U, H, L, use_res, compute_bf16, 0.f, 0ULL, ws,
+                                    dx, dx_ld, dx_bs, dparams, B, F, D, U, H, L, use_res, compute_bf16, 0.f, 0ULL, nullptr, ws,
                                     ws_bytes, stream);
 }
 

@@ -60,7 +60,12 @@ __device__ __forceinline__ void project_row(const float* __restrict__ Ws,
 // index (+ seed) are >= rate * 2^24; kept weights are scaled by 1 / (1 - rate).  Counter-based, so the
 // backward (row pass AND column pass) regenerates any element's mask from its indices, and
 // oracle/oracle_np.py::dropout_scale reproduces it bit for bit.
-struct DropCfg { float rate; float inv_keep; unsigned long long seed; };
+struct DropCfg { float rate; float inv_keep; unsigned long long seed; const unsigned long long* step; };
+// effective seed of this launch: seed + golden-ratio * (*step) when a device-side step counter is given (a captured
+// CUDA graph bakes scalar arguments in; the counter lives in device memory and advances between replays)
+__device__ __forceinline__ void drop_resolve(DropCfg& dc) {
+  if (dc.step) dc.seed += 0x9E3779B97F4A7C15ULL * (*dc.step);
+}
 
 __device__ __forceinline__ float drop_scale(const DropCfg& dc, unsigned long long idx) {
   unsigned long long z = idx + dc.seed;
@@ -198,6 +203,7 @@ interacting_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, cons
                        const float* __restrict__ beta, float eps, T* __restrict__ y, int64_t y_ld, int64_t y_bs,
                        float* __restrict__ saved, int B, int F, int L, int use_res, DropCfg dc) {
   static_assert(U <= 32, "tmask is 32 bits");
+  drop_resolve(dc);
   constexpr int DH = U / H;
   constexpr int N4 = 4 * U;
   constexpr int SK = 2 * U + 4;  // K|V row stride (forward needs only K and V)
@@ -291,6 +297,7 @@ interacting_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, cons
                        const T* __restrict__ dy, int64_t dy_ld, int64_t dy_bs, T* __restrict__ dx, int64_t dx_ld,
                        int64_t dx_bs,
                        float* __restrict__ part, int B, int F, int L, int use_res, DropCfg dc) {
+  drop_resolve(dc);
   constexpr int DH = U / H;
   constexpr int N4 = 4 * U;
   using S = ISmem<D, U>;
@@ -601,8 +608,9 @@ static __global__ void reduce_partials_kernel(const float* __restrict__ part, fl
 }
 
 // ------------------------------------------------------------ host dispatch
-static inline DropCfg drop_cfg(float rate, unsigned long long seed) {
+static inline DropCfg drop_cfg(float rate, unsigned long long seed, const unsigned long long* step) {
   DropCfg dc;
+  dc.step = step;
   dc.rate = rate;
   dc.inv_keep = rate > 0.f ? 1.f / (1.f - rate) : 1.f;
   dc.seed = seed;
@@ -644,7 +652,7 @@ static int launch_fwd(const IFwdArgs& a) {
   int grid = sm_count() * resident_ctas((const void*)kern, NT, smem, 8);
   if (grid > ntiles) grid = ntiles;
   kern<<<grid, NT, smem, a.st>>>((const T*)a.x, a.x_ld, a.x_bs, a.W, a.b, a.gm, a.bt, a.eps, (T*)a.y, a.y_ld, a.y_bs,
-                                 (float*)a.saved, a.B, a.F, a.L, a.use_res, drop_cfg(a.drop_rate, a.drop_seed));
+                                 (float*)a.saved, a.B, a.F, a.L, a.use_res, drop_cfg(a.drop_rate, a.drop_seed, a.drop_step));
   return check_launch("interacting_fwd");
 }
 
@@ -661,7 +669,7 @@ static int launch_bwd(const IBwdArgs& a) {
   }
   kern<<<grid, NT, smem, a.st>>>((const T*)a.x, a.x_ld, a.x_bs, (const float*)a.saved, a.W, a.b, a.gm, a.bt, a.eps,
                                  (const T*)a.dy, a.dy_ld, a.dy_bs, (T*)a.dx, a.dx_ld, a.dx_bs, (float*)a.ws, a.B, a.F,
-                                 a.L, a.use_res, drop_cfg(a.drop_rate, a.drop_seed));
+                                 a.L, a.use_res, drop_cfg(a.drop_rate, a.drop_seed, a.drop_step));
   if (int e = check_launch("interacting_bwd")) return e;
   reduce_partials_kernel<<<(np * 32 + 255) / 256, 256, 0, a.st>>>((const float*)a.ws, a.dparams, grid, np);
   return check_launch("interacting_bwd_reduce");

@@ -213,7 +213,7 @@ def interacting_saved(B, F, U, L, device):
 
 
 def interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res=True, save=True, compute_bf16=False,
-                    dropout_rate=0.0, dropout_seed=0):
+                    dropout_rate=0.0, dropout_seed=0, dropout_step=None):
     B, F, D = x.shape
     U = Wqkvr.shape[1] // 4
     _need(x.is_contiguous(), "x must be contiguous")
@@ -221,12 +221,12 @@ def interacting_fwd(x, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, use_res=True, sa
     saved = interacting_saved(B, F, U, L, x.device) if save else None
     call("rs_interacting_fwd_dropout", _ptr(x), D, 0, _dt(x), _ptr(Wqkvr), _ptr(bqkvr), _ptr(gamma), _ptr(beta),
          ln_eps, _ptr(y), U, 0, _ptr(saved), B, F, D, U, H, L, int(use_res), int(compute_bf16),
-         float(dropout_rate), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _stream())
+         float(dropout_rate), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _ptr(dropout_step), _stream())
     return y, saved
 
 
 def interacting_bwd(x, saved, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, dy, use_res=True, compute_bf16=False,
-                    dropout_rate=0.0, dropout_seed=0):
+                    dropout_rate=0.0, dropout_seed=0, dropout_step=None):
     B, F, D = x.shape
     U = Wqkvr.shape[1] // 4
     dx = torch.empty_like(x)
@@ -236,7 +236,8 @@ def interacting_bwd(x, saved, Wqkvr, bqkvr, gamma, beta, ln_eps, H, L, dy, use_r
     dy = dy.contiguous()
     call("rs_interacting_bwd_dropout", _ptr(x), D, 0, _ptr(saved), _dt(x), _ptr(Wqkvr), _ptr(bqkvr), _ptr(gamma),
          _ptr(beta), ln_eps, _ptr(dy), U, 0, _ptr(dx), D, 0, _ptr(dparams), B, F, D, U, H, L, int(use_res),
-         int(compute_bf16), float(dropout_rate), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _ptr(ws), ws.numel(), _stream())
+         int(compute_bf16), float(dropout_rate), int(dropout_seed) & 0xFFFFFFFFFFFFFFFF, _ptr(dropout_step), _ptr(ws),
+         ws.numel(), _stream())
     nW = D * 4 * U
     return dx, dparams[:nW].view(D, 4 * U), dparams[nW:nW + 4 * U], dparams[nW + 4 * U:nW + 5 * U], dparams[nW + 5 * U:]
 
@@ -402,3 +403,32 @@ def binary_metrics_result(state, num_thresholds, out=None):
     out = torch.empty(6, dtype=torch.float64, device=state.device) if out is None else out
     call("rs_binary_metrics_result", _ptr(state), int(num_thresholds), _ptr(out), _stream())
     return out
+
+
+# ------------------------------------------------------------ cross network
+
+
+def cross_fwd(x, W, b):
+    """DCN-v1 cross layers x_{l+1} = x0 (x_l . w_l) + b_l + x_l (rough_rank/layer.py:256-264, staytime/layer.py:66-72).
+    x [B, dim] (fp32 / bf16, row stride allowed), W, b fp32 [L, dim]."""
+    _need(x.dim() == 2 and x.stride(1) == 1, "cross: x must be [B, dim] with contiguous rows")
+    B, dim = x.shape
+    L = W.shape[0]
+    out = torch.empty(B, dim, dtype=x.dtype, device=x.device)
+    ws = WS.get("cross", cabi.load().rs_cross_workspace_bytes(B, dim, L), x.device)
+    call("rs_cross_fwd", _ptr(x), x.stride(0), _dt(x), _ptr(W), _ptr(b), _ptr(out), dim, B, dim, L, _ptr(ws), ws.numel(),
+         _stream())
+    return out
+
+
+def cross_bwd(x, dout, W, b):
+    _need(x.stride(1) == 1 and dout.stride(1) == 1, "cross: contiguous rows")
+    B, dim = x.shape
+    L = W.shape[0]
+    dx = torch.empty(B, dim, dtype=x.dtype, device=x.device)
+    dW = torch.empty(L, dim, dtype=torch.float32, device=x.device)
+    db = torch.empty(L, dim, dtype=torch.float32, device=x.device)
+    ws = WS.get("cross", cabi.load().rs_cross_workspace_bytes(B, dim, L), x.device)
+    call("rs_cross_bwd", _ptr(x), x.stride(0), _ptr(dout), dout.stride(0), _dt(x), _ptr(W), _ptr(b), _ptr(dx), dim,
+         _ptr(dW), _ptr(db), B, dim, L, _ptr(ws), ws.numel(), _stream())
+    return dx, dW, db

@@ -201,14 +201,22 @@ def test_embedding_features_and_sparse_optimizers(cuda_dev):
 def test_multihead_autoint_builder(cuda_dev):
     from recommendsystem_b200.api.builders import AUTOINT, AutoInt, cross_entropy
     slots = [str(1000 + i) for i in range(12)]
-    model = AUTOINT(slots, bucket_size=1000, dnn_hidden_units=(32, 16), device=cuda_dev)
+    # the reference signature (rank/multi_head/multidnn.py:214) and return type (ModelResult, :246-250)
+    ret = AUTOINT(slots, [], True, dnn_hidden_units=(32, 16), bucket_size=1000, device=cuda_dev)
+    model = ret.model
+    assert ret.sub_model is model.sub_model and callable(ret.model_predict)
     g = torch.Generator().manual_seed(0)
     B = 64
     inputs = {s: torch.randint(0, 10 ** 6, (B,), generator=g).to(cuda_dev) for s in slots}
     labels = (torch.rand(B, 7, generator=g) < 0.3).float().to(cuda_dev)
     l0, pred = model.train_step(inputs, labels)
     assert pred.shape == (B, 7) and torch.isfinite(l0)
-    model.opt.param_groups[0]["lr"] = 1e-2
+    assert ret.model_predict(inputs).shape == (B, 7)
+    names = set(dict(ret.sub_model.named_parameters()))
+    for k in ("dnn_0.kernel", "expert_7_fc1.kernel", "gate_6_fc2.bias", "unlike_pred.kernel",
+              "interacting_layer.query_dense_kernel"):
+        assert k in names, k                                   # Keras layer names of the reference graph
+    model.opt.lr = 1e-2
     model.emb.opt.learning_rate = 1e-2
     for _ in range(60):
         l, _ = model.train_step(inputs, labels)
@@ -222,3 +230,31 @@ def test_multihead_autoint_builder(cuda_dev):
     out = AutoInt(cfg, device=cuda_dev).run()
     p = out["predict"](torch.randint(0, 100, (32, 39), device=cuda_dev))
     assert p.shape == (32, 1) and float(p.min()) >= 1e-6 and float(p.max()) <= 1.0
+
+
+@pytest.mark.parametrize("B,dim,L", [(20, 12, 2), (700, 1712, 3), (1025, 400, 3), (3, 8, 1)])
+def test_cross_network_kernels_fwd_bwd(cuda_dev, B, dim, L):
+    """rs_cross_fwd / rs_cross_bwd (one fused row kernel for all cross layers) against the reference recurrence
+    x_{l+1} = x0 (x_l . w_l) + b_l + x_l written out in float64 (rough_rank/layer.py:256-264, staytime/layer.py:66-72),
+    forward 1e-5 and every gradient (inputs, kernels, biases) 1e-5 via torch float64 autograd; deterministic."""
+    from recommendsystem_b200.api.functional import CrossFn
+    g = torch.Generator(device=cuda_dev).manual_seed(B + dim)
+    x = torch.randn(B, dim, device=cuda_dev, generator=g, requires_grad=True)
+    W = (torch.randn(L, dim, device=cuda_dev, generator=g) * (2.0 / dim) ** 0.5).requires_grad_(True)
+    b = (0.1 * torch.randn(L, dim, device=cuda_dev, generator=g)).requires_grad_(True)
+    dout = torch.randn(B, dim, device=cuda_dev, generator=g)
+    y = CrossFn.apply(x, W, b)
+    y.backward(dout)
+    x64, W64, b64 = (t.detach().double().requires_grad_(True) for t in (x, W, b))
+    xl = x64
+    for l in range(L):
+        xl = x64 * (xl @ W64[l]).unsqueeze(1) + b64[l] + xl
+    xl.backward(dout.double())
+    assert_close(f64(y), f64(xl), REL_F32, "cross fwd")
+    assert_close(f64(x.grad), f64(x64.grad), REL_F32, "cross dx")
+    assert_close(f64(W.grad), f64(W64.grad), REL_F32, "cross dW")
+    assert_close(f64(b.grad), f64(b64.grad), REL_F32, "cross db")
+    x2 = x.detach().clone().requires_grad_(True)
+    W2 = W.detach().clone().requires_grad_(True)
+    CrossFn.apply(x2, W2, b.detach()).backward(dout)
+    assert torch.equal(x2.grad, x.grad) and torch.equal(W2.grad, W.grad)

@@ -64,7 +64,10 @@ def test_video_dnn_sub_model(cuda_dev, B, T, units):
     for name in ("senet_squeeze_layer1.kernel", "experts.expert_output_0_0.kernel", "experts.gate_1_1_2.kernel",
                  "task_gates.gate_output_2.kernel", "staytime_output.kernel", "din.din_2125.layer_1_kernel",
                  "cross.W.1", "ffm.ffm_x_1568_1591_8.kernel", "tower_out.longplay_pred.bias"):
-        assert_close(sd[name].grad.cpu().numpy(), tP[name].grad.numpy(), 5 * REL_F32, "d/d " + name)
+        # the cross kernels' weight gradient multiplies the incoming gradient's round-off by the 1712-wide input row:
+        # 1e-4 there (the kernels alone hold 1e-5 against float64, test_cross_network_kernels_fwd_bwd)
+        tol = 10 * REL_F32 if name.startswith("cross.") else 5 * REL_F32
+        assert_close(sd[name].grad.cpu().numpy(), tP[name].grad.numpy(), tol, "d/d " + name)
 
 
 def test_dssm_sub_model(cuda_dev):
@@ -175,13 +178,68 @@ def test_graphed_train_step_matches_eager(cuda_dev):
         pa, pb = list(a.sub_model.parameters()), list(b.sub_model.parameters())
         assert len(pa) > 10 and all(torch.equal(x, y) for x, y in zip(pa, pb)), "same seed must give the same initial weights"
         eager = [float(a.train_step(inp, lab)[0]) for _ in range(6)]
-        gs = GraphedTrainStep(b, inp, lab, warmup=3)               # 3 real steps, then the capture
-        graphed = [float(gs(inp, lab)[0]) for _ in range(3)]
-        assert graphed == eager[3:], (kind, eager, graphed)        # bit for bit: deterministic kernels
-        for x, y in zip(pa, pb):
+        gs = GraphedTrainStep(b, inp, lab, warmup=3)               # 3 warm-up steps, UNDONE, then the capture
+        graphed = [float(gs(inp, lab)[0]) for _ in range(6)]
+        assert graphed == eager, (kind, eager, graphed)            # bit for bit from step 1: deterministic kernels,
+        for x, y in zip(pa, pb):                                   # and the warm-up left no trace
             assert torch.equal(x, y), kind
         assert torch.equal(a.emb.table, b.emb.table), kind
         # new data through the static buffers
         lab2 = {k: 1.0 - v if v.shape[-1] == 1 else v for k, v in lab.items()}
         l2 = float(gs(inp, lab2)[0])
         assert np.isfinite(l2) and l2 != graphed[-1]
+
+
+@pytest.mark.parametrize("B,F,training", [(7, 5, False), (64, 39, False), (64, 39, True), (33, 12, True)])
+def test_autoint_multihead_sub_model(cuda_dev, B, F, training):
+    """create_autoint_sub_model (rank/multi_head/multidnn.py:14-212) through api.builders.AUTOINT's sub-model against
+    the oracle restatement (oracle_models.autoint_multihead_fwd): forward 1e-5, gradients w.r.t. the slot embeddings and
+    representative weights 5e-5, weights loaded BY KERAS NAME.  training=True runs the attention dropout (rate 0.2,
+    :54) with the same counter-based mask on both sides."""
+    from oracle import oracle_models as om
+    from recommendsystem_b200.api.builders import AUTOINT, AUTOINT_LABELS
+    assert AUTOINT_LABELS == om.AUTOINT_LABELS
+    rng = np.random.default_rng(B + F)
+    slots = [str(2000 + i) for i in range(F)]
+    ret = AUTOINT(list(reversed(slots)), ["d0"], training, dnn_hidden_units=(32, 16), bucket_size=100, device=cuda_dev)
+    model = ret.sub_model
+    embs = [(0.5 * rng.standard_normal((B, 8))).astype(np.float32) for _ in range(F)]
+    te = [torch.from_numpy(e).to(cuda_dev).requires_grad_(True) for e in embs]
+    with torch.no_grad():
+        model([t.detach() for t in te])                      # lazy build
+    P = {}
+    for name, p_ in model.named_parameters():
+        shape = tuple(p_.shape)
+        if name.endswith("kernel"):
+            P[name] = (rng.standard_normal(shape) * (1.5 / np.sqrt(shape[0]))).astype(np.float32)
+        elif name.endswith("gamma"):
+            P[name] = (1.0 + 0.1 * rng.standard_normal(shape)).astype(np.float32)
+        else:
+            P[name] = (0.1 * rng.standard_normal(shape)).astype(np.float32)
+    _load(model, P, cuda_dev)
+    il = model.interacting_layer
+    il._dropout_calls = 0
+    if il._drop_step is not None:
+        il._drop_step.zero_()
+    pred = model(te)
+    dropout = (0.2, il.last_dropout_seed) if training else None
+    assert (il.last_dropout_seed is not None) == training
+    ref = om.autoint_multihead_fwd(om.NP, [e.astype(np.float64) for e in embs], _f64(P), (32, 16), dropout)
+    assert pred.shape == (B, 7)
+    assert_close(pred.detach().cpu().numpy(), ref, REL_F32, "AUTOINT predictions [B,7]")
+    wv = torch.from_numpy(rng.standard_normal(7)).to(cuda_dev, torch.float32)
+    (pred * wv).sum().backward()
+    tP = {k: torch.from_numpy(v).requires_grad_(True) for k, v in _f64(P).items()}
+    re = [torch.from_numpy(e.astype(np.float64)).requires_grad_(True) for e in embs]
+    ro = om.autoint_multihead_fwd(om.TH, re, tP, (32, 16), dropout)
+    (ro * wv.double().cpu()).sum().backward()
+    assert_close(np.stack([t.grad.cpu().numpy() for t in te]), np.stack([r.grad.numpy() for r in re]), 5 * REL_F32,
+                 "d/d slot embeddings")
+    sd = dict(model.named_parameters())
+    for name in ("dnn_0.kernel", "dnn_1.bias", "expert_0_fc1.kernel", "expert_6_fc1.bias", "gate_3_fc2.kernel",
+                 "like_pred.kernel", "unlike_pred.bias", "interacting_layer.query_dense_kernel",
+                 "interacting_layer.res_dense_bias", "interacting_layer.layer_norm_gamma"):
+        assert_close(sd[name].grad.cpu().numpy(), tP[name].grad.numpy(), 5 * REL_F32, "d/d " + name)
+    # the 8th expert is built but unused (:80-92): it gets no gradient
+    g7 = sd["expert_7_fc1.kernel"].grad
+    assert g7 is None or float(g7.abs().max()) == 0.0

@@ -75,3 +75,41 @@ def test_rough_rank_config_ids():
     assert C.get_feature_id("2597") == "2597"
     with pytest.raises(ValueError, match="feature: nope not found"):
         C.get_feature_id("nope")
+
+
+def test_autoint_multihead_oracle_np_matches_torch():
+    """The two statements of create_autoint_sub_model (numpy forward oracle, torch autograd gradient oracle) agree
+    to round-off, with and without the counter-based attention dropout."""
+    import torch
+    from oracle import oracle_models as om
+    rng = np.random.default_rng(5)
+    B, F = 9, 11
+    embs = [0.5 * rng.standard_normal((B, 8)) for _ in range(F)]
+    P = {}
+    for nm in ("query", "key", "value", "res"):
+        P["interacting_layer.%s_dense_kernel" % nm] = rng.standard_normal((8, 8)) * 0.4
+        P["interacting_layer.%s_dense_bias" % nm] = rng.standard_normal(8) * 0.1
+    P["interacting_layer.layer_norm_gamma"] = 1 + 0.1 * rng.standard_normal(8)
+    P["interacting_layer.layer_norm_beta"] = 0.1 * rng.standard_normal(8)
+    width = 8 * F
+    for i, u in enumerate((32, 16)):
+        P["dnn_%d.kernel" % i] = rng.standard_normal((width, u)) / np.sqrt(width)
+        P["dnn_%d.bias" % i] = 0.1 * rng.standard_normal(u)
+        width = u
+    cat = 16 + 8 * F
+    for i in range(8):
+        P["expert_%d_fc1.kernel" % i] = rng.standard_normal((cat, 32)) / np.sqrt(cat)
+        P["expert_%d_fc1.bias" % i] = 0.1 * rng.standard_normal(32)
+    for i in range(7):
+        P["gate_%d_fc2.kernel" % i] = rng.standard_normal((cat, 7)) / np.sqrt(cat)
+        P["gate_%d_fc2.bias" % i] = 0.1 * rng.standard_normal(7)
+    for lab in om.AUTOINT_LABELS:
+        P[lab + ".kernel"] = rng.standard_normal((32, 1)) * 0.3
+        P[lab + ".bias"] = 0.1 * rng.standard_normal(1)
+    for dropout in (None, (0.2, 12345)):
+        a = om.autoint_multihead_fwd(om.NP, embs, P, (32, 16), dropout)
+        b = om.autoint_multihead_fwd(om.TH, [torch.from_numpy(e) for e in embs], {k: torch.from_numpy(v) for k, v in P.items()},
+                                     (32, 16), dropout)
+        assert a.shape == (B, 7) and np.all((a > 0) & (a < 1))
+        assert np.max(np.abs(a - b.numpy())) < 1e-12
+    assert np.max(np.abs(om.autoint_multihead_fwd(om.NP, embs, P, (32, 16), (0.2, 1)) - a)) > 1e-6   # the mask matters
