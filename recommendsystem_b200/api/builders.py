@@ -207,10 +207,13 @@ def AUTOINT(linear_features, dense_features, training, dnn_hidden_units=(32, 16)
     features = sorted(set(linear_features))                                   # :215-218
     cols = [embedding_column(category_column(s, bucket_size), dimension=8, combiner="mean") for s in features]
     E = embedding_cls or EmbeddingFeatures
-    kw = {"group": group} if embedding_cls is not None else {}
+    kw = {"group": group} if embedding_cls is not None else {}      # None = the default process group
     emb = E(cols, Adam(5e-5, 0.9, 0.999, 1e-8), "linear", device=device, seed=seed, **kw)
     sub_model = create_autoint_sub_model([(s, None) for s in linear_features], {k: None for k in dense_features},
                                          dnn_hidden_units, training, device=device)
+    if embedding_cls is not None and group is None:
+        from .optim import _world_group
+        group = _world_group()
     full = _AutoIntFullModel(list(linear_features), emb, sub_model, training, group=group)
     ret = ModelResult()
     ret.model = full                                                           # :247

@@ -82,28 +82,41 @@ class EmbeddingFeatures:
         rows = np.asarray([c.categorical_column.bucket_size for c in self.cols], np.int64)
         self.base = np.concatenate([[0], np.cumsum(rows)[:-1]]).astype(np.int64)
         self.rows = rows
-        total = int(rows.sum())
-        gen = torch.Generator(device=self.dev).manual_seed(seed)
-        scale = getattr(sparse_opt, "initial_scale", 0.1) if isinstance(sparse_opt, AdaGrad) else 0.1
-        if isinstance(sparse_opt, Adam):
-            # one [w | m | v] record per row: the sparse update touches ONE contiguous 12d-byte
-            # block per row instead of three far-apart ones (random DRAM / TLB accesses, not bytes, bound it)
-            self.arena = torch.zeros(total, 3, self.d, device=self.dev)
-            self.table, self.m, self.v = self.arena[:, 0, :], self.arena[:, 1, :], self.arena[:, 2, :]
-            chunk = 1 << 22
-            for r0 in range(0, total, chunk):
-                r1 = min(total, r0 + chunk)
-                self.table[r0:r1] = torch.empty(r1 - r0, self.d, device=self.dev).normal_(0.0, float(scale), generator=gen)
-            self.scalars = torch.zeros(4, device=self.dev)
-        elif isinstance(sparse_opt, AdaGrad):
-            self.table = torch.empty(total, self.d, device=self.dev).normal_(0.0, float(scale), generator=gen)
-            shape = (total, self.d) if sparse_opt.per_element else (total,)
-            self.g2sum = torch.full(shape, float(sparse_opt.initial_g2sum), device=self.dev)
-        else:
+        if not isinstance(sparse_opt, (Adam, AdaGrad)):
             raise TypeError("sparse_opt must be api.embedding.Adam or AdaGrad")
+        total = self._alloc_tables(seed)
         self.row_bits = ops.row_bits(total)
         self._last = None
         self._geom_cache = {}
+
+    def _init_scale(self):
+        return float(getattr(self.opt, "initial_scale", 0.1) if isinstance(self.opt, AdaGrad) else 0.1)
+
+    def _alloc_state(self, n_rows):
+        """Storage for `n_rows` table rows + optimizer state: Adam keeps one [w | m | v] record per row (DESIGN.md 2:
+        the sparse update touches ONE contiguous 12d-byte block per row instead of three far-apart ones)."""
+        if isinstance(self.opt, Adam):
+            self.arena = torch.zeros(n_rows, 3, self.d, device=self.dev)
+            self.table, self.m, self.v = self.arena[:, 0, :], self.arena[:, 1, :], self.arena[:, 2, :]
+            self.table_ld = 3 * self.d
+            self.scalars = torch.zeros(4, device=self.dev)
+        else:
+            self.table = torch.zeros(n_rows, self.d, device=self.dev)
+            self.table_ld = self.d
+            shape = (n_rows, self.d) if self.opt.per_element else (n_rows,)
+            self.g2sum = torch.full(shape, float(self.opt.initial_g2sum), device=self.dev)
+
+    def _alloc_tables(self, seed) -> int:
+        """Allocate and initialise (N(0, scale), one generator stream over the rows in arena order); returns the number
+        of rows the sort keys must address."""
+        total = int(self.rows.sum())
+        self._alloc_state(total)
+        gen = torch.Generator(device=self.dev).manual_seed(seed)
+        chunk = 1 << 22
+        for r0 in range(0, total, chunk):
+            r1 = min(total, r0 + chunk)
+            self.table[r0:r1] = torch.empty(r1 - r0, self.d, device=self.dev).normal_(0.0, self._init_scale(), generator=gen)
+        return total
 
     def __call__(self, inputs: Dict[str, torch.Tensor]):
         out, plan = {}, []

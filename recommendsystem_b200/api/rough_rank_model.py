@@ -15,7 +15,7 @@ import torch
 from torch import nn
 
 from .builders import _KerasDense
-from .optim import DenseAdam
+from .optim import DenseAdam, _world_group
 from .embedding import Adam, EmbeddingFeatures, category_column, embedding_column
 from .rough_rank_layer import DNN, PLE, CrossNet, KDLoss
 
@@ -161,14 +161,16 @@ class DssmNet:
     for the user and item feature ids + the dense mask input '4575'."""
 
     def __init__(self, user_ids=C.USER_FEATURE_IDS, item_ids=C.ITEM_FEATURE_IDS, bucket_size=25600,
-                 device="cuda:0", seed=0):
+                 device="cuda:0", seed=0, embedding_cls=None, group=None):
+        self.group = group if (group is not None or embedding_cls is None) else _world_group()
         self.ids = list(user_ids) + list(item_ids)
         dims = [C.USER_OUTPUT_DIM] * len(user_ids) + [C.ITEM_OUTPUT_DIM] * len(item_ids)
         cols = [embedding_column(category_column(C.get_feature_id(f) if f in C.ALL_FEATURE_ID_2_SLOT else f,
                                                  bucket_size), dimension=d, combiner="mean")
                 for f, d in zip(self.ids, dims)]
-        self.emb = EmbeddingFeatures(cols, Adam(learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8),
-                                     "sparse_emb_input", device=device, seed=seed)
+        E, kw = (embedding_cls, {"group": group}) if embedding_cls is not None else (EmbeddingFeatures, {})
+        self.emb = E(cols, Adam(learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8),
+                     "sparse_emb_input", device=device, seed=seed, **kw)
         self.sub_model = DssmSubModel(user_ids, item_ids).to(device)
         self.opt = None
 

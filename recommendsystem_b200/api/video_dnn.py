@@ -18,7 +18,7 @@ import torch
 from torch import nn
 
 from .builders import _KerasDense
-from .optim import DenseAdam
+from .optim import DenseAdam, _world_group
 from .embedding import AdaGrad, EmbeddingFeatures, category_column, embedding_column
 from .staytime_config import Config as C
 from .staytime_layer import DIN, DeepCrossLayer
@@ -178,14 +178,18 @@ class MtlNet:
     reference; `train_step` adds the compile() of staytime/model.py:72-90 (dense Adam 5e-4, weighted losses)."""
 
     def __init__(self, slots, seq_slots, seq_max_len, dnn_hidden_units=(64, 32), bucket_size=81920, device="cuda:0",
-                 seed=0):
+                 seed=0, embedding_cls=None, group=None):
+        # embedding_cls = api.sharded_embedding.ShardedEmbeddingFeatures (+ its process group): row-sharded tables
+        # over the ranks, dense gradients averaged over them (staytime/parse.py:77-79)
+        self.group = group if (group is not None or embedding_cls is None) else _world_group()
         self.slots, self.seq_slots = list(slots), list(seq_slots)
         cats = {s: category_column(s, bucket_size) for s in self.slots}                                  # :219-220
         cols = [embedding_column(cats[s], 32, combiner="mean", name="emb_col_%s" % s) for s in self.slots]
         cols += [embedding_column(cats[s], 32, combiner=None, seq_max_len=seq_max_len, name="emb_col_seq_%s" % s)
                  for s in self.seq_slots]                                                                # :228-231
-        self.emb = EmbeddingFeatures(cols, AdaGrad(learning_rate=0.005, initial_g2sum=0.1, initial_scale=0.1),
-                                     "sparse_emb_input", device=device, seed=seed)
+        E, kw = (embedding_cls, {"group": group}) if embedding_cls is not None else (EmbeddingFeatures, {})
+        self.emb = E(cols, AdaGrad(learning_rate=0.005, initial_g2sum=0.1, initial_scale=0.1),
+                     "sparse_emb_input", device=device, seed=seed, **kw)
         self.sub_model = VideoDnnSubModel(self.slots, self.seq_slots, dnn_hidden_units).to(device)
         self.opt = None
 

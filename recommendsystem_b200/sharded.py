@@ -57,6 +57,30 @@ def shard_layout(rows_per_field, world):
     return local_rows, local_base
 
 
+def map_peer_buffers(tensor, world, rank, group, opened):
+    """Exchange CUDA-IPC handles of `tensor` (one per rank of `group`) and map every rank's copy into this process.
+    Returns a ctypes array of `world` device pointers (a kernel argument).  `opened` caches the imported allocations
+    (an allocation may be opened once per process).  Collective, host-synchronising: setup time only."""
+    handle = (ctypes.c_ubyte * 64)()
+    off = ctypes.c_ulonglong(0)
+    cabi.call("rs_ipc_export", tensor.data_ptr(), ctypes.addressof(handle), ctypes.addressof(off))
+    everyone = [None] * world
+    dist.all_gather_object(everyone, (bytes(handle), int(off.value)), group=group)
+    ptrs = (ctypes.c_void_p * world)()
+    for r, (h, o) in enumerate(everyone):
+        if r == rank:
+            ptrs[r] = tensor.data_ptr()
+            continue
+        if (r, h) not in opened:
+            hb = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+            base = ctypes.c_void_p(0)
+            cabi.call("rs_ipc_import", ctypes.addressof(hb), 0, ctypes.addressof(base))
+            opened[(r, h)] = base.value
+        ptrs[r] = opened[(r, h)] + o
+    dist.barrier(group=group)
+    return ptrs
+
+
 class Exchange:
     """The three all-to-alls of a sharded step (equal splits of `cap` slots per peer)."""
 
@@ -119,26 +143,9 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
     def _map_peers(self, tensor, group):
         """Exchange CUDA-IPC handles of `tensor` (one per rank) and map every rank's copy into this process;
         returns a host array of W device pointers (a kernel argument)."""
-        handle = (ctypes.c_ubyte * 64)()
-        off = ctypes.c_ulonglong(0)
-        cabi.call("rs_ipc_export", tensor.data_ptr(), ctypes.addressof(handle), ctypes.addressof(off))
-        everyone = [None] * self.world
-        dist.all_gather_object(everyone, (bytes(handle), int(off.value)), group=group)
-        ptrs = (ctypes.c_void_p * self.world)()
-        opened = getattr(self, "_ipc_opened", {})
-        for r, (h, o) in enumerate(everyone):
-            if r == self.rank:
-                ptrs[r] = tensor.data_ptr()
-                continue
-            if (r, h) not in opened:                  # an allocation may be opened once per process
-                hb = (ctypes.c_ubyte * 64).from_buffer_copy(h)
-                base = ctypes.c_void_p(0)
-                cabi.call("rs_ipc_import", ctypes.addressof(hb), 0, ctypes.addressof(base))
-                opened[(r, h)] = base.value
-            ptrs[r] = opened[(r, h)] + o
-        self._ipc_opened = opened
-        dist.barrier(group=group)
-        return ptrs
+        if not hasattr(self, "_ipc_opened"):
+            self._ipc_opened = {}
+        return map_peer_buffers(tensor, self.world, self.rank, group, self._ipc_opened)
 
     def _map_peer_tables(self, group):
         self.peer_ptrs = self._map_peers(self.table, group)          # every rank's table shard
