@@ -81,7 +81,7 @@ class ShardedEmbeddingFeatures(EmbeddingFeatures):
         return n_local
 
     # ---- exchange buffers ------------------------------------------------------------------------------------
-    def _group(self, gkey, n, cols) -> _Group:
+    def _group(self, gkey, n, cols, padded=False) -> _Group:
         g = self._groups.get((gkey, n))
         if g is not None:
             return g
@@ -90,7 +90,9 @@ class ShardedEmbeddingFeatures(EmbeddingFeatures):
         W, d, dev = self.world, self.d, self.dev
         g = _Group()
         g.n, g.F = n, len(cols)
-        g.cap = bucket_capacity(n, W, self.capacity_factor)
+        # Padding ids (< 0) all travel in their rank's owner-0 bucket (rs_route_ids_padded's convention, row -1): a
+        # group that may carry padding (sequence / bag columns) sizes every bucket for the worst case, all n lookups.
+        g.cap = n if padded else bucket_capacity(n, W, self.capacity_factor)
         idx = list(cols)
         g.lbase_t = torch.as_tensor(self.local_base[idx], device=dev)
         g.rows_t = torch.as_tensor(self.rows[idx], device=dev)
@@ -106,11 +108,11 @@ class ShardedEmbeddingFeatures(EmbeddingFeatures):
         self._groups[(gkey, n)] = g
         return g
 
-    def _lookup(self, gkey, ids: torch.Tensor, cols) -> torch.Tensor:
+    def _lookup(self, gkey, ids: torch.Tensor, cols, padded=False) -> torch.Tensor:
         """ids int64 [N, len(cols)] (id < 0 = padding) -> fp32 [N, len(cols), d]; registers the owners' keys."""
         ids = ids.contiguous()
         n = ids.numel()
-        g = self._group(gkey, n, tuple(cols))
+        g = self._group(gkey, n, tuple(cols), padded)
         out = torch.empty(ids.shape[0], g.F, self.d, dtype=torch.float32, device=self.dev)
         st = ops._stream()
         cabi.call("rs_embed_gather_peer_fwd", ctypes.addressof(self.peer_tables), self.table_ld, self.world, ids.data_ptr(),
@@ -140,12 +142,12 @@ class ShardedEmbeddingFeatures(EmbeddingFeatures):
             if c.combiner is None:                               # sequence column -> ([B,T,d], mask)
                 T = c.seq_max_len or ids.shape[1]
                 seq = ids[:, :T].contiguous()
-                emb, g = self._lookup(("seq", ci), seq.reshape(-1, 1), [ci])
+                emb, g = self._lookup(("seq", ci), seq.reshape(-1, 1), [ci], padded=True)
                 out[c.key] = (emb.view(seq.shape[0], T, self.d).to(self.out_dtype), seq >= 0)
                 plan.append((c.key, g, None))
             else:                                                # combiner='mean' over the valid ids of a padded bag
                 B, bag = ids.shape
-                emb, g = self._lookup(("bag", ci), ids.reshape(-1, 1), [ci])
+                emb, g = self._lookup(("bag", ci), ids.reshape(-1, 1), [ci], padded=True)
                 cnt = (ids >= 0).sum(1).clamp(min=1).to(torch.float32)
                 out[c.key] = (emb.view(B, bag, self.d).sum(1) / cnt[:, None]).to(self.out_dtype)
                 plan.append((c.key, g, (bag, cnt)))
