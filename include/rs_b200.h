@@ -148,6 +148,17 @@ int rs_embed_gather_bag_mean(const float* table, const int64_t* ids,
                              const int64_t* offsets, const int64_t* row_base,
                              const int64_t* rows, int64_t n_bags, int F, int d,
                              void* out, int out_dtype, void* stream);
+/* The same lookup for TRAINING: table with an explicit row stride (0 = d; 3d for [w|m|v] records), and the two
+ * by-products the backward needs: sort_keys[p] = (arena row << 32 | p) for every occurrence p (padding id < 0 ->
+ * all-ones key, skipped by the segment sum) and inv_cnt[b] = 1 / #valid ids of bag b (0 if empty).  Either may be NULL.
+ * rs_embed_bag_grad is the mean combiner's backward: g_occ[p, :] = dout[b(p), :] * inv_cnt[b(p)] (fp32 [nnz, d]), the
+ * per-occurrence gradient rows that rs_embed_sort_keys + rs_embed_segsum_* consume. */
+int rs_embed_bag_fwd_ld(const float* table, int64_t table_ld, const int64_t* ids,
+                        const int64_t* offsets, const int64_t* row_base, const int64_t* rows,
+                        int64_t n_bags, int F, int d, void* out, int out_dtype,
+                        uint64_t* sort_keys, float* inv_cnt, void* stream);
+int rs_embed_bag_grad(const void* dout, int dtype, const int64_t* offsets, const float* inv_cnt,
+                      int64_t n_bags, int d, float* g_occ, void* stream);
 
 /* --------------------------------- K3 sparse gradient + fused optimizer --
  * Replaces the backward of EmbeddingFeatures + the server-side sparse

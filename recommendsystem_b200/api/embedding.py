@@ -14,7 +14,7 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
-from .. import ops
+from .. import cabi, ops
 
 
 @dataclass
@@ -123,6 +123,7 @@ class EmbeddingFeatures:
         # single-valued mean columns (ids [B] / [B,1], the Criteo-shaped case) share ONE gather launch over
         # the stacked ids [B, F'] (per-column row_base / bucket size) and one sorted-segment push
         single = [ci for ci, c in enumerate(self.cols) if c.combiner is not None and
+                  not isinstance(inputs[c.categorical_column.key], (tuple, list)) and
                   (inputs[c.categorical_column.key].dim() == 1 or inputs[c.categorical_column.key].shape[1] == 1)]
         if len(single) > 1:
             ids = torch.stack([inputs[self.cols[ci].categorical_column.key].reshape(-1) for ci in single], dim=1)
@@ -137,8 +138,26 @@ class EmbeddingFeatures:
         for ci, c in enumerate(self.cols):
             if ci in single:
                 continue
-            ids = inputs[c.categorical_column.key].to(self.dev, torch.int64)
+            raw = inputs[c.categorical_column.key]
             base, rows = self._geom((ci,))
+            if isinstance(raw, (tuple, list)):
+                # variable-length bag in CSR form (values int64 [nnz], offsets int64 [B+1]): the VarLenFeature /
+                # SparseTensor input of the reference (staytime/parse.py:22-23), combiner='mean' (VideoDnn.py:224-226)
+                if c.combiner is None:
+                    raise ValueError("CSR (values, offsets) inputs are for combiner='mean' columns")
+                vals = raw[0].to(self.dev, torch.int64).contiguous()
+                offs = raw[1].to(self.dev, torch.int64).contiguous()
+                nb = offs.numel() - 1
+                emb = torch.empty(nb, self.d, dtype=torch.float32, device=self.dev)
+                keys = torch.empty(vals.numel(), dtype=torch.int64, device=self.dev)
+                inv = torch.empty(nb, dtype=torch.float32, device=self.dev)
+                cabi.call("rs_embed_bag_fwd_ld", self.table.data_ptr(), self.table_ld, vals.data_ptr(), offs.data_ptr(),
+                          base.data_ptr(), rows.data_ptr(), nb, 1, self.d, emb.data_ptr(), cabi.RS_F32, keys.data_ptr(),
+                          inv.data_ptr(), ops._stream())
+                out[c.key] = emb.to(self.out_dtype)
+                plan.append((c.key, keys, None, ("csr", offs, inv)))
+                continue
+            ids = raw.to(self.dev, torch.int64)
             if c.combiner is None:                               # sequence column -> ([B,T,d], mask)
                 T = c.seq_max_len or ids.shape[1]
                 seq = ids[:, :T].contiguous()
@@ -218,7 +237,13 @@ class EmbeddingFeatures:
             if isinstance(g, tuple):
                 g = g[0]
             g = g.reshape(-1, self.d)
-            if bag is not None:                                   # mean combiner: 1/count per occurrence
+            if bag is not None and bag[0] == "csr":               # CSR bag: one gradient row per occurrence
+                _, offs, inv = bag
+                gc = g.contiguous()
+                g = torch.empty(keys.numel(), self.d, dtype=torch.float32, device=self.dev)
+                cabi.call("rs_embed_bag_grad", gc.data_ptr(), ops._dt(gc), offs.data_ptr(), inv.data_ptr(),
+                          offs.numel() - 1, self.d, g.data_ptr(), ops._stream())
+            elif bag is not None:                                 # mean combiner: 1/count per occurrence
                 b, cnt = bag
                 g = (g.float() / cnt[:, None]).repeat_interleave(b, dim=0)
             g = g.contiguous()

@@ -29,6 +29,8 @@ PROTOTYPES = {
     "rs_embed_gather_rows": (_i, [_p, _p, _i64, _i, _p, _i, _p, _p, _p]),
     "rs_embed_gather_rows_ld": (_i, [_p, _i64, _p, _i64, _i, _p, _i, _p, _p, _p]),
     "rs_embed_gather_bag_mean": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _p, _i, _p]),
+    "rs_embed_bag_fwd_ld": (_i, [_p, _i64, _p, _p, _p, _p, _i64, _i, _i, _p, _i, _p, _p, _p]),
+    "rs_embed_bag_grad": (_i, [_p, _i, _p, _p, _i64, _i, _p, _p]),
     "rs_embed_sort_workspace_bytes": (_sz, [_i64]),
     "rs_embed_gather_peer_fwd": (_i, [_p, _i64, _i, _p, _p, _p, _i64, _i, _i, _p, _i, _p]),
     "rs_scatter_rows_peer": (_i, [_p, _p, _i, _i, _p, _i64, _i, _i, _p]),

@@ -257,6 +257,61 @@ __global__ void embed_bag_mean_kernel(const float* __restrict__ table,
   store4<OutT>(out + bag * d + gl * 4, acc);
 }
 
+
+// CSR bags for TRAINING: mean over the valid ids of bag b (combiner='mean' on VarLenFeature ids, staytime/parse.py:22-23,
+// staytime/VideoDnn.py:224-226) from a table with an explicit row stride ([w|m|v] records), plus what the backward needs:
+// sort_keys[p] = (row << 32 | p) per occurrence p (padding / empty -> all-ones key, skipped by the segment sum) and
+// inv_cnt[b] = 1 / (number of valid ids of bag b) (0 for an empty bag).
+template <typename OutT>
+__global__ void embed_bag_fwd_kernel(const float* __restrict__ table, int64_t table_ld, const int64_t* __restrict__ ids,
+                                     const int64_t* __restrict__ offsets, const int64_t* __restrict__ row_base,
+                                     const int64_t* __restrict__ rows, int64_t n_bags, int F, int d, int G,
+                                     OutT* __restrict__ out, uint64_t* __restrict__ sort_keys, float* __restrict__ inv_cnt) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t bag = t / G;
+  const int gl = (int)(t % G);
+  if (bag >= n_bags || gl * 4 >= d) return;
+  const int f = (int)(bag % F);
+  const int64_t lo = offsets[bag], hi = offsets[bag + 1];
+  const uint64_t R = (uint64_t)rows[f];
+  const int64_t rb = row_base[f];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cnt = 0;
+  for (int64_t p = lo; p < hi; ++p) {
+    const int64_t id = ids[p];
+    if (id < 0) {
+      if (gl == 0 && sort_keys) sort_keys[p] = ~0ULL;
+      continue;
+    }
+    const int64_t r = rb + (int64_t)((uint64_t)id % R);
+    if (gl == 0 && sort_keys) sort_keys[p] = ((uint64_t)r << 32) | (uint64_t)(uint32_t)p;
+    const float4 v = ldg_row_f4(reinterpret_cast<const float4*>(table + r * table_ld) + gl);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    ++cnt;
+  }
+  const float inv = cnt > 0 ? 1.f / (float)cnt : 0.f;
+  acc.x *= inv; acc.y *= inv; acc.z *= inv; acc.w *= inv;
+  store4<OutT>(out + bag * d + gl * 4, acc);
+  if (gl == 0 && inv_cnt) inv_cnt[bag] = inv;
+}
+
+// backward of the mean combiner: occurrence p of bag b receives dout[b] / count(b)  (one row per occurrence, the
+// layout the sorted-segment sum consumes)
+template <typename T>
+__global__ void embed_bag_grad_kernel(const T* __restrict__ dout, const int64_t* __restrict__ offsets,
+                                      const float* __restrict__ inv_cnt, int64_t n_bags, int d, int G,
+                                      float* __restrict__ g_occ) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t bag = t / G;
+  const int gl = (int)(t % G);
+  if (bag >= n_bags || gl * 4 >= d) return;
+  const float4 g = load4<T>(dout + bag * d + gl * 4);
+  const float s = inv_cnt[bag];
+  const float4 v = make_float4(g.x * s, g.y * s, g.z * s, g.w * s);
+  for (int64_t p = offsets[bag]; p < offsets[bag + 1]; ++p)
+    *reinterpret_cast<float4*>(g_occ + p * d + gl * 4) = v;
+}
+
 // ----------------------------------------------- segment sum + optimizers ---
 enum { OPT_NONE = 0, OPT_ADAM = 1, OPT_ADAGRAD_ROW = 2, OPT_ADAGRAD_ELEM = 3 };
 
@@ -824,6 +879,45 @@ int rs_embed_gather_bag_mean(const float* table, const int64_t* ids, const int64
     embed_bag_mean_kernel<__nv_bfloat16><<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(
         table, ids, offsets, row_base, rows, n_bags, F, d, G, (__nv_bfloat16*)out);
   return check_launch("embed_bag_mean");
+}
+
+int rs_embed_bag_fwd_ld(const float* table, int64_t table_ld, const int64_t* ids, const int64_t* offsets,
+                        const int64_t* row_base, const int64_t* rows, int64_t n_bags, int F, int d, void* out,
+                        int out_dtype, uint64_t* sort_keys, float* inv_cnt, void* stream) {
+  if (table_ld == 0) table_ld = d;
+  RS_REQUIRE(d > 0 && d % 4 == 0 && d <= 128 && F > 0, "embed_bag_fwd: F=%d d=%d", F, d);
+  RS_REQUIRE(table_ld >= d && table_ld % 4 == 0, "embed_bag_fwd: table row stride %lld", (long long)table_ld);
+  RS_REQUIRE(out_dtype == RS_F32 || out_dtype == RS_BF16, "embed_bag_fwd: bad out dtype %d", out_dtype);
+  if (n_bags == 0) return 0;
+  int G = 1;
+  while (G * 4 < d) G <<= 1;
+  const int threads = 128;
+  const int64_t blocks = cdiv(n_bags * G, threads);
+  if (out_dtype == RS_F32)
+    embed_bag_fwd_kernel<float><<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(
+        table, table_ld, ids, offsets, row_base, rows, n_bags, F, d, G, (float*)out, sort_keys, inv_cnt);
+  else
+    embed_bag_fwd_kernel<__nv_bfloat16><<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(
+        table, table_ld, ids, offsets, row_base, rows, n_bags, F, d, G, (__nv_bfloat16*)out, sort_keys, inv_cnt);
+  return check_launch("embed_bag_fwd");
+}
+
+int rs_embed_bag_grad(const void* dout, int dtype, const int64_t* offsets, const float* inv_cnt, int64_t n_bags, int d,
+                      float* g_occ, void* stream) {
+  RS_REQUIRE(d > 0 && d % 4 == 0 && d <= 128, "embed_bag_grad: d=%d", d);
+  RS_REQUIRE(dtype == RS_F32 || dtype == RS_BF16, "embed_bag_grad: bad dtype %d", dtype);
+  if (n_bags == 0) return 0;
+  int G = 1;
+  while (G * 4 < d) G <<= 1;
+  const int threads = 128;
+  const int64_t blocks = cdiv(n_bags * G, threads);
+  if (dtype == RS_F32)
+    embed_bag_grad_kernel<float><<<(unsigned)blocks, threads, 0, as_stream(stream)>>>((const float*)dout, offsets, inv_cnt,
+                                                                                      n_bags, d, G, g_occ);
+  else
+    embed_bag_grad_kernel<__nv_bfloat16><<<(unsigned)blocks, threads, 0, as_stream(stream)>>>(
+        (const __nv_bfloat16*)dout, offsets, inv_cnt, n_bags, d, G, g_occ);
+  return check_launch("embed_bag_grad");
 }
 
 size_t rs_embed_sort_workspace_bytes(int64_t n) {

@@ -258,3 +258,45 @@ def test_cross_network_kernels_fwd_bwd(cuda_dev, B, dim, L):
     W2 = W.detach().clone().requires_grad_(True)
     CrossFn.apply(x2, W2, b.detach()).backward(dout)
     assert torch.equal(x2.grad, x.grad) and torch.equal(W2.grad, W.grad)
+
+
+@pytest.mark.parametrize("opt_name", ["adam", "adagrad"])
+def test_embedding_features_csr_bags(cuda_dev, opt_name):
+    """True variable-length bags (VarLenFeature ids as CSR values/offsets, staytime/parse.py:22-23) through
+    EmbeddingFeatures with combiner='mean' (VideoDnn.py:224-226): forward = mean over the valid ids of each bag (empty
+    bag -> zeros), backward = 1/count per occurrence, duplicate rows summed, sparse optimizer applied — against a
+    dense float64 restatement; and identical to the padded-[B, bag] input path."""
+    from recommendsystem_b200.api.embedding import Adam, AdaGrad, EmbeddingFeatures, category_column, embedding_column
+    mk = (lambda: Adam(1e-2, 0.9, 0.999, 1e-8)) if opt_name == "adam" else (lambda: AdaGrad(1e-2, 0.1, 0.1))
+    rng = np.random.default_rng(4)
+    B, R, d, maxbag = 37, 50, 16, 6
+    lens = rng.integers(0, maxbag + 1, size=B)
+    lens[0], lens[1] = 0, maxbag
+    vals = rng.integers(0, 10 ** 9, size=int(lens.sum())).astype(np.int64)
+    vals[3] = -1                                             # a padding id inside a bag is ignored
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    padded = -np.ones((B, maxbag), np.int64)
+    for b in range(B):
+        padded[b, :lens[b]] = vals[offs[b]:offs[b + 1]]
+    col = lambda: [embedding_column(category_column("s", R), d, combiner="mean")]
+    a = EmbeddingFeatures(col(), mk(), device=cuda_dev, seed=5)
+    c = EmbeddingFeatures(col(), mk(), device=cuda_dev, seed=5)
+    t0 = a.table.clone().double().cpu().numpy()
+    csr = (torch.from_numpy(vals).to(cuda_dev), torch.from_numpy(offs).to(cuda_dev))
+    oa = a({"s": csr})["s"]
+    oc = c({"s": torch.from_numpy(padded).to(cuda_dev)})["s"]
+    ref = np.zeros((B, d))
+    for b in range(B):
+        v = [x for x in vals[offs[b]:offs[b + 1]] if x >= 0]
+        if v:
+            ref[b] = t0[np.asarray(v) % R].mean(0)
+    assert_close(f64(oa), ref, REL_F32, "CSR bag mean")
+    assert_close(f64(oc), ref, REL_F32, "padded bag mean")
+    g = torch.from_numpy(rng.standard_normal((B, d)).astype(np.float32)).to(cuda_dev)
+    a.backward({"s": g})
+    c.backward({"s": g})
+    assert_close(f64(a.table), f64(c.table), 1e-6, "CSR update == padded update")
+    # rows that no bag touched did not move; touched rows did
+    touched = np.unique(vals[vals >= 0] % R)
+    moved = np.abs(f64(a.table) - t0).max(1) > 0
+    assert set(np.nonzero(moved)[0]) == set(touched.tolist())
