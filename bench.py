@@ -179,6 +179,8 @@ def algorithmic(phase, B, act_bytes, n_unique):
         # x in, y out, + per iteration the saved pre-LayerNorm row and the H softmax statistics (fp32) the tcgen05
         # forward writes / backward reads
         "interacting_fwd": (n * (D + U) * act_bytes + L * n * (U + H) * 4, inter_f),
+        # + the fused lookup: id 8 B + fp32 table row + sort key 8 B (X is then a WRITE of the kernel, not a read)
+        "interacting_fwd_fused": (n * (8 + D * 4 + 8) + n * (D + U) * act_bytes + L * n * (U + H) * 4, inter_f),
         "interacting_bwd": (n * (U + 2 * D) * act_bytes + L * n * (U + H) * 4, 3 * inter_f),
         "mlp_fwd": (B * (F * D + 2 * MLP[0] + MLP[1]) * act_bytes, gemm),
         "mlp_bwd": (B * (2 * MLP[0] + 3 * MLP[1]) * act_bytes, 2 * B * MLP[0] * MLP[1]),     # act_bwd + dgrad (main stream)
@@ -421,8 +423,9 @@ def run_own(args):
     pk = peaks()
     step_ms_sum = sum(v[0] for v in phases.values())
     kernels = []
+    fused = bool(getattr(tr, "fused", False))
     for name, (pms, nl) in sorted(phases.items(), key=lambda kv: -kv[1][0]):
-        by, fl = algorithmic(name, BATCH, act_bytes, n_unique)
+        by, fl = algorithmic(name + "_fused" if (fused and name == "interacting_fwd") else name, BATCH, act_bytes, n_unique)
         kernels.append({"phase": name, "ms": round(pms, 4), "share": round(pms / step_ms_sum, 4), "launches": nl,
                         "alg_bytes": by, "alg_flops": fl,
                         "GBps": round(by / pms / 1e6, 1) if by else None,
@@ -442,12 +445,28 @@ def run_own(args):
                 tr.saved.data_ptr(), BATCH, F, D, U, H, L, 1, int(args.dtype == "bf16"), st_()),
             "interacting_bwd": lambda: tr._interacting_bwd(tr.flat_g[tr.spec[0][2]:], st_(), T_),
             "embed_gather": lambda: tr._embed_forward(lambda name: _NullCtx(), st_(), T_),
+            "embed_segsum_adam": lambda: ops_mod.segsum_adam(tr.table, tr.table_m, tr.table_v, tr.dX.view(-1, D), tr.keys_sorted,
+                                                             cfg.lr_sparse, cfg.beta1, cfg.beta2, cfg.eps, tr.adam_scalars),
         }
+        if fused:
+            tabs_, w_, lb_, keys_ = tr._lookup_args()
+            singles["interacting_fwd"] = lambda: cabi.call(
+                "rs_interacting_fwd_gather", tabs_, tr.table_ld, w_, tr.ids.data_ptr(), lb_.data_ptr(), tr.rows_t.data_ptr(),
+                tr.X.data_ptr(), D, 0, keys_, T_, tr.P["Wqkvr"].data_ptr(), tr.P["bqkvr"].data_ptr(), tr.P["gamma"].data_ptr(),
+                tr.P["beta"].data_ptr(), cfg.ln_eps, tr.Z[:, tr.n_deep:].data_ptr(), U, tr.zw, tr.saved.data_ptr(), BATCH, F, D,
+                U, H, L, 1, st_())
+            singles["interacting_bwd"] = lambda: tr._interacting_bwd_fused(tr.flat_g[tr.spec[0][2]:], st_(), T_, None)
         for name, fn in singles.items():
             try:
                 iso[name] = _graph_time_us(fn) / 1e3
             except Exception as e:
                 iso[name + "_error"] = repr(e)[:120]
+        if "embed_gather" in iso and not any(k["phase"] == "embed_gather" for k in kernels):
+            by_, _ = algorithmic("embed_gather", BATCH, act_bytes, n_unique)
+            embed_alone = {"gather_alone_ms": round(iso["embed_gather"], 4), "gather_alone_GBps": round(by_ / iso["embed_gather"] / 1e6, 1),
+                           "note": "the separate gather kernel, NOT part of the fused step; timed for reference"}
+        else:
+            embed_alone = None
         for k in kernels:
             if k["phase"] in iso:
                 by, fl = k["alg_bytes"], k["alg_flops"]
@@ -474,13 +493,24 @@ def run_own(args):
     # share of the STEP: the kernel's event-timed duration over the graph-replayed step time the headline is made of
     roof.update({"kernel": top["phase"], "peak_source": pk["source"] + " (sustained: kernel timed inside the step)",
                  "share_of_step": round(top["ms"] / (ms / K), 4), "share_of_phase_sum": top["share"]})
-    gk = next(k for k in kernels if k["phase"] in ("embed_gather", "embed_gather_peer"))
+    gk = next((k for k in kernels if k["phase"] in ("embed_gather", "embed_gather_peer")), None)
     sk = next(k for k in kernels if k["phase"] == "embed_segsum_adam")
-    embed = {"gather_GBps": gk["GBps"], "gather_frac_of_measured_hbm": gk["GBps"] / pk["hbm_gbs"],
-             "gather_frac_of_8TBps": gk["GBps"] / 8000.0, "scatter_adam_GBps": sk["GBps"],
-             "scatter_adam_frac_of_measured_hbm": sk["GBps"] / pk["hbm_gbs"], "unique_rows": n_unique,
-             "gather_kernel": gk["phase"]}
-    if world == 1:
+    embed = {"scatter_adam_GBps": sk["GBps"], "scatter_adam_frac_of_measured_hbm": sk["GBps"] / pk["hbm_gbs"],
+             "unique_rows": n_unique}
+    if gk is not None:
+        embed.update({"gather_GBps": gk["GBps"], "gather_frac_of_measured_hbm": gk["GBps"] / pk["hbm_gbs"],
+                      "gather_frac_of_8TBps": gk["GBps"] / 8000.0, "gather_kernel": gk["phase"]})
+    else:
+        embed["gather_kernel"] = ("fused into interacting_fwd (rs_interacting_fwd_gather): no gather launch in the step; "
+                                  "its ids + rows + X + keys bytes are counted in interacting_fwd's algorithmic bytes")
+    if world == 1 and "embed_segsum_adam" in iso:
+        by_s, _ = algorithmic("embed_segsum_adam", BATCH, act_bytes, n_unique)
+        embed.update({"scatter_adam_ms_in_graph": round(iso["embed_segsum_adam"], 4),
+                      "scatter_adam_GBps_in_graph": round(by_s / iso["embed_segsum_adam"] / 1e6, 1),
+                      "scatter_adam_frac_of_measured_hbm_in_graph": round(by_s / iso["embed_segsum_adam"] / 1e6 / pk["hbm_gbs"], 4)})
+    if world == 1 and embed_alone is not None:
+        embed["separate_gather_kernel"] = embed_alone
+    if world == 1 and gk is not None:
         # The per-phase times above come from an eager pass with one CUDA-event pair per phase: for a 13 us kernel
         # the pair itself adds several us.  Time the same gather launch (this batch's ids, the trainer's table)
         # ten times inside one CUDA graph as well.

@@ -299,6 +299,33 @@ int rs_interacting_fwd(const void* x, int64_t x_ld, int64_t x_bs, int dtype,
                        void* y, int64_t y_ld, int64_t y_bs, void* saved,
                        int B, int F, int D, int U, int H, int L, int use_res,
                        int compute_bf16, void* stream);
+/* K1 fused into K4 (tensor-core path only; rs_interacting_path(...) == RS_PATH_TCGEN05, no dropout): the forward's
+ * tile loader performs the embedding lookup itself (tn.layers.EmbeddingFeatures call sites, rank/ctr/base_model.py:216)
+ * — ids [B, F] int64 (id < 0 = padding -> zero row), row = id mod rows[f], owner = row mod world, local row =
+ * local_base[f] + row div world, read from peer_tables[owner] (fp32, row stride table_ld floats, 64-byte aligned rows;
+ * world == 1: the local table) — and writes, as by-products, x_out = RNE(dtype) of the rows ([B,F,D], what
+ * rs_embed_gather_fwd would have written: the MLP tower and the backward read it) and, if not NULL,
+ * sort_keys[i] = (local row << 32 | i) for rs_embed_sort_keys.  Bit-identical to rs_embed_gather_* + rs_interacting_fwd. */
+int rs_interacting_fwd_gather(const float* const* peer_tables, int64_t table_ld, int world,
+                              const int64_t* ids, const int64_t* local_base, const int64_t* rows,
+                              void* x_out, int64_t x_ld, int64_t x_bs, unsigned long long* sort_keys,
+                              int dtype, const float* Wqkvr, const float* bqkvr,
+                              const float* ln_gamma, const float* ln_beta, float ln_eps,
+                              void* y, int64_t y_ld, int64_t y_bs, void* saved,
+                              int B, int F, int D, int U, int H, int L, int use_res, void* stream);
+/* The backward with the embedding-gradient exchange fused in (tensor-core path only): dx_add (may be NULL) is added
+ * to the layer's input gradient row by row (the MLP tower's dX, same strides as dx; dx_add == dx is allowed), and when
+ * `inverse` is not NULL the finished row of lookup i is stored straight into slot (rank * cap + inverse[i] mod cap) of
+ * peer_recv[inverse[i] / cap] (peer stores over NVLink; inverse / cap from rs_route_ids_padded) instead of dx —
+ * rs_scatter_rows_peer without the extra pass over dX.  inverse == NULL: dx = gradient (+ dx_add). */
+int rs_interacting_bwd_scatter(const void* x, int64_t x_ld, int64_t x_bs, const void* saved, int dtype,
+                               const float* Wqkvr, const float* bqkvr,
+                               const float* ln_gamma, const float* ln_beta, float ln_eps,
+                               const void* dy, int64_t dy_ld, int64_t dy_bs,
+                               void* dx, int64_t dx_ld, int64_t dx_bs, const void* dx_add,
+                               void* const* peer_recv, int world, int rank, const int* inverse, int cap,
+                               float* dparams, int B, int F, int D, int U, int H, int L, int use_res,
+                               void* ws, size_t ws_bytes, void* stream);
 /* Training-mode attention-weight dropout (InteractingLayer.py:53-54; use_dropout=True at
  * rank/multi_head/multidnn.py:54 and rank/ctr/model_init.py:54-59): the softmax weights are multiplied by an
  * inverted-dropout mask before P.V.  The mask is a pure function of (dropout_seed, iteration, sample, head,

@@ -85,6 +85,9 @@ class AutoIntConfig:
     eps: float = 1e-8
     table_init_scale: float = 0.1
     seed: int = 20261018
+    # bf16 / tcgen05 mode: the embedding lookup runs inside the InteractingLayer forward's tile loader and the
+    # embedding-gradient push (multi-GPU) inside its backward's epilogue; False = separate gather / scatter kernels
+    fuse_embedding: bool = True
 
     def rows(self) -> List[int]:
         if isinstance(self.rows_per_field, int):
@@ -166,6 +169,8 @@ class AutoIntTrainer:
             self._refresh_wt()
         self.side = torch.cuda.Stream(device=self.dev)
         self.sort_done = torch.cuda.Event()
+        self.fused = bool(cfg.fuse_embedding and self.bf16 and ops.interacting_path(
+            F, d, U, cfg.head_num, torch.bfloat16, True) == cabi.PATH_TCGEN05 and self.table_ld % 16 == 0)
         self.graph = None
         self.timer = None               # set to a PhaseTimer for an instrumented (eager) step
         n_ws = max(cabi.load().rs_interacting_workspace_bytes(B, F, d, U),
@@ -246,20 +251,34 @@ class AutoIntTrainer:
         P, G = self.P, self.G
         nmlp = len(c.mlp_hidden)
         ph = lambda name: _Phase(self.timer, name)
-        # K1: gather (+ sort keys emitted for the backward)
-        self._embed_forward(ph, st, T)
-        # the key sort only needs the forward's keys: run it on the side stream, hidden behind the
-        # dense forward/backward (a parallel branch of the captured graph)
         main = torch.cuda.current_stream(self.dev)
-        self._sort_keys(ph)
-        # K4: InteractingLayer forward
-        with ph("interacting_fwd"):
-            # writes Flatten(A) straight into its columns of the concat buffer Z (autoint:36,45)
-            cabi.call("rs_interacting_fwd", self.X.data_ptr(), d, 0, T, P["Wqkvr"].data_ptr(),
-                      P["bqkvr"].data_ptr(), P["gamma"].data_ptr(), P["beta"].data_ptr(), c.ln_eps,
-                      self.Z[:, self.n_deep:].data_ptr(), U, self.zw,
-                      self.saved.data_ptr(), B, F, d, U,
-                      c.head_num, c.layer_num, int(c.use_res), int(self.act_dtype == torch.bfloat16), st)
+        if self.fused:
+            # K1 inside K4: the forward's tile loader reads the embedding rows itself (local table, or the owners' HBM
+            # over NVLink) and writes X and the sort keys as by-products; only the owners' key work (multi-GPU) is a
+            # separate branch
+            self._embed_forward(ph, st, T, gather=False)
+            tabs, world, lbase_t, keys = self._lookup_args()
+            with ph("interacting_fwd"):
+                cabi.call("rs_interacting_fwd_gather", tabs, self.table_ld, world, self.ids.data_ptr(), lbase_t.data_ptr(),
+                          self.rows_t.data_ptr(), self.X.data_ptr(), d, 0, keys, T, P["Wqkvr"].data_ptr(),
+                          P["bqkvr"].data_ptr(), P["gamma"].data_ptr(), P["beta"].data_ptr(), c.ln_eps,
+                          self.Z[:, self.n_deep:].data_ptr(), U, self.zw, self.saved.data_ptr(), B, F, d, U,
+                          c.head_num, c.layer_num, int(c.use_res), st)
+            self._sort_keys(ph)
+        else:
+            # K1: gather (+ sort keys emitted for the backward)
+            self._embed_forward(ph, st, T)
+            # the key sort only needs the forward's keys: run it on the side stream, hidden behind the
+            # dense forward/backward (a parallel branch of the captured graph)
+            self._sort_keys(ph)
+            # K4: InteractingLayer forward
+            with ph("interacting_fwd"):
+                # writes Flatten(A) straight into its columns of the concat buffer Z (autoint:36,45)
+                cabi.call("rs_interacting_fwd", self.X.data_ptr(), d, 0, T, P["Wqkvr"].data_ptr(),
+                          P["bqkvr"].data_ptr(), P["gamma"].data_ptr(), P["beta"].data_ptr(), c.ln_eps,
+                          self.Z[:, self.n_deep:].data_ptr(), U, self.zw,
+                          self.saved.data_ptr(), B, F, d, U,
+                          c.head_num, c.layer_num, int(c.use_res), int(self.act_dtype == torch.bfloat16), st)
         # K5: MLP tower; last hidden layer lands in Z[:, :n_deep], Flatten(A) in Z[:, n_deep:]
         Xf = self.X.view(B, F * d)
         acts = [Xf] + self.H + [self.Z[:, :self.n_deep]]
@@ -287,16 +306,25 @@ class AutoIntTrainer:
         nW = d * 4 * U
         dparams = self.flat_g[self.spec[0][2]:]       # Wqkvr | bqkvr | gamma | beta are contiguous
         assert self.spec[1][2] == nW and self.spec[2][2] == nW + 4 * U and self.spec[3][2] == nW + 5 * U
-        with ph("interacting_bwd"):
-            self._interacting_bwd(dparams, st, T)
+        if self.fused:
+            # the tower's input gradient first (plain store into dX); the InteractingLayer backward adds it to its own
+            # dX row by row and, multi-GPU, stores the sum straight into the owners' receive buffers
+            with ph("mlp_dgrad_x"):
+                ops.gemm(self.dH[0], self._w("mlp_W0"), self.dX.view(B, F * d), transB=True)
+            with ph("interacting_bwd"):
+                self._interacting_bwd_fused(dparams, st, T, main)
+        else:
+            with ph("interacting_bwd"):
+                self._interacting_bwd(dparams, st, T)
         # all dense gradients exist now: their all-reduce (multi-GPU) and then the dense Adam run on the side
         # stream beside the embedding backward
         ops.adam_advance(self.adam_scalars, c.beta1, c.beta2)
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
             self._dense_sync(ph)
-        with ph("mlp_dgrad_x"):
-            ops.gemm(self.dH[0], self._w("mlp_W0"), self.dX.view(B, F * d), epilogue=E.EPI_ACCUM, transB=True)
+        if not self.fused:
+            with ph("mlp_dgrad_x"):
+                ops.gemm(self.dH[0], self._w("mlp_W0"), self.dX.view(B, F * d), epilogue=E.EPI_ACCUM, transB=True)
         self.side.wait_stream(main)          # the last reader of the bf16 weight shadows is done
         with torch.cuda.stream(self.side):
             with ph("dense_adam"):
@@ -319,9 +347,35 @@ class AutoIntTrainer:
             self.sort_done.record(self.side)
 
     # ---- embedding halves of the step (overridden by the row-sharded multi-GPU trainer)
-    def _embed_forward(self, ph, st, T):
+    def _lookup_args(self):
+        """(address of the W table pointers, W, per-field local row base, sort-key buffer) of the fused lookup."""
+        if not hasattr(self, "_tab1"):
+            import ctypes
+            self._tab1 = (ctypes.c_void_p * 1)(self.table.data_ptr())
+        import ctypes
+        return ctypes.addressof(self._tab1), 1, self.base_t, self.keys.data_ptr()
+
+    def _scatter_args(self):
+        """(address of the W receive-buffer pointers, W, rank, inverse, cap) of the fused gradient push; None on one GPU."""
+        return None
+
+    def _interacting_bwd_fused(self, dparams, st, T, main):
+        c = self.cfg
+        F, d, U, B = c.num_fields, c.embed_dim, c.unit_num, c.batch
+        P = self.P
+        sa = self._scatter_args()
+        recv, world, rank, inverse, cap = sa if sa is not None else (None, 1, 0, None, 0)
+        cabi.call("rs_interacting_bwd_scatter", self.X.data_ptr(), d, 0, self.saved.data_ptr(), T,
+                  P["Wqkvr"].data_ptr(), P["bqkvr"].data_ptr(), P["gamma"].data_ptr(), P["beta"].data_ptr(), c.ln_eps,
+                  self.dZ[:, self.n_deep:].data_ptr(), U, self.zw, self.dX.data_ptr(), d, 0, self.dX.data_ptr(),
+                  recv, world, rank, inverse, cap, dparams.data_ptr(), B, F, d, U, c.head_num, c.layer_num,
+                  int(c.use_res), self.ws.data_ptr(), self.ws.numel(), st)
+
+    def _embed_forward(self, ph, st, T, gather=True):
         c = self.cfg
         n = c.batch * c.num_fields
+        if not gather:
+            return
         with ph("embed_gather"):
             cabi.call("rs_embed_gather_fwd_ld", self.table.data_ptr(), self.table_ld, self.ids.data_ptr(),
                       self.base_t.data_ptr(), self.rows_t.data_ptr(), n, c.num_fields, c.embed_dim, self.X.data_ptr(), T,

@@ -70,6 +70,54 @@ int rs_interacting_fwd_dropout(const void* x, int64_t x_ld, int64_t x_bs, int dt
   return RS_ERR_UNSUPPORTED;
 }
 
+int rs_interacting_fwd_gather(const float* const* peer_tables, int64_t table_ld, int world, const int64_t* ids,
+                              const int64_t* local_base, const int64_t* rows, void* x_out, int64_t x_ld, int64_t x_bs,
+                              unsigned long long* sort_keys, int dtype, const float* Wqkvr, const float* bqkvr,
+                              const float* ln_gamma, const float* ln_beta, float ln_eps, void* y, int64_t y_ld,
+                              int64_t y_bs, void* saved, int B, int F, int D, int U, int H, int L, int use_res,
+                              void* stream) {
+  RS_REQUIRE(rs_interacting_path(F, D, U, H, dtype, 1, 0.f) == RS_PATH_TCGEN05,
+             "interacting_fwd_gather: only the tensor-core path fuses the lookup (F=%d D=%d U=%d H=%d dtype=%d)", F, D, U, H,
+             dtype);
+  RS_REQUIRE(B > 0 && L >= 1 && world >= 1 && world <= RS_MAX_PEERS, "interacting_fwd_gather: B=%d L=%d world=%d", B, L, world);
+  RS_REQUIRE(table_ld >= D && table_ld % 16 == 0, "interacting_fwd_gather: table row stride %lld (64-byte aligned rows)",
+             (long long)table_ld);
+  RS_REQUIRE(x_ld % 4 == 0 && y_ld % 4 == 0, "interacting_fwd_gather: leading dims must be multiples of 4");
+  if (x_bs == 0) x_bs = (int64_t)F * x_ld;
+  if (y_bs == 0) y_bs = (int64_t)F * y_ld;
+  RS_REQUIRE(x_bs % 4 == 0 && y_bs % 4 == 0, "interacting_fwd_gather: batch strides must be multiples of 4");
+  IFwdArgs a{x_out, x_ld, x_bs, Wqkvr, bqkvr, ln_gamma, ln_beta, ln_eps, y, y_ld, y_bs, saved, B, F, L, use_res,
+             dtype, as_stream(stream)};
+  IGatherArgs g{peer_tables, table_ld, world, ids, local_base, rows, (uint64_t*)sort_keys};
+  a.gather = &g;
+  return interacting_tc_fwd(a);
+}
+
+int rs_interacting_bwd_scatter(const void* x, int64_t x_ld, int64_t x_bs, const void* saved, int dtype,
+                               const float* Wqkvr, const float* bqkvr, const float* ln_gamma, const float* ln_beta,
+                               float ln_eps, const void* dy, int64_t dy_ld, int64_t dy_bs, void* dx, int64_t dx_ld,
+                               int64_t dx_bs, const void* dx_add, void* const* peer_recv, int world, int rank,
+                               const int* inverse, int cap, float* dparams, int B, int F, int D, int U, int H, int L,
+                               int use_res, void* ws, size_t ws_bytes, void* stream) {
+  RS_REQUIRE(rs_interacting_path(F, D, U, H, dtype, 1, 0.f) == RS_PATH_TCGEN05,
+             "interacting_bwd_scatter: only the tensor-core path fuses the gradient push (F=%d D=%d U=%d H=%d)", F, D, U, H);
+  RS_REQUIRE(B > 0 && L >= 1 && saved != nullptr, "interacting_bwd_scatter: B=%d L=%d saved=%p", B, L, saved);
+  RS_REQUIRE(x_ld % 4 == 0 && dy_ld % 4 == 0 && dx_ld % 4 == 0, "interacting_bwd_scatter: leading dims must be multiples of 4");
+  if (x_bs == 0) x_bs = (int64_t)F * x_ld;
+  if (dy_bs == 0) dy_bs = (int64_t)F * dy_ld;
+  if (dx_bs == 0) dx_bs = (int64_t)F * dx_ld;
+  IBwdArgs a{x, x_ld, x_bs, saved, Wqkvr, bqkvr, ln_gamma, ln_beta, ln_eps, dy, dy_ld, dy_bs, dx, dx_ld, dx_bs, dparams,
+             B, F, L, use_res, dtype, ws, ws_bytes, as_stream(stream)};
+  a.dx_add = dx_add;
+  IScatterArgs s{peer_recv, world, rank, (const int32_t*)inverse, cap};
+  if (inverse != nullptr) {
+    RS_REQUIRE(world >= 1 && world <= RS_MAX_PEERS && rank >= 0 && rank < world && cap > 0 && peer_recv != nullptr,
+               "interacting_bwd_scatter: world=%d rank=%d cap=%d", world, rank, cap);
+    a.scatter = &s;
+  }
+  return interacting_tc_bwd(a);
+}
+
 int rs_interacting_fwd(const void* x, int64_t x_ld, int64_t x_bs, int dtype, const float* Wqkvr,
                        const float* bqkvr, const float* ln_gamma, const float* ln_beta,
                        float ln_eps, void* y, int64_t y_ld, int64_t y_bs, void* saved, int B, int F, int D, int U,

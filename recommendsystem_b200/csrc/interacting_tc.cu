@@ -1,25 +1,27 @@
 // interacting_tc.cu — K4 on the 5th-gen tensor cores (bf16 mode): fused InteractingLayer
-// forward (InteractingLayer.py:37-61) with every contraction issued as tcgen05.mma.
+// forward (InteractingLayer.py:37-61) with every contraction issued as tcgen05.mma and every A operand
+// resident in TMEM.
 //
-// A CTA of 128 threads owns a tile of SPT whole samples; sample s occupies the tile rows
-// [s*FP, s*FP + F) with FP = F rounded up to 8 (F = 39 -> 3 samples at rows 0/40/80).  Thread t
-// IS tile row t and TMEM lane t, so every accumulator row comes back to the thread that owns
-// the (sample, field) row and the row-wise softmax / residual / ReLU / LayerNorm need no
-// cross-thread traffic at all.  Per iteration of the layer_num loop (weights shared):
+// A CTA of 384 threads keeps THREE 128-row tiles in flight, one per warpgroup (own TMEM columns, own mbarrier,
+// own named barrier); a tile holds SPT whole samples, sample s in tile rows [s*FP, s*FP + F) with FP = F rounded up
+// to 8 (F = 39 -> 3 samples at rows 0 / 40 / 80).  Thread t of a warpgroup IS tile row t and TMEM lane t, so every
+// accumulator row comes back to the thread that owns the (sample, field) row and the row-wise softmax / residual /
+// ReLU / LayerNorm need no cross-thread traffic.  Per iteration of the layer_num loop (weights shared):
 //
-//   1. Z[128,4U]  = X[128,D] Wqkvr[D,4U]        kind::tf32, 3xTF32 split (fp32-grade), six MMAs of K = 8
-//      thread: tcgen05.ld its Z row, +bias, ReLU -> q, k, v, r
-//   2. S_h[128,128] = Q_h K_h^T  per head        kind::tf32, K = U/H = 8, one MMA per head
-//      (block diagonal in effect: a thread reads only the FP columns of its own sample)
-//      thread: masked softmax over its F keys (scale folded into exp2), unnormalised p -> bf16
-//   3. O_h[128,U]  = P_h[128,128] V[128,U]       kind::f16, 8 MMAs of K = 16 per head; P rows are
-//      zero outside the sample's own key window, so other samples never contribute
-//      thread: O/l + r -> ReLU -> LayerNorm -> y (next iteration's X)
+//   1. Z[128,4U]  = [X | 1] [Wqkvr ; b]         kind::tf32, 3xTF32 split (fp32-grade), A = [x_hi | x_lo | 1 1 0..]
+//      written to TMEM by the row's thread (tcgen05.st); bias rides in the MMA
+//   2. S_h[128,FP] = Qx_h Kx_h^T  per head      kind::tf32, A = the row's q placed in the K slot of its own sample
+//      (zeros elsewhere), B row j = [k_(0,j) | k_(1,j) | ..]: every row finds ITS sample's FP keys in the same FP
+//      accumulator columns — no 128-wide block-diagonal product, no per-lane window select
+//      thread: softmax over its F keys (exp2, FFMA2 / FADD2 packed math), unnormalised bf16 P -> TMEM
+//   3. O_h[128,32] = P_h V_h                    kind::f16, A = P from TMEM, B = [key][(sample, e)]: a row keeps the 8
+//      columns of its own sample;  thread: O/l + r -> ReLU -> LayerNorm -> y (next iteration's X)
 //
-// Shared-memory operand tiles are written by the owning threads directly in the canonical UMMA
-// layouts (no-swizzle 8x16B core matrices for X/W/Q/K/V, SWIZZLE_128B for P); the P buffers are
-// zero-filled once per CTA because a row's key window never moves.  TMEM: 256 columns
-// (S_0 | S_1, with Z and O_h aliased onto dead S columns) => 2 CTAs per SM.
+// Saved for the backward: the pre-LayerNorm activations of every iteration and the per-head softmax statistics
+// lse = max + log2(sum) (so the backward recomputes P already normalised).  Optional fused lookup (K1 inside K4):
+// the tile loader reads the embedding rows itself — from this GPU's table or, row-sharded, straight from the owners'
+// HBM over NVLink — two tiles ahead for the ids and one for the rows, writes X (bf16, for the MLP tower and the
+// backward) and the sort keys as by-products: the gather kernel disappears from the step.
 #include "tc_common.cuh"
 #include "interacting_args.cuh"
 
@@ -31,9 +33,32 @@ namespace rs {
 // (packed bf16) over its first KP/2 columns and [x_hi | x_lo] over [64,96) before S is issued ; [1 1 0..] at 160
 constexpr uint32_t ITC_TILE_COLS = 168;
 
-template <int NCHF, typename T>
+// fused embedding lookup (K1 inside K4): ids [B, F] -> rows of the (row-sharded) tables.  tab[r] = rank r's shard
+// (CUDA-IPC mapping; tab[0] = the local table when world == 1), row stride tld floats, owner = row mod world.
+struct ItcGather {
+  const float* tab[RS_MAX_PEERS];
+  int64_t tld;
+  int world;
+  const int64_t* ids;
+  const int64_t* lbase;      // [F] first local row of field f on every rank
+  const int64_t* rows;       // [F] rows of field f (ids are taken mod rows)
+  uint64_t* keys;            // [B*F] (local arena row << 32 | position) for the sorted-segment update, or NULL
+};
+
+__device__ __forceinline__ void ld_row64(const float* p, uint32_t (&v)[16]) {
+  // one 64-byte embedding row as two 32-byte requests (LDG.256): a row-per-thread loader must not split a row into
+  // four 16-byte requests (the NVLink path is request-rate bound)
+  asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p) : "memory");
+  asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "l"(p + 8) : "memory");
+}
+
+template <int NCHF, typename T, bool GATHER>
 __global__ void __launch_bounds__(384, 1)
-interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, const float* __restrict__ W,
+interacting_tc_fwd_kernel(const ItcGather ga, T* __restrict__ x, int64_t x_ld, int64_t x_bs, const float* __restrict__ W,
                           const float* __restrict__ bias, const float* __restrict__ gamma,
                           const float* __restrict__ beta, float eps, T* __restrict__ y, int64_t y_ld,
                           int64_t y_bs, float* __restrict__ saved, int B, int F, int L, int use_res) {
@@ -118,11 +143,64 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       for (int c = 0; c < D; ++c) dst[c] = 0.f;
     }
   };
+  // ---- fused lookup: id of (tile, row) ; its table row (raw fp32 bits, zeros for padding / idle rows)
+  uint64_t g_R = 1;
+  int64_t g_lb = 0;
+  if (GATHER && in_tile && f_loc < F) { g_R = (uint64_t)ga.rows[f_loc]; g_lb = ga.lbase[f_loc]; }
+  auto load_id = [&](int tile_) -> int64_t {
+    const int64_t smp_ = (int64_t)tile_ * SPT + s_loc;
+    if (tile_ < ntiles && in_tile && f_loc < F && smp_ < B) return ga.ids[smp_ * F + f_loc];
+    return -1;
+  };
+  auto load_row = [&](int64_t id, uint32_t (&raw)[D], int32_t& lrow) {
+    lrow = -1;
+#pragma unroll
+    for (int c = 0; c < D; ++c) raw[c] = 0u;
+    if (id >= 0) {
+      uint64_t rr;
+      if (((uint64_t)id | g_R) >> 32) rr = (uint64_t)id % g_R;
+      else rr = (uint32_t)id % (uint32_t)g_R;
+      const uint32_t owner = ga.world == 1 ? 0u : (uint32_t)(rr % (uint64_t)ga.world);
+      const int64_t lr = g_lb + (int64_t)(ga.world == 1 ? rr : rr / (uint64_t)ga.world);
+      lrow = (int32_t)lr;
+      ld_row64(ga.tab[owner] + lr * ga.tld, raw);
+    }
+  };
+  // row consumed: X = RNE bf16 of the fp32 row (what the separate gather kernel writes), stored for the MLP tower
+  // and the backward; the layer's input is that bf16 value; sort key of the lookup
+  auto consume_row = [&](int tile_, const uint32_t (&raw)[D], int32_t lrow, float (&dst)[D]) {
+    const int64_t smp_ = (int64_t)tile_ * SPT + s_loc;
+    const bool act_ = in_tile && f_loc < F && smp_ < B;
+    uint32_t pk[D / 2];
+#pragma unroll
+    for (int c = 0; c < D; c += 2) {
+      pk[c / 2] = pack_bf16x2(__uint_as_float(raw[c]), __uint_as_float(raw[c + 1]));
+      dst[c] = __uint_as_float(pk[c / 2] << 16);
+      dst[c + 1] = __uint_as_float(pk[c / 2] & 0xFFFF0000u);
+    }
+    if (act_) {
+      T* xo = x + smp_ * x_bs + (int64_t)f_loc * x_ld;
+#pragma unroll
+      for (int c = 0; c < D / 2; c += 2) *reinterpret_cast<uint2*>(xo + 2 * c) = make_uint2(pk[c], pk[c + 1]);
+      if (ga.keys) ga.keys[smp_ * F + f_loc] = ((uint64_t)(uint32_t)lrow << 32) | (uint64_t)(uint32_t)(smp_ * F + f_loc);
+    }
+  };
   auto wg_sync = [&]() { named_bar_sync(1 + wg, 128); };
 
   int tile = (int)blockIdx.x * 3 + (int)wg;
   float xr[D];
-  if (tile < ntiles) load_x(tile, xr);
+  uint32_t rawn[D];              // GATHER: the next tile's table row in flight
+  int32_t lrown = -1;
+  int64_t idn = -1;              // GATHER: the id of the tile after the next
+  if (GATHER) {
+    if (tile < ntiles) {
+      load_row(load_id(tile), rawn, lrown);
+      consume_row(tile, rawn, lrown, xr);
+      idn = load_id(tile + tstride);
+    }
+  } else if (tile < ntiles) {
+    load_x(tile, xr);
+  }
   for (; tile < ntiles; tile += tstride) {
     const int64_t smp = (int64_t)tile * SPT + s_loc;
     const bool active = in_tile && f_loc < F && smp < B;
@@ -149,7 +227,12 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
         tc_mma_tf32_ts(tmem + C_Z, tmem + C_ONE, make_nosw_desc(sbase + OFF_BT, 128, 256), ID_Z, 1u);
         tc_commit(bar);
       }
-      if (it + 1 == L && tile + tstride < ntiles) load_x(tile + tstride, xn);      // next tile's rows: a whole step of cover
+      if (GATHER) {
+        // the id fetched a tile ago turns into the next tile's row loads; the id of the tile after it is requested
+        if (it + 1 == L && tile + tstride < ntiles) { load_row(idn, rawn, lrown); idn = load_id(tile + 2 * tstride); }
+      } else if (it + 1 == L && tile + tstride < ntiles) {
+        load_x(tile + tstride, xn);                                     // next tile's rows: a whole step of cover
+      }
       mbar_wait(bar, phase); phase ^= 1u;
       tc_fence_after();
       float r[U];
@@ -323,8 +406,12 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
       for (int u = 0; u < U; u += 4)
         store4<T>(y + smp * y_bs + (int64_t)f_loc * y_ld + u, make_float4(yv[u], yv[u + 1], yv[u + 2], yv[u + 3]));
     }
+    if (GATHER) {
+      if (tile + tstride < ntiles) consume_row(tile + tstride, rawn, lrown, xr);
+    } else {
 #pragma unroll
-    for (int c = 0; c < D; ++c) xr[c] = xn[c];
+      for (int c = 0; c < D; ++c) xr[c] = xn[c];
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -336,15 +423,26 @@ interacting_tc_fwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
 
 template <int NCHF, typename T>
 static int launch_itc_fwd(const IFwdArgs& a) {
-  auto kern = interacting_tc_fwd_kernel<NCHF, T>;
   using G = ItcGeom<NCHF>;
   constexpr int smem = 3 * (2 * G::KX_BYTES + 2 * G::VX_BYTES) + 8192 + 2048 + 128 + 64;
-  RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int ntiles = (a.B + G::SPT - 1) / G::SPT;
   int grid = sm_count();
   if (grid * 3 > ntiles) grid = (ntiles + 2) / 3;
-  kern<<<grid, 384, smem, a.st>>>((const T*)a.x, a.x_ld, a.x_bs, a.W, a.b, a.gm, a.bt, a.eps, (T*)a.y, a.y_ld,
-                                  a.y_bs, (float*)a.saved, a.B, a.F, a.L, a.use_res);
+  ItcGather ga{};
+  if (a.gather) {
+    for (int r = 0; r < RS_MAX_PEERS; ++r) ga.tab[r] = r < a.gather->world ? a.gather->tables[r] : nullptr;
+    ga.tld = a.gather->table_ld; ga.world = a.gather->world; ga.ids = a.gather->ids; ga.lbase = a.gather->local_base;
+    ga.rows = a.gather->rows; ga.keys = a.gather->sort_keys;
+    auto kern = interacting_tc_fwd_kernel<NCHF, T, true>;
+    RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, 384, smem, a.st>>>(ga, (T*)a.x, a.x_ld, a.x_bs, a.W, a.b, a.gm, a.bt, a.eps, (T*)a.y, a.y_ld, a.y_bs,
+                                    (float*)a.saved, a.B, a.F, a.L, a.use_res);
+  } else {
+    auto kern = interacting_tc_fwd_kernel<NCHF, T, false>;
+    RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kern<<<grid, 384, smem, a.st>>>(ga, (T*)a.x, a.x_ld, a.x_bs, a.W, a.b, a.gm, a.bt, a.eps, (T*)a.y, a.y_ld, a.y_bs,
+                                    (float*)a.saved, a.B, a.F, a.L, a.use_res);
+  }
   return check_launch("interacting_tc_fwd");
 }
 

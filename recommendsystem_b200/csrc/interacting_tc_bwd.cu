@@ -45,6 +45,15 @@ __device__ __forceinline__ uint32_t bf16x2_pos_mask(uint32_t v) {
 
 struct uint4x2_t { uint4 a, b; };
 
+// fused gradient push (K3's exchange inside K4's backward): the finished dx row of lookup i goes straight into slot
+// (rank * cap + k) of the receive buffer of owner = inverse[i] / cap over NVLink (peer stores), the layout the
+// all-to-all of the routed gradients would have produced.  inverse == NULL: plain store to dx.
+struct ItbScatter {
+  void* recv[RS_MAX_PEERS];
+  const int32_t* inverse;
+  int cap, rank;
+};
+
 template <int NCHF> struct ItbSmem {
   using G = ItcGeom<NCHF>;
   static constexpr int PC_BYTES = 16 * NCHF * 128 + 1024;    // [128][FP] bf16 + zeroed pad (operand over-reads)
@@ -73,7 +82,8 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
                           const float* __restrict__ W, const float* __restrict__ bias,
                           const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                           const T* __restrict__ dy, int64_t dy_ld, int64_t dy_bs, T* __restrict__ dx, int64_t dx_ld,
-                          int64_t dx_bs, float* __restrict__ part, int B, int F, int L, int use_res) {
+                          int64_t dx_bs, float* __restrict__ part, int B, int F, int L, int use_res,
+                          const T* __restrict__ dx_add, const ItbScatter sc) {
   constexpr int D = 16, U = 16, H = 2, DH = 8, N4 = 64;
   using G = ItcGeom<NCHF>;
   using SM = ItbSmem<NCHF>;
@@ -391,6 +401,21 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
     float2 lse_n = make_float2(INFINITY, INFINITY);
     if (!last) { load_xsrc(ntile, nit, xs_n); lse_n = load_lse(ntile, nit); }
     if (!last && new_tile) load_tile_head(ntile, a_n, g_n);
+    // the layer's first iteration ends the tile: rows to add to dx (the MLP tower's input gradient) and the
+    // lookup's slot at its owner, requested a whole step before they are used
+    uint32_t add_raw[U / 2];
+    int32_t slot = -1;
+    if (it == 0 && active) {
+      if (dx_add) {
+        const T* ap = dx_add + smp * dx_bs + (int64_t)f_loc * dx_ld;
+#pragma unroll
+        for (int c = 0; c < U; c += 4) {
+          const uint2 t2 = ldg_nc_u2(reinterpret_cast<const uint2*>(ap + c));
+          add_raw[c / 2] = t2.x; add_raw[c / 2 + 1] = t2.y;
+        }
+      }
+      if (sc.inverse) slot = sc.inverse[smp * F + f_loc];
+    }
 
     // ================= per head: T2 (P, dS) ; the transposed / plain gradient products ; T3 (dq dk dv -> dZ)
     auto softmax_bwd = [&](int h) {
@@ -574,11 +599,28 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
         for (int u = 0; u < U; ++u) g[u] = __uint_as_float(dxr[u]);      // stays fp32 between iterations
       } else {
         if (active) {
-          T* dp_ = dx + smp * dx_bs + (int64_t)f_loc * dx_ld;
+          uint32_t pk[U / 2];
 #pragma unroll
-          for (int u = 0; u < U; u += 4)
-            store4<T>(dp_ + u, make_float4(__uint_as_float(dxr[u]), __uint_as_float(dxr[u + 1]), __uint_as_float(dxr[u + 2]),
-                                           __uint_as_float(dxr[u + 3])));
+          for (int u = 0; u < U; u += 2) {
+            float v0 = __uint_as_float(dxr[u]), v1 = __uint_as_float(dxr[u + 1]);
+            if (dx_add) {
+              const float2 a2 = unpack_bf16x2(add_raw[u / 2]);
+              v0 += a2.x; v1 += a2.y;
+            }
+            pk[u / 2] = pack_bf16x2(v0, v1);
+          }
+          if (sc.inverse) {
+            if (slot >= 0) {
+              const int owner = slot / sc.cap, k = slot - owner * sc.cap;
+              uint4* dst = reinterpret_cast<uint4*>(sc.recv[owner]) + ((int64_t)sc.rank * sc.cap + k) * 2;
+              dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          } else {
+            T* dp_ = dx + smp * dx_bs + (int64_t)f_loc * dx_ld;
+#pragma unroll
+            for (int u = 0; u < U / 2; u += 2) *reinterpret_cast<uint2*>(dp_ + 2 * u) = make_uint2(pk[u], pk[u + 1]);
+          }
         }
         if (!last) {
 #pragma unroll
@@ -648,9 +690,14 @@ static int launch_itc_bwd(const IBwdArgs& a) {
     set_error("interacting_tc_bwd: workspace %zu < %zu", a.ws_bytes, (size_t)grid * np * sizeof(float));
     return RS_ERR_WORKSPACE;
   }
+  ItbScatter sc{};
+  if (a.scatter) {
+    for (int r = 0; r < RS_MAX_PEERS; ++r) sc.recv[r] = r < a.scatter->world ? a.scatter->peer_recv[r] : nullptr;
+    sc.inverse = a.scatter->inverse; sc.cap = a.scatter->cap; sc.rank = a.scatter->rank;
+  }
   kern<<<grid, 128, smem, a.st>>>((const T*)a.x, a.x_ld, a.x_bs, (const float*)a.saved, a.W, a.b, a.gm, a.bt, a.eps,
                                   (const T*)a.dy, a.dy_ld, a.dy_bs, (T*)a.dx, a.dx_ld, a.dx_bs, (float*)a.ws, a.B, a.F,
-                                  a.L, a.use_res);
+                                  a.L, a.use_res, (const T*)a.dx_add, sc);
   if (int e = check_launch("interacting_tc_bwd")) return e;
   itb_reduce_partials_kernel<<<(np * 32 + 255) / 256, 256, 0, a.st>>>((const float*)a.ws, a.dparams, grid, np);
   return check_launch("interacting_tc_bwd_reduce");

@@ -139,6 +139,9 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
             self._map_peer_tables(group)
             self.side2 = torch.cuda.Stream(device=dev)
             self.route_done = torch.cuda.Event()
+            self.inverse_done = torch.cuda.Event()
+        else:
+            self.fused = False                       # the all-NCCL path keeps the separate gather / scatter kernels
 
     def _map_peers(self, tensor, group):
         """Exchange CUDA-IPC handles of `tensor` (one per rank) and map every rank's copy into this process;
@@ -181,9 +184,21 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
         self.row_bits = ops.row_bits(n_local)
 
     # ---- embedding halves of the step -----------------------------------------------------
-    def _embed_forward(self, ph, st, T):
+    def _lookup_args(self):
+        return ctypes.addressof(self.peer_ptrs), self.world, self.lbase_t, None      # the owners make the keys
+
+    def _scatter_args(self):
+        return ctypes.addressof(self.peer_grecv), self.world, self.rank, self.inverse.data_ptr(), self.cap
+
+    def _interacting_bwd_fused(self, dparams, st, T, main):
+        main.wait_event(self.inverse_done)          # this step's slots (rs_route_ids_padded on the side stream)
+        super()._interacting_bwd_fused(dparams, st, T, main)
+
+    def _embed_forward(self, ph, st, T, gather=True):
         c = self.cfg
         F, d = c.num_fields, c.embed_dim
+        if not gather and not self.peer_gather:
+            raise RuntimeError("the fused lookup needs peer_gather=True (rows are read from the owners' HBM)")
         if self.peer_gather:
             main = torch.cuda.current_stream(self.dev)
             # owners' view of the step (keys for the backward): routing, id all-to-all, key sort — all on a
@@ -193,6 +208,7 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
                 with ph("route_ids"):
                     ops.route_ids_padded(self.ids, F, self.rows_t, self.lbase_t, self.world, self.cap, self.send_rows,
                                          self.inverse, self.send_counts, self.overflow)
+                self.inverse_done.record(self.side2)
                 with ph("a2a_ids"):
                     self.ex.all_to_all(self.recv_rows, self.send_rows)
                 with ph("sort_keys"):
@@ -200,6 +216,8 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
                               self.recv_rows.numel(), d, None, T, None, self.keys.data_ptr(), ops._stream())
                     ops.sort_keys(self.keys, self.row_bits, out=self.keys_sorted)
                 self.route_done.record(self.side2)
+            if not gather:
+                return
             with ph("embed_gather_peer"):
                 cabi.call("rs_embed_gather_peer_fwd", ctypes.addressof(self.peer_ptrs), self.table_ld, self.world,
                           self.ids.data_ptr(), self.lbase_t.data_ptr(), self.rows_t.data_ptr(),
@@ -230,10 +248,11 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
         if self.peer_gather:
             # gradient rows go straight into the owners' receive buffers (peer stores over NVLink): the permute
             # and the all-to-all in one kernel; a one-element all-reduce separates the stores from the owners' reads
-            with ph("scatter_grads_peer"):
-                row_bytes = d * self.dX.element_size()
-                cabi.call("rs_scatter_rows_peer", self.dX.data_ptr(), ctypes.addressof(self.peer_grecv), self.world,
-                          self.rank, self.inverse.data_ptr(), c.batch * c.num_fields, self.cap, row_bytes, st)
+            if not self.fused:                 # (fused: the InteractingLayer backward already stored the rows)
+                with ph("scatter_grads_peer"):
+                    row_bytes = d * self.dX.element_size()
+                    cabi.call("rs_scatter_rows_peer", self.dX.data_ptr(), ctypes.addressof(self.peer_grecv), self.world,
+                              self.rank, self.inverse.data_ptr(), c.batch * c.num_fields, self.cap, row_bytes, st)
             self._barrier(ph, "peer_barrier")
         else:
             with ph("permute_grads"):
