@@ -117,10 +117,31 @@ class DenseFn(torch.autograd.Function):
         ctx.in_dtype = x2.dtype
         if x2.dtype == torch.bfloat16 and not ctx.tc:
             x2 = x2.float()
+        ctx.pad = None
         if ctx.tc:
             wt = ops.transpose2d(kernel.to(torch.bfloat16).contiguous())          # [out,in] K-major
             y = ops.gemm(x2, wt, bias=bias, epilogue=epi, transB=True)
         else:
+            # fp32: the 3xTF32 tensor-core GEMM needs 16-byte TMA rows (in / out multiples of 4, >= 8).  Narrow or odd
+            # layers (SENet 1456 -> 22 -> 91, gates -> 3, heads -> 1) are zero-padded to the next such shape instead of
+            # dropping to the FFMA kernel: the padded columns / rows are exact zeros and are sliced away again.
+            M = x2.shape[0]
+            Kp, Np = max(8, (K + 3) // 4 * 4), max(8, (N + 3) // 4 * 4)
+            if (Kp != K or Np != N) and M * Kp * Np >= (1 << 20):
+                ctx.pad = (K, N, Kp, Np)
+                wp = torch.zeros(Kp, Np, dtype=kernel.dtype, device=kernel.device)
+                wp[:K, :N] = kernel
+                bp = torch.zeros(Np, dtype=bias.dtype, device=bias.device)
+                bp[:N] = bias
+                if Kp != K:
+                    xp = torch.zeros(M, Kp, dtype=x2.dtype, device=x2.device)
+                    xp[:, :K] = x2
+                    x2 = xp
+                y = ops.gemm(x2, wp, bias=bp, epilogue=epi)
+                ctx.act = act
+                ctx.save_for_backward(x2, wp, y)
+                ctx.lead = lead
+                return y[:, :N].reshape(*lead, N).to(ctx.in_dtype)
             y = ops.gemm(x2, kernel.contiguous(), bias=bias, epilogue=epi)
         ctx.act = act
         ctx.save_for_backward(x2, kernel, y)
@@ -131,6 +152,19 @@ class DenseFn(torch.autograd.Function):
     def backward(ctx, dy):
         x2, kernel, y = ctx.saved_tensors
         dy2 = dy.reshape(-1, dy.shape[-1]).to(y.dtype)
+        if ctx.pad is not None:
+            K, N, Kp, Np = ctx.pad                                               # padded fp32 layer (see forward)
+            dyp = torch.zeros(dy2.shape[0], Np, dtype=y.dtype, device=y.device)
+            dyp[:, :N] = dy2
+            if ctx.act == "relu":
+                dyp = ops.act_bwd(dyp, y, 0)
+            elif ctx.act == "sigmoid":
+                dyp = ops.act_bwd(dyp, y, 1)
+            db = ops.colsum(dyp)[:N]
+            dx = ops.gemm(dyp, kernel, transB=True)[:, :K] if ctx.needs_input_grad[0] else None
+            dW = ops.gemm(x2, dyp, transA=True)[:K, :N]
+            dx = dx.reshape(*ctx.lead, K).to(ctx.in_dtype) if dx is not None else None
+            return dx, dW.contiguous(), db.contiguous(), None
         if dy2.stride(-1) != 1:
             dy2 = dy2.contiguous()
         if ctx.act == "relu":

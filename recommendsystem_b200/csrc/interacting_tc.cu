@@ -229,7 +229,8 @@ interacting_tc_fwd_kernel(const ItcGather ga, T* __restrict__ x, int64_t x_ld, i
       }
       if (GATHER) {
         // the id fetched a tile ago turns into the next tile's row loads; the id of the tile after it is requested
-        if (it + 1 == L && tile + tstride < ntiles) { load_row(idn, rawn, lrown); idn = load_id(tile + 2 * tstride); }
+        // (requested at the tile's FIRST iteration: a whole tile, ~10 us, of cover for the NVLink round trip)
+        if (it == 0 && tile + tstride < ntiles) { load_row(idn, rawn, lrown); idn = load_id(tile + 2 * tstride); }
       } else if (it + 1 == L && tile + tstride < ntiles) {
         load_x(tile + tstride, xn);                                     // next tile's rows: a whole step of cover
       }
