@@ -333,17 +333,47 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
         const float dA = (gg[u] - m1 - xhat[u] * m2) * rstd;
         dT[u] = a[u] > 0.f ? dA : 0.f;             // rows outside a sample have g = 0 -> dA = 0
       }
-      // ---- operands.  shared memory: B of S / dP (tf32), of dQ / dK / dV (bf16); dr, g*xhat, g columns of dZ
+      // ---- operands of head 0's S / dP first (B tiles in shared memory, expanded q / dO in TMEM), then the MMAs are
+      //      issued and everything else of this step's staging runs UNDER them
+      auto stage_kv = [&](int h) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          *reinterpret_cast<float4*>(smem + SM::OFF_KX + h * G::KX_BYTES + nosw_off<NCHK>(f_loc, s_loc * 2 + c)) =
+              make_float4(qk[U + h * DH + c * 4], qk[U + h * DH + c * 4 + 1], qk[U + h * DH + c * 4 + 2], qk[U + h * DH + c * 4 + 3]);
+          *reinterpret_cast<float4*>(smem + SM::OFF_VX + h * G::KX_BYTES + nosw_off<NCHK>(f_loc, s_loc * 2 + c)) =
+              make_float4(vv[h * DH + c * 4], vv[h * DH + c * 4 + 1], vv[h * DH + c * 4 + 2], vv[h * DH + c * 4 + 3]);
+        }
+      };
+      if (s_loc < SPT) stage_kv(0);
+      // TMEM: head 0's expanded q / dO (own sample's slot; the other slots stay zero)
+      for (uint32_t s = ws_lo; s <= ws_hi; ++s) {
+        uint32_t v8[8], w8[8];
+#pragma unroll
+        for (int e = 0; e < DH; ++e) {
+          v8[e] = (int)s == s_loc ? __float_as_uint(qk[e]) : 0u;
+          w8[e] = (int)s == s_loc ? __float_as_uint(dT[e]) : 0u;
+        }
+        tc_st_32x8(tl + C_QX + s * 8, v8);
+        tc_st_32x8(tl + C_DOX + s * 8, w8);
+      }
+      fence_async_smem();
+      tc_wait_st();
+      tc_fence_before();
+      __syncthreads();
+      if (wq == 0 && elect_one()) {
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < SPT; ++ks) {
+          tc_mma_tf32_ts(tmem + C_S, tmem + C_QX + ks * 8, mk_desc(b16, SM::OFF_KX + ks * 256, 128, NCHK * 128), ID_S, ks ? 1u : 0u);
+          tc_mma_tf32_ts(tmem + C_DP, tmem + C_DOX + ks * 8, mk_desc(b16, SM::OFF_VX + ks * 256, 128, NCHK * 128), ID_S, ks ? 1u : 0u);
+        }
+        tc_commit(bar);
+      }
+      // ---- under the MMAs: head 1's B tiles, the bf16 operands of dQ / dK / dV, the dr, g*xhat, g columns of dZ
       if (s_loc < SPT) {
+        stage_kv(1);
 #pragma unroll
         for (int h = 0; h < H; ++h) {
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            *reinterpret_cast<float4*>(smem + SM::OFF_KX + h * G::KX_BYTES + nosw_off<NCHK>(f_loc, s_loc * 2 + c)) =
-                make_float4(qk[U + h * DH + c * 4], qk[U + h * DH + c * 4 + 1], qk[U + h * DH + c * 4 + 2], qk[U + h * DH + c * 4 + 3]);
-            *reinterpret_cast<float4*>(smem + SM::OFF_VX + h * G::KX_BYTES + nosw_off<NCHK>(f_loc, s_loc * 2 + c)) =
-                make_float4(vv[h * DH + c * 4], vv[h * DH + c * 4 + 1], vv[h * DH + c * 4 + 2], vv[h * DH + c * 4 + 3]);
-          }
           *reinterpret_cast<uint4*>(smem + SM::OFF_K16 + h * G::VX_BYTES + nosw_off<4>(f_loc, s_loc)) = pack8_bf16(qk + U + h * DH);
           const uint4 qp = pack8_bf16(qk + h * DH);
           q16[h * 4 + 0] = qp.x; q16[h * 4 + 1] = qp.y; q16[h * 4 + 2] = qp.z; q16[h * 4 + 3] = qp.w;
@@ -368,32 +398,8 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
           *reinterpret_cast<uint4*>(smem + SM::OFF_DZ + nosw_off<12>(row, 10 + h)) = pack8_bf16(g + h * DH);
         }
       }
-      // TMEM: head 0's expanded q / dO (own sample's slot; the other slots stay zero)
-      for (uint32_t s = ws_lo; s <= ws_hi; ++s) {
-        uint32_t v8[8], w8[8];
-#pragma unroll
-        for (int e = 0; e < DH; ++e) {
-          v8[e] = (int)s == s_loc ? __float_as_uint(qk[e]) : 0u;
-          w8[e] = (int)s == s_loc ? __float_as_uint(dT[e]) : 0u;
-        }
-        tc_st_32x8(tl + C_QX + s * 8, v8);
-        tc_st_32x8(tl + C_DOX + s * 8, w8);
-      }
 #pragma unroll
       for (int e = 0; e < DH; ++e) { q1[e] = qk[DH + e]; dO1[e] = dT[DH + e]; }
-    }
-    fence_async_smem();
-    tc_wait_st();
-    tc_fence_before();
-    __syncthreads();
-    if (wq == 0 && elect_one()) {
-      tc_fence_after();
-#pragma unroll
-      for (int ks = 0; ks < SPT; ++ks) {
-        tc_mma_tf32_ts(tmem + C_S, tmem + C_QX + ks * 8, mk_desc(b16, SM::OFF_KX + ks * 256, 128, NCHK * 128), ID_S, ks ? 1u : 0u);
-        tc_mma_tf32_ts(tmem + C_DP, tmem + C_DOX + ks * 8, mk_desc(b16, SM::OFF_VX + ks * 256, 128, NCHK * 128), ID_S, ks ? 1u : 0u);
-      }
-      tc_commit(bar);
     }
     // ---- prefetch the next step's rows: a whole step of latency cover
     uint32_t xs_n[U], g_n[U / 2];
