@@ -159,8 +159,8 @@ def workload_config(args, dtype):
 # `ncu --set full` capture of THIS workload (profiles/r1d_ncu_full_metrics.csv; batch 8192, bf16, 1 GPU).  ncu
 # replays kernels serialised and cold, so these are per-launch byte counts, not timings.
 NCU_TRAFFIC_BYTES = {
-    "interacting_bwd": 89.581e6 + 4.252e6,      # profiles/r2_ncu_full_metrics.csv (round-2 kernels)
-    "interacting_fwd": 10.270e6 + 24.399e6,
+    "interacting_bwd": 100.531e6 + 5.835e6,     # profiles/r2_ncu_full_metrics.csv (round-2 kernels, inside a real step)
+    "interacting_fwd": 23.019e6 + 42.803e6,     # with the fused lookup: ids + table rows read, X + y + saved written
     "embed_gather": 22.937e6 + 0.326e6,         # profiles/r1d_ncu_full_metrics.csv (kernel unchanged)
     "embed_segsum_adam": 73.986e6 + 23.438e6,
 }

@@ -47,11 +47,11 @@ struct ItcGather {
 
 __device__ __forceinline__ void ld_row64(const float* p, uint32_t (&v)[16]) {
   // one 64-byte embedding row as two 32-byte requests (LDG.256): a row-per-thread loader must not split a row into
-  // four 16-byte requests (the NVLink path is request-rate bound)
-  asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  // four 16-byte requests (the NVLink path is request-rate bound); L2::64B: a miss fetches the 64-byte row, not 128 B
+  asm volatile("ld.global.L1::no_allocate.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "l"(p) : "memory");
-  asm volatile("ld.global.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  asm volatile("ld.global.L1::no_allocate.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                : "l"(p + 8) : "memory");
 }

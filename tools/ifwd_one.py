@@ -1,19 +1,16 @@
-"""Developer tool (GPU box): a few launches of the tcgen05 InteractingLayer forward + backward at the bench shape
-(for ncu captures)."""
+"""Developer tool (GPU box): a few launches of the tcgen05 InteractingLayer forward (with the fused embedding lookup) +
+backward at the bench shape through the trainer's own calls (for ncu captures)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from recommendsystem_b200 import ops
+from recommendsystem_b200.autoint import AutoIntConfig, AutoIntTrainer
 
 dev = torch.device("cuda:0")
+tr = AutoIntTrainer(AutoIntConfig(batch=8192, dtype="bf16", rows_per_field=1_000_000), dev)
 g = torch.Generator(device=dev).manual_seed(0)
-B, F, D, L = 8192, 39, 16, 3
-x = torch.randn(B, F, D, device=dev, generator=g).bfloat16()
-dy = torch.randn(B, F, D, device=dev, generator=g).bfloat16()
-W = (torch.rand(D, 64, device=dev, generator=g) - 0.5) * 0.8
-b = torch.zeros(64, device=dev); gm = torch.ones(D, device=dev); bt = torch.zeros(D, device=dev)
 for _ in range(3):
-    y, saved = ops.interacting_fwd(x, W, b, gm, bt, 1e-3, 2, L, True, compute_bf16=True)
-    ops.interacting_bwd(x, saved, W, b, gm, bt, 1e-3, 2, L, dy, True, compute_bf16=True)
+    ids = torch.randint(0, 1_000_000, (8192, 39), device=dev, generator=g)
+    y = (torch.rand(8192, 1, device=dev, generator=g) < 0.25).float()
+    tr.step(ids, y)
 torch.cuda.synchronize()
-print("ok")
+print("ok", float(tr.loss))
