@@ -250,6 +250,12 @@ int rs_route_ids_padded(const int64_t* ids, int64_t n, int F, const int64_t* row
                         const int64_t* local_base, int world, int capacity,
                         int32_t* send_rows, int32_t* inverse, int32_t* send_counts,
                         int32_t* overflow, void* ws, size_t ws_bytes, void* stream);
+/* The same with padding ids (< 0) spread over the owners (owner = ((uint32(i) * 0x9E3779B1) >> 16) mod world, row -1)
+ * instead of all in owner 0's bucket: inputs that are mostly padding (sequence / bag columns) keep the buckets balanced. */
+int rs_route_ids_padded_spread(const int64_t* ids, int64_t n, int F, const int64_t* rows,
+                        const int64_t* local_base, int world, int capacity,
+                        int32_t* send_rows, int32_t* inverse, int32_t* send_counts,
+                        int32_t* overflow, void* ws, size_t ws_bytes, void* stream);
 /* out[i, :] = src[index[i], :] (un-permute received rows; index < 0 -> zeros) and
  * its adjoint out[index[i], :] = src[i, :] (index < 0 skipped). */
 int rs_permute_rows(const void* src, void* out, const int32_t* index, int64_t n,

@@ -222,17 +222,18 @@ def dense_adam(w, m, v, g, lr, beta1, beta2, eps, corr):
 # ---------------------------------------------------------------- K7 routing
 
 
-def route_ids(ids, F, rows, local_base, world):
+def route_ids(ids, F, rows, local_base, world, pad_spread=False):
     """Row-sharded tables: r = id mod rows[f]; owner = r mod world;
     local row = local_base[f] + r // world.  Stable bucket-by-owner.
     Returns send_rows[n], inverse[n], send_counts[world], send_offsets[world+1].
-    Padding ids (<0) go to owner 0 with row -1.  (Replaces TensorNet's
+    Padding ids (<0) go to owner 0 with row -1 (pad_spread: to owner ((uint32(i) * 0x9E3779B1) >> 16) mod world).  (Replaces TensorNet's
     sign->shard routing; only trace in the reference: staytime/parse.py:78-79.)"""
     ids = np.asarray(ids, dtype=np.int64).reshape(-1)
     n = len(ids)
     f = np.arange(n) % F
     r = np.mod(ids, np.asarray(rows, np.int64)[f])
-    owner = np.where(ids >= 0, r % world, 0)
+    spread = ((((np.arange(n, dtype=np.uint64) * np.uint64(0x9E3779B1)) & np.uint64(0xFFFFFFFF)) >> np.uint64(16)) % np.uint64(world)).astype(np.int64)
+    owner = np.where(ids >= 0, r % world, spread if pad_spread else 0)
     lrow = np.where(ids >= 0, np.asarray(local_base, np.int64)[f] + r // world, -1)
     order = np.argsort(owner, kind="stable")
     send_rows = lrow[order].astype(np.int32)
@@ -244,10 +245,10 @@ def route_ids(ids, F, rows, local_base, world):
     return send_rows, inverse, counts, offsets
 
 
-def route_ids_padded(ids, F, rows, local_base, world, capacity):
+def route_ids_padded(ids, F, rows, local_base, world, capacity, pad_spread=False):
     """Fixed-capacity layout of route_ids: bucket o owns slots [o*capacity, (o+1)*capacity),
     unused slots hold row -1; returns send_rows[world*capacity], inverse[n], counts, overflow."""
-    sr, inv, cnt, off = route_ids(ids, F, rows, local_base, world)
+    sr, inv, cnt, off = route_ids(ids, F, rows, local_base, world, pad_spread)
     send = np.full(world * capacity, -1, np.int32)
     inverse = np.full(len(inv), -1, np.int32)
     owner_of_slot = np.searchsorted(off, np.arange(len(sr)), side="right") - 1

@@ -90,9 +90,10 @@ class ShardedEmbeddingFeatures(EmbeddingFeatures):
         W, d, dev = self.world, self.d, self.dev
         g = _Group()
         g.n, g.F = n, len(cols)
-        # Padding ids (< 0) all travel in their rank's owner-0 bucket (rs_route_ids_padded's convention, row -1): a
-        # group that may carry padding (sequence / bag columns) sizes every bucket for the worst case, all n lookups.
-        g.cap = n if padded else bucket_capacity(n, W, self.capacity_factor)
+        # Groups that may carry padding (sequence / bag columns) spread it over the owners by a hash of the lookup index
+        # (rs_route_ids_padded_spread): the buckets stay balanced and the usual capacity holds.
+        g.cap = bucket_capacity(n, W, self.capacity_factor)
+        g.pad_spread = bool(padded)
         idx = list(cols)
         g.lbase_t = torch.as_tensor(self.local_base[idx], device=dev)
         g.rows_t = torch.as_tensor(self.rows[idx], device=dev)
@@ -118,7 +119,7 @@ class ShardedEmbeddingFeatures(EmbeddingFeatures):
         cabi.call("rs_embed_gather_peer_fwd", ctypes.addressof(self.peer_tables), self.table_ld, self.world, ids.data_ptr(),
                   g.lbase_t.data_ptr(), g.rows_t.data_ptr(), n, g.F, self.d, out.data_ptr(), cabi.RS_F32, st)
         ops.route_ids_padded(ids, g.F, g.rows_t, g.lbase_t, self.world, g.cap, g.send_rows, g.inverse, g.send_counts,
-                             self.overflow)
+                             self.overflow, pad_spread=g.pad_spread)
         dist.all_to_all_single(g.recv_rows, g.send_rows, group=self.group)
         cabi.call("rs_embed_gather_rows_ld", self.table.data_ptr(), self.table_ld, g.recv_rows.data_ptr(),
                   g.recv_rows.numel(), self.d, None, cabi.RS_F32, None, g.keys.data_ptr(), st)

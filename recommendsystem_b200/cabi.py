@@ -47,6 +47,7 @@ PROTOTYPES = {
     "rs_route_workspace_bytes": (_sz, [_i64, _i]),
     "rs_route_ids": (_i, [_p, _i64, _i, _p, _p, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "rs_route_ids_padded": (_i, [_p, _i64, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "rs_route_ids_padded_spread": (_i, [_p, _i64, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "rs_permute_rows": (_i, [_p, _p, _p, _i64, _i, _i, _i, _p]),
     "rs_interacting_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "rs_interacting_saved_bytes": (_sz, [_i, _i, _i, _i]),

@@ -601,12 +601,15 @@ __global__ void dense_adam_kernel(float* __restrict__ w, float* __restrict__ m,
 constexpr int ROUTE_BLOCK = 256;
 constexpr int ROUTE_MAX_WORLD = 64;
 
+// pad_spread: padding ids (< 0) take a slot at owner hash(i) mod world (Fibonacci hash of the lookup index: padding
+// sits at the tail of every sequence, a plain i mod world inherits that pattern) instead of owner 0, so that inputs that are mostly
+// padding (sequence / bag columns) keep the buckets balanced (rs_route_ids_padded_spread)
 __device__ __forceinline__ void route_of(const int64_t* ids, const int64_t* rows,
                                          const int64_t* local_base, int64_t i, int F, int world,
-                                         int& owner, int32_t& lrow) {
+                                         int& owner, int32_t& lrow, int pad_spread = 0) {
   const int64_t id = ids[i];
-  if (id < 0) {  // padding: keep it on its own rank as row -1 (owner 0 by convention)
-    owner = 0; lrow = -1; return;
+  if (id < 0) {  // padding: row -1; owner 0 by convention, or round-robin over the owners
+    owner = pad_spread ? (int)((((uint32_t)i * 0x9E3779B1u) >> 16) % (uint32_t)world) : 0; lrow = -1; return;
   }
   const int f = (int)(i % F);
   const uint64_t r = (uint64_t)id % (uint64_t)rows[f];
@@ -615,14 +618,15 @@ __device__ __forceinline__ void route_of(const int64_t* ids, const int64_t* rows
 }
 
 __global__ void route_hist_kernel(const int64_t* ids, int64_t n, int F, const int64_t* rows,
-                                  const int64_t* local_base, int world, int32_t* hist /*[world][nblk]*/) {
+                                  const int64_t* local_base, int world, int32_t* hist /*[world][nblk]*/,
+                                  int pad_spread = 0) {
   __shared__ int cnt[ROUTE_MAX_WORLD];
   if (threadIdx.x < ROUTE_MAX_WORLD) cnt[threadIdx.x] = 0;
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * ROUTE_BLOCK + threadIdx.x;
   if (i < n) {
     int owner; int32_t lrow;
-    route_of(ids, rows, local_base, i, F, world, owner, lrow);
+    route_of(ids, rows, local_base, i, F, world, owner, lrow, pad_spread);
     atomicAdd(&cnt[owner], 1);
   }
   __syncthreads();
@@ -698,12 +702,12 @@ __global__ void route_scatter_padded_kernel(const int64_t* ids, int64_t n, int F
                                             const int64_t* local_base, int world, int cap,
                                             const int32_t* hist /*exclusive, [world][nblk]*/,
                                             const int32_t* send_offsets, int32_t* send_rows,
-                                            int32_t* inverse, int32_t* overflow) {
+                                            int32_t* inverse, int32_t* overflow, int pad_spread) {
   __shared__ int warp_cnt[ROUTE_BLOCK / 32][ROUTE_MAX_WORLD];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * ROUTE_BLOCK + threadIdx.x;
   int owner = -1; int32_t lrow = -1;
-  if (i < n) route_of(ids, rows, local_base, i, F, world, owner, lrow);
+  if (i < n) route_of(ids, rows, local_base, i, F, world, owner, lrow, pad_spread);
   int my_rank = 0;
   for (int o = 0; o < world; ++o) {
     const unsigned m = __ballot_sync(0xffffffffu, owner == o);
@@ -1028,10 +1032,10 @@ int rs_route_ids(const int64_t* ids, int64_t n, int F, const int64_t* rows,
   return check_launch("route_scatter");
 }
 
-int rs_route_ids_padded(const int64_t* ids, int64_t n, int F, const int64_t* rows,
-                        const int64_t* local_base, int world, int capacity, int32_t* send_rows,
-                        int32_t* inverse, int32_t* send_counts, int32_t* overflow, void* ws,
-                        size_t ws_bytes, void* stream) {
+static int route_ids_padded_impl(const int64_t* ids, int64_t n, int F, const int64_t* rows,
+                                 const int64_t* local_base, int world, int capacity, int32_t* send_rows,
+                                 int32_t* inverse, int32_t* send_counts, int32_t* overflow, void* ws,
+                                 size_t ws_bytes, void* stream, int pad_spread) {
   RS_REQUIRE(world >= 1 && world <= ROUTE_MAX_WORLD, "route_ids_padded: world=%d", world);
   RS_REQUIRE(F > 0 && n >= 0 && n < ((int64_t)1 << 31) && capacity > 0, "route_ids_padded: n/F/capacity out of range");
   RS_REQUIRE((int64_t)world * capacity < ((int64_t)1 << 31), "route_ids_padded: world*capacity too large");
@@ -1042,13 +1046,28 @@ int rs_route_ids_padded(const int64_t* ids, int64_t n, int F, const int64_t* row
   int32_t* offsets = (int32_t*)((char*)ws + rs_route_workspace_bytes(n, world));
   const int nblk = (int)cdiv(n > 0 ? n : 1, ROUTE_BLOCK);
   RS_CUDA(cudaMemsetAsync(send_rows, 0xFF, (size_t)world * capacity * sizeof(int32_t), st));   // row -1 = padding
-  route_hist_kernel<<<nblk, ROUTE_BLOCK, 0, st>>>(ids, n, F, rows, local_base, world, hist);
+  route_hist_kernel<<<nblk, ROUTE_BLOCK, 0, st>>>(ids, n, F, rows, local_base, world, hist, pad_spread);
   if (int e = check_launch("route_hist")) return e;
   route_scan_kernel<<<1, 1024, 0, st>>>(hist, (int64_t)nblk * world, nblk, world, send_counts, offsets);
   if (int e = check_launch("route_scan")) return e;
   route_scatter_padded_kernel<<<nblk, ROUTE_BLOCK, 0, st>>>(ids, n, F, rows, local_base, world, capacity, hist,
-                                                            offsets, send_rows, inverse, overflow);
+                                                            offsets, send_rows, inverse, overflow, pad_spread);
   return check_launch("route_scatter_padded");
+}
+
+int rs_route_ids_padded(const int64_t* ids, int64_t n, int F, const int64_t* rows,
+                        const int64_t* local_base, int world, int capacity, int32_t* send_rows,
+                        int32_t* inverse, int32_t* send_counts, int32_t* overflow, void* ws,
+                        size_t ws_bytes, void* stream) {
+  return route_ids_padded_impl(ids, n, F, rows, local_base, world, capacity, send_rows, inverse, send_counts, overflow, ws,
+                               ws_bytes, stream, 0);
+}
+int rs_route_ids_padded_spread(const int64_t* ids, int64_t n, int F, const int64_t* rows,
+                               const int64_t* local_base, int world, int capacity, int32_t* send_rows,
+                               int32_t* inverse, int32_t* send_counts, int32_t* overflow, void* ws,
+                               size_t ws_bytes, void* stream) {
+  return route_ids_padded_impl(ids, n, F, rows, local_base, world, capacity, send_rows, inverse, send_counts, overflow, ws,
+                               ws_bytes, stream, 1);
 }
 
 int rs_permute_rows(const void* src, void* out, const int32_t* index, int64_t n, int d, int dtype,

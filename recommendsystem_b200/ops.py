@@ -173,7 +173,7 @@ def route_ids(ids, F, rows, local_base, world):
 
 
 def route_ids_padded(ids, F, rows, local_base, world, capacity, send_rows=None, inverse=None, counts=None,
-                     overflow=None):
+                     overflow=None, pad_spread=False):
     n = ids.numel()
     dev = ids.device
     send_rows = torch.empty(world * capacity, dtype=torch.int32, device=dev) if send_rows is None else send_rows
@@ -182,7 +182,8 @@ def route_ids_padded(ids, F, rows, local_base, world, capacity, send_rows=None, 
     overflow = torch.zeros(1, dtype=torch.int32, device=dev) if overflow is None else overflow
     nbytes = cabi.load().rs_route_workspace_bytes(n, world) + (world + 1) * 4
     ws = WS.get("route", nbytes, dev)
-    call("rs_route_ids_padded", _ptr(ids), n, F, _ptr(rows), _ptr(local_base), world, capacity, _ptr(send_rows),
+    call("rs_route_ids_padded_spread" if pad_spread else "rs_route_ids_padded", _ptr(ids), n, F, _ptr(rows),
+         _ptr(local_base), world, capacity, _ptr(send_rows),
          _ptr(inverse), _ptr(counts), _ptr(overflow), _ptr(ws), ws.numel(), _stream())
     return send_rows, inverse, counts, overflow
 

@@ -206,6 +206,33 @@ def test_dense_adam(cuda_dev):
     assert torch.equal(shadow, wt.to(torch.bfloat16))
 
 
+@pytest.mark.parametrize("n_b,T,world", [(64, 50, 8), (333, 7, 2), (100, 20, 4)])
+def test_route_ids_padded_spread_bit_exact(cuda_dev, n_b, T, world):
+    """rs_route_ids_padded_spread: a sequence column that is ~60 % padding.  Padding ids take a slot at owner
+    hash(i) mod world: the buckets stay balanced (the default capacity holds, where owner-0 padding would overflow it) and
+    the layout equals the oracle's bit for bit."""
+    from oracle import oracle_np as onp
+    from recommendsystem_b200 import ops
+    from recommendsystem_b200.sharded import bucket_capacity
+    rng = np.random.default_rng(n_b + T + world)
+    rows = np.asarray([7919], np.int64)
+    lbase = np.zeros(1, np.int64)
+    ids = rng.integers(0, 2 ** 45, size=(n_b, T)).astype(np.int64)
+    lens = rng.integers(0, T + 1, size=n_b)
+    ids[np.arange(T)[None, :] >= (lens * 0.8).astype(np.int64)[:, None]] = -1
+    flat = ids.reshape(-1, 1)
+    cap = bucket_capacity(flat.size, world)
+    sr, inv, cnt, ovf = onp.route_ids_padded(flat, 1, rows, lbase, world, cap, pad_spread=True)
+    assert ovf == 0
+    assert onp.route_ids_padded(flat, 1, rows, lbase, world, cap)[3] == 1 or world == 2      # owner-0 padding overflows
+    g_sr, g_inv, g_cnt, g_ovf = ops.route_ids_padded(_t(flat, cuda_dev), 1, _t(rows, cuda_dev), _t(lbase, cuda_dev),
+                                                     world, cap, pad_spread=True)
+    assert int(g_ovf.item()) == 0
+    assert np.array_equal(g_cnt.cpu().numpy(), cnt)
+    assert np.array_equal(g_inv.cpu().numpy(), inv)
+    assert np.array_equal(g_sr.cpu().numpy(), sr)
+
+
 @pytest.mark.parametrize("n_b,F,world,cap", [(300, 39, 8, 1700), (1024, 39, 2, 20096), (77, 5, 4, 128),
                                              (64, 1, 2, 16)])
 def test_route_ids_padded_bit_exact(cuda_dev, n_b, F, world, cap):
