@@ -361,7 +361,13 @@ static int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, void* C, in
 }
 
 // splits * M * N <= (sms / tiles) * tiles * 128 * 128 floats
-size_t gemm_tc_workspace_bytes() { return (size_t)sm_count() * TC_BM * 128 * sizeof(float); }
+// split-K partials: one 128 x 128 fp32 tile per SM for the bf16 kernel; the fp32 3xTF32 kernel caps an accumulation
+// chain at K = 4096 and needs room for ceil(K / 4096) full [M, N] partials — 64 MiB covers the widest weight gradient
+// of the composed models (staytime_output 1840 x 401 over a batch of 16 384 fell to the FFMA kernel for 1.8 ms without it)
+size_t gemm_tc_workspace_bytes() {
+  const size_t a = (size_t)sm_count() * TC_BM * 128 * sizeof(float), b = (size_t)64 << 20;
+  return a > b ? a : b;
+}
 
 int gemm_bf16_tc(const void* A, int64_t lda, int transA, const void* B, int64_t ldb, int transB, void* C,
                  int64_t ldc, const float* bias, const void* aux, int64_t ldaux, int epilogue, int M, int N,
