@@ -133,8 +133,11 @@ class EmbeddingFeatures:
             for j, ci in enumerate(single):
                 out[self.cols[ci].key] = emb[:, j, :].to(self.out_dtype)
             plan.append(([self.cols[ci].key for ci in single], keys, 1.0, None))
+            # the gather output as it lies: (column keys, [B, F', d]) for consumers that work on the stacked tensor
+            self.last_stacked = ([self.cols[ci].key for ci in single], emb.to(self.out_dtype))
         else:
             single = []
+            self.last_stacked = None
         for ci, c in enumerate(self.cols):
             if ci in single:
                 continue

@@ -136,6 +136,9 @@ class ShardedEmbeddingFeatures(EmbeddingFeatures):
             for j, ci in enumerate(single):
                 out[self.cols[ci].key] = emb[:, j, :].to(self.out_dtype)
             plan.append(([self.cols[ci].key for ci in single], g, None))
+            self.last_stacked = ([self.cols[ci].key for ci in single], emb.to(self.out_dtype))
+        else:
+            self.last_stacked = None
         for ci, c in enumerate(self.cols):
             if ci in single:
                 continue

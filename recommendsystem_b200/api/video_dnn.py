@@ -77,36 +77,52 @@ class VideoDnnSubModel(nn.Module):
         self.tower_out = nn.ModuleDict({t: D(1, "sigmoid") for t in C.task_names[1:]})                # :184,190
         self.register_buffer("wt_bins", torch.tensor(C.bin_list, dtype=torch.float32).view(C.multiclass_num, 1))
 
-    def forward(self, embs: Dict[str, torch.Tensor], seqs: Dict[str, tuple]):
-        general = {s: embs[s][:, 0:16] for s in self.slots}                                           # :47-48
-        general_inputs = [general[s] for s in self.slots]
-        bias_inputs = [embs[s][:, 16:] for s in self.slots if s in BIAS_SLOTS]                        # :45-46
+    def _slot_indices(self, pos, bias_idx, device):
+        """Index tensors of the user / item / bias slots on `device`, created once (a host->device copy is not
+        capturable in a CUDA graph)."""
+        cache = self.__dict__.setdefault("_idx_cache", {})
+        if device not in cache:
+            cache[device] = (torch.as_tensor([pos[s] for s in USER_SLOTS], device=device),
+                             torch.as_tensor([pos[s] for s in ITEM_SLOTS], device=device),
+                             torch.as_tensor(bias_idx, device=device))
+        return cache[device]
+
+    def forward(self, embs, seqs: Dict[str, tuple]):
+        """embs: dict slot -> [B,32], or ONE stacked tensor [B, n, 32] whose slot axis is in sorted-slot order (what
+        MtlNet hands over: the embedding layer's gather output as it lies).  Every per-slot step of the reference
+        (slicing :45-48, SENet re-weighting :94-96, FM :107-115) is evaluated on the stacked tensor — one launch
+        instead of one per slot."""
+        G = torch.stack([embs[s] for s in self.slots], dim=1) if isinstance(embs, dict) else embs    # [B, n, 32]
+        B, n = G.shape[0], G.shape[1]
+        pos = {s: i for i, s in enumerate(self.slots)}
+        general = G[:, :, 0:16]                                                                       # :47-48
+        bias_idx = [pos[s] for s in self.slots if s in BIAS_SLOTS]                                    # :45-46
         din_embs = []
         for s in self.seq_slots:                                                                      # :53-77
             seq, mask = seqs[s]
-            query = general[DIN_QUERY.get(s, "1737")]
+            query = general[:, pos[DIN_QUERY.get(s, "1737")], :]
             din_embs.append(self.din["din_%s" % s](query.contiguous(), seq[:, :, 0:16], mask))
         # SENet re-weighting on a stop-gradient copy (:80-96)
-        squeeze = torch.cat(general_inputs, dim=-1).detach()
+        squeeze = general.reshape(B, n * 16).detach()
         w = 2.0 * self.senet_extract_layer2(self.senet_squeeze_layer1(squeeze))                       # [B, n]
-        reweight = [g * w[:, i:i + 1] for i, g in enumerate(general_inputs)]
+        reweight = general * w.unsqueeze(-1)                                                          # [B, n, 16]
         # user x item products (:98-105), un-reweighted embeddings
-        mult = torch.relu(torch.cat([general[s] for s in USER_SLOTS], -1) * torch.cat([general[s] for s in ITEM_SLOTS], -1))
+        uidx, iidx, bidx = self._slot_indices(pos, bias_idx, G.device)
+        mult = torch.relu(general.index_select(1, uidx).reshape(B, -1) * general.index_select(1, iidx).reshape(B, -1))
         # FM second-order term over the re-weighted embeddings (:107-115)
-        stack = torch.stack(reweight, dim=0)
-        sum_embs = stack.sum(0)
-        cross_term = sum_embs * sum_embs - (stack * stack).sum(0)
+        sum_embs = reweight.sum(1)
+        cross_term = sum_embs * sum_embs - (reweight * reweight).sum(1)
         fm_logit = 0.5 * cross_term.sum(-1, keepdim=True)
         # FFM (:117-120, 11-25)
         ffm = []
         for xs, ys, dim in FFM_SLOTS:
             for x in xs:
                 for y in ys:
-                    ffm.append(self.ffm["ffm_x_%s_%s_%d" % (x, y, dim)](general[x].contiguous()) *
-                               self.ffm["ffm_y_%s_%s_%d" % (x, y, dim)](general[y].contiguous()))
+                    ffm.append(self.ffm["ffm_x_%s_%s_%d" % (x, y, dim)](general[:, pos[x], :].contiguous()) *
+                               self.ffm["ffm_y_%s_%s_%d" % (x, y, dim)](general[:, pos[y], :].contiguous()))
         ffm = torch.cat(ffm, dim=-1)
-        concated = torch.cat(reweight + [cross_term, mult, ffm] + din_embs, dim=-1)                   # :122-123
-        gate_input = torch.cat(bias_inputs, dim=-1)                                                   # :126
+        concated = torch.cat([reweight.reshape(B, n * 16), cross_term, mult, ffm] + din_embs, dim=-1)   # :122-123
+        gate_input = G.index_select(1, bidx)[:, :, 16:].reshape(B, -1)                                # :126
         # PPNet-gated experts (:130-148)
         expert_outs = []
         for i in range(C.num_experts):
@@ -184,7 +200,9 @@ class MtlNet:
         self.group = group if (group is not None or embedding_cls is None) else _world_group()
         self.slots, self.seq_slots = list(slots), list(seq_slots)
         cats = {s: category_column(s, bucket_size) for s in self.slots}                                  # :219-220
-        cols = [embedding_column(cats[s], 32, combiner="mean", name="emb_col_%s" % s) for s in self.slots]
+        # single-valued columns in sorted-slot order: the stacked gather output [B, n, 32] then IS the sub-model's
+        # slot axis (mtl_net visits the slots sorted, :282,296) and no per-slot tensor is ever materialised
+        cols = [embedding_column(cats[s], 32, combiner="mean", name="emb_col_%s" % s) for s in sorted(self.slots)]
         cols += [embedding_column(cats[s], 32, combiner=None, seq_max_len=seq_max_len, name="emb_col_seq_%s" % s)
                  for s in self.seq_slots]                                                                # :228-231
         E, kw = (embedding_cls, {"group": group}) if embedding_cls is not None else (EmbeddingFeatures, {})
@@ -195,7 +213,12 @@ class MtlNet:
 
     def _embed(self, inputs):
         e = self.emb(inputs)
-        embs = {s: e["emb_col_%s" % s] for s in self.slots}
+        st = getattr(self.emb, "last_stacked", None)
+        want = ["emb_col_%s" % s for s in sorted(self.slots)]
+        if st is not None and st[0] == want:
+            embs = st[1]                                       # [B, n, 32], sorted-slot order, as gathered
+        else:
+            embs = {s: e["emb_col_%s" % s] for s in self.slots}
         seqs = {s: e["emb_col_seq_%s" % s] for s in self.seq_slots}
         return embs, seqs
 
@@ -210,7 +233,8 @@ class MtlNet:
 
     def train_step(self, inputs, labels: Dict[str, torch.Tensor]):
         embs, seqs = self._embed(inputs)
-        le = {s: v.detach().requires_grad_(True) for s, v in embs.items()}
+        stacked = not isinstance(embs, dict)
+        le = embs.detach().requires_grad_(True) if stacked else {s: v.detach().requires_grad_(True) for s, v in embs.items()}
         ls = {s: (v[0].detach().requires_grad_(True), v[1]) for s, v in seqs.items()}
         out, _ = self.sub_model(le, ls)
         if self.opt is None:
@@ -219,7 +243,10 @@ class MtlNet:
         self.opt.zero_grad()
         loss.backward()
         self.opt.step()
-        grads = {"emb_col_%s" % s: v.grad for s, v in le.items()}
+        if stacked:
+            grads = {"emb_col_%s" % s: le.grad[:, i, :] for i, s in enumerate(sorted(self.slots))}
+        else:
+            grads = {"emb_col_%s" % s: v.grad for s, v in le.items()}
         grads.update({"emb_col_seq_%s" % s: v[0].grad for s, v in ls.items()})
         self.emb.backward(grads)
         return loss.detach(), {k: v.detach() for k, v in out.items()}
