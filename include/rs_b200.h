@@ -31,7 +31,8 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 4   /* 4: + rs_interacting_path; saved buffer grows by the per-head softmax statistics */
+#define RS_ABI_VERSION 5   /* 4: + rs_interacting_path; saved buffer grows by the per-head softmax statistics.
+                              5: + deferred parameter-gradient reductions (rs_logit_head_reduce, rs_interacting_bwd_reduce) */
 
 enum rs_dtype { RS_F32 = 0, RS_BF16 = 1 };
 
@@ -67,6 +68,10 @@ const char* rs_last_error(void);
 uint64_t rs_launch_count(void);
 /* 1 if the library was compiled for sm_100a (it never is anything else). */
 int rs_built_for_sm100a(void);
+/* Measurement aid (tools/step_timeline.py): a one-thread kernel that stores %globaltimer (ns) into *dst when the stream
+ * reaches it — inside a captured CUDA graph it timestamps the phase boundaries of a replay.  Not counted by
+ * rs_launch_count; never launched by the product path unless a trainer's `stamps` buffer is set. */
+int rs_debug_timestamp(unsigned long long* dst, void* stream);
 
 /* ------------------------------------------------- K1/K2 embedding gather --
  * Replaces tn.layers.EmbeddingFeatures(...)(inputs) for single-valued slots
@@ -332,6 +337,12 @@ int rs_interacting_bwd_scatter(const void* x, int64_t x_ld, int64_t x_bs, const 
                                void* const* peer_recv, int world, int rank, const int* inverse, int cap,
                                float* dparams, int B, int F, int D, int U, int H, int L, int use_res,
                                void* ws, size_t ws_bytes, void* stream);
+/* Deferred tail of rs_interacting_bwd_scatter: called with dparams == NULL it leaves the per-CTA partial sums of
+ * [dW | db | dgamma | dbeta] in `ws`; this sums them in CTA order into dparams (same values as the undeferred call).
+ * May run on another stream (ordered after the backward by the caller): the embedding update that follows the backward
+ * does not read dparams, only the dense optimizer does.  B, F, D, U, H as passed to the backward. */
+int rs_interacting_bwd_reduce(const void* ws, size_t ws_bytes, float* dparams, int B, int F, int D, int U, int H,
+                              void* stream);
 /* Training-mode attention-weight dropout (InteractingLayer.py:53-54; use_dropout=True at
  * rank/multi_head/multidnn.py:54 and rank/ctr/model_init.py:54-59): the softmax weights are multiplied by an
  * inverted-dropout mask before P.V.  The mask is a pure function of (dropout_seed, iteration, sample, head,
@@ -472,6 +483,12 @@ int rs_logit_head_fwd_bwd_relu(const void* Z, int64_t ldz, int dtype, const floa
                           const float* bias, const float* y, float a, void* p_out,
                           float* loss_out, void* dZ, int64_t lddz, float* dw, float* db,
                           int B, int zw, int relu_cols, void* ws, size_t ws_bytes, void* stream);
+/* Deferred tail of the two calls above.  With dw == NULL they leave the per-CTA partial sums of dw / db / loss in
+ * `ws` (dZ and p_out are complete); this sums them in fixed order.  It may run on another stream than the head (ordered
+ * after it by the caller): only the dense optimizer (dense_feature_optimizer, rank/ctr/dnn_optimizer.py) reads
+ * dw / db, so the tower's backward does not have to wait for the reduction. */
+int rs_logit_head_reduce(const void* ws, size_t ws_bytes, float* dw, float* db, float* loss_out, int B, int zw,
+                         void* stream);
 
 /* dst[n, m] = src[m, n] (2-D transpose with leading dims; bf16 or fp32).  Used to
  * present activations K-major to the tensor-core weight-gradient GEMMs. */

@@ -168,15 +168,22 @@ class AutoIntTrainer:
                          for i in range(len(cfg.mlp_hidden))}
             self._refresh_wt()
         self.side = torch.cuda.Stream(device=self.dev)
+        # Further branches of the step (see _launch_step): the InteractingLayer kernels are persistent and fill every SM,
+        # so whatever side work is not finished when the backward starts runs AFTER it; as one serial chain that tail was
+        # ~75 us, as parallel branches (weight gradients | bias gradients | reductions) it hides behind the sparse update.
+        self.branch = [torch.cuda.Stream(device=self.dev) for _ in range(3)]
         self.sort_done = torch.cuda.Event()
+        self.adam_done = torch.cuda.Event()
         self.fused = bool(cfg.fuse_embedding and self.bf16 and ops.interacting_path(
             F, d, U, cfg.head_num, torch.bfloat16, True) == cabi.PATH_TCGEN05 and self.table_ld % 16 == 0)
         self.graph = None
         self.timer = None               # set to a PhaseTimer for an instrumented (eager) step
+        self.stamps, self.stamp_names = None, {}     # set `stamps` to an int64 buffer for tools/step_timeline.py
         n_ws = max(cabi.load().rs_interacting_workspace_bytes(B, F, d, U),
                    cabi.load().rs_embed_sort_workspace_bytes(B * F),
                    cabi.load().rs_colsum_workspace_bytes(B, max(widths + [self.zw])))
         self.ws = torch.empty(int(n_ws) + 256, dtype=torch.uint8, device=self.dev)
+        self.head_ws = ops.logit_head_workspace(B, self.zw, self.dev)     # head partials, reduced on the side stream
 
     # ------------------------------------------------------------------ setup
     def _alloc_tables(self, tables):
@@ -252,6 +259,13 @@ class AutoIntTrainer:
         nmlp = len(c.mlp_hidden)
         ph = lambda name: _Phase(self.timer, name)
         main = torch.cuda.current_stream(self.dev)
+        self._stamp("step_begin")
+        # Adam's step counter / bias corrections are read by the two optimizer kernels at the end of the step only:
+        # advance them on the side stream now instead of between the backward and the sparse update
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            ops.adam_advance(self.adam_scalars, c.beta1, c.beta2)
+            self.adam_done.record(self.side)
         if self.fused:
             # K1 inside K4: the forward's tile loader reads the embedding rows itself (local table, or the owners' HBM
             # over NVLink) and writes X and the sort keys as by-products; only the owners' key work (multi-GPU) is a
@@ -279,29 +293,48 @@ class AutoIntTrainer:
                           self.Z[:, self.n_deep:].data_ptr(), U, self.zw,
                           self.saved.data_ptr(), B, F, d, U,
                           c.head_num, c.layer_num, int(c.use_res), int(self.act_dtype == torch.bfloat16), st)
+        self._stamp("interacting_fwd_end")
         # K5: MLP tower; last hidden layer lands in Z[:, :n_deep], Flatten(A) in Z[:, n_deep:]
         Xf = self.X.view(B, F * d)
         acts = [Xf] + self.H + [self.Z[:, :self.n_deep]]
         with ph("mlp_fwd"):
             for i in range(nmlp):
                 self._dense_fwd(acts[i], f"mlp_W{i}", f"mlp_b{i}", acts[i + 1])
+        self._stamp("mlp_fwd_end")
         with ph("logits_loss"):
             # final Dense(1, sigmoid) + clip + BCE + the head's backward, one pass over Z
             # dZ[:, :n_deep] leaves the head already multiplied by relu'(last hidden layer): it IS dH[nmlp-1]
+            # (its own parameter gradients and the loss are summed on the side stream: only the dense Adam and the
+            # host read them, the tower's backward needs dZ alone)
             ops.logit_head(self.Z, P["out_W"], P["out_b"], self.labels, self.dZ, G["out_W"], G["out_b"],
-                           p_out=self.p_raw, loss=self.loss, relu_cols=self.n_deep)
+                           p_out=self.p_raw, loss=self.loss, relu_cols=self.n_deep, ws=self.head_ws, defer_reduce=True)
+        bw, bb, br = self.branch          # weight gradients | bias gradients | small reductions
+        br.wait_stream(main)
+        with torch.cuda.stream(br):
+            with ph("logits_loss_reduce"):
+                ops.logit_head_reduce(self.head_ws, G["out_W"], G["out_b"], self.loss, B, self.zw)
+        self._stamp("head_end")
         # MLP backward (relu masks from the saved activations)
         with ph("mlp_bwd"):
             for i in reversed(range(nmlp)):
-                # weight / bias gradients are only consumed by the dense Adam at the end of the step: they run
-                # on the side stream (after the key sort), off the dgrad -> InteractingLayer-backward chain
-                self.side.wait_stream(main)
-                with torch.cuda.stream(self.side):
+                # weight / bias gradients are only consumed by the dense Adam at the end of the step: they run as
+                # parallel branches off the dgrad -> InteractingLayer-backward chain (two streams, alternating, for
+                # the weight-gradient GEMMs of successive layers; one for the column sums)
+                # (launched as soon as their inputs exist: deferring them until after the backward leaves the tower's
+                # window to the GEMMs — 11 us — but the tail then outlasts the sparse update by 18 us)
+                sw = bw if (nmlp - 1 - i) % 2 == 0 else br
+                sw.wait_stream(main)
+                with torch.cuda.stream(sw):
                     with ph("mlp_wgrad"):
-                        self._wgrad(acts[i], self.dH[i], f"mlp_W{i}", f"mlp_b{i}")
+                        ops.gemm(acts[i], self.dH[i], self.G[f"mlp_W{i}"], transA=True)   # x^T dy, operands as they lie
+                bb.wait_stream(main)
+                with torch.cuda.stream(bb):
+                    with ph("mlp_bgrad"):
+                        ops.colsum(self.dH[i], out=self.G[f"mlp_b{i}"])
                 if i > 0:   # dH[i-1] = (dH[i] @ W_i^T) * relu'(h_{i-1}); W_i [in,out] is the K-major B operand
                     ops.gemm(self.dH[i], self._w(f"mlp_W{i}"), self.dH[i - 1], aux=acts[i],
                              epilogue=E.EPI_MUL_RELU_MASK, transB=True)
+        self._stamp("mlp_bwd_end")
         # InteractingLayer backward -> dX, then dX += dH0 @ W0^T
         nW = d * 4 * U
         dparams = self.flat_g[self.spec[0][2]:]       # Wqkvr | bqkvr | gamma | beta are contiguous
@@ -311,32 +344,58 @@ class AutoIntTrainer:
             # dX row by row and, multi-GPU, stores the sum straight into the owners' receive buffers
             with ph("mlp_dgrad_x"):
                 ops.gemm(self.dH[0], self._w("mlp_W0"), self.dX.view(B, F * d), transB=True)
+            self._stamp("mlp_dgrad_x_end")
             with ph("interacting_bwd"):
-                self._interacting_bwd_fused(dparams, st, T, main)
+                self._interacting_bwd_fused(None, st, T, main)      # parameter-gradient partials stay in self.ws
         else:
             with ph("interacting_bwd"):
                 self._interacting_bwd(dparams, st, T)
+        self._stamp("interacting_bwd_end")
         # all dense gradients exist now: their all-reduce (multi-GPU) and then the dense Adam run on the side
         # stream beside the embedding backward
-        ops.adam_advance(self.adam_scalars, c.beta1, c.beta2)
-        self.side.wait_stream(main)
-        with torch.cuda.stream(self.side):
-            self._dense_sync(ph)
         if not self.fused:
             with ph("mlp_dgrad_x"):
                 ops.gemm(self.dH[0], self._w("mlp_W0"), self.dX.view(B, F * d), epilogue=E.EPI_ACCUM, transB=True)
-        self.side.wait_stream(main)          # the last reader of the bf16 weight shadows is done
-        with torch.cuda.stream(self.side):
+        bw.wait_stream(main)                 # the last reader of the weights (and their bf16 shadows) is done
+        with torch.cuda.stream(bw):
+            if self.fused:
+                with ph("interacting_bwd_reduce"):
+                    cabi.call("rs_interacting_bwd_reduce", self.ws.data_ptr(), self.ws.numel(), dparams.data_ptr(), B, F, d,
+                              U, c.head_num, ops._stream())
+            bw.wait_stream(bb)
+            bw.wait_stream(br)
+            bw.wait_event(self.adam_done)
+            self._dense_sync(ph)
             with ph("dense_adam"):
                 ops.dense_adam(self.flat, self.flat_m, self.flat_v, self.flat_g, c.lr_dense, c.beta1, c.beta2, c.eps,
                                self.adam_scalars, self.flat_bf16)
-                if self.bf16:
-                    self._refresh_wt()
+            if self.bf16:                    # transposed bf16 shadows of the tower weights: one branch each
+                for j, (k, wt) in enumerate(self.WT16.items()):
+                    sj = (bw, bb, br)[j % 3]
+                    if sj is not bw:
+                        sj.wait_stream(bw)
+                    with torch.cuda.stream(sj):
+                        with ph("weight_shadows"):
+                            ops.transpose2d(self.P16[k], wt)
+            self._stamp("side_end")
         # K3: sparse Adam on touched rows
+        main.wait_event(self.adam_done)
         self._embed_backward(ph, st, T, main)
+        self._stamp("embed_backward_end")
         main.wait_stream(self.side)
+        for sj in self.branch:
+            main.wait_stream(sj)
         if getattr(self, "_join_side2", False):      # peer-gather barrier stream joins the step
             main.wait_stream(self.side2)
+        self._stamp("step_end")
+
+    def _stamp(self, name):
+        """Measurement aid (tools/step_timeline.py): with `self.stamps` set to an int64 device buffer, a one-thread
+        kernel stores the GPU's global timer when the CURRENT stream reaches this point of the step."""
+        if getattr(self, "stamps", None) is None:
+            return
+        i = self.stamp_names.setdefault(name, len(self.stamp_names))
+        cabi.call("rs_debug_timestamp", self.stamps[i:].data_ptr(), ops._stream())
 
     def _sort_keys(self, ph):
         main = torch.cuda.current_stream(self.dev)
@@ -345,6 +404,7 @@ class AutoIntTrainer:
             with ph("sort_keys"):
                 ops.sort_keys(self.keys, self.row_bits, out=self.keys_sorted)
             self.sort_done.record(self.side)
+            self._stamp("side_sort_end")
 
     # ---- embedding halves of the step (overridden by the row-sharded multi-GPU trainer)
     def _lookup_args(self):
@@ -368,7 +428,8 @@ class AutoIntTrainer:
         cabi.call("rs_interacting_bwd_scatter", self.X.data_ptr(), d, 0, self.saved.data_ptr(), T,
                   P["Wqkvr"].data_ptr(), P["bqkvr"].data_ptr(), P["gamma"].data_ptr(), P["beta"].data_ptr(), c.ln_eps,
                   self.dZ[:, self.n_deep:].data_ptr(), U, self.zw, self.dX.data_ptr(), d, 0, self.dX.data_ptr(),
-                  recv, world, rank, inverse, cap, dparams.data_ptr(), B, F, d, U, c.head_num, c.layer_num,
+                  recv, world, rank, inverse, cap, None if dparams is None else dparams.data_ptr(), B, F, d, U,
+                  c.head_num, c.layer_num,
                   int(c.use_res), self.ws.data_ptr(), self.ws.numel(), st)
 
     def _embed_forward(self, ph, st, T, gather=True):

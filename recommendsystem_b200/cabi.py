@@ -21,6 +21,7 @@ _p, _i, _i64, _f, _sz, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_siz
 # name -> (restype, argtypes); mirrors include/rs_b200.h one to one.
 PROTOTYPES = {
     "rs_abi_version": (_i, []),
+    "rs_debug_timestamp": (_i, [_p, _p]),
     "rs_last_error": (C.c_char_p, []),
     "rs_launch_count": (_u64, []),
     "rs_built_for_sm100a": (_i, []),
@@ -56,6 +57,7 @@ PROTOTYPES = {
                                        _i, _i, _i, _i, _i, _i, _i, _p]),
     "rs_interacting_bwd_scatter": (_i, [_p, _i64, _i64, _p, _i, _p, _p, _p, _p, _f, _p, _i64, _i64, _p, _i64, _i64, _p,
                                         _p, _i, _i, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    "rs_interacting_bwd_reduce": (_i, [_p, _sz, _p, _i, _i, _i, _i, _i, _p]),
     "rs_interacting_fwd": (_i, [_p, _i64, _i64, _i, _p, _p, _p, _p, _f, _p, _i64, _i64, _p,
                                 _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "rs_interacting_fwd_dropout": (_i, [_p, _i64, _i64, _i, _p, _p, _p, _p, _f, _p, _i64, _i64, _p,
@@ -79,6 +81,7 @@ PROTOTYPES = {
     "rs_logit_head_workspace_bytes": (_sz, [_i, _i]),
     "rs_logit_head_fwd_bwd": (_i, [_p, _i64, _i, _p, _p, _p, _f, _p, _p, _p, _i64, _p, _p, _i, _i, _p, _sz, _p]),
     "rs_logit_head_fwd_bwd_relu": (_i, [_p, _i64, _i, _p, _p, _p, _f, _p, _p, _p, _i64, _p, _p, _i, _i, _i, _p, _sz, _p]),
+    "rs_logit_head_reduce": (_i, [_p, _sz, _p, _p, _p, _i, _i, _p]),
     "rs_cross_workspace_bytes": (_sz, [_i, _i, _i]),
     "rs_cross_fwd": (_i, [_p, _i64, _i, _p, _p, _p, _i64, _i, _i, _i, _p, _sz, _p]),
     "rs_cross_bwd": (_i, [_p, _i64, _p, _i64, _i, _p, _p, _p, _i64, _p, _p, _i, _i, _i, _p, _sz, _p]),

@@ -100,6 +100,28 @@ __device__ __forceinline__ void epilogue_rows(const float* stg, int rows_here, i
   }
 }
 
+// RS_EPI_MUL_RELU_MASK on a full 32-row x 128-column bf16 block whose aux values (`pre`: this lane's four bf16 of each
+// of the 32 rows) were loaded BEFORE the accumulator wait: the dgrad GEMMs of the tower are two K slabs deep, so eight
+// dependent batches of aux loads after the MMAs (the generic path) cost more than the MMAs themselves.
+template <int BN, typename CT>
+__device__ __forceinline__ void epilogue_mask_pre(const float* stg, int lane, CT* c_rows, int64_t ldc,
+                                                  const uint32_t (&pre)[64]) {
+  static_assert(BN == 128 && sizeof(CT) == 2, "prefetched mask epilogue: 128-wide bf16 tiles");
+  constexpr int PITCH = BN + 4;
+  const int col = lane * 4;
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr) {
+    const float4 a = *reinterpret_cast<const float4*>(stg + rr * PITCH + col);
+    const uint32_t m01 = pre[2 * rr], m23 = pre[2 * rr + 1];
+    float4 v;
+    v.x = __uint_as_float(m01 << 16) > 0.f ? a.x : 0.f;
+    v.y = __uint_as_float(m01 & 0xffff0000u) > 0.f ? a.y : 0.f;
+    v.z = __uint_as_float(m23 << 16) > 0.f ? a.z : 0.f;
+    v.w = __uint_as_float(m23 & 0xffff0000u) > 0.f ? a.w : 0.f;
+    store4<CT>(c_rows + (int64_t)rr * ldc + col, v);
+  }
+}
+
 // split-K partial tile rows (fp32, [splits][M][N])
 template <int BN>
 __device__ __forceinline__ void epilogue_partial(const float* stg, int rows_here, int lane, int ncols, int N, float* dst_rows) {
@@ -170,6 +192,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  __syncthreads();
+  auto issue_load = [&](int i) {
+    const int s = i % TC_STAGES;
+    mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+    uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+    if constexpr (!MN) {
+      tma_load_2d(a_dst, &tmA, &full_bar[s], (kb0 + i) * TC_BK, m0);
+      tma_load_2d(a_dst + S::A_BYTES, &tmB, &full_bar[s], (kb0 + i) * TC_BK, n0);
+    } else {
+      // MN-major operands (A stored [K, M], B stored [K, N]: weight gradients x^T dy with no
+      // transposed copies): one box = 64 K rows x 64 M|N elements (128 B, SWIZZLE_128B) = one
+      // canonical MN-major swizzle atom column of 8 KB
+#pragma unroll
+      for (int at = 0; at < TC_BM / 64; ++at)
+        tma_load_2d(a_dst + at * 8192, &tmA, &full_bar[s], m0 + at * 64, (kb0 + i) * TC_BK);
+#pragma unroll
+      for (int at = 0; at < BN / 64; ++at)
+        tma_load_2d(a_dst + S::A_BYTES + at * 8192, &tmB, &full_bar[s], n0 + at * 64, (kb0 + i) * TC_BK);
+    }
+  };
+  // the first pass through the ring needs the barriers only: those loads are in flight while warp 1 allocates TMEM
+  const int nfirst = nkb < TC_STAGES ? nkb : TC_STAGES;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    for (int i = 0; i < nfirst; ++i) issue_load(i);
+  }
   if (warp == 1) {   // TMEM: BN fp32 accumulator columns (power of two >= 32)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -182,28 +231,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-      for (int i = 0; i < nkb; ++i) {
+      for (int i = nfirst; i < nkb; ++i) {
         const int s = i % TC_STAGES;
         const uint32_t ph = (uint32_t)(i / TC_STAGES) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);            // first pass through the ring falls through
-        mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
-        uint8_t* a_dst = smem + s * S::STAGE_BYTES;
-        if constexpr (!MN) {
-          tma_load_2d(a_dst, &tmA, &full_bar[s], (kb0 + i) * TC_BK, m0);
-          tma_load_2d(a_dst + S::A_BYTES, &tmB, &full_bar[s], (kb0 + i) * TC_BK, n0);
-        } else {
-          // MN-major operands (A stored [K, M], B stored [K, N]: weight gradients x^T dy with no
-          // transposed copies): one box = 64 K rows x 64 M|N elements (128 B, SWIZZLE_128B) = one
-          // canonical MN-major swizzle atom column of 8 KB
-#pragma unroll
-          for (int at = 0; at < TC_BM / 64; ++at)
-            tma_load_2d(a_dst + at * 8192, &tmA, &full_bar[s], m0 + at * 64, (kb0 + i) * TC_BK);
-#pragma unroll
-          for (int at = 0; at < BN / 64; ++at)
-            tma_load_2d(a_dst + S::A_BYTES + at * 8192, &tmB, &full_bar[s], n0 + at * 64, (kb0 + i) * TC_BK);
-        }
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        issue_load(i);
       }
     }
   } else if (warp == 1) {
@@ -243,6 +275,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // touches only its own 32 rows, __syncwarp suffices) -> lane = column group, and every warp
     // instruction reads aux / writes C as ONE contiguous row segment.
     const int lg = warp & 3;
+    // relu-mask epilogue on a full bf16 block of a one-CTA-per-SM launch: fetch the mask while the MMAs run
+    constexpr bool PRE_OK = STAGES > 2 && BN == 128 && sizeof(CT) == 2;
+    uint32_t pre[PRE_OK ? 64 : 1];
+    bool use_pre = false;
+    if constexpr (PRE_OK) {
+      use_pre = epi == RS_EPI_MUL_RELU_MASK && aux != nullptr && partial == nullptr && vec_ok &&
+                m0 + lg * 32 + 32 <= M && n0 + BN <= N;
+      if (use_pre) {
+        const CT* src = aux + (int64_t)(m0 + lg * 32) * ldaux + n0 + lane * 4;
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) {
+          const uint2 v = __ldg(reinterpret_cast<const uint2*>(src + (int64_t)rr * ldaux));
+          pre[2 * rr] = v.x; pre[2 * rr + 1] = v.y;
+        }
+      }
+    }
     mbar_wait(acc_bar, 0);
     if (threadIdx.x == 64) { GPROF(4) }
     tc_fence_after();
@@ -267,6 +315,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int ncols = N - n0;
 #define RS_EPI_GO(E) epilogue_rows<BN, E, CT>(stg, rows_here, lane, ncols, N, c_rows, ldc, a_rows, ldaux, bias ? bias + n0 : nullptr, vec_ok)
       if (part_rows) epilogue_partial<BN>(stg, rows_here, lane, ncols, N, part_rows);
+      else if (use_pre) {
+        if constexpr (PRE_OK) epilogue_mask_pre<BN, CT>(stg, lane, c_rows, ldc, pre);
+      }
       else switch (epi) {
         case RS_EPI_BIAS: RS_EPI_GO(RS_EPI_BIAS); break;
         case RS_EPI_BIAS_RELU: RS_EPI_GO(RS_EPI_BIAS_RELU); break;
@@ -302,9 +353,49 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
   }
 }
 
+// Same sums, same order, four adjacent outputs per thread and eight splits' loads in flight per step (N % 4 == 0 and
+// 16-byte aligned rows): the scalar kernel above is one dependent 4-byte load per split.
+template <typename CT>
+__global__ void splitk_reduce_vec_kernel(const float* __restrict__ partial, int splits, CT* __restrict__ C,
+                                         int64_t ldc, int M, int N, int accumulate) {
+  const int64_t total = (int64_t)M * N;
+  const int n4 = N >> 2;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < (int64_t)M * n4; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = q / n4;
+    const int n = (int)(q % n4) * 4;
+    const float* p = partial + m * N + n;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (accumulate) s = load4<CT>(C + m * ldc + n);
+    int z = 0;
+    for (; z + 8 <= splits; z += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(p + (int64_t)(z + u) * total);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
+    for (; z < splits; ++z) {
+      const float4 v = *reinterpret_cast<const float4*>(p + (int64_t)z * total);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    store4<CT>(C + m * ldc + n, s);
+  }
+}
+
 int splitk_reduce(const float* partial, int splits, void* C, int64_t ldc, int M, int N, int accumulate,
                   int dtype_c, cudaStream_t st) {
   const int64_t total = (int64_t)M * N;
+  const int esz = dtype_c == RS_F32 ? 4 : 2;
+  if (N % 4 == 0 && ((uintptr_t)C % (4 * esz)) == 0 && ((ldc * esz) % (4 * esz)) == 0 && ((uintptr_t)partial % 16) == 0) {
+    int64_t blocks = cdiv(total / 4, 128);
+    if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+    if (dtype_c == RS_F32)
+      splitk_reduce_vec_kernel<float><<<(unsigned)blocks, 128, 0, st>>>(partial, splits, (float*)C, ldc, M, N, accumulate);
+    else
+      splitk_reduce_vec_kernel<__nv_bfloat16><<<(unsigned)blocks, 128, 0, st>>>(partial, splits, (__nv_bfloat16*)C, ldc,
+                                                                               M, N, accumulate);
+    return check_launch("splitk_reduce");
+  }
   int64_t blocks = cdiv(total, 256);
   if (blocks > (int64_t)sm_count() * 8) blocks = (int64_t)sm_count() * 8;
   if (dtype_c == RS_F32)

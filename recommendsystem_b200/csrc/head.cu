@@ -136,6 +136,9 @@ using namespace rs;
 
 extern "C" {
 
+int rs_logit_head_reduce(const void* ws, size_t ws_bytes, float* dw, float* db, float* loss_out, int B, int zw,
+                         void* stream);
+
 size_t rs_logit_head_workspace_bytes(int B, int zw) {
   return (size_t)head_grid(B > 0 ? B : 1) * (size_t)(zw + 2) * sizeof(float);
 }
@@ -169,8 +172,19 @@ int rs_logit_head_fwd_bwd_relu(const void* Z, int64_t ldz, int dtype, const floa
   }
 #undef RS_HEAD_GO
   if (int e = check_launch("logit_head")) return e;
-  logit_head_reduce_kernel<<<(unsigned)cdiv((zw + 2) * 32, 256), 256, 0, st>>>((const float*)ws, grid, zw, dw, db,
-                                                                         loss_out, 1.f / (float)B);
+  // dw == NULL: the per-CTA partials stay in `ws` and the caller sums them with rs_logit_head_reduce — on another
+  // stream if it wishes (only the dense optimizer reads dw / db / loss; dZ, which the tower's backward waits for, is
+  // complete here)
+  if (dw == nullptr) return 0;
+  return rs_logit_head_reduce(ws, ws_bytes, dw, db, loss_out, B, zw, stream);
+}
+
+int rs_logit_head_reduce(const void* ws, size_t ws_bytes, float* dw, float* db, float* loss_out, int B, int zw,
+                         void* stream) {
+  RS_REQUIRE(B > 0 && zw > 0 && dw != nullptr && db != nullptr && loss_out != nullptr, "logit_head_reduce: B=%d zw=%d", B, zw);
+  if (ws_bytes < rs_logit_head_workspace_bytes(B, zw)) { set_error("logit_head_reduce: workspace too small"); return RS_ERR_WORKSPACE; }
+  logit_head_reduce_kernel<<<(unsigned)cdiv((zw + 2) * 32, 256), 256, 0, as_stream(stream)>>>(
+      (const float*)ws, head_grid(B), zw, dw, db, loss_out, 1.f / (float)B);
   return check_launch("logit_head_reduce");
 }
 

@@ -15,6 +15,7 @@ RS_INTERACT_SHAPES(RS_DECL)
 bool interacting_tc_supported(int F, int D, int U, int H, int dtype);
 int interacting_tc_fwd(const IFwdArgs& a);
 int interacting_tc_bwd(const IBwdArgs& a);
+int interacting_tc_bwd_reduce(const void* ws, size_t ws_bytes, float* dparams, int B, int F, cudaStream_t st);
 }  // namespace rs
 
 using namespace rs;
@@ -116,6 +117,14 @@ int rs_interacting_bwd_scatter(const void* x, int64_t x_ld, int64_t x_bs, const 
     a.scatter = &s;
   }
   return interacting_tc_bwd(a);
+}
+
+int rs_interacting_bwd_reduce(const void* ws, size_t ws_bytes, float* dparams, int B, int F, int D, int U, int H,
+                              void* stream) {
+  RS_REQUIRE(rs_interacting_path(F, D, U, H, RS_BF16, 1, 0.f) == RS_PATH_TCGEN05,
+             "interacting_bwd_reduce: only the tensor-core backward defers its reduction (F=%d D=%d U=%d H=%d)", F, D, U, H);
+  RS_REQUIRE(B > 0 && ws != nullptr && dparams != nullptr, "interacting_bwd_reduce: B=%d ws=%p dparams=%p", B, ws, (void*)dparams);
+  return interacting_tc_bwd_reduce(ws, ws_bytes, dparams, B, F, as_stream(stream));
 }
 
 int rs_interacting_fwd(const void* x, int64_t x_ld, int64_t x_bs, int dtype, const float* Wqkvr,

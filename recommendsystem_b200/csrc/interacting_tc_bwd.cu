@@ -678,16 +678,25 @@ static __global__ void itb_reduce_partials_kernel(const float* __restrict__ part
   if ((threadIdx.x & 31) == 0) out[i] = s;
 }
 
+constexpr int ITB_NP = 16 * 64 + 6 * 16;     // floats of one CTA's [dW | db | dgamma | dbeta] partial
+
+// CTAs of the backward (= partial blocks in the workspace): two per SM, at most one per tile of `spt` samples.
+// (A grid trimmed to the number of rounds — 274 CTAs do 2731 tiles in the same 10 rounds as 296 — was measured: the
+// freed slots did not speed the step's side branches up enough to matter, and the backward got 3 % slower.)
+static int itb_grid(int B, int spt) {
+  const int ntiles = (B + spt - 1) / spt;
+  const int grid = sm_count() * 2;
+  return grid > ntiles ? ntiles : grid;
+}
+
 template <int NCHF, typename T>
 static int launch_itc_bwd(const IBwdArgs& a) {
   auto kern = interacting_tc_bwd_kernel<NCHF, T>;
   constexpr int smem = ItbSmem<NCHF>::TOTAL;
   RS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   using G = ItcGeom<NCHF>;
-  const int ntiles = (a.B + G::SPT - 1) / G::SPT;
-  int grid = sm_count() * 2;
-  if (grid > ntiles) grid = ntiles;
-  const int np = 16 * 64 + 6 * 16;
+  const int grid = itb_grid(a.B, G::SPT);
+  const int np = ITB_NP;
   if (a.saved == nullptr) {
     set_error("interacting_tc_bwd: the saved activations of the tensor-core forward are required");
     return RS_ERR_INVALID;
@@ -705,7 +714,30 @@ static int launch_itc_bwd(const IBwdArgs& a) {
                                   (const T*)a.dy, a.dy_ld, a.dy_bs, (T*)a.dx, a.dx_ld, a.dx_bs, (float*)a.ws, a.B, a.F,
                                   a.L, a.use_res, (const T*)a.dx_add, sc);
   if (int e = check_launch("interacting_tc_bwd")) return e;
+  if (a.dparams == nullptr) return 0;       // deferred: interacting_tc_bwd_reduce (rs_interacting_bwd_reduce)
   itb_reduce_partials_kernel<<<(np * 32 + 255) / 256, 256, 0, a.st>>>((const float*)a.ws, a.dparams, grid, np);
+  return check_launch("interacting_tc_bwd_reduce");
+}
+
+// Deferred reduction of the per-CTA partials (a.dparams == nullptr above), same geometry as the launch.
+static int itb_spt(int F) {
+  switch ((F + 7) / 8) {       // the dispatch of interacting_tc_bwd below
+    case 1:
+    case 2: return ItcGeom<2>::SPT;
+    case 3: return ItcGeom<3>::SPT;
+    case 4: return ItcGeom<4>::SPT;
+    case 5: return ItcGeom<5>::SPT;
+    default: return ItcGeom<6>::SPT;
+  }
+}
+
+int interacting_tc_bwd_reduce(const void* ws, size_t ws_bytes, float* dparams, int B, int F, cudaStream_t st) {
+  const int grid = itb_grid(B, itb_spt(F));
+  if (ws_bytes < (size_t)grid * ITB_NP * sizeof(float)) {
+    set_error("interacting_tc_bwd_reduce: workspace %zu < %zu", ws_bytes, (size_t)grid * ITB_NP * sizeof(float));
+    return RS_ERR_WORKSPACE;
+  }
+  itb_reduce_partials_kernel<<<(ITB_NP * 32 + 255) / 256, 256, 0, st>>>((const float*)ws, dparams, grid, ITB_NP);
   return check_launch("interacting_tc_bwd_reduce");
 }
 

@@ -309,16 +309,30 @@ def transpose2d(src, out=None):
     return out
 
 
-def logit_head(Z, w, bias, y, dZ, dw, db, p_out=None, loss=None, a=1.0, relu_cols=0):
+def logit_head_workspace(B, zw, device):
+    """A caller-owned partial-sum buffer for logit_head(..., ws=, defer_reduce=True) + logit_head_reduce."""
+    return torch.empty(cabi.load().rs_logit_head_workspace_bytes(B, zw), dtype=torch.uint8, device=device)
+
+
+def logit_head(Z, w, bias, y, dZ, dw, db, p_out=None, loss=None, a=1.0, relu_cols=0, ws=None, defer_reduce=False):
     """Fused Dense(1, sigmoid) + clip + BCE + head backward (rs_logit_head_fwd_bwd[_relu]); dZ[:, :relu_cols] comes
-    out multiplied by relu'(Z)."""
+    out multiplied by relu'(Z).  defer_reduce: dw / db / loss are NOT written; the partial sums stay in `ws` (caller
+    owned) for logit_head_reduce, which may run on another stream."""
     B, zw = Z.shape
     p_out = torch.empty(B, 1, dtype=Z.dtype, device=Z.device) if p_out is None else p_out
     loss = torch.empty(1, dtype=torch.float32, device=Z.device) if loss is None else loss
-    ws = WS.get("head", cabi.load().rs_logit_head_workspace_bytes(B, zw), Z.device)
+    _need(not defer_reduce or ws is not None, "logit_head: defer_reduce needs a caller-owned workspace")
+    if ws is None:
+        ws = WS.get("head", cabi.load().rs_logit_head_workspace_bytes(B, zw), Z.device)
     call("rs_logit_head_fwd_bwd_relu", _ptr(Z), Z.stride(0), _dt(Z), _ptr(w), _ptr(bias), _ptr(y), a, _ptr(p_out),
-         _ptr(loss), _ptr(dZ), dZ.stride(0), _ptr(dw), _ptr(db), B, zw, int(relu_cols), _ptr(ws), ws.numel(), _stream())
+         _ptr(loss), _ptr(dZ), dZ.stride(0), None if defer_reduce else _ptr(dw), _ptr(db), B, zw, int(relu_cols),
+         _ptr(ws), ws.numel(), _stream())
     return p_out, loss
+
+
+def logit_head_reduce(ws, dw, db, loss, B, zw):
+    """Sums the head's per-CTA partials (logit_head(..., defer_reduce=True)) into dw / db / loss on the current stream."""
+    call("rs_logit_head_reduce", _ptr(ws), ws.numel(), _ptr(dw), _ptr(db), _ptr(loss), B, zw, _stream())
 
 
 def colsum(x, out=None):

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
     exported = set(re.findall(r"\bT (rs_[a-z0-9_]+)", out))
     declared = set(_declared())
     assert declared <= exported, sorted(declared - exported)
-    assert lib.rs_abi_version() == 4 and lib.rs_built_for_sm100a() == 1
+    assert lib.rs_abi_version() == 5 and lib.rs_built_for_sm100a() == 1
 
 
 def test_prototype_table_matches_header():

@@ -202,6 +202,16 @@ def test_logit_head(cuda_dev, B, zw, dt):
     assert_close(dZ.double().cpu().numpy(), dz @ w.astype(np.float64).T, rel, "dZ")
     assert_close(dw.cpu().numpy(), (Z.T @ dz)[:, 0], 3 * rel, "dw")
     assert_close(db.cpu().numpy(), dz.sum(0), 3 * rel, "db")
+    # deferred reduction (the trainer sums the partials on its side stream): same dw / db / loss bit for bit
+    ws = ops.logit_head_workspace(B, zw, cuda_dev)
+    dZ2, dw2, db2 = torch.empty_like(dZ), torch.full_like(dw, float("nan")), torch.full_like(db, float("nan"))
+    l2 = torch.full((1,), float("nan"), device=cuda_dev)
+    p2, _ = ops.logit_head(Zt, _t(w, cuda_dev), _t(b, cuda_dev), _t(y, cuda_dev), dZ2, dw2, db2, loss=l2, ws=ws,
+                           defer_reduce=True)
+    assert torch.isnan(dw2).all() and torch.isnan(l2).all()      # untouched until the reduce
+    ops.logit_head_reduce(ws, dw2, db2, l2, B, zw)
+    assert torch.equal(dZ2, dZ) and torch.equal(p2, p) and torch.equal(dw2, dw) and torch.equal(db2, db)
+    assert torch.equal(l2, l)
 
 
 @pytest.mark.parametrize("M,N,K", [(624, 256, 8192), (752, 1, 8192), (130, 70, 3000)])

@@ -235,6 +235,35 @@ def test_interacting_path_is_exported(cuda_dev):
     assert ops.interacting_path(39, 24, 24, 2, bf, True) == cabi.PATH_NONE       # not built at all
 
 
+@pytest.mark.parametrize("B,F", [(257, 39), (2000, 20), (3, 48)])
+def test_interacting_tc_bwd_deferred_reduce(cuda_dev, B, F):
+    """rs_interacting_bwd_scatter(dparams = NULL) + rs_interacting_bwd_reduce (the trainer runs the reduction on its
+    side stream) gives the parameter gradients of the undeferred call bit for bit, and the same dx."""
+    from recommendsystem_b200 import cabi, ops
+    L, D, U, H = 2, 16, 16, 2
+    rng = np.random.default_rng(B + F)
+    W, b, gamma, beta = [_t(a, cuda_dev) for a in interacting_params(rng, D, U)]
+    xt = _t(rng.standard_normal((B, F, D)).astype(np.float32), cuda_dev, torch.bfloat16)
+    dy = _t(rng.standard_normal((B, F, U)).astype(np.float32), cuda_dev, torch.bfloat16)
+    assert ops.interacting_path(F, D, U, H, torch.bfloat16, True) == cabi.PATH_TCGEN05
+    _, saved = ops.interacting_fwd(xt, W, b, gamma, beta, 1e-3, H, L, True, compute_bf16=True)
+    dx0, dW0, db0, dg0, dbt0 = ops.interacting_bwd(xt, saved, W, b, gamma, beta, 1e-3, H, L, dy, compute_bf16=True)
+    ref = torch.cat([dW0.reshape(-1), db0, dg0, dbt0]).clone()
+    ws = torch.empty(cabi.load().rs_interacting_workspace_bytes(B, F, D, U), dtype=torch.uint8, device=cuda_dev)
+    dx = torch.empty_like(xt)
+    st = ops._stream()
+    cabi.call("rs_interacting_bwd_scatter", xt.data_ptr(), D, 0, saved.data_ptr(), cabi.RS_BF16, W.data_ptr(), b.data_ptr(),
+              gamma.data_ptr(), beta.data_ptr(), 1e-3, dy.data_ptr(), U, 0, dx.data_ptr(), D, 0, None, None, 1, 0, None, 0,
+              None, B, F, D, U, H, L, 1, ws.data_ptr(), ws.numel(), st)
+    out = torch.full_like(ref, float("nan"))
+    cabi.call("rs_interacting_bwd_reduce", ws.data_ptr(), ws.numel(), out.data_ptr(), B, F, D, U, H, st)
+    torch.cuda.synchronize()
+    assert torch.equal(dx, dx0)
+    assert torch.equal(out, ref)
+    with pytest.raises(cabi.RsError):      # too small a workspace is refused, not read out of bounds
+        cabi.call("rs_interacting_bwd_reduce", ws.data_ptr(), 16, out.data_ptr(), B, F, D, U, H, st)
+
+
 def test_interacting_tc_bench_size(cuda_dev):
     """The benchmarked launch itself: B = 8192, F = 39, L = 3 (2731 tiles over the persistent CTAs, every
     accumulator alias and the cross-tile prefetch exercised thousands of times) forward and backward against the
