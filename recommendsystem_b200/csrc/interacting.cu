@@ -24,7 +24,7 @@ extern "C" {
 
 size_t rs_interacting_workspace_bytes(int B, int F, int D, int U) {
   (void)B; (void)F;
-  return (size_t)(sm_count() * 2) * (size_t)(D * 4 * U + 6 * U) * sizeof(float);
+  return 16 + (size_t)(sm_count() * 2) * (size_t)(D * 4 * U + 6 * U) * sizeof(float);   // 16-byte header (tensor-core bwd)
 }
 
 size_t rs_interacting_saved_bytes(int B, int F, int U, int L) {

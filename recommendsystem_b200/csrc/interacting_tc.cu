@@ -429,6 +429,9 @@ static int launch_itc_fwd(const IFwdArgs& a) {
   const int ntiles = (a.B + G::SPT - 1) / G::SPT;
   int grid = sm_count();
   if (grid * 3 > ntiles) grid = (ntiles + 2) / 3;
+  // (A grid trimmed to the number of rounds — 2731 tiles need 7 rounds of three tile streams on 148 CTAs and still 7 on
+  // 131 — leaves 17 SMs to the step's other branches.  Measured on one and two GPUs: the key sort / NCCL kernels that
+  // moved there ran 3x slower on so few SMs and slowed the step; every SM takes part.)
   ItcGather ga{};
   if (a.gather) {
     for (int r = 0; r < RS_MAX_PEERS; ++r) ga.tab[r] = r < a.gather->world ? a.gather->tables[r] : nullptr;

@@ -654,6 +654,7 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
   {
     uint32_t acc[32];
     tc_ld_32x32(tl + C_DW, acc);
+    if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<int*>(part)[-4] = (int)gridDim.x;   // header: partial blocks written
     float* mine = part + (int64_t)blockIdx.x * (D * N4 + 6 * U);
     if (row < N4) {
 #pragma unroll
@@ -671,9 +672,11 @@ interacting_tc_bwd_kernel(const T* __restrict__ x, int64_t x_ld, int64_t x_bs, c
 
 // out[i] = sum over CTAs of part[cta][i]; one warp per output, fixed order (deterministic)
 static __global__ void itb_reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out,
-                                                  int nparts, int n) {
+                                                  int max_parts, int n) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= n) return;
+  int nparts = reinterpret_cast<const int*>(part)[-4];        // written by the backward that filled `part`
+  nparts = nparts < 0 ? 0 : (nparts > max_parts ? max_parts : nparts);
   const float s = warp_ordered_sum(part + i, nparts, n);
   if ((threadIdx.x & 31) == 0) out[i] = s;
 }
@@ -681,8 +684,8 @@ static __global__ void itb_reduce_partials_kernel(const float* __restrict__ part
 constexpr int ITB_NP = 16 * 64 + 6 * 16;     // floats of one CTA's [dW | db | dgamma | dbeta] partial
 
 // CTAs of the backward (= partial blocks in the workspace): two per SM, at most one per tile of `spt` samples.
-// (A grid trimmed to the number of rounds — 274 CTAs do 2731 tiles in the same 10 rounds as 296 — was measured: the
-// freed slots did not speed the step's side branches up enough to matter, and the backward got 3 % slower.)
+// (A grid trimmed to the number of rounds — 274 CTAs do 2731 tiles in the same 10 rounds as 296 — was measured on one
+// and two GPUs: the side branches that moved into the freed slots slowed the backward by 3 - 10 %.)
 static int itb_grid(int B, int spt) {
   const int ntiles = (B + spt - 1) / spt;
   const int grid = sm_count() * 2;
@@ -701,21 +704,22 @@ static int launch_itc_bwd(const IBwdArgs& a) {
     set_error("interacting_tc_bwd: the saved activations of the tensor-core forward are required");
     return RS_ERR_INVALID;
   }
-  if (a.ws_bytes < (size_t)grid * np * sizeof(float)) {
-    set_error("interacting_tc_bwd: workspace %zu < %zu", a.ws_bytes, (size_t)grid * np * sizeof(float));
+  if (a.ws_bytes < 16 + (size_t)grid * np * sizeof(float)) {
+    set_error("interacting_tc_bwd: workspace %zu < %zu", a.ws_bytes, 16 + (size_t)grid * np * sizeof(float));
     return RS_ERR_WORKSPACE;
   }
+  float* part = (float*)a.ws + 4;              // 16-byte header: the number of partial blocks this launch writes
   ItbScatter sc{};
   if (a.scatter) {
     for (int r = 0; r < RS_MAX_PEERS; ++r) sc.recv[r] = r < a.scatter->world ? a.scatter->peer_recv[r] : nullptr;
     sc.inverse = a.scatter->inverse; sc.cap = a.scatter->cap; sc.rank = a.scatter->rank;
   }
   kern<<<grid, 128, smem, a.st>>>((const T*)a.x, a.x_ld, a.x_bs, (const float*)a.saved, a.W, a.b, a.gm, a.bt, a.eps,
-                                  (const T*)a.dy, a.dy_ld, a.dy_bs, (T*)a.dx, a.dx_ld, a.dx_bs, (float*)a.ws, a.B, a.F,
+                                  (const T*)a.dy, a.dy_ld, a.dy_bs, (T*)a.dx, a.dx_ld, a.dx_bs, part, a.B, a.F,
                                   a.L, a.use_res, (const T*)a.dx_add, sc);
   if (int e = check_launch("interacting_tc_bwd")) return e;
   if (a.dparams == nullptr) return 0;       // deferred: interacting_tc_bwd_reduce (rs_interacting_bwd_reduce)
-  itb_reduce_partials_kernel<<<(np * 32 + 255) / 256, 256, 0, a.st>>>((const float*)a.ws, a.dparams, grid, np);
+  itb_reduce_partials_kernel<<<(np * 32 + 255) / 256, 256, 0, a.st>>>(part, a.dparams, grid, np);
   return check_launch("interacting_tc_bwd_reduce");
 }
 
@@ -732,12 +736,12 @@ static int itb_spt(int F) {
 }
 
 int interacting_tc_bwd_reduce(const void* ws, size_t ws_bytes, float* dparams, int B, int F, cudaStream_t st) {
-  const int grid = itb_grid(B, itb_spt(F));
-  if (ws_bytes < (size_t)grid * ITB_NP * sizeof(float)) {
-    set_error("interacting_tc_bwd_reduce: workspace %zu < %zu", ws_bytes, (size_t)grid * ITB_NP * sizeof(float));
+  const int grid = itb_grid(B, itb_spt(F));       // upper bound; the launch recorded its own count in the header
+  if (ws_bytes < 16 + (size_t)grid * ITB_NP * sizeof(float)) {
+    set_error("interacting_tc_bwd_reduce: workspace %zu < %zu", ws_bytes, 16 + (size_t)grid * ITB_NP * sizeof(float));
     return RS_ERR_WORKSPACE;
   }
-  itb_reduce_partials_kernel<<<(ITB_NP * 32 + 255) / 256, 256, 0, st>>>((const float*)ws, dparams, grid, ITB_NP);
+  itb_reduce_partials_kernel<<<(ITB_NP * 32 + 255) / 256, 256, 0, st>>>((const float*)ws + 4, dparams, grid, ITB_NP);
   return check_launch("interacting_tc_bwd_reduce");
 }
 

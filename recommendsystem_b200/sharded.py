@@ -209,13 +209,16 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
                     ops.route_ids_padded(self.ids, F, self.rows_t, self.lbase_t, self.world, self.cap, self.send_rows,
                                          self.inverse, self.send_counts, self.overflow)
                 self.inverse_done.record(self.side2)
+                self._stamp("owners_route_end")
                 with ph("a2a_ids"):
                     self.ex.all_to_all(self.recv_rows, self.send_rows)
+                self._stamp("owners_a2a_ids_end")
                 with ph("sort_keys"):
                     cabi.call("rs_embed_gather_rows_ld", self.table.data_ptr(), self.table_ld, self.recv_rows.data_ptr(),
                               self.recv_rows.numel(), d, None, T, None, self.keys.data_ptr(), ops._stream())
                     ops.sort_keys(self.keys, self.row_bits, out=self.keys_sorted)
                 self.route_done.record(self.side2)
+                self._stamp("owners_sort_end")
             if not gather:
                 return
             with ph("embed_gather_peer"):
@@ -244,16 +247,19 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
         c = self.cfg
         d = c.embed_dim
         if self.peer_gather:
-            main.wait_event(self.route_done)   # inverse permutation + sorted keys of this step
-        if self.peer_gather:
             # gradient rows go straight into the owners' receive buffers (peer stores over NVLink): the permute
-            # and the all-to-all in one kernel; a one-element all-reduce separates the stores from the owners' reads
+            # and the all-to-all in one kernel; a flag barrier separates the stores from the owners' reads
             if not self.fused:                 # (fused: the InteractingLayer backward already stored the rows)
+                main.wait_event(self.inverse_done)
                 with ph("scatter_grads_peer"):
                     row_bytes = d * self.dX.element_size()
                     cabi.call("rs_scatter_rows_peer", self.dX.data_ptr(), ctypes.addressof(self.peer_grecv), self.world,
                               self.rank, self.inverse.data_ptr(), c.batch * c.num_fields, self.cap, row_bytes, st)
             self._barrier(ph, "peer_barrier")
+            self._stamp("push_barrier_end")
+            # the owners' sorted keys of this step (side stream: behind the forward it often finishes only now, while
+            # the barrier above — which does not need them — is already under way)
+            main.wait_event(self.route_done)
         else:
             with ph("permute_grads"):
                 self.g_send.zero_()
@@ -272,11 +278,14 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
             self.side2.wait_stream(main)
             with torch.cuda.stream(self.side2):
                 self._barrier(ph, "peer_barrier_end")
+                self._stamp("update_barrier_end")
             self._join_side2 = True
 
     def _dense_sync(self, ph):
+        self._stamp("allreduce_begin")
         with ph("allreduce_dense"):
             self.ex.all_reduce_mean(self.flat_g)
+        self._stamp("allreduce_end")
 
     def _touched_rows(self) -> torch.Tensor:
         """LOCAL arena rows the step on the current static id buffers of ALL ranks updates on this rank."""

@@ -33,15 +33,25 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--rows", type=int, default=1_000_000)
     args = ap.parse_args()
-    dev = torch.device("cuda:0")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
     cfg = AutoIntConfig(num_fields=39, rows_per_field=args.rows, embed_dim=16, unit_num=16, head_num=2, layer_num=3,
                         mlp_hidden=(256, 128), batch=args.batch, dtype="bf16")
-    g = torch.Generator(device="cpu").manual_seed(0)
+    if world > 1:       # torchrun: the row-sharded trainer (rank 0 prints its own timeline)
+        import torch.distributed as dist
+        from recommendsystem_b200.sharded import ShardedAutoIntTrainer
+        dist.init_process_group("nccl", device_id=dev)
+        make = lambda: ShardedAutoIntTrainer(cfg, dev)
+    else:
+        make = lambda: AutoIntTrainer(cfg, dev)
+    g = torch.Generator(device="cpu").manual_seed(rank)
     ids = torch.randint(0, 2 ** 40, (args.batch, 39), generator=g).to(dev)
     y = (torch.rand(args.batch, 1, generator=g) < 0.25).float().to(dev)
     out = {}
     for instrumented in (False, True):
-        tr = AutoIntTrainer(cfg, dev)
+        tr = make()
         if instrumented:
             tr.stamps = torch.zeros(64, dtype=torch.int64, device=dev)
         tr.ids.copy_(ids)
@@ -57,12 +67,17 @@ def main():
                 t = tr.stamps[:len(names)].cpu().numpy().astype(np.int64)
                 rows.append((t - t[tr.stamp_names["step_begin"]]) / 1e3)
             med = np.median(np.stack(rows), 0)
-            print(f"graph replay: {out[False] * 1e3:.1f} us plain, {out[True] * 1e3:.1f} us with {len(names)} stamps")
-            print("median time (us after step_begin) at which the stream reached each boundary:")
-            for n, v in sorted(zip(names, med), key=lambda kv: kv[1]):
-                print(f"  {v:8.1f}  {n}")
+            if rank == 0:
+                print(f"graph replay: {out[False] * 1e3:.1f} us plain, {out[True] * 1e3:.1f} us with {len(names)} stamps")
+                print("median time (us after step_begin) at which the stream reached each boundary:")
+                for n, v in sorted(zip(names, med), key=lambda kv: kv[1]):
+                    print(f"  {v:8.1f}  {n}")
         del tr
         torch.cuda.empty_cache()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
