@@ -36,6 +36,8 @@ PROTOTYPES = {
     "rs_embed_gather_peer_fwd": (_i, [_p, _i64, _i, _p, _p, _p, _i64, _i, _i, _p, _i, _p]),
     "rs_scatter_rows_peer": (_i, [_p, _p, _i, _i, _p, _i64, _i, _i, _p]),
     "rs_peer_barrier": (_i, [_p, _i, _i, _p]),
+    "rs_peer_all_to_all_i32": (_i, [_p, _p, _i, _i, _i, _p]),
+    "rs_embed_keys_from_rows": (_i, [_p, _i64, _p, _p]),
     "rs_ipc_export": (_i, [_p, _p, _p]),
     "rs_ipc_import": (_i, [_p, _u64, _p]),
     "rs_embed_sort_keys": (_i, [_p, _p, _i64, _i, _p, _sz, _p]),

@@ -28,6 +28,7 @@ is device-agnostic so that the protocol is tested on CPU with the gloo backend.
 from __future__ import annotations
 
 import ctypes
+import os
 import math
 
 import numpy as np
@@ -109,7 +110,7 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
 
     def __init__(self, cfg: AutoIntConfig, device, group=None, global_tables: torch.Tensor | None = None,
                  dense_init: dict | None = None, capacity_factor: float | None = None,
-                 peer_gather: bool | None = None, capacity: int | None = None):
+                 peer_gather: bool | None = None, capacity: int | None = None, peer_ids: bool | None = None):
         self.ex = Exchange(group)
         self.world, self.rank = self.ex.world, self.ex.rank
         self._global_tables = global_tables
@@ -135,6 +136,13 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
         if peer_gather is None:
             peer_gather = dist.get_backend(group) == "nccl" and W <= 8
         self.peer_gather = bool(peer_gather)
+        # peer_ids: the routed ids reach their owners by peer stores + a flag barrier (rs_peer_all_to_all_i32, 16 us)
+        # instead of a NCCL all-to-all (38 us).  Opt-in (argument, or RS_PEER_IDS=1): at W = 2 the owners' key sort
+        # still ends with the backward either way (it shares the tower's window with the GEMMs), the step gains 3 us,
+        # and only W = 2 was run; the NCCL exchange is the one proven at W = 8.
+        if peer_ids is None:
+            peer_ids = os.environ.get("RS_PEER_IDS", "0") == "1"
+        self.peer_ids = bool(peer_ids) and self.peer_gather
         if self.peer_gather:
             self._map_peer_tables(group)
             self.side2 = torch.cuda.Stream(device=dev)
@@ -156,6 +164,12 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
         self.flags = torch.zeros(16, dtype=torch.int32, device=self.dev)   # RS_MAX_PEERS slots + the epoch
         torch.cuda.synchronize(self.dev)
         self.peer_flags = self._map_peers(self.flags, group)
+        if self.peer_ids:
+            self.peer_recv_rows = self._map_peers(self.recv_rows, group)  # every rank's routed-id receive buffer
+            # its barrier runs on the owners' side stream, unordered with the main stream's push barrier: own flags
+            self.flags_ids = torch.zeros(16, dtype=torch.int32, device=self.dev)
+            torch.cuda.synchronize(self.dev)
+            self.peer_flags_ids = self._map_peers(self.flags_ids, group)
 
     def _barrier(self, ph, name):
         """Cross-rank barrier on the current stream: a flag kernel over peer memory (rs_peer_barrier)."""
@@ -211,11 +225,17 @@ class ShardedAutoIntTrainer(AutoIntTrainer):
                 self.inverse_done.record(self.side2)
                 self._stamp("owners_route_end")
                 with ph("a2a_ids"):
-                    self.ex.all_to_all(self.recv_rows, self.send_rows)
+                    if self.peer_ids:
+                        cabi.call("rs_peer_all_to_all_i32", self.send_rows.data_ptr(), ctypes.addressof(self.peer_recv_rows),
+                                  self.world, self.rank, self.cap, ops._stream())
+                        cabi.call("rs_peer_barrier", ctypes.addressof(self.peer_flags_ids), self.world, self.rank,
+                                  ops._stream())
+                    else:
+                        self.ex.all_to_all(self.recv_rows, self.send_rows)
                 self._stamp("owners_a2a_ids_end")
                 with ph("sort_keys"):
-                    cabi.call("rs_embed_gather_rows_ld", self.table.data_ptr(), self.table_ld, self.recv_rows.data_ptr(),
-                              self.recv_rows.numel(), d, None, T, None, self.keys.data_ptr(), ops._stream())
+                    cabi.call("rs_embed_keys_from_rows", self.recv_rows.data_ptr(), self.recv_rows.numel(),
+                              self.keys.data_ptr(), ops._stream())
                     ops.sort_keys(self.keys, self.row_bits, out=self.keys_sorted)
                 self.route_done.record(self.side2)
                 self._stamp("owners_sort_end")

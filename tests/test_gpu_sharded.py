@@ -11,12 +11,12 @@ torch = pytest.importorskip("torch")
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _run(n, *args, port=29731):
+def _run(n, *args, port=29731, env=None):
     if not torch.cuda.is_available() or torch.cuda.device_count() < n:
         pytest.skip(f"needs >= {n} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "sharded_worker.py"), *args]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=400, env=dict(os.environ, **(env or {})))
     print(r.stdout[-6000:])
     print(r.stderr[-3000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
@@ -37,6 +37,12 @@ def test_sharded_benchmarked_path(n, cap):
     the whole step in one CUDA graph, at W = 2 and W = 8, with the default bucket capacity and with buckets filled
     to the last slot; against the same-dtype single-GPU trainer on the global batch; first-step gather bit-exact."""
     _run(n, "graph", "bf16", "512", cap, port=29741 + n)
+
+
+def test_sharded_benchmarked_path_peer_id_exchange():
+    """Same check with the routed ids exchanged by peer stores + flag barrier (rs_peer_all_to_all_i32, RS_PEER_IDS=1)
+    instead of the NCCL all-to-all, buckets filled to the last slot."""
+    _run(2, "graph", "bf16", "512", "tight", port=29751, env={"RS_PEER_IDS": "1"})
 
 
 @pytest.mark.parametrize("n", [2, 8])
