@@ -10,7 +10,8 @@ reference runs in numpy float64 (forward oracle) and in torch float64 with autog
 Keras layer names (the state_dict keys of recommendsystem_b200.api.video_dnn / rough_rank_model).
 
 Parity unpinned against TensorFlow itself (no TF / tensornet offline, the reference has no golden
-vectors): see DESIGN.md §5.
+vectors): see DESIGN.md §5.  The layer-level pieces (din_b, deep_cross, cross_net, _interacting) are pinned against
+the reference's own layer code executed under a numpy stand-in of the TF ops (tests/test_oracle_reference_pin.py).
 """
 import numpy as np
 

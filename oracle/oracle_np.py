@@ -4,13 +4,19 @@ TEST INFRASTRUCTURE ONLY.  Nothing under recommendsystem_b200/ imports this
 module; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference legs may.  It is the checker, never the product.
 
-PARITY UNPINNED: the reference (yueshifeng/recommendSystem) ships no tests, no
-golden vectors and depends on TensorFlow + tensornet, neither of which is
-installable here (no network).  The functions below are line-by-line
-restatements of the reference's Python sources (cited per function, paths
-relative to the reference root); tests/golden/ holds vectors produced by THIS
-module (oracle/gen_golden.py), cross-checked against an independent torch-CPU
-restatement (oracle/oracle_torch.py).  Third-party arithmetic restated from
+PINNING: the reference (yueshifeng/recommendSystem) ships no tests, no golden
+vectors and depends on TensorFlow + tensornet, neither of which is installable
+here (no network), so parity against TensorFlow's own arithmetic stays UNPINNED.
+What IS pinned: the layer functions below (InteractingLayer, both DIN units,
+Dense stacks) reproduce, to fp64 round-off, the outputs of the reference's own
+layer files EXECUTED unmodified with `tensorflow` replaced by a numpy stand-in of
+the individual TF ops (oracle/tf_numpy_shim.py, tools/gen_reference_layer_golden.py,
+tests/golden/ref_layers.npz, tests/test_oracle_reference_pin.py) — i.e. the
+reference's composition of those ops, not a re-reading of it.  The functions are
+line-by-line restatements of the reference's Python sources (cited per function,
+paths relative to the reference root); the other tests/golden/ vectors are
+produced by THIS module (oracle/gen_golden.py), cross-checked against an
+independent torch-CPU restatement (oracle/oracle_torch.py).  Third-party arithmetic restated from
 published semantics: tf.keras.layers.Dense (y = act(x @ kernel[in,out] + bias)),
 tf.nn.softmax (last axis), tf.keras.layers.LayerNormalization (biased variance
 over the last axis, gamma/beta), tf.sequence_mask, Keras/TF Adam.

@@ -1,0 +1,147 @@
+"""Pins the oracle to the reference's own code: tests/golden/ref_layers.npz holds what the reference's layer files
+(InteractingLayer.py, din.py, staytime/layer.py, rough_rank/layer.py) RETURNED when executed unmodified on seeded fp64
+inputs / weights, with `tensorflow` replaced by the numpy stand-in oracle/tf_numpy_shim.py
+(tools/gen_reference_layer_golden.py, run where /root/reference exists).  oracle/oracle_np.py and oracle/oracle_models.py
+— the checkers of every GPU parity test — must reproduce those outputs to fp64 round-off."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_models as om
+from oracle import oracle_np as onp
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_layers.npz"))
+TOL = 1e-12
+
+
+def close(got, want, what):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    err = np.max(np.abs(got - want) / (1.0 + np.abs(want)))
+    assert err <= TOL, (what, err)
+
+
+@pytest.mark.parametrize("tag", ["cfg1", "rankctr", "nores", "h1"])
+def test_interacting_layer_matches_reference_code(tag):
+    """InteractingLayer.call (InteractingLayer.py:37-61): head split / concat order, 1/sqrt(d_head) scaling, softmax,
+    residual, relu, LayerNorm, the SAME four Dense layers re-applied layer_num times; with and without use_res."""
+    H, L, res = (int(v) for v in G[f"inter_{tag}_cfg"])
+    y = onp.interacting_fwd(G[f"inter_{tag}_x"], G[f"inter_{tag}_W"], G[f"inter_{tag}_b"], G[f"inter_{tag}_gamma"],
+                            G[f"inter_{tag}_beta"], float(G[f"inter_{tag}_eps"]), H, L, use_res=bool(res))
+    close(y, G[f"inter_{tag}_y"], f"InteractingLayer {tag}")
+
+
+def test_interacting_layer_models_restatement_matches_reference_code():
+    """The second restatement (oracle_models._interacting, used by the composed-model oracles) against the same run."""
+    tag = "rankctr"
+    H, L, _ = (int(v) for v in G[f"inter_{tag}_cfg"])
+    W, b = G[f"inter_{tag}_W"], G[f"inter_{tag}_b"]
+    U = W.shape[1] // 4
+    P = {}
+    for j, n in enumerate(["query", "key", "value", "res"]):
+        P[f"il.{n}_dense_kernel"], P[f"il.{n}_dense_bias"] = W[:, j * U:(j + 1) * U], b[j * U:(j + 1) * U]
+    P["il.layer_norm_gamma"], P["il.layer_norm_beta"] = G[f"inter_{tag}_gamma"], G[f"inter_{tag}_beta"]
+    try:
+        y = om._interacting(om.NP, G[f"inter_{tag}_x"], P, "il", H, L, eps=float(G[f"inter_{tag}_eps"]))
+    except KeyError as e:       # parameter naming of the restatement differs: report it instead of passing silently
+        pytest.fail(f"oracle_models._interacting parameter names changed: {e}")
+    close(y, G[f"inter_{tag}_y"], "oracle_models._interacting")
+
+
+def test_din_a_matches_reference_code():
+    """din.py:18-47 incl. tf.sequence_mask lengths 0 / 1 / T."""
+    y = onp.din_a_fwd(G["dina_q"], G["dina_keys"], G["dina_values"], G["dina_seq_len"], G["dina_W1"], G["dina_b1"],
+                      G["dina_W2"], G["dina_b2"])
+    close(y, G["dina_y"], "DIN A")
+
+
+def test_din_b_matches_reference_code():
+    """staytime/layer.py:16-41 incl. a mask wider than the sequence (tf.slice) and a fully masked row."""
+    T = G["dinb_facts"].shape[1]
+    y = onp.din_b_fwd(G["dinb_q"], G["dinb_facts"], G["dinb_mask"][:, :T], G["dinb_W1"], G["dinb_b1"], G["dinb_W2"],
+                      G["dinb_b2"])
+    close(y, G["dinb_y"], "DIN B (oracle_np)")
+    P = {"d.layer_1_kernel": G["dinb_W1"], "d.layer_1_bias": G["dinb_b1"], "d.layer_2_kernel": G["dinb_W2"],
+         "d.layer_2_bias": G["dinb_b2"]}
+    close(om.din_b(om.NP, G["dinb_q"], G["dinb_facts"], G["dinb_mask"], P, "d"), G["dinb_y"], "DIN B (oracle_models)")
+
+
+def test_cross_layers_match_reference_code():
+    """DeepCrossLayer.call (staytime/layer.py:66-72) and CrossNet.call (rough_rank/layer.py:256-264)."""
+    P = {}
+    for i in range(3):
+        P[f"c.W.{i}"], P[f"c.b.{i}"] = G["dcross_W"][i], G["dcross_b"][i]
+    close(om.deep_cross(om.NP, G["dcross_x"], P, "c", 3), G["dcross_y"], "DeepCrossLayer")
+    P = {}
+    for i in range(2):
+        P[f"n.kernels.{i}"], P[f"n.bias.{i}"] = G["cnet_k"][i], G["cnet_b"][i]
+    close(om.cross_net(om.NP, G["cnet_x"], P, "n", 2), G["cnet_y"], "CrossNet")
+
+
+def test_fm_and_dnn_match_reference_code():
+    """FMLayer.call (staytime/layer.py:100-111) and DNN.call (rough_rank/layer.py:100-109, output_activation)."""
+    x = G["fm_x"]
+    s = x.sum(1)
+    close(0.5 * (s * s - (x * x).sum(1)).sum(-1, keepdims=True), G["fm_y"], "FMLayer")
+    h = G["dnn_x"]
+    for i, act in enumerate(["relu", "relu", "sigmoid"]):
+        h = onp.dense(h, G[f"dnn_k{i}"], G[f"dnn_b{i}"], act)
+    close(h, G["dnn_y"], "DNN")
+
+
+def test_video_dnn_sub_model_matches_reference_code():
+    """The whole dense graph of BASELINE configs[4]: staytime/VideoDnn.py::create_moe_sub_model (DIN x3, SENet on a
+    stop-gradient copy, FM, FFM, PPNet-gated experts, MMoE gates, DeepCross, 400-way stay-time head, two towers) as the
+    reference's own Keras functional code computed it on seeded inputs — against oracle_models.video_dnn_fwd, the checker
+    of the VideoDnn GPU parity tests.  18 slots (every user / item / bias slot), T = 5, units (16, 8)."""
+    slots, seq_slots = [str(s) for s in G["vd_slots"]], [str(s) for s in G["vd_seq_slots"]]
+    embs = {s: G[f"vd_emb_{s}"] for s in slots}
+    seqs = {s: (G[f"vd_seq_{s}"], G[f"vd_mask_{s}"]) for s in seq_slots}
+    P = {k[len("vd_P_"):]: G[k] for k in G.files if k.startswith("vd_P_")}
+    out = om.video_dnn_fwd(om.NP, embs, seqs, P, slots, seq_slots, units=(16, 8))
+    pre = "video_id_rank_staytime_mtl_ppnet_v7_"
+    close(out["staytime"], G["vd_train_" + pre + "staytime"], "VideoDnn stay-time distribution + expectation")
+    close(out["staytime_pred"], G["vd_predict_" + pre + "staytime"], "VideoDnn stay-time prediction")
+    close(out["shortplay"], G["vd_train_" + pre + "shortplay"], "VideoDnn shortplay")
+    close(out["longplay"], G["vd_train_" + pre + "longplay"], "VideoDnn longplay")
+    p = np.asarray(G["vd_train_" + pre + "staytime"])[:, :400]
+    assert p.max() < 0.9 and p.min() > 1e-12          # the fixture's softmax is not saturated
+
+
+def test_autoint_multihead_sub_model_matches_reference_code():
+    """BASELINE configs[3]: rank/multi_head/multidnn.py::create_autoint_sub_model (its own InteractingLayer copy, the
+    DNN, 8 experts of which the first 7 are mixed, 7 softmax gates, 7 sigmoid heads in MultiLabelInfo.label_list order)
+    as the reference's code computed it (dropout layers at inference) — against oracle_models.autoint_multihead_fwd."""
+    assert [str(v) for v in G["ai_labels"]] == om.AUTOINT_LABELS
+    P = {k[len("ai_P_"):]: G[k] for k in G.files if k.startswith("ai_P_")}
+    y = om.autoint_multihead_fwd(om.NP, list(G["ai_embs"]), P, deep_hidden_units=(32, 16), dropout=None,
+                                 eps=float(G["ai_eps"]))
+    close(y, G["ai_y"], "AUTOINT sub-model")
+    assert "expert_7_fc1.kernel" in P          # the eighth expert the reference builds and never uses (:80-92)
+
+
+def test_ple_matches_reference_code():
+    """PLE.call (rough_rank/layer.py:211-224) as create_tower builds it (2 tasks, 4 shared + 4 specific experts of one
+    Dense(32, relu) each, softmax gates over the 8 experts) — against oracle_models.ple (the DSSM oracle's towers)."""
+    P = {k[len("ple_P_"):]: G[k] for k in G.files if k.startswith("ple_P_")}
+    ys = om.ple(om.NP, G["ple_x"], P, "p", 2, 4, 4)
+    close(np.stack(ys), G["ple_y"], "PLE")
+
+
+def test_losses_match_reference_code():
+    """cross_entropy (rank/ctr/base_model.py:7-12) against oracle_np.bce_loss (the checker of the fused head kernel), and
+    the product's own stay-time losses (api/video_dnn.py, plain torch: they run on CPU tensors) against
+    staytime/model.py:20-60 as the reference's code evaluated them."""
+    loss, _ = onp.bce_loss(G["bce_p"], G["bce_y"])
+    close(loss, G["bce_loss"], "cross_entropy (rank/ctr)")
+    torch = pytest.importorskip("torch")
+    from recommendsystem_b200.api import video_dnn as V
+    t = lambda k: torch.from_numpy(np.asarray(G[k], np.float64))
+    close(V.custom_kl_loss(t("kl_y"), t("kl_p")).numpy(), G["kl_loss"], "custom_kl_loss")
+    ce = -t("ce_y") * torch.log(t("ce_p") + 1e-6) - (1 - t("ce_y")) * torch.log(1.0 - t("ce_p") + 1e-6)
+    close(ce.numpy(), G["ce_loss"], "cross_entropy (staytime) formula")
+    got = V.cross_entropy(t("ce_y"), t("ce_p")).numpy()           # the product casts labels to fp32 like the reference
+    assert np.max(np.abs(got - G["ce_loss"])) <= 1e-6
+    assert abs(float(V.mse_loss(t("mse_y"), t("mse_p"))) - float(G["mse_loss"])) <= 1e-6       # labels cast to fp32
+    close(V.huber_loss(t("mse_y"), t("mse_p")).numpy(), G["huber_loss"], "huber_loss")
