@@ -6,7 +6,7 @@ tests/test_oracle_reference_pin.py checks oracle/oracle_np.py + oracle/oracle_mo
 then pinned to the reference's own code path (its order of splits, concats, masks, residuals), with only the meaning of
 each individual TF op restated here.  Each op follows its documented TensorFlow semantics:
 
-  tf.concat / split (equal parts) / transpose(perm) / reshape / tile / squeeze / expand_dims / slice / where / equal /
+  tf.concat / split (n equal parts, or a list of sizes) / transpose(perm) / reshape / tile / squeeze / expand_dims / slice / where / equal /
   zeros_like / ones_like / square / identity / clip_by_value / shape / newaxis / tensordot / matmul (batched, transpose_b)
   tf.math.reduce_sum(axis, keepdims); tf.nn.softmax (last axis) / relu / sigmoid / bias_add; tf.sequence_mask
   tf.keras.layers.Layer (build on first call, add_weight), Dense, Dropout (inference: identity), Activation, Flatten,
@@ -65,6 +65,8 @@ def concat(values, axis):
 
 
 def split(value, num_or_size_splits, axis=0):
+    if isinstance(num_or_size_splits, (list, tuple)):          # tf: a list holds the SIZES of the parts
+        num_or_size_splits = np.cumsum([int(n) for n in num_or_size_splits])[:-1]
     return [T(p) for p in np.split(np.asarray(value), num_or_size_splits, axis=axis)]
 
 
@@ -154,6 +156,27 @@ def _activation(a):
 # ---------------------------------------------------------------------------------------------- keras
 LAYERS = []        # every layer the executed reference code created, in creation order (weights are read back by name)
 FEEDS = {}         # name -> array handed out by tn.layers.Input(name=...)
+WEIGHT_LOG = []    # every weight array in creation order: with the seed, a run's weights can be re-drawn (replay_weights)
+
+
+def draw_weight(rng, shape):
+    """The shim's one initialiser: matrices ~ N(0, 1/fan_in) so that deep stacks keep O(1) activations (no saturated
+    softmax hiding an error), everything else (biases, gamma - 1, beta, vectors) ~ N(0, 0.3^2)."""
+    shape = tuple(int(s) for s in shape)
+    scale = 1.0 / np.sqrt(shape[0]) if len(shape) == 2 and shape[0] > 1 else 0.3
+    return rng.standard_normal(shape) * scale
+
+
+def replay_weights(seed_, manifest):
+    """Re-draws the weights of a run from its seed and its manifest [[key, shape, offset], ...] (creation order; key ""
+    = a weight the oracle has no name for): the fixtures store the manifest instead of megabytes of random numbers."""
+    rng = np.random.default_rng(int(seed_))
+    P = {}
+    for key, shape, offset in manifest:
+        w = draw_weight(rng, shape) + float(offset)
+        if key:
+            P[key] = w
+    return P
 
 
 class Layer:
@@ -167,11 +190,9 @@ class Layer:
         self.built = True
 
     def add_weight(self, name=None, shape=None, initializer=None, regularizer=None, trainable=True, **kw):
-        shape = tuple(int(s) for s in shape)
-        # matrices ~ 1/sqrt(fan_in) so that deep stacks keep O(1) activations (no saturated softmax hiding an error)
-        scale = 1.0 / np.sqrt(shape[0]) if len(shape) == 2 and shape[0] > 1 else 0.3
-        w = T(_RNG.standard_normal(shape) * scale)
+        w = T(draw_weight(_RNG, shape))
         self._w[name] = w
+        WEIGHT_LOG.append(w)
         return w
 
     def __call__(self, *args, **kwargs):
@@ -256,7 +277,8 @@ class Model:
 
 
 def Input(name=None, **kwargs):
-    return T(FEEDS[name])
+    v = FEEDS.get(name)
+    return T(np.zeros((0,))) if v is None else T(v)       # id inputs feed nothing in the dense graphs: placeholder
 
 
 class LayerNormalization(Layer):

@@ -15,6 +15,14 @@ G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "
 TOL = 1e-12
 
 
+def weights(prefix):
+    """The weights the reference's layers drew in that run: re-drawn from (seed, creation-order manifest) instead of
+    being stored (oracle/tf_numpy_shim.py::replay_weights), keyed by the oracle's parameter names."""
+    import json
+    from oracle.tf_numpy_shim import replay_weights
+    return replay_weights(int(G[prefix + "_seed"]), json.loads(str(G[prefix + "_manifest"])))
+
+
 def close(got, want, what):
     got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
     assert got.shape == want.shape, (what, got.shape, want.shape)
@@ -98,7 +106,7 @@ def test_video_dnn_sub_model_matches_reference_code():
     slots, seq_slots = [str(s) for s in G["vd_slots"]], [str(s) for s in G["vd_seq_slots"]]
     embs = {s: G[f"vd_emb_{s}"] for s in slots}
     seqs = {s: (G[f"vd_seq_{s}"], G[f"vd_mask_{s}"]) for s in seq_slots}
-    P = {k[len("vd_P_"):]: G[k] for k in G.files if k.startswith("vd_P_")}
+    P = weights("vd")
     out = om.video_dnn_fwd(om.NP, embs, seqs, P, slots, seq_slots, units=(16, 8))
     pre = "video_id_rank_staytime_mtl_ppnet_v7_"
     close(out["staytime"], G["vd_train_" + pre + "staytime"], "VideoDnn stay-time distribution + expectation")
@@ -114,7 +122,7 @@ def test_autoint_multihead_sub_model_matches_reference_code():
     DNN, 8 experts of which the first 7 are mixed, 7 softmax gates, 7 sigmoid heads in MultiLabelInfo.label_list order)
     as the reference's code computed it (dropout layers at inference) — against oracle_models.autoint_multihead_fwd."""
     assert [str(v) for v in G["ai_labels"]] == om.AUTOINT_LABELS
-    P = {k[len("ai_P_"):]: G[k] for k in G.files if k.startswith("ai_P_")}
+    P = weights("ai")
     y = om.autoint_multihead_fwd(om.NP, list(G["ai_embs"]), P, deep_hidden_units=(32, 16), dropout=None,
                                  eps=float(G["ai_eps"]))
     close(y, G["ai_y"], "AUTOINT sub-model")
@@ -145,3 +153,21 @@ def test_losses_match_reference_code():
     assert np.max(np.abs(got - G["ce_loss"])) <= 1e-6
     assert abs(float(V.mse_loss(t("mse_y"), t("mse_p"))) - float(G["mse_loss"])) <= 1e-6       # labels cast to fp32
     close(V.huber_loss(t("mse_y"), t("mse_p")).numpy(), G["huber_loss"], "huber_loss")
+
+
+def test_rank_ctr_production_model_matches_reference_code():
+    """rank/ctr: base_model.py::BaseModel.__init__ (SingleSlot slicing of the config's features into structure / bias /
+    gate columns) + model_init.py::Model.model_layer (SENet on a stop-gradient copy, one linear map per field,
+    InteractingLayer, PPNet gates split 256|64|8|256|64|8|32|16, CAN co-action with per-sample 8x6 and 6x4 matrices,
+    gated experts, MMoE, two towers, clip) executed as they are on the synthetic config of the GPU parity test — against
+    oracle_models.rank_ctr_layout + rank_ctr_fwd."""
+    import json
+    cfg = json.loads(str(G["rc_config"]))
+    me, st, b, gt = om.rank_ctr_layout(cfg)
+    emb = {k[len("rc_emb_"):]: G[k] for k in G.files if k.startswith("rc_emb_")}
+    assert all(v.shape[1] == me for v in emb.values())
+    P = weights("rc")
+    out = om.rank_ctr_fwd(om.NP, emb, P, st, b, gt)
+    close(out["task0"], G["rc_task0"], "rank/ctr click")
+    close(out["task1"], G["rc_task1"], "rank/ctr effect_click")
+    assert 1e-3 < float(np.min(G["rc_task0"])) and float(np.max(G["rc_task0"])) < 1 - 1e-3      # not saturated / clipped

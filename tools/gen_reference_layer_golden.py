@@ -7,6 +7,7 @@
     staytime/VideoDnn.py::create_moe_sub_model            (the whole dense graph of BASELINE configs[4], Keras functional
                                                            code run eagerly on seeded inputs)
     rank/multi_head/multidnn.py::create_autoint_sub_model (BASELINE configs[3]; with rank/multi_head/interacting_layer.py)
+    rank/ctr/base_model.py::BaseModel.__init__ + model_init.py::Model.model_layer  (the production rank/ctr model)
     rank/ctr/base_model.py::cross_entropy, staytime/model.py::custom_kl_loss / cross_entropy / mse_loss / huber_loss
 
 TensorFlow is not installable offline, so `tensorflow` is replaced by oracle/tf_numpy_shim.py — a numpy fp64 stand-in
@@ -45,6 +46,16 @@ def load(path, name, package=None):
     sys.modules[name] = mod
     spec.loader.exec_module(mod)
     return mod
+
+
+def manifest(keys_by_id):
+    """[[oracle key | "", shape, offset], ...] of the weights drawn since the last shim.seed, in creation order."""
+    import json
+    rows = []
+    for w in shim.WEIGHT_LOG:
+        key, off = keys_by_id.get(id(w), ("", 0.0))
+        rows.append([key, list(w.shape), off])
+    return np.asarray(json.dumps(rows))
 
 
 def main():
@@ -158,7 +169,7 @@ def main():
     seq_slots = sorted(cfgm.Config.SEQ_SLOTS)
     Bv, Tv = 6, 5
     shim.seed(16)
-    del shim.LAYERS[:]
+    del shim.LAYERS[:], shim.WEIGHT_LOG[:]
     feats = {s: types.SimpleNamespace(feature_id=s) for s in slots + seq_slots}
     for s_ in slots:
         shim.FEEDS[s_] = 0.3 * rng.standard_normal((Bv, 32))
@@ -174,15 +185,17 @@ def main():
         out["vd_train_" + k_] = np.asarray(v_)
     for k_, v_ in models["sub_model_predict"].outputs.items():
         out["vd_predict_" + k_] = np.asarray(v_)
-    # weights by the layer names the reference gave them (the oracle's / the product's state_dict keys)
+    # weights: re-drawn by the test from (seed, manifest); keyed by the layer names the reference gave them (the
+    # oracle's / the product's state_dict keys)
+    ids = {}
     for layer in shim.LAYERS:
         n_ = layer.name
         if isinstance(layer, stay.DIN):
-            out[f"vd_P_din.{n_}.layer_1_kernel"], out[f"vd_P_din.{n_}.layer_1_bias"] = layer.layer_1.kernel, layer.layer_1.bias
-            out[f"vd_P_din.{n_}.layer_2_kernel"], out[f"vd_P_din.{n_}.layer_2_bias"] = layer.layer_2.kernel, layer.layer_2.bias
+            for a_, d_ in (("layer_1", layer.layer_1), ("layer_2", layer.layer_2)):
+                ids[id(d_.kernel)], ids[id(d_.bias)] = (f"din.{n_}.{a_}_kernel", 0.0), (f"din.{n_}.{a_}_bias", 0.0)
         elif isinstance(layer, stay.DeepCrossLayer):
             for i in range(layer.num_layer):
-                out[f"vd_P_cross.W.{i}"], out[f"vd_P_cross.b.{i}"] = layer.W[i], layer.bias[i]
+                ids[id(layer.W[i])], ids[id(layer.bias[i])] = (f"cross.W.{i}", 0.0), (f"cross.b.{i}", 0.0)
         elif isinstance(layer, shim.Dense) and n_:
             if n_.startswith("ffm_"):
                 key = "ffm." + n_
@@ -196,7 +209,8 @@ def main():
                 key = "tower_out." + n_
             else:
                 key = n_
-            out[f"vd_P_{key}.kernel"], out[f"vd_P_{key}.bias"] = layer.kernel, layer.bias
+            ids[id(layer.kernel)], ids[id(layer.bias)] = (key + ".kernel", 0.0), (key + ".bias", 0.0)
+    out["vd_seed"], out["vd_manifest"] = np.asarray(16), manifest(ids)
     out["vd_slots"], out["vd_seq_slots"] = np.asarray(slots), np.asarray(seq_slots)
 
     # ---- the dense graph of BASELINE configs[3]: rank/multi_head/multidnn.py::create_autoint_sub_model (InteractingLayer
@@ -222,7 +236,7 @@ def main():
     il = load("rank/multi_head/interacting_layer.py", "interact_multihead_autoint_alllabel.model.interacting_layer")
     md = load("rank/multi_head/multidnn.py", "ref_multidnn")
     shim.seed(17)
-    del shim.LAYERS[:]
+    del shim.LAYERS[:], shim.WEIGHT_LOG[:]
     Ba, Fa = 5, 39
     embs_a = [0.5 * rng.standard_normal((Ba, 8)) for _ in range(Fa)]
     for i_, e_ in enumerate(embs_a):
@@ -231,16 +245,96 @@ def main():
     out["ai_embs"] = np.stack(embs_a)
     out["ai_y"] = np.concatenate([np.asarray(o) for o in model.outputs], 1)
     out["ai_labels"] = np.asarray(sys.modules["src.pipeline.multi_label"].MultiLabelInfo.label_list)
+    ids = {}
     for layer in shim.LAYERS:
         if isinstance(layer, il.InteractingLayer):
             for nm in ("query", "key", "value", "res"):
                 d_ = getattr(layer, nm + "_dense")
-                out[f"ai_P_interacting_layer.{nm}_dense_kernel"], out[f"ai_P_interacting_layer.{nm}_dense_bias"] = d_.kernel, d_.bias
-            out["ai_P_interacting_layer.layer_norm_gamma"] = np.asarray(layer.layer_norm.gamma)
-            out["ai_P_interacting_layer.layer_norm_beta"] = np.asarray(layer.layer_norm.beta)
+                ids[id(d_.kernel)], ids[id(d_.bias)] = (f"interacting_layer.{nm}_dense_kernel", 0.0), (f"interacting_layer.{nm}_dense_bias", 0.0)
+            ids[id(layer.layer_norm._w["gamma"])] = ("interacting_layer.layer_norm_gamma", 1.0)
+            ids[id(layer.layer_norm._w["beta"])] = ("interacting_layer.layer_norm_beta", 0.0)
             out["ai_eps"] = np.asarray(layer.layer_norm.eps)
         elif isinstance(layer, shim.Dense) and layer.name:
-            out[f"ai_P_{layer.name}.kernel"], out[f"ai_P_{layer.name}.bias"] = layer.kernel, layer.bias
+            ids[id(layer.kernel)], ids[id(layer.bias)] = (layer.name + ".kernel", 0.0), (layer.name + ".bias", 0.0)
+    out["ai_seed"], out["ai_manifest"] = np.asarray(17), manifest(ids)
+
+    # ---- the production model of rank/ctr: base_model.py::BaseModel.__init__ (slot slicing) + model_init.py::Model.
+    # model_layer (SENet, per-field linear maps, InteractingLayer, PPNet gates, CAN co-action, gated experts, MMoE, two
+    # towers), on the small model_config of the GPU parity test (tests/util_models.py::rank_ctr_config)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import json
+    import util_models as um
+    cfg_rc = um.rank_ctr_config(np.random.default_rng(2))
+    Brc = 4
+
+    class Feature:
+        def __init__(self, feature_id=None, feature_slot=None, sparse=True, **kw):
+            self.feature_id = feature_id
+
+        def __lt__(self, other):
+            return self.feature_id < other.feature_id
+
+    class EmbeddingFeatures:
+        def __init__(self, cols, opt, name=None):
+            self.dim = cols[0][1]
+
+        def __call__(self, inputs):
+            embs_ = {}
+            for fea_id in inputs:
+                embs_[fea_id] = shim.T(0.3 * rng.standard_normal((Brc, self.dim)))
+                shim.FEEDS["emb_%s" % fea_id] = embs_[fea_id]
+            return embs_
+    tnm = sys.modules["tensornet"]
+    tnm.feature_column = types.SimpleNamespace(FeatureSlot=lambda s_: s_, Feature=Feature,
+                                               category_column=lambda key, bucket_size: key)
+    tnm.core = types.SimpleNamespace(Adam=lambda **kw: None)
+    tnm.layers.EmbeddingFeatures = EmbeddingFeatures
+    sys.modules["tensorflow"].feature_column = types.SimpleNamespace(
+        embedding_column=lambda col, dimension, combiner: (col, dimension))
+    stub("rcpkg")
+    stub("rcpkg.common_module")
+    stub("rcpkg.common_module.interacting_layer", InteractingLayer=inter.InteractingLayer)
+    stub("rcpkg.common_module.multi_dense_layer", MultiLayerDense=None)       # imported, its only use is commented out
+    load("rank/ctr/base_model.py", "rcpkg.base_model", package="rcpkg")
+    mi = load("rank/ctr/model_init.py", "rcpkg.model_init", package="rcpkg")
+    shim.seed(19)
+    del shim.LAYERS[:], shim.WEIGHT_LOG[:]
+    shim.FEEDS.clear()
+    model = mi.Model(cfg_rc)
+    model.model_layer()
+    out["rc_config"] = np.asarray(json.dumps(cfg_rc))
+    for k_, v_ in shim.FEEDS.items():
+        out["rc_" + k_] = np.asarray(v_)
+    for i_, t_ in enumerate(['video_id_rank_hp_ctr_addfeasetwo_click', 'video_id_rank_hp_ctr_addfeasetwo_effect_click']):
+        out["rc_task%d" % i_] = np.asarray(model.output[t_])
+    ids = {}
+    unnamed = [l_ for l_ in shim.LAYERS if isinstance(l_, shim.Dense) and not l_.name and l_.units == 1]
+    for layer in shim.LAYERS:
+        n_ = layer.name
+        if isinstance(layer, inter.InteractingLayer):
+            for nm in ("query", "key", "value", "res"):
+                d_ = getattr(layer, nm + "_dense")
+                ids[id(d_.kernel)], ids[id(d_.bias)] = (f"interact.{nm}_dense_kernel", 0.0), (f"interact.{nm}_dense_bias", 0.0)
+            ids[id(layer.layer_norm._w["gamma"])] = ("interact.layer_norm_gamma", 1.0)
+            ids[id(layer.layer_norm._w["beta"])] = ("interact.layer_norm_beta", 0.0)
+            out["rc_eps"] = np.asarray(layer.layer_norm.eps)
+        elif isinstance(layer, shim.Dense) and n_:
+            if n_.startswith("emb_linear_map_"):
+                key = "emb_linear_map." + n_[len("emb_linear_map_"):]
+            elif n_ in ("dnn_0", "dnn_1"):
+                key = "dnn." + n_[4:]
+            elif n_.startswith("expert_output_") or (n_.startswith("gate_") and n_.count("_") == 3):
+                key = "experts." + n_
+            elif n_.startswith("gate_"):
+                key = "task_gates." + n_
+            elif n_.startswith("task") and "_dnn2_" in n_:
+                key = "task_dnn2." + n_
+            else:
+                key = n_
+            ids[id(layer.kernel)], ids[id(layer.bias)] = (key + ".kernel", 0.0), (key + ".bias", 0.0)
+    for i_, layer in enumerate(unnamed):                                    # the two unnamed Dense(1, sigmoid) heads (:156)
+        ids[id(layer.kernel)], ids[id(layer.bias)] = ("task_out.%d.kernel" % i_, 0.0), ("task_out.%d.bias" % i_, 0.0)
+    out["rc_seed"], out["rc_manifest"] = np.asarray(19), manifest(ids)
 
     # ---- the losses: rank/ctr/base_model.py:7-12, rank/multi_head/model.py:18-22, staytime/model.py:20-60
     base = load("rank/ctr/base_model.py", "ref_rank_ctr_base_model")
