@@ -171,3 +171,20 @@ def test_rank_ctr_production_model_matches_reference_code():
     close(out["task0"], G["rc_task0"], "rank/ctr click")
     close(out["task1"], G["rc_task1"], "rank/ctr effect_click")
     assert 1e-3 < float(np.min(G["rc_task0"])) and float(np.max(G["rc_task0"])) < 1 - 1e-3      # not saturated / clipped
+
+
+def test_headline_autoint_model_matches_reference_code():
+    """THE benchmarked model (BASELINE configs[0] / [1]): /root/reference/autoint::AutoInt.model_layer — 39 fields x 16
+    stacked on axis 1, InteractingLayer(layer_num=3, unit_num=16, head_num=2), Flatten, DNN 256-128 on the flattened
+    fields, concat [deep | autoint], Dense(1, sigmoid), clip_by_value(1e-6, 1) — executed on BaseModel's own field list,
+    against oracle_np.autoint_fwd_bwd (the checker of the trainer's parity tests and of smoke())."""
+    W = weights("hl")
+    P = {"Wqkvr": np.concatenate([W[n + "_kernel"] for n in ("query", "key", "value", "res")], 1),
+         "bqkvr": np.concatenate([W[n + "_bias"] for n in ("query", "key", "value", "res")]),
+         "gamma": W["gamma"], "beta": W["beta"], "mlp_W": [W["mlp_W0"], W["mlp_W1"]], "mlp_b": [W["mlp_b0"], W["mlp_b1"]],
+         "out_W": W["out_W"], "out_b": W["out_b"]}
+    X = G["hl_X"]
+    y = np.zeros((X.shape[0], 1))
+    res = onp.autoint_fwd_bwd(X, P, y, 2, 3, float(G["hl_eps"]))
+    p_raw = res["p_raw"] if "p_raw" in res else res["logits"]
+    close(np.clip(p_raw, 1e-6, 1.0), G["hl_p"], "AutoInt.model_layer")

@@ -8,6 +8,8 @@
                                                            code run eagerly on seeded inputs)
     rank/multi_head/multidnn.py::create_autoint_sub_model (BASELINE configs[3]; with rank/multi_head/interacting_layer.py)
     rank/ctr/base_model.py::BaseModel.__init__ + model_init.py::Model.model_layer  (the production rank/ctr model)
+    autoint::AutoInt.model_layer                          (THE HEADLINE MODEL, BASELINE configs[0] / [1]; MultiLayerDense,
+                                                           a file missing from the reference tree, restated as a Dense stack)
     rank/ctr/base_model.py::cross_entropy, staytime/model.py::custom_kl_loss / cross_entropy / mse_loss / huber_loss
 
 TensorFlow is not installable offline, so `tensorflow` is replaced by oracle/tf_numpy_shim.py — a numpy fp64 stand-in
@@ -335,6 +337,59 @@ def main():
     for i_, layer in enumerate(unnamed):                                    # the two unnamed Dense(1, sigmoid) heads (:156)
         ids[id(layer.kernel)], ids[id(layer.bias)] = ("task_out.%d.kernel" % i_, 0.0), ("task_out.%d.bias" % i_, 0.0)
     out["rc_seed"], out["rc_manifest"] = np.asarray(19), manifest(ids)
+
+    # ---- THE HEADLINE MODEL: /root/reference/autoint::AutoInt.model_layer on BaseModel's field list (39 fields x 16,
+    # InteractingLayer x3 / 2 heads, DNN 256-128, Dense(1, sigmoid), clip) — BASELINE configs[0] / configs[1].
+    # `.common_module.multi_dense_layer.MultiLayerDense` is imported by the reference but NOT in its tree: restated here as
+    # what its call sites say (units list + one activation: a stack of Dense layers).
+    class MultiLayerDense(shim.Layer):
+        def __init__(self, units, activation=None, **kw):
+            super().__init__()
+            self.stack = [shim.Dense(u, activation=activation, name="mld_%d" % i) for i, u in enumerate(units)]
+
+        def build(self, input_shape):
+            self.built = True
+
+        def call(self, x):
+            for d_ in self.stack:
+                x = d_(x)
+            return x
+    sys.modules["rcpkg.common_module.multi_dense_layer"].MultiLayerDense = MultiLayerDense
+    import importlib.machinery
+    loader = importlib.machinery.SourceFileLoader("rcpkg.autoint", os.path.join(REF, "autoint"))
+    spec = importlib.util.spec_from_loader("rcpkg.autoint", loader)
+    am = importlib.util.module_from_spec(spec)
+    am.__package__ = "rcpkg"
+    sys.modules["rcpkg.autoint"] = am
+    loader.exec_module(am)
+    Fh, Bh = 39, 4
+    cfg_h = {"feature_slot": {"sparse_feature": {"f%02d" % i: {"emb_size": 16, "slot_id": [str(1000 + i)]} for i in range(Fh)},
+                              "sequence_feature": {}, "dense_feature": {}},
+             "model_param": {"interact": {"layer_num": 3, "unit_num": 16, "head_num": 2, "use_dropout": False,
+                                          "dropout_rate": 0.0, "use_res": True},
+                             "mlp": {"hidden_units": [256, 128], "activation": "relu"},
+                             "logits": {"hidden_units": [1], "activation": "sigmoid"}}}
+    shim.seed(20)
+    del shim.LAYERS[:], shim.WEIGHT_LOG[:]
+    shim.FEEDS.clear()
+    model = am.AutoInt(cfg_h)
+    model.model_layer()
+    out["hl_X"] = np.stack([np.asarray(shim.FEEDS["emb_%d" % (1000 + i)]) for i in range(Fh)], 1)     # [B, F, 16]
+    out["hl_p"] = np.asarray(model.output)
+    ids = {}
+    mlds = [l_ for l_ in shim.LAYERS if isinstance(l_, MultiLayerDense)]
+    for layer in shim.LAYERS:
+        if isinstance(layer, inter.InteractingLayer):
+            for nm in ("query", "key", "value", "res"):
+                d_ = getattr(layer, nm + "_dense")
+                ids[id(d_.kernel)], ids[id(d_.bias)] = (f"{nm}_kernel", 0.0), (f"{nm}_bias", 0.0)
+            ids[id(layer.layer_norm._w["gamma"])] = ("gamma", 1.0)
+            ids[id(layer.layer_norm._w["beta"])] = ("beta", 0.0)
+            out["hl_eps"] = np.asarray(layer.layer_norm.eps)
+    for i_, d_ in enumerate(mlds[0].stack):
+        ids[id(d_.kernel)], ids[id(d_.bias)] = ("mlp_W%d" % i_, 0.0), ("mlp_b%d" % i_, 0.0)
+    ids[id(mlds[1].stack[0].kernel)], ids[id(mlds[1].stack[0].bias)] = ("out_W", 0.0), ("out_b", 0.0)
+    out["hl_seed"], out["hl_manifest"] = np.asarray(20), manifest(ids)
 
     # ---- the losses: rank/ctr/base_model.py:7-12, rank/multi_head/model.py:18-22, staytime/model.py:20-60
     base = load("rank/ctr/base_model.py", "ref_rank_ctr_base_model")
