@@ -114,7 +114,7 @@ def slice_(t, begin, size):
     return T(t[idx])
 
 
-def where(cond, x, y):
+def where(cond, x, y, name=None):
     return T(np.where(np.asarray(cond).astype(bool), np.asarray(x), np.asarray(y)))
 
 
@@ -270,10 +270,39 @@ class Lambda(Layer):
 
 
 class Model:
-    """tn.model.Model / tf.keras.Model of an eagerly executed functional graph: keeps the outputs."""
+    """tn.model.Model / tf.keras.Model of an eagerly executed functional graph: keeps the outputs; calling it (the
+    reference applies a sub-model to the tensors its Inputs were registered with) hands them back."""
 
     def __init__(self, inputs=None, outputs=None, name=None, **kwargs):
-        self.inputs, self.outputs, self.name = inputs, outputs, name
+        self.inputs, self.outputs, self.output, self.name = inputs, outputs, outputs, name
+
+    def __call__(self, *args, **kwargs):
+        return self.outputs
+
+
+def identity(t, name=None):
+    """tf.identity.  A NAMED result is also registered as FEEDS["shallow_<name>"]: rough_rank/model.py feeds the towers'
+    named outputs to create_shallow_tower's Inputs of exactly that name (:72-73, :157-163)."""
+    t = T(t)
+    if name is not None:
+        t.name = name + ":0"
+        FEEDS.setdefault("shallow_" + name, t)
+    return t
+
+
+def cast(t, dtype):
+    a = np.asarray(t)
+    return T(a.astype(bool)) if dtype in ("bool", bool) else T(a.astype(np.float64))
+
+
+class MeanSquaredError:
+    """tf.keras.losses.MeanSquaredError(reduction=NONE): mean over the last axis."""
+
+    def __init__(self, reduction=None, **kw):
+        pass
+
+    def __call__(self, y_true, y_pred):
+        return T(np.mean((np.asarray(y_pred) - np.asarray(y_true)) ** 2, axis=-1))
 
 
 def Input(name=None, **kwargs):
@@ -310,7 +339,10 @@ def install():
     tf.zeros_like = lambda t: T(np.zeros_like(np.asarray(t)))
     tf.ones_like = lambda t: T(np.ones_like(np.asarray(t)))
     tf.square = lambda t: T(np.square(np.asarray(t)))
-    tf.identity = lambda t, name=None: T(t)
+    tf.identity = identity
+    tf.sigmoid = sigmoid
+    tf.add = lambda a, b: T(np.asarray(a) + np.asarray(b))
+    tf.greater = lambda a, b: T(np.asarray(a) > np.asarray(b))
     tf.clip_by_value = lambda t, lo, hi: T(np.clip(np.asarray(t), lo, hi))
     tf.newaxis = None
     tf.multiply = lambda a, b, name=None: T(np.asarray(a) * np.asarray(b))
@@ -322,7 +354,7 @@ def install():
                                                                 keepdims=keepdims))
     tf.math = types.SimpleNamespace(reduce_sum=reduce_sum, reduce_mean=reduce_mean, log=lambda t: T(np.log(np.asarray(t))))
     tf.reduce_sum, tf.reduce_mean = reduce_sum, reduce_mean
-    tf.cast = lambda t, dtype: T(np.asarray(t).astype(np.float64))      # the reference only casts labels to float
+    tf.cast = cast                                                       # labels -> float (fp64 here), masks -> bool
     tf.abs = lambda t: T(np.abs(np.asarray(t)))
     tf.summary = types.SimpleNamespace(scalar=lambda *a, **k: None)
     tf.nn = types.SimpleNamespace(softmax=softmax, relu=relu, sigmoid=sigmoid,
@@ -354,6 +386,7 @@ def install():
     python.keras = pkeras
     tf.python = python
     keras.Model = Model
+    keras.losses = types.SimpleNamespace(MeanSquaredError=MeanSquaredError, Reduction=types.SimpleNamespace(NONE="none"))
     # tensornet (the reference's parameter-server framework): only what the dense sub-graph builders touch
     tn = types.ModuleType("tensornet")
     tn.layers = types.SimpleNamespace(Input=Input)

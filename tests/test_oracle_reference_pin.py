@@ -188,3 +188,19 @@ def test_headline_autoint_model_matches_reference_code():
     res = onp.autoint_fwd_bwd(X, P, y, 2, 3, float(G["hl_eps"]))
     p_raw = res["p_raw"] if "p_raw" in res else res["logits"]
     close(np.clip(p_raw, 1e-6, 1.0), G["hl_p"], "AutoInt.model_layer")
+
+
+def test_dssm_matches_reference_code():
+    """rough_rank/model.py::DSSM on the reference's own feature lists (rough_rank/config): user tower (PLE with two tasks,
+    one of the two heads selected per sample by the dense feature 4575), item tower, teacher (CrossNet + DNN), the
+    shallow student tower on the two tower embeddings and the distillation loss — against oracle_models.dssm_fwd."""
+    user_ids, item_ids = [str(v) for v in G["ds_user_ids"]], [str(v) for v in G["ds_item_ids"]]
+    embs = {k: G["ds_emb_" + k] for k in user_ids + item_ids}
+    out = om.dssm_fwd(om.NP, embs, G["ds_mask"], weights("ds"), user_ids, item_ids)
+    close(out["user_emb"], G["ds_user_emb"], "DSSM user tower")
+    close(out["item_emb"], G["ds_item_emb"], "DSSM item tower")
+    close(out["teacher"], G["ds_teacher"], "DSSM teacher")
+    close(out["student"], G["ds_student"], "DSSM student")
+    close(out["distill"], G["ds_distill"], "DSSM distillation loss")
+    sel = G["ds_mask"].ravel() == 1
+    assert sel.any() and (~sel).any()                 # both user heads are exercised

@@ -8,6 +8,7 @@
                                                            code run eagerly on seeded inputs)
     rank/multi_head/multidnn.py::create_autoint_sub_model (BASELINE configs[3]; with rank/multi_head/interacting_layer.py)
     rank/ctr/base_model.py::BaseModel.__init__ + model_init.py::Model.model_layer  (the production rank/ctr model)
+    rough_rank/model.py::DSSM                             (user / item / teacher / shallow towers + distillation)
     autoint::AutoInt.model_layer                          (THE HEADLINE MODEL, BASELINE configs[0] / [1]; MultiLayerDense,
                                                            a file missing from the reference tree, restated as a Dense stack)
     rank/ctr/base_model.py::cross_entropy, staytime/model.py::custom_kl_loss / cross_entropy / mse_loss / huber_loss
@@ -390,6 +391,79 @@ def main():
         ids[id(d_.kernel)], ids[id(d_.bias)] = ("mlp_W%d" % i_, 0.0), ("mlp_b%d" % i_, 0.0)
     ids[id(mlds[1].stack[0].kernel)], ids[id(mlds[1].stack[0].bias)] = ("out_W", 0.0), ("out_b", 0.0)
     out["hl_seed"], out["hl_manifest"] = np.asarray(20), manifest(ids)
+
+    # ---- DSSM (rough_rank/model.py::DSSM): user tower (PLE, 2 tasks, selected per sample by the dense feature 4575),
+    # item tower (PLE), teacher (CrossNet + DNN), shallow student tower on the two tower outputs, distillation loss —
+    # on the reference's own feature lists (rough_rank/config)
+    stub("rrpkg")
+    stub("rrpkg.config").__path__ = [os.path.join(REF, "rough_rank", "config")]
+    stub("rrpkg.sub")
+    load("rough_rank/config/feature_id.py", "rrpkg.config.feature_id", package="rrpkg.config")
+    rcfg = load("rough_rank/config/config.py", "rrpkg.config.config", package="rrpkg.config")
+    sys.modules["rrpkg.config"].config = rcfg
+    sys.modules["rrpkg.sub.layer"] = rough
+    Bd = 5
+    dense_mask = np.array([[1.0], [0.0], [1.0], [0.0], [0.0]])
+
+    class Feature2:
+        def __init__(self, feature_id=None, feature_slot=None, sparse=True, feature_name=None, **kw):
+            self.feature_id, self.feature_name = feature_id, feature_name
+
+    class EmbeddingFeatures2:
+        def __init__(self, cols, opt, name=None):
+            self.cols = cols
+
+        def __call__(self, inputs):
+            embs_ = {}
+            for key, dim in self.cols:
+                embs_[key] = shim.T(0.3 * rng.standard_normal((Bd, dim)))
+                for tower in ("user", "item", "teacher"):
+                    shim.FEEDS["emb_%s_%s" % (tower, key)] = embs_[key]
+            return embs_
+    tnm.feature_column = types.SimpleNamespace(FeatureSlot=lambda s_: s_, Feature=Feature2,
+                                               category_column=lambda key, bucket_size: key)
+    tnm.layers.EmbeddingFeatures = EmbeddingFeatures2
+    shim.seed(21)
+    del shim.LAYERS[:], shim.WEIGHT_LOG[:]
+    shim.FEEDS.clear()
+    shim.FEEDS["dense_weight_4575"] = dense_mask
+    dm = load("rough_rank/model.py", "rrpkg.sub.model", package="rrpkg.sub")
+    models = dm.DSSM()
+    outs = models["train"].outputs
+    user_ids, item_ids = [str(v) for v in rcfg.USER_FEATURE_IDS], [str(v) for v in rcfg.ITEM_FEATURE_IDS]
+    out["ds_user_ids"], out["ds_item_ids"], out["ds_mask"] = np.asarray(user_ids), np.asarray(item_ids), dense_mask
+    for k_ in rcfg.USER_FEATURE_IDS + rcfg.ITEM_FEATURE_IDS:
+        out["ds_emb_%s" % k_] = np.asarray(shim.FEEDS["emb_teacher_%s" % k_])
+    out["ds_student"], out["ds_teacher"], out["ds_distill"] = (np.asarray(outs[k_]) for k_ in ("student", "teacher", "distill"))
+    out["ds_user_emb"] = np.asarray(shim.FEEDS["shallow_user_emb_output"])
+    out["ds_item_emb"] = np.asarray(shim.FEEDS["shallow_item_emb_output"])
+    ids = {}
+
+    def dnn_keys(net, key):
+        for i_ in range(len(net.kernels)):
+            ids[id(net.kernels[i_])], ids[id(net.bias[i_])] = ("%s.kernels.%d" % (key, i_), 0.0), ("%s.bias.%d" % (key, i_), 0.0)
+    teacher_dense = [l_ for l_ in shim.LAYERS if isinstance(l_, shim.Dense) and not l_.name]
+    for i_, d_ in enumerate(teacher_dense):                     # Dense(128), Dense(64), Dense(16) of create_tower_teacher
+        ids[id(d_.kernel)], ids[id(d_.bias)] = ("teacher.dense%d.kernel" % i_, 0.0), ("teacher.dense%d.bias" % i_, 0.0)
+    for layer in shim.LAYERS:
+        n_ = layer.name
+        if isinstance(layer, rough.PLE):
+            tower = n_[len("ple_"):]
+            for e_, net in enumerate(layer.shared_expert_nets):
+                dnn_keys(net, "%s.ple.shared_expert_nets.%d" % (tower, e_))
+            for t_ in range(layer.num_tasks):
+                for e_, net in enumerate(layer.specific_expert_nets[t_]):
+                    dnn_keys(net, "%s.ple.specific_expert_nets.%d.%d" % (tower, t_, e_))
+                dnn_keys(layer.gate_nets[t_], "%s.ple.gate_nets.%d" % (tower, t_))
+        elif isinstance(layer, rough.DNN) and n_ in ("td_user_emb", "hpld_user_emb", "item_emb"):
+            dnn_keys(layer, {"td_user_emb": "user.heads.0", "hpld_user_emb": "user.heads.1", "item_emb": "item.heads.0"}[n_])
+        elif isinstance(layer, rough.CrossNet):
+            for i_ in range(layer.layer_num):
+                ids[id(layer.kernels[i_])], ids[id(layer.bias[i_])] = ("teacher.cross.kernels.%d" % i_, 0.0), ("teacher.cross.bias.%d" % i_, 0.0)
+        elif isinstance(layer, shim.Dense) and n_:
+            key = {"pred_teacher": "teacher.pred", "shallow_dnn_0": "shallow.shallow_dnn_0", "logit_shallow": "shallow.logit_shallow"}[n_]
+            ids[id(layer.kernel)], ids[id(layer.bias)] = (key + ".kernel", 0.0), (key + ".bias", 0.0)
+    out["ds_seed"], out["ds_manifest"] = np.asarray(21), manifest(ids)
 
     # ---- the losses: rank/ctr/base_model.py:7-12, rank/multi_head/model.py:18-22, staytime/model.py:20-60
     base = load("rank/ctr/base_model.py", "ref_rank_ctr_base_model")
