@@ -156,6 +156,7 @@ def _activation(a):
 # ---------------------------------------------------------------------------------------------- keras
 LAYERS = []        # every layer the executed reference code created, in creation order (weights are read back by name)
 FEEDS = {}         # name -> array handed out by tn.layers.Input(name=...)
+PARSED = {}        # what tf.io.parse_example returns (staytime/parse.py)
 WEIGHT_LOG = []    # every weight array in creation order: with the seed, a run's weights can be re-drawn (replay_weights)
 
 
@@ -357,6 +358,19 @@ def install():
     tf.cast = cast                                                       # labels -> float (fp64 here), masks -> bool
     tf.abs = lambda t: T(np.abs(np.asarray(t)))
     tf.summary = types.SimpleNamespace(scalar=lambda *a, **k: None)
+    # staytime/parse.py::parse_input_func: the parsed example is handed in ready (PARSED), the label arithmetic runs here
+    import re as _re
+    tf.io = types.SimpleNamespace(FixedLenFeature=lambda *a, **k: None, VarLenFeature=lambda *a, **k: None,
+                                  parse_example=lambda proto, desc: dict(PARSED))
+    tf.string, tf.int64 = "string", "int64"
+    tf.divide = lambda a, b: T(np.asarray(a, np.float64) / np.asarray(b, np.float64))
+    tf.repeat = lambda t, n, axis=None: T(np.repeat(np.asarray(t), int(n), axis=axis))
+    tf.math.subtract = lambda a, b: T(np.asarray(a) - np.asarray(b))
+    tf.math.square = lambda t: T(np.square(np.asarray(t)))
+    tf.math.abs = lambda t: T(np.abs(np.asarray(t)))
+    tf.math.exp = lambda t: T(np.exp(np.asarray(t)))
+    tf.strings = types.SimpleNamespace(regex_full_match=lambda t, pat: T(np.vectorize(
+        lambda v: _re.fullmatch(pat, v.decode() if isinstance(v, bytes) else str(v)) is not None)(np.asarray(t))))
     tf.nn = types.SimpleNamespace(softmax=softmax, relu=relu, sigmoid=sigmoid,
                                   bias_add=lambda x, b: T(np.asarray(x) + np.asarray(b)))
     layers = types.ModuleType("tensorflow.keras.layers")

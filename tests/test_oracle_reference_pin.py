@@ -204,3 +204,15 @@ def test_dssm_matches_reference_code():
     close(out["distill"], G["ds_distill"], "DSSM distillation loss")
     sel = G["ds_mask"].ravel() == 1
     assert sel.any() and (~sel).any()                 # both user heads are exercised
+
+
+def test_staytime_labels_match_reference_code():
+    """staytime/parse.py::parse_input_func (:30-68) executed on a hand-made parsed example: short / long play thresholds
+    at 7000 / 18000 ms (strict), the 160 s cap, the 400-bin gaussian label scaled by the bin width, the clipped watch
+    time in column 400 and the x5 landing-page sample weight — against oracle_metrics.staytime_labels (fp64), the
+    checker of rs_staytime_labels."""
+    from oracle import oracle_metrics as omet
+    lab, sh, lo, w = omet.staytime_labels(G["lab_watch"], G["lab_landing"].astype(np.int64), dtype=np.float64)
+    close(lab, G["lab_staytime"], "stay-time label")
+    assert np.array_equal(sh, G["lab_short"]) and np.array_equal(lo, G["lab_long"])
+    close(w, G["lab_weight"], "sample weight")

@@ -9,6 +9,7 @@
     rank/multi_head/multidnn.py::create_autoint_sub_model (BASELINE configs[3]; with rank/multi_head/interacting_layer.py)
     rank/ctr/base_model.py::BaseModel.__init__ + model_init.py::Model.model_layer  (the production rank/ctr model)
     rough_rank/model.py::DSSM                             (user / item / teacher / shallow towers + distillation)
+    staytime/parse.py::parse_input_func                   (the label transform; tf.io.parse_example handed in ready)
     autoint::AutoInt.model_layer                          (THE HEADLINE MODEL, BASELINE configs[0] / [1]; MultiLayerDense,
                                                            a file missing from the reference tree, restated as a Dense stack)
     rank/ctr/base_model.py::cross_entropy, staytime/model.py::custom_kl_loss / cross_entropy / mse_loss / huber_loss
@@ -487,6 +488,20 @@ def main():
     ym, pm = rng.random((7, 1)) * 4, rng.random((7, 1)) * 3
     out.update(mse_y=ym, mse_p=pm, mse_loss=np.asarray(smod.mse_loss(shim.T(ym), shim.T(pm))),
                huber_loss=np.asarray(smod.huber_loss(shim.T(ym), shim.T(pm))))
+
+    # ---- the label transform: staytime/parse.py::parse_input_func (watch time -> short / long play labels, the 400-bin
+    # gaussian stay-time label + clipped watch time, landing-page sample weight) on a hand-made parsed example
+    pr = load("staytime/parse.py", "ref_staytime_parse")
+    watch = np.array([0, 6999, 7000, 7001, 18000, 18001, 65432, 159999, 160000, 160001, 400000, 12345], np.int64)
+    extra = np.array(["label", "x_video_homepage_landing_y", "video_homepage_landing", "other", "label", "label",
+                      "a video_homepage_landing", "label", "label", "label", "zzz", "label"])
+    shim.PARSED.clear()
+    shim.PARSED.update(extra_info=shim.T(extra), video_duration=shim.T(watch), watch_duration=shim.T(watch))
+    _, y_lab, w_lab = pr.parse_input_func(None)
+    pre_ = "video_id_rank_staytime_mtl_ppnet_v7_"
+    out.update(lab_watch=watch, lab_landing=np.array(["video_homepage_landing" in e_ for e_ in extra]),
+               lab_staytime=np.asarray(y_lab[pre_ + "staytime"]), lab_short=np.asarray(y_lab[pre_ + "shortplay"]),
+               lab_long=np.asarray(y_lab[pre_ + "longplay"]), lab_weight=np.asarray(w_lab))
 
     np.savez_compressed(OUT, **{k: np.asarray(v) for k, v in out.items()})
     print("wrote", OUT, len(out), "arrays,", os.path.getsize(OUT), "bytes")
