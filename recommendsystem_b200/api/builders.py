@@ -83,6 +83,17 @@ class _KerasDense(nn.Module):
         return dense(x, self.kernel, self.bias, self.activation)
 
 
+def fused_dense(x, layers, activation):
+    """Dense layers of the reference that read the SAME input (the per-expert / per-gate first layers of the MMoE blocks,
+    staytime/VideoDnn.py:130-164, rank/multi_head/multidnn.py:80-99) evaluated as ONE GEMM over their kernels laid side by
+    side — x is read once, the input gradient is one dgrad GEMM instead of one per layer plus their sum.  The layers keep
+    their own parameters (Keras names, state_dict keys); returns [.., sum(units)], split it with `[l.units for l in layers]`."""
+    for l in layers:
+        if l.kernel is None:
+            l(x[:1])                                  # first call: creates kernel / bias exactly as the layer itself would
+    return dense(x, torch.cat([l.kernel for l in layers], dim=1), torch.cat([l.bias for l in layers]), activation)
+
+
 # rank/multi_head/multidnn.py:206-209 MultiLabelInfo.label_list: the names (and order) of the 7 outputs
 AUTOINT_LABELS = ["like_pred", "click_comment_pred", "comment_pred", "click_sharing_pred", "follow_pred",
                   "click_avatar_pred", "unlike_pred"]
@@ -118,14 +129,22 @@ class AutoIntSubModel(nn.Module):
         for i in range(self.n_deep):
             deep = getattr(self, "dnn_%d" % i)(deep)                      # :62-63
         result = torch.cat([deep, autoint], dim=1)                        # :72
-        # every expert is evaluated as the reference builds it; only [0:7] feed the gates (:92)
-        experts = [getattr(self, "expert_%d_fc1" % i)(result) for i in range(self.expert_num + 1)]
-        experts = torch.stack(experts[: self.expert_num], dim=1)
-        preds = []
-        for i, label in enumerate(AUTOINT_LABELS):
-            gate = getattr(self, "gate_%d_fc2" % i)(result).unsqueeze(-1)             # :97-104
-            preds.append(getattr(self, label)((experts * gate).sum(dim=1)))           # :106-116, heads :118-206
-        return torch.cat(preds, dim=1)                                    # [B,7] in label_list order
+        # every expert is evaluated as the reference builds it; only [0:7] feed the gates (:92).  The 8 experts
+        # (Dense(32, relu)) and the 7 gates (Dense(7, softmax)) all read `result`: one GEMM each group
+        B, E, L = result.shape[0], self.expert_num, self.NUM_LABELS
+        ex_layers = [getattr(self, "expert_%d_fc1" % i) for i in range(E + 1)]
+        experts = fused_dense(result, ex_layers, "relu").view(B, E + 1, ex_layers[0].units)[:, :E]       # [B,7,32]
+        gates = fused_dense(result, [getattr(self, "gate_%d_fc2" % i) for i in range(L)], None)
+        gates = torch.softmax(gates.view(B, L, E), dim=-1)                                              # :97-99
+        mixed = (experts.unsqueeze(1) * gates.unsqueeze(-1)).sum(dim=2)                                  # :104-108 [B,L,32]
+        # the 7 sigmoid heads Dense(1) (:118-206): pred_l = sigmoid(mixed_l . w_l + b_l)
+        heads = [getattr(self, label) for label in AUTOINT_LABELS]
+        for l, h in enumerate(heads):
+            if h.kernel is None:
+                h(mixed[:1, l])
+        Wh = torch.stack([h.kernel[:, 0] for h in heads], dim=0)                                         # [L,32]
+        bh = torch.cat([h.bias for h in heads])
+        return torch.sigmoid((mixed * Wh.unsqueeze(0)).sum(dim=-1) + bh)  # [B,7] in label_list order
 
 
 class ModelResult:

@@ -17,7 +17,7 @@ from typing import Dict, Sequence
 import torch
 from torch import nn
 
-from .builders import _KerasDense
+from .builders import _KerasDense, fused_dense
 from .optim import DenseAdam, _world_group
 from .embedding import AdaGrad, EmbeddingFeatures, category_column, embedding_column
 from .staytime_config import Config as C
@@ -124,19 +124,25 @@ class VideoDnnSubModel(nn.Module):
         concated = torch.cat([reweight.reshape(B, n * 16), cross_term, mult, ffm] + din_embs, dim=-1)   # :122-123
         gate_input = G.index_select(1, bidx)[:, :, 16:].reshape(B, -1)                                # :126
         # PPNet-gated experts (:130-148)
+        # layers that read the same tensor run as ONE GEMM over their kernels side by side (fused_dense): the first
+        # expert layer of every expert and the first gate layer of every task all read `concated` (six Dense(relu));
+        # the first PPNet gate layer of every (expert, level) reads `gate_input` (six Dense(relu))
+        E, T, nu = C.num_experts, C.num_tasks, len(self.units)
+        first = [self.experts["expert_output_%d_0" % i] for i in range(E)] + [self.task_gates["gate_%d_0" % i] for i in range(T)]
+        first_out = torch.split(fused_dense(concated, first, "relu"), [l.units for l in first], dim=1)
+        g1 = [self.experts["gate_%d_%d_1" % (i, j)] for i in range(E) for j in range(nu)]
+        g1_out = torch.split(fused_dense(gate_input, g1, "relu"), [l.units for l in g1], dim=1)
         expert_outs = []
-        for i in range(C.num_experts):
+        for i in range(E):
             deep = concated
-            for j in range(len(self.units)):
-                g = self.experts["gate_%d_%d_2" % (i, j)](self.experts["gate_%d_%d_1" % (i, j)](gate_input)) * 2.0
-                deep = g * self.experts["expert_output_%d_%d" % (i, j)](deep)
+            for j in range(nu):
+                g = self.experts["gate_%d_%d_2" % (i, j)](g1_out[i * nu + j]) * 2.0
+                deep = g * (first_out[i] if j == 0 else self.experts["expert_output_%d_%d" % (i, j)](deep))
             expert_outs.append(deep)
         expert_concat = torch.stack(expert_outs, dim=1)                                               # [B, E, dim]
         mmoe = []
-        for i in range(C.num_tasks):                                                                  # :153-164
-            go = concated
-            for j in range(2):
-                go = self.task_gates["gate_%d_%d" % (i, j)](go)
+        for i in range(T):                                                                            # :153-164
+            go = self.task_gates["gate_%d_1" % i](first_out[E + i])
             go = self.task_gates["gate_output_%d" % i](go).unsqueeze(-1)
             mmoe.append((expert_concat * go).sum(dim=1))
         # stay-time head: 400-way softmax + expectation over the bins (:167-179)
