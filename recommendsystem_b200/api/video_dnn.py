@@ -114,13 +114,18 @@ class VideoDnnSubModel(nn.Module):
         cross_term = sum_embs * sum_embs - (reweight * reweight).sum(1)
         fm_logit = 0.5 * cross_term.sum(-1, keepdim=True)
         # FFM (:117-120, 11-25)
+        # (the |ys| projections of one user slot read the same 16 columns, and so do the |xs| projections of one item slot:
+        # one GEMM per slot instead of one per pair, then ONE product over the [x, y, dim] grid)
         ffm = []
         for xs, ys, dim in FFM_SLOTS:
-            for x in xs:
-                for y in ys:
-                    ffm.append(self.ffm["ffm_x_%s_%s_%d" % (x, y, dim)](general[:, pos[x], :].contiguous()) *
-                               self.ffm["ffm_y_%s_%s_%d" % (x, y, dim)](general[:, pos[y], :].contiguous()))
-        ffm = torch.cat(ffm, dim=-1)
+            gx = [general[:, pos[x], :].contiguous() for x in xs]
+            gy = [general[:, pos[y], :].contiguous() for y in ys]
+            px = torch.stack([fused_dense(gx[i], [self.ffm["ffm_x_%s_%s_%d" % (x, y, dim)] for y in ys], None)
+                              for i, x in enumerate(xs)], dim=1).view(B, len(xs), len(ys), dim)       # [B, x, y, dim]
+            py = torch.stack([fused_dense(gy[j], [self.ffm["ffm_y_%s_%s_%d" % (x, y, dim)] for x in xs], None)
+                              .view(B, len(xs), dim) for j, y in enumerate(ys)], dim=2)               # [B, x, y, dim]
+            ffm.append((px * py).reshape(B, -1))                                                      # x-major, as :14-21
+        ffm = torch.cat(ffm, dim=-1) if len(ffm) > 1 else ffm[0]
         concated = torch.cat([reweight.reshape(B, n * 16), cross_term, mult, ffm] + din_embs, dim=-1)   # :122-123
         gate_input = G.index_select(1, bidx)[:, :, 16:].reshape(B, -1)                                # :126
         # PPNet-gated experts (:130-148)
