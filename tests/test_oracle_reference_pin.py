@@ -204,6 +204,9 @@ def test_dssm_matches_reference_code():
     close(out["distill"], G["ds_distill"], "DSSM distillation loss")
     sel = G["ds_mask"].ravel() == 1
     assert sel.any() and (~sel).any()                 # both user heads are exercised
+    # the product's resolved feature lists (api/rough_rank_model.py::config) are what rough_rank/config evaluates to
+    from recommendsystem_b200.api.rough_rank_model import config as C
+    assert list(C.USER_FEATURE_IDS) == user_ids and list(C.ITEM_FEATURE_IDS) == item_ids
 
 
 def test_staytime_labels_match_reference_code():
