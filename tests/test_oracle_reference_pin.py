@@ -219,3 +219,21 @@ def test_staytime_labels_match_reference_code():
     close(lab, G["lab_staytime"], "stay-time label")
     assert np.array_equal(sh, G["lab_short"]) and np.array_equal(lo, G["lab_long"])
     close(w, G["lab_weight"], "sample weight")
+
+
+def test_reference_arm_model_matches_reference_code():
+    """oracle_torch.AutoIntCPU — the model that `bench.py --impl reference` and `cpu_baseline` TIME on the host cores —
+    computes what the reference's own autoint::AutoInt.model_layer computed (and its loss is the reference's
+    cross_entropy): the baseline the speed-up is quoted against is the reference's graph, not a lighter stand-in."""
+    torch = pytest.importorskip("torch")
+    from oracle import oracle_torch as ot
+    W = weights("hl")
+    t = lambda a: torch.from_numpy(np.asarray(a, np.float64))
+    params = {"Wqkvr": t(np.concatenate([W[n + "_kernel"] for n in ("query", "key", "value", "res")], 1)),
+              "bqkvr": t(np.concatenate([W[n + "_bias"] for n in ("query", "key", "value", "res")])),
+              "gamma": t(W["gamma"]), "beta": t(W["beta"]), "mlp_W0": t(W["mlp_W0"]), "mlp_b0": t(W["mlp_b0"]),
+              "mlp_W1": t(W["mlp_W1"]), "mlp_b1": t(W["mlp_b1"]), "out_W": t(W["out_W"]), "out_b": t(W["out_b"])}
+    X = t(G["hl_X"])
+    model = ot.AutoIntCPU(torch.zeros(1, X.shape[-1], dtype=torch.float64), params, 2, 3, float(G["hl_eps"]))
+    close(model.forward(X).detach().numpy(), G["hl_p"], "AutoIntCPU.forward")
+    close(float(ot.cross_entropy(t(G["bce_y"]), t(G["bce_p"]))), G["bce_loss"], "oracle_torch.cross_entropy")
