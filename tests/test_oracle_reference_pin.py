@@ -237,3 +237,27 @@ def test_reference_arm_model_matches_reference_code():
     model = ot.AutoIntCPU(torch.zeros(1, X.shape[-1], dtype=torch.float64), params, 2, 3, float(G["hl_eps"]))
     close(model.forward(X).detach().numpy(), G["hl_p"], "AutoIntCPU.forward")
     close(float(ot.cross_entropy(t(G["bce_y"]), t(G["bce_p"]))), G["bce_loss"], "oracle_torch.cross_entropy")
+
+
+def test_oracle_gradients_are_the_derivative_of_the_pinned_forward():
+    """The reference has no backward code (TensorFlow differentiates its graph); the oracle's analytic InteractingLayer
+    backward — the checker of the CUDA backward kernels — must therefore be THE derivative of the forward that is pinned
+    above: central differences of the pinned forward along random directions in x and in every parameter, fp64, on the
+    reference-run configuration (39 fields x 16, 3 layers, 2 heads)."""
+    tag = "cfg1"
+    H, L, res = (int(v) for v in G[f"inter_{tag}_cfg"])
+    x, W, b = G[f"inter_{tag}_x"], G[f"inter_{tag}_W"], G[f"inter_{tag}_b"]
+    gamma, beta, eps = G[f"inter_{tag}_gamma"], G[f"inter_{tag}_beta"], float(G[f"inter_{tag}_eps"])
+    rng = np.random.default_rng(5)
+    dy = rng.standard_normal(G[f"inter_{tag}_y"].shape)
+    f = lambda x_, W_, b_, g_, bt_: float((onp.interacting_fwd(x_, W_, b_, g_, bt_, eps, H, L, use_res=bool(res)) * dy).sum())
+    dx, dW, db, dg, dbt = onp.interacting_bwd(x, W, b, gamma, beta, eps, H, L, dy, use_res=bool(res))
+    args, grads = [x, W, b, gamma, beta], [dx, dW, db, dg, dbt]
+    h = 1e-6
+    for i, (a, g) in enumerate(zip(args, grads)):
+        v = rng.standard_normal(a.shape)
+        plus = [q + h * v if j == i else q for j, q in enumerate(args)]
+        minus = [q - h * v if j == i else q for j, q in enumerate(args)]
+        num = (f(*plus) - f(*minus)) / (2 * h)
+        ana = float((np.asarray(g).reshape(a.shape) * v).sum())
+        assert abs(num - ana) <= 1e-6 * max(1.0, abs(ana)), (i, num, ana)
