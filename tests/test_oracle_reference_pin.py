@@ -153,6 +153,11 @@ def test_losses_match_reference_code():
     assert np.max(np.abs(got - G["ce_loss"])) <= 1e-6
     assert abs(float(V.mse_loss(t("mse_y"), t("mse_p"))) - float(G["mse_loss"])) <= 1e-6       # labels cast to fp32
     close(V.huber_loss(t("mse_y"), t("mse_p")).numpy(), G["huber_loss"], "huber_loss")
+    # the 7-label loss of rank/multi_head/model.py:18-22 (sum over the labels, keepdims) and its batch-mean form of
+    # rank/ctr/base_model.py:7-12, as api.builders.cross_entropy (what AUTOINT.train_step / RankCtrNet minimise)
+    from recommendsystem_b200.api.builders import cross_entropy
+    close(cross_entropy(t("ce7_y"), t("ce7_p")).numpy(), G["ce7_loss"], "cross_entropy (multi_head)")
+    close(float(cross_entropy(t("bce_y"), t("bce_p"), reduce_mean=True)), G["bce_loss"], "cross_entropy (rank/ctr form)")
 
 
 def test_rank_ctr_production_model_matches_reference_code():

@@ -489,6 +489,14 @@ def main():
     out.update(mse_y=ym, mse_p=pm, mse_loss=np.asarray(smod.mse_loss(shim.T(ym), shim.T(pm))),
                huber_loss=np.asarray(smod.huber_loss(shim.T(ym), shim.T(pm))))
 
+    # ---- rank/multi_head/model.py::cross_entropy (:18-22): per-sample sum over the 7 labels, keepdims
+    stub("interact_multihead_autoint_alllabel.model.config", Config=types.SimpleNamespace(LINEAR_SLOTS=[], DENSE_SLOTS=[]))
+    stub("interact_multihead_autoint_alllabel.model.mutiDnnAutointOrigin", AUTOINT=md.AUTOINT)
+    mh = load("rank/multi_head/model.py", "ref_multi_head_model")
+    y7 = (rng.random((6, 7)) < 0.3).astype(np.float64)
+    p7 = np.clip(rng.random((6, 7)), 1e-6, 1.0)
+    out.update(ce7_y=y7, ce7_p=p7, ce7_loss=np.asarray(mh.cross_entropy(shim.T(y7), shim.T(p7))))
+
     # ---- the label transform: staytime/parse.py::parse_input_func (watch time -> short / long play labels, the 400-bin
     # gaussian stay-time label + clipped watch time, landing-page sample weight) on a hand-made parsed example
     pr = load("staytime/parse.py", "ref_staytime_parse")
