@@ -266,3 +266,31 @@ def test_oracle_gradients_are_the_derivative_of_the_pinned_forward():
         num = (f(*plus) - f(*minus)) / (2 * h)
         ana = float((np.asarray(g).reshape(a.shape) * v).sum())
         assert abs(num - ana) <= 1e-6 * max(1.0, abs(ana)), (i, num, ana)
+
+
+def test_gradient_oracles_forward_matches_reference_code():
+    """The GPU tests take their GRADIENT references from torch autograd through the same model restatements evaluated in
+    the torch namespace (oracle_models.TH, fp64).  Their forward — the function autograd differentiates — reproduces the
+    reference-code outputs too, for all four composed graphs."""
+    torch = pytest.importorskip("torch")
+    import json
+    t = lambda a: torch.from_numpy(np.asarray(a, np.float64))
+    tP = lambda prefix: {k: t(v) for k, v in weights(prefix).items()}
+    pre = "video_id_rank_staytime_mtl_ppnet_v7_"
+    slots, seq_slots = [str(s) for s in G["vd_slots"]], [str(s) for s in G["vd_seq_slots"]]
+    out = om.video_dnn_fwd(om.TH, {s: t(G[f"vd_emb_{s}"]) for s in slots},
+                           {s: (t(G[f"vd_seq_{s}"]), torch.from_numpy(G[f"vd_mask_{s}"])) for s in seq_slots}, tP("vd"),
+                           slots, seq_slots, units=(16, 8))
+    close(out["staytime"].numpy(), G["vd_train_" + pre + "staytime"], "VideoDnn (torch)")
+    close(out["longplay"].numpy(), G["vd_train_" + pre + "longplay"], "VideoDnn longplay (torch)")
+    y = om.autoint_multihead_fwd(om.TH, [t(e) for e in G["ai_embs"]], tP("ai"), (32, 16), None, eps=float(G["ai_eps"]))
+    close(y.numpy(), G["ai_y"], "AUTOINT (torch)")
+    cfg = json.loads(str(G["rc_config"]))
+    me, st, b, gt = om.rank_ctr_layout(cfg)
+    emb = {k[len("rc_emb_"):]: t(G[k]) for k in G.files if k.startswith("rc_emb_")}
+    out = om.rank_ctr_fwd(om.TH, emb, tP("rc"), st, b, gt)
+    close(out["task0"].numpy(), G["rc_task0"], "rank/ctr (torch)")
+    uid, iid = [str(v) for v in G["ds_user_ids"]], [str(v) for v in G["ds_item_ids"]]
+    out = om.dssm_fwd(om.TH, {k: t(G["ds_emb_" + k]) for k in uid + iid}, t(G["ds_mask"]), tP("ds"), uid, iid)
+    close(out["student"].numpy(), G["ds_student"], "DSSM student (torch)")
+    close(out["distill"].numpy(), G["ds_distill"], "DSSM distill (torch)")
